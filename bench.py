@@ -1,0 +1,393 @@
+#!/usr/bin/env python
+"""Headline benchmark: hybrid top-10 queries/s over 10 M x 384 chunks (BASELINE.json
+config C4: fp16 chunk matrix + BM25 postings over a 50 k-term Zipf vocabulary, one user
+query = 4 fan-out sub-queries, RRF fusion), strong-scaled over 1/2/4/8 B200.
+
+    python bench.py --gpus N --steps K --warmup W            # our CUDA path
+    python bench.py --impl reference --gpus N ...            # the reference's CPU path
+    torchrun ... bench.py --gpus N ...                       # N > 1, one rank per GPU
+
+One JSON line on stdout (rank 0).  A "step" is one user query: K2 (dense scan + top-k)
+-> K3 (BM25) -> all-gather of candidate records (N > 1) -> K4 (fusion).  `value` is
+measured with the queries already resident in HBM; `e2e` goes through the host-buffer
+C-ABI call with the H2D / D2H copies inside the timed region.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import sys
+import threading
+import time
+from pathlib import Path
+
+import numpy as np
+
+ROOT = Path(__file__).resolve().parent
+sys.path.insert(0, str(ROOT))
+
+K_TOP = 10
+N_SUB = 4                      # fan-out sub-queries per user query (orchestrator.py:39-48)
+N_TERMS = 8                    # BM25 tokens per sub-query
+WEIGHTS = [0.5, 0.6, 0.5, 0.6]  # orchestrator.py:56
+POOL = 16                      # distinct user queries cycled through the timed steps
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=200)
+    ap.add_argument("--warmup", type=int, default=10)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--rows", type=int, default=10_000_000)
+    ap.add_argument("--fusion", default="rrf", choices=["rrf", "linear"])
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--cpu-sample-rows", type=int, default=1_000_000)
+    return ap.parse_args()
+
+
+# ------------------------------------------------------------------ clocks
+class ClockSampler:
+    """Samples SM clock / throttle reasons of one GPU while the timed region runs."""
+
+    def __init__(self, index: int):
+        self.index = index
+        self.samples = []
+        self.reasons = set()
+        self.max_mhz = None
+        self._stop = threading.Event()
+        self._t = None
+        self._nvml = None
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            self._nvml = pynvml
+            self._h = pynvml.nvmlDeviceGetHandleByIndex(index)
+            self.max_mhz = pynvml.nvmlDeviceGetMaxClockInfo(self._h, pynvml.NVML_CLOCK_SM)
+        except Exception:
+            self._nvml = None
+
+    def _loop(self):
+        nv = self._nvml
+        names = {}
+        for n in dir(nv):
+            if n.startswith("nvmlClocksThrottleReason") or n.startswith("nvmlClocksEventReason"):
+                v = getattr(nv, n)
+                if isinstance(v, int) and v not in (0,):
+                    names[v] = n.replace("nvmlClocksThrottleReason", "").replace("nvmlClocksEventReason", "")
+        while not self._stop.is_set():
+            try:
+                self.samples.append(nv.nvmlDeviceGetClockInfo(self._h, nv.NVML_CLOCK_SM))
+                mask = nv.nvmlDeviceGetCurrentClocksThrottleReasons(self._h)
+                for bit, name in names.items():
+                    if mask & bit and bit & (bit - 1) == 0:
+                        self.reasons.add(name)
+            except Exception:
+                pass
+            self._stop.wait(0.05)
+
+    def start(self):
+        if self._nvml is not None:
+            self._t = threading.Thread(target=self._loop, daemon=True)
+            self._t.start()
+
+    def stop(self):
+        self._stop.set()
+        if self._t is not None:
+            self._t.join()
+        reasons = sorted(r for r in self.reasons if r not in ("GpuIdle", "None", "ApplicationsClocksSetting"))
+        return {"sm_mhz": float(np.median(self.samples)) if self.samples else None,
+                "sm_max_mhz": self.max_mhz, "reasons": reasons, "samples": len(self.samples)}
+
+
+# ------------------------------------------------------------- query pool
+def make_query_pool(seed=999):
+    from legal_rag_engine_b200 import synth
+    q = synth.host_queries(POOL * N_SUB, seed=4321).reshape(POOL, N_SUB, 384)
+    terms, _ = synth.host_query_terms(POOL * N_SUB, N_TERMS, seed=seed)
+    terms = terms.reshape(POOL, N_SUB * N_TERMS)
+    ptr = (np.arange(N_SUB + 1) * N_TERMS).astype(np.int32)
+    return q, terms, ptr
+
+
+# ------------------------------------------------------------ CPU baseline
+def cpu_reference_step(sample_rows: int, rows_total: int, threads: int, steps: int = 1):
+    """The reference's CPU path for one user query, on a bounded sample, extrapolated
+    linearly in the number of chunks (both stages are O(N) scans):
+      dense : FAISS-style fp32 sequential scan + heap, one core per sub-query
+              (oracle/c/flat_ip_scan.c), on `sample_rows` rows;
+      BM25  : rank_bm25's dict-per-document list-comprehension, literally
+              (oracle.bm25.BM25OkapiLiteral), on a 20 000-document sample;
+      fusion: retrieval_engine.py:71-96 loop + stable sort.
+    Returns (seconds per user query at rows_total, description)."""
+    from legal_rag_engine_b200 import synth
+    from oracle import cbaseline, fusion
+    from oracle import bm25 as obm25
+    rng = np.random.default_rng(5)
+    xs = rng.standard_normal((sample_rows, 384), dtype=np.float32)
+    xs /= np.linalg.norm(xs, axis=1, keepdims=True)
+    q, terms, ptr = make_query_pool()
+    bm_docs = 20_000
+    idx = synth.host_bm25(bm_docs, seed=777)
+    # token lists for the literal (string-keyed dict) form
+    term_of = np.repeat(np.arange(idx.n_terms), np.diff(idx.term_ptr.astype(np.int64)))
+    order = np.argsort(idx.postings[:, 0], kind="stable")
+    docs = [[] for _ in range(bm_docs)]
+    for t, d, f in zip(term_of[order], idx.postings[order, 0], idx.postings[order, 1]):
+        docs[d].extend([str(t)] * int(f))
+    lit = obm25.BM25OkapiLiteral(docs)
+    t_dense = t_bm = t_fuse = 0.0
+    for s in range(steps):
+        qs = q[s % POOL].astype(np.float32)
+        t0 = time.perf_counter()
+        D, I = cbaseline.flat_ip_search_f32(xs, qs, 2 * K_TOP, threads)
+        t1 = time.perf_counter()
+        scores = []
+        for b in range(N_SUB):
+            toks = [str(t) for t in terms[s % POOL][b * N_TERMS:(b + 1) * N_TERMS]]
+            scores.append(lit.get_scores(toks))
+        t2 = time.perf_counter()
+        for b in range(N_SUB):
+            bm = scores[b]
+            mx = max(bm) if max(bm) > 0 else 1.0       # the two Python max() sweeps (:74)
+            Ib = np.minimum(I[b], bm_docs - 1)
+            fusion.linear_fuse(D[b], Ib, bm, mx, K_TOP, WEIGHTS[b])
+        t3 = time.perf_counter()
+        t_dense += t1 - t0; t_bm += t2 - t1; t_fuse += t3 - t2
+    sec = (t_dense * rows_total / sample_rows + (t_bm + t_fuse) * rows_total / bm_docs) / steps
+    desc = (f"dense: fp32 seq scan+heap on {sample_rows} rows x {N_SUB} sub-queries "
+            f"({min(threads, N_SUB)} threads, one per sub-query as FAISS nq<20); BM25: literal "
+            f"rank_bm25 dict loop on {bm_docs} docs x {N_SUB}x{N_TERMS} tokens (1 thread, pure "
+            f"Python as the reference); both scaled linearly to {rows_total} rows; "
+            f"split s/query@full: dense {t_dense * rows_total / sample_rows / steps:.2f}, "
+            f"bm25+max+fuse {(t_bm + t_fuse) * rows_total / bm_docs / steps:.2f}")
+    return sec, desc
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    threads = os.cpu_count() or 1
+    # warmup + steps on bounded samples
+    cpu_reference_step(100_000, args.rows, threads, steps=1)
+    steps = max(1, min(args.steps, 3))
+    sec, desc = cpu_reference_step(args.cpu_sample_rows, args.rows, threads, steps=steps)
+    qps = 1.0 / sec
+    line = {
+        "impl": "reference", "metric": "hybrid top-10 queries/sec @10Mx384 chunks",
+        "value": qps, "unit": "queries/s", "n_gpus": args.gpus, "steps": steps,
+        "warmup": 1, "ms_per_step": sec * 1e3, "higher_is_better": True, "scaling": "strong",
+        "vs_baseline": None, "dtype": "f32/f64", "data": "synthetic",
+        "config": workload_config(args),
+        "cpu_baseline": {"value": qps, "unit": "queries/s", "cores": threads, "kind": "port",
+                         "sample": desc},
+        "e2e": {"value": qps, "unit": "queries/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }
+    print(json.dumps(line), flush=True)
+
+
+def workload_config(args):
+    return {"workload": f"C4: {args.rows} x 384 fp16 chunks + BM25 postings (50k-term Zipf vocab), "
+                        f"{N_SUB} fan-out sub-queries x {N_TERMS} tokens per user query, top-{K_TOP}, "
+                        f"fusion={args.fusion}",
+            "rows": args.rows, "sub_queries": N_SUB, "k": K_TOP, "fusion": args.fusion,
+            "encoder": "excluded (queries enter as fp16 vectors + term ids)",
+            "l2": "inputs larger than L2 (>= 0.96 GB matrix shard per GPU streamed every step)"}
+
+
+# ------------------------------------------------------------------- ours
+def run_ours(args):
+    import torch
+    import torch.distributed as dist
+    from legal_rag_engine_b200 import synth
+    from legal_rag_engine_b200.bm25_index import okapi_idf
+    from legal_rag_engine_b200.device_index import DeviceIndex, FUSION
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if world != args.gpus:
+        if world == 1 and args.gpus > 1:
+            raise SystemExit("launch with torchrun for --gpus > 1")
+    torch.cuda.set_device(local)
+    device = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=device)
+
+    # ---- this rank's shard: contiguous global id range
+    per = -(-args.rows // world)
+    lo, hi = rank * per, min(args.rows, (rank + 1) * per)
+    n_local = hi - lo
+    t_build = time.time()
+    x = synth.device_vectors(n_local, device, seed=1234 + rank)
+    bm = synth.device_bm25(n_local, device, seed=777 + rank)
+    df = bm["df"].clone()
+    tot_len = torch.tensor([int(bm["doc_len"].sum().item())], dtype=torch.int64, device=device)
+    if world > 1:
+        dist.all_reduce(df)
+        dist.all_reduce(tot_len)
+    idf, _ = okapi_idf(df.cpu().numpy(), args.rows)
+    avgdl = int(tot_len.item()) / args.rows
+    dev = DeviceIndex(local, rank, world)
+    dev.set_corpus(x, lo)
+    dev.set_postings(bm["term_ptr"], bm["postings"], bm["doc_len"], idf, avgdl)
+    nnz_local = bm["nnz"]
+    df_local = bm["df"].cpu().numpy()
+    del bm
+    torch.cuda.synchronize()
+    t_build = time.time() - t_build
+
+    mode = FUSION[args.fusion]
+    qh, th, ptr_h = make_query_pool()
+    q_dev = torch.from_numpy(qh).to(device)
+    t_dev = torch.from_numpy(th).to(device)
+    ptr_dev = torch.from_numpy(ptr_h).to(device)
+    w_dev = torch.tensor(WEIGHTS, dtype=torch.float64, device=device)
+    pb = dev.packed_bytes(N_SUB, K_TOP)
+    packed = torch.empty(pb, dtype=torch.uint8, device=device)
+    packed_all = torch.empty(pb * world, dtype=torch.uint8, device=device) if world > 1 else packed
+    outs = dev.alloc_outputs(N_SUB, K_TOP)
+
+    def step(i):
+        p = i % POOL
+        dev.search_local_packed(q_dev[p], t_dev[p], ptr_dev, K_TOP, mode, packed)
+        if world > 1:
+            dist.all_gather_into_tensor(packed_all, packed)
+        dev.search_finish_packed(packed_all, world, N_SUB, K_TOP, mode, w_dev, outs)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for i in range(max(args.warmup, 3)):
+        step(i)
+    barrier()
+    assert int(outs[4].sum().item()) == 0, "exactness guard tripped on the benchmark queries"
+
+    # ---- timed region: device-resident queries
+    clocks = ClockSampler(local)
+    launches0 = dev.launches
+    dev.profile(True)
+    dev.profile_read(0); dev.profile_read(1)
+    barrier()
+    clocks.start()
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    ev0.record()
+    for i in range(args.steps):
+        step(i)
+    ev1.record()
+    barrier()
+    clk = clocks.stop()
+    ms = ev0.elapsed_time(ev1)
+    scan_ms, scan_n = dev.profile_read(0)
+    bm_ms, bm_n = dev.profile_read(1)
+    dev.profile(False)
+    launches = dev.launches - launches0
+    tms = torch.tensor([ms], dtype=torch.float64, device=device)
+    if world > 1:
+        dist.all_reduce(tms, op=dist.ReduceOp.MAX)
+    ms = float(tms.item())
+
+    # ---- end to end: host buffers through the public call, copies inside the timed region
+    pin_q = torch.from_numpy(qh).pin_memory()
+    pin_t = torch.from_numpy(th).pin_memory()
+    pin_out = [torch.empty(o.shape, dtype=o.dtype).pin_memory() for o in outs[:4]]
+    h2d = N_SUB * 384 * 2 + N_SUB * N_TERMS * 4 + (N_SUB + 1) * 4 + N_SUB * 8
+    d2h = N_SUB * K_TOP * (8 * 4) + N_SUB * 4
+
+    if world == 1:
+        lists = [[th[p][b * N_TERMS:(b + 1) * N_TERMS].tolist() for b in range(N_SUB)] for p in range(POOL)]
+
+        def e2e_step(i):
+            p = i % POOL
+            return dev.search_batch_host(qh[p], lists[p], K_TOP, WEIGHTS, args.fusion)
+    else:
+        qd = torch.empty_like(q_dev[0]); td = torch.empty_like(t_dev[0])
+
+        def e2e_step(i):
+            p = i % POOL
+            qd.copy_(pin_q[p], non_blocking=True)
+            td.copy_(pin_t[p], non_blocking=True)
+            dev.search_local_packed(qd, td, ptr_dev, K_TOP, mode, packed)
+            dist.all_gather_into_tensor(packed_all, packed)
+            dev.search_finish_packed(packed_all, world, N_SUB, K_TOP, mode, w_dev, outs)
+            for o, po in zip(outs[:4], pin_out):
+                po.copy_(o, non_blocking=True)
+            torch.cuda.current_stream().synchronize()
+
+    for i in range(3):
+        e2e_step(i)
+    barrier()
+    e2e_steps = max(10, args.steps // 2)
+    ev0.record()
+    for i in range(e2e_steps):
+        e2e_step(i)
+    ev1.record()
+    barrier()
+    e2e_ms = torch.tensor([ev0.elapsed_time(ev1)], dtype=torch.float64, device=device)
+    if world > 1:
+        dist.all_reduce(e2e_ms, op=dist.ReduceOp.MAX)
+    e2e_ms = float(e2e_ms.item())
+
+    # ---- roofline of the dominant kernel (dense_scan_kernel), algorithmic bytes / event time
+    peaks = {}
+    try:
+        peaks = json.loads((ROOT / "MEASURED_PEAKS.json").read_text())
+    except Exception:
+        pass
+    peak = float(peaks.get("hbm_gbs", 6650.0))
+    peak_src = "measured (MEASURED_PEAKS.json hbm_gbs)" if "hbm_gbs" in peaks else "fallback 6650 GB/s"
+    scan_bytes = n_local * 768
+    scan_gbs = scan_bytes / (scan_ms / max(scan_n, 1) * 1e-3) / 1e9 if scan_ms > 0 else 0.0
+    # BM25 kernel: sum over query tokens of df_local * 8 B, averaged over the pool
+    bm_bytes = float(np.mean([df_local[th[p]].sum() * 8 for p in range(POOL)]))
+    bm_gbs = bm_bytes / (bm_ms / max(bm_n, 1) * 1e-3) / 1e9 if bm_ms > 0 else 0.0
+
+    if rank == 0:
+        qps = args.steps / (ms * 1e-3)
+        line = {
+            "metric": "hybrid top-10 queries/sec @10Mx384 chunks",
+            "value": qps, "unit": "queries/s", "n_gpus": world, "steps": args.steps,
+            "warmup": max(args.warmup, 3), "ms_per_step": ms / args.steps,
+            "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
+            "dtype": "fp16 data, fp32 scan + exact f64 re-score / f64 BM25", "data": "synthetic",
+            "config": dict(workload_config(args), parallelism=f"row-shard x{world}",
+                           rows_per_gpu=n_local, nnz_per_gpu=nnz_local, build_s=round(t_build, 1)),
+            "e2e": {"value": e2e_steps / (e2e_ms * 1e-3), "unit": "queries/s",
+                    "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+                    "ms_per_step": e2e_ms / e2e_steps},
+            "gpu_launches": int(launches),
+            "clocks": clk,
+            "roofline": {"bound": "hbm", "kernel": "dense_scan_kernel<4>", "achieved": scan_gbs,
+                         "peak": peak, "unit": "GB/s", "frac": scan_gbs / peak, "peak_source": peak_src,
+                         "frac_of_8TBs_nominal": scan_gbs / 8000.0, "traffic": None,
+                         "bytes_per_launch": scan_bytes, "ms_per_launch": scan_ms / max(scan_n, 1),
+                         "launches_timed": int(scan_n),
+                         "share_of_step": (scan_ms / max(scan_n, 1)) * (scan_n / args.steps) / (ms / args.steps)},
+            "bm25_kernel": {"achieved": bm_gbs, "unit": "GB/s", "frac": bm_gbs / peak,
+                            "bytes_per_launch": bm_bytes, "ms_per_launch": bm_ms / max(bm_n, 1)},
+        }
+        if world == 1 and not args.no_cpu_baseline:
+            threads = os.cpu_count() or 1
+            sec, desc = cpu_reference_step(args.cpu_sample_rows, args.rows, threads, steps=1)
+            line["cpu_baseline"] = {"value": 1.0 / sec, "unit": "queries/s", "cores": threads,
+                                    "kind": "port", "sample": desc}
+        print(json.dumps(line), flush=True)
+    dev.close()
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    args = parse()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

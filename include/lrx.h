@@ -1,0 +1,168 @@
+/*
+ * lrx.h -- C ABI of the B200-native hybrid-retrieval hot path.
+ *
+ * Drop-in boundary for MET4L-DS/Legal-RAG-engine's `RetrievalEngine`
+ * (reference: src/retrieval/retrieval_engine.py:23-96, create_vector_store.py:14-83,
+ * src/retrieval/orchestrator.py:38-62).  The reference has no FFI of its own: every
+ * FLOP of this path runs inside three PyPI wheels.  Each entry point below names the
+ * reference call site it replaces; INTEGRATION.md shows the ctypes stub a maintainer
+ * would add to the reference.
+ *
+ * Conventions
+ *  - plain C types only; every function returns 0 on success or a negative LRX_E* code;
+ *    lrx_last_error() returns the message of the last failure (handle-owned storage,
+ *    or a process-wide slot when the handle is NULL).
+ *  - one handle per GPU rank.  The handle owns its workspaces and the CUDA stream
+ *    binding; it never frees caller memory.  Every entry point calls cudaSetDevice,
+ *    so a handle may be created on one host thread and used (sequentially) from
+ *    another (reference: src/server/app.py:65-70 vs :110-120).
+ *  - pointers named dev_* are device pointers on the handle's GPU; host_* are host
+ *    pointers (pinned or pageable).  Nothing here falls back to the CPU: a missing
+ *    GPU or a non-sm_100 device is LRX_E_DEVICE at lrx_open.
+ *  - ids are GLOBAL chunk ids (int64) = id_base + local row; -1 pads short lists.
+ *  - all kernels run on the stream set with lrx_set_stream (default: the legacy
+ *    default stream), so PyTorch code can order them with its own work and with
+ *    the NCCL all-gather between lrx_search_local and lrx_search_finish.
+ */
+#ifndef LRX_H
+#define LRX_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define LRX_DIM 384                 /* all-MiniLM-L6-v2 embedding width */
+#define LRX_MAX_BATCH 64            /* sub-queries per lrx_search_* call */
+#define LRX_MAX_DEPTH 256           /* max candidate depth K (= 2k) per list */
+#define LRX_MAX_QUERY_TERMS 64      /* BM25 term slots per sub-query */
+
+enum {
+    LRX_OK = 0,
+    LRX_E_ARG = -1,        /* bad argument */
+    LRX_E_DEVICE = -2,     /* no CUDA device / not sm_100 */
+    LRX_E_CUDA = -3,       /* CUDA runtime error (message has the detail) */
+    LRX_E_STATE = -4,      /* corpus / postings / weights not set */
+    LRX_E_AMBIGUOUS = -5,  /* exactness guard could not be met */
+    LRX_E_NOMEM = -6
+};
+
+enum { LRX_FUSE_LINEAR = 0, LRX_FUSE_RRF = 1 };
+
+typedef struct lrx_handle lrx_handle;
+
+typedef struct lrx_config {
+    int32_t device;        /* CUDA ordinal */
+    int32_t dim;           /* must be LRX_DIM */
+    int32_t rank;          /* shard index of this handle (0 when unsharded) */
+    int32_t world;         /* number of shards (1 when unsharded) */
+} lrx_config;
+
+/* One candidate of one sub-query on one shard; the unit the all-gather moves
+ * (SURVEY.md section 8e).  24 bytes. */
+typedef struct lrx_record {
+    int64_t id;            /* global chunk id, -1 = empty slot */
+    double dense;          /* exact inner product (see oracle/flat_ip.py)   */
+    double bm25;           /* exact BM25Okapi score of that chunk            */
+} lrx_record;
+
+/* ---- lifetime ---------------------------------------------------------- */
+int lrx_open(const lrx_config* cfg, lrx_handle** out);
+int lrx_close(lrx_handle* h);
+const char* lrx_last_error(const lrx_handle* h);
+int lrx_set_stream(lrx_handle* h, void* cuda_stream);
+/* ABI / build identification: "lrx <version> sm_100a". */
+const char* lrx_version(void);
+
+/* ---- index residency (replaces faiss.read_index + pickle.load(bm25.pkl),
+ *      retrieval_engine.py:36-47; the data stay owned by the caller) ------- */
+/* Row-major fp16 [n_local, 384] chunk matrix (768 B/row, 16-byte aligned). */
+int lrx_set_corpus(lrx_handle* h, const void* dev_x_fp16, int64_t n_local, int64_t id_base,
+                   int32_t dim);
+/* Term-major CSR postings restricted to this shard's documents, doc ids LOCAL and
+ * ascending within a term.  dev_postings: nnz pairs {u32 doc_local, u32 tf}.
+ * idf/avgdl/k1/b are the GLOBAL BM25Okapi statistics (rank_bm25 semantics). */
+int lrx_set_postings(lrx_handle* h, const uint64_t* dev_term_ptr, const void* dev_postings,
+                     const uint32_t* dev_doc_len, const double* dev_idf, int64_t n_terms,
+                     int64_t nnz, double avgdl, double k1, double b);
+
+/* ---- stage kernels (device pointers) ----------------------------------- */
+/* K2: replaces IndexFlatIP.search(x, K)  (retrieval_engine.py:64).
+ * dev_q_fp16 [B,384]; outputs [B,K]: exact float64 score, float32 D, int64 I,
+ * best first, (score desc, id asc); pads (-inf, -FLT_MAX, -1).
+ * dev_flags [B]: 0 = exact, 1 = exactness guard failed (caller should retry with
+ * lrx_dense_topk_ex and a larger width). */
+int lrx_dense_topk(lrx_handle* h, const void* dev_q_fp16, int32_t B, int32_t K,
+                   double* dev_exact, float* dev_D, int64_t* dev_I, int32_t* dev_flags);
+int lrx_dense_topk_ex(lrx_handle* h, const void* dev_q_fp16, int32_t B, int32_t K,
+                      int32_t width, double* dev_exact, float* dev_D, int64_t* dev_I,
+                      int32_t* dev_flags);
+/* Exact inner products at given global ids (ids outside the shard or -1 -> -inf). */
+int lrx_dense_at(lrx_handle* h, const void* dev_q_fp16, int32_t B, const int64_t* dev_ids,
+                 int32_t n, double* dev_out);
+
+/* K3: replaces BM25Okapi.get_scores + max()  (retrieval_engine.py:68,74).
+ * dev_q_terms: concatenated term ids (-1 = out of vocabulary), dev_q_ptr [B+1].
+ * Emits (i) exact scores at dev_cand_ids [B,n_cand] (may be NULL / n_cand 0; ids outside
+ * the shard or -1 give 0), (ii) dev_max [B]: max over the shard's POSITIVE scores, 0 when
+ * none, (iii) the shard's top-K positive-score list [B,K] (score desc, id asc; pads
+ * (0,-1)); K may be 0. */
+int lrx_bm25(lrx_handle* h, const int32_t* dev_q_terms, const int32_t* dev_q_ptr, int32_t B,
+             const int64_t* dev_cand_ids, int32_t n_cand, double* dev_cand_scores,
+             double* dev_max, int32_t K, double* dev_top_scores, int64_t* dev_top_ids);
+
+/* ---- K5: the whole of RetrievalEngine.search for a batch of sub-queries ---
+ * lrx_search_local: K2 + K3 on this shard.  Writes, per sub-query b, the shard's
+ *   records: dev_records [B][2][K]  ([b][0] = dense list, [b][1] = BM25 list, the
+ *   latter all-empty in linear mode) and dev_maxbm25 [B].
+ * (all-gather dev_records / dev_maxbm25 across shards -- NCCL, done by the caller)
+ * lrx_search_finish: K4.  dev_records_all [world][B][2][K], dev_max_all [world][B];
+ *   outputs [B,k]: ids (-1 pad), fused score, semantic, keyword; dev_status [B] is the
+ *   OR of the exactness flags (non-zero: rerun with a larger width). */
+int lrx_search_local(lrx_handle* h, const void* dev_q_fp16, const int32_t* dev_q_terms,
+                     const int32_t* dev_q_ptr, int32_t B, int32_t k, int32_t mode,
+                     int32_t width, lrx_record* dev_records, double* dev_maxbm25,
+                     int32_t* dev_flags);
+int lrx_search_finish(lrx_handle* h, const lrx_record* dev_records_all,
+                      const double* dev_max_all, const int32_t* dev_flags_all, int32_t world,
+                      int32_t B, int32_t k, int32_t mode, const double* dev_weights,
+                      int64_t* dev_ids, double* dev_score, double* dev_sem, double* dev_kw,
+                      int32_t* dev_status);
+
+/* Packed form: the shard's records, maxima and flags in ONE contiguous block of
+ * lrx_packed_bytes(B,k) bytes ([B][2][2k] records | [B] double | [B] int32, 16-byte
+ * padded), so the exchange is a single all-gather per query batch; the gathered buffer
+ * [world][packed] goes straight into lrx_search_finish_packed. */
+int64_t lrx_packed_bytes(int32_t B, int32_t k);
+int lrx_search_local_packed(lrx_handle* h, const void* dev_q_fp16, const int32_t* dev_q_terms,
+                            const int32_t* dev_q_ptr, int32_t B, int32_t k, int32_t mode,
+                            int32_t width, void* dev_packed);
+int lrx_search_finish_packed(lrx_handle* h, const void* dev_packed_all, int32_t world, int32_t B,
+                             int32_t k, int32_t mode, const double* dev_weights, int64_t* dev_ids,
+                             double* dev_score, double* dev_sem, double* dev_kw,
+                             int32_t* dev_status);
+
+/* Host-buffer form of the whole search on ONE shard (world == 1): copies the
+ * inputs in, runs K2..K4, copies the results out and synchronises.  This is the
+ * call `RetrievalEngine.search` / `search_batch` makes (retrieval_engine.py:59). */
+int lrx_search_batch_host(lrx_handle* h, const void* host_q_fp16, const int32_t* host_q_terms,
+                          const int32_t* host_q_ptr, const double* host_weights, int32_t B,
+                          int32_t k, int32_t mode, int64_t* host_ids, double* host_score,
+                          double* host_sem, double* host_kw);
+
+/* Number of kernels launched by this handle since lrx_open (bench.py's gpu_launches). */
+int64_t lrx_launch_count(const lrx_handle* h);
+
+
+/* Per-kernel timing for bench.py's roofline line: when enabled, CUDA events are recorded
+ * on the launch stream around every launch of the two streaming kernels
+ * (which = 0: dense_scan_kernel, 1: bm25_scan_kernel).  lrx_profile_read synchronises,
+ * returns the summed device time and launch count since the last read, and resets. */
+int lrx_profile_enable(lrx_handle* h, int32_t on);
+int lrx_profile_read(lrx_handle* h, int32_t which, double* total_ms, int64_t* n_launches);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* LRX_H */

@@ -1,0 +1,492 @@
+// The C ABI of include/lrx.h: argument checking, error strings, workspace
+// management and the K5 launch sequence (all sub-queries of a fan-out batched
+// through one K2 -> K3 -> K4 chain).  No CPU fallback anywhere.
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <new>
+
+#include "common.cuh"
+#include "handle.h"
+
+namespace lrx {
+
+cudaError_t ensure_ws(void** p, size_t* have, size_t need) {
+    if (*have >= need && *p != nullptr) return cudaSuccess;
+    if (*p != nullptr) {
+        cudaError_t e = cudaFree(*p);   // synchronises: safe against in-flight users
+        *p = nullptr;
+        *have = 0;
+        if (e != cudaSuccess) return e;
+    }
+    size_t sz = need + need / 4 + 256;
+    cudaError_t e = cudaMalloc(p, sz);
+    if (e == cudaSuccess) *have = sz;
+    return e;
+}
+
+void prof_begin(lrx_handle* h, int which) {
+    if (!h->prof) return;
+    cudaEvent_t e;
+    if (cudaEventCreate(&e) != cudaSuccess) return;
+    cudaEventRecord(e, h->stream);
+    h->prof_ev[which].push_back(e);
+}
+void prof_end(lrx_handle* h, int which) { prof_begin(h, which); }
+
+static std::string g_err;   // failures before a handle exists
+static std::mutex g_err_mu;
+
+static int fail(lrx_handle* h, int code, const char* fmt, ...) {
+    char buf[512];
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(buf, sizeof(buf), fmt, ap);
+    va_end(ap);
+    if (h != nullptr) {
+        h->err = buf;
+    } else {
+        std::lock_guard<std::mutex> g(g_err_mu);
+        g_err = buf;
+    }
+    return code;
+}
+
+#define LRX_CUDA(h, expr)                                                                   \
+    do {                                                                                    \
+        cudaError_t _e = (expr);                                                            \
+        if (_e != cudaSuccess)                                                              \
+            return fail((h), LRX_E_CUDA, "%s: %s (%s:%d)", #expr, cudaGetErrorString(_e),   \
+                        __FILE__, __LINE__);                                                \
+    } while (0)
+
+static size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
+
+}  // namespace lrx
+
+using namespace lrx;
+
+extern "C" {
+
+const char* lrx_version(void) { return "lrx 0.1 sm_100a"; }
+
+const char* lrx_last_error(const lrx_handle* h) {
+    if (h != nullptr) return h->err.c_str();
+    return g_err.c_str();
+}
+
+int lrx_open(const lrx_config* cfg, lrx_handle** out) {
+    if (cfg == nullptr || out == nullptr) return fail(nullptr, LRX_E_ARG, "lrx_open: null argument");
+    if (cfg->dim != LRX_DIM) return fail(nullptr, LRX_E_ARG, "lrx_open: dim must be %d", LRX_DIM);
+    int ndev = 0;
+    cudaError_t e = cudaGetDeviceCount(&ndev);
+    if (e != cudaSuccess || ndev <= 0)
+        return fail(nullptr, LRX_E_DEVICE, "lrx_open: no CUDA device (%s); there is no CPU fallback",
+                    cudaGetErrorString(e));
+    if (cfg->device < 0 || cfg->device >= ndev)
+        return fail(nullptr, LRX_E_DEVICE, "lrx_open: device %d out of range (%d devices)",
+                    cfg->device, ndev);
+    cudaDeviceProp prop;
+    e = cudaGetDeviceProperties(&prop, cfg->device);
+    if (e != cudaSuccess)
+        return fail(nullptr, LRX_E_DEVICE, "lrx_open: cudaGetDeviceProperties: %s",
+                    cudaGetErrorString(e));
+    if (prop.major != 10)
+        return fail(nullptr, LRX_E_DEVICE,
+                    "lrx_open: device %d is sm_%d%d; this library is built for sm_100a only",
+                    cfg->device, prop.major, prop.minor);
+    e = cudaSetDevice(cfg->device);
+    if (e != cudaSuccess)
+        return fail(nullptr, LRX_E_DEVICE, "lrx_open: cudaSetDevice: %s", cudaGetErrorString(e));
+    lrx_handle* h = new (std::nothrow) lrx_handle();
+    if (h == nullptr) return fail(nullptr, LRX_E_NOMEM, "lrx_open: out of memory");
+    h->device = cfg->device;
+    h->num_sms = prop.multiProcessorCount;
+    h->rank = cfg->rank;
+    h->world = cfg->world > 0 ? cfg->world : 1;
+    *out = h;
+    return LRX_OK;
+}
+
+int lrx_close(lrx_handle* h) {
+    if (h == nullptr) return LRX_OK;
+    cudaSetDevice(h->device);
+    cudaDeviceSynchronize();
+    void* ws[] = {h->ws_dense_part, h->ws_dense_merged, h->ws_bm_part, h->ws_bm_max, h->ws_misc,
+                  h->ws_io};
+    for (void* p : ws)
+        if (p != nullptr) cudaFree(p);
+    if (h->ws_host != nullptr) cudaFreeHost(h->ws_host);
+    delete h;
+    return LRX_OK;
+}
+
+int lrx_set_stream(lrx_handle* h, void* cuda_stream) {
+    if (h == nullptr) return fail(nullptr, LRX_E_ARG, "lrx_set_stream: null handle");
+    std::lock_guard<std::mutex> g(h->mu);
+    h->stream = (cudaStream_t)cuda_stream;
+    return LRX_OK;
+}
+
+int64_t lrx_launch_count(const lrx_handle* h) { return h ? h->launches : 0; }
+
+int lrx_profile_enable(lrx_handle* h, int32_t on) {
+    if (h == nullptr) return fail(nullptr, LRX_E_ARG, "lrx_profile_enable: null handle");
+    std::lock_guard<std::mutex> g(h->mu);
+    h->prof = (on != 0);
+    return LRX_OK;
+}
+
+int lrx_profile_read(lrx_handle* h, int32_t which, double* total_ms, int64_t* n_launches) {
+    if (h == nullptr) return fail(nullptr, LRX_E_ARG, "lrx_profile_read: null handle");
+    std::lock_guard<std::mutex> g(h->mu);
+    if (which < 0 || which > 1 || total_ms == nullptr || n_launches == nullptr)
+        return fail(h, LRX_E_ARG, "lrx_profile_read: bad argument");
+    LRX_CUDA(h, cudaSetDevice(h->device));
+    LRX_CUDA(h, cudaStreamSynchronize(h->stream));
+    std::vector<cudaEvent_t>& ev = h->prof_ev[which];
+    double ms = 0.0;
+    int64_t n = 0;
+    for (size_t i = 0; i + 1 < ev.size(); i += 2) {
+        float t = 0.f;
+        if (cudaEventElapsedTime(&t, ev[i], ev[i + 1]) == cudaSuccess) {
+            ms += t;
+            ++n;
+        }
+    }
+    for (cudaEvent_t e : ev) cudaEventDestroy(e);
+    ev.clear();
+    *total_ms = ms;
+    *n_launches = n;
+    return LRX_OK;
+}
+
+int lrx_set_corpus(lrx_handle* h, const void* dev_x_fp16, int64_t n_local, int64_t id_base,
+                   int32_t dim) {
+    if (h == nullptr) return fail(nullptr, LRX_E_ARG, "lrx_set_corpus: null handle");
+    std::lock_guard<std::mutex> g(h->mu);
+    if (dim != LRX_DIM) return fail(h, LRX_E_ARG, "lrx_set_corpus: dim must be %d", LRX_DIM);
+    if (n_local < 0 || n_local >= (1ll << 32))
+        return fail(h, LRX_E_ARG, "lrx_set_corpus: n_local %lld out of range", (long long)n_local);
+    if (id_base < 0 || id_base + n_local >= (1ll << 32))
+        return fail(h, LRX_E_ARG, "lrx_set_corpus: global ids must stay below 2^32");
+    if (n_local > 0 && (dev_x_fp16 == nullptr || ((uintptr_t)dev_x_fp16 & 15) != 0))
+        return fail(h, LRX_E_ARG, "lrx_set_corpus: matrix pointer must be non-null, 16-byte aligned");
+    h->x = dev_x_fp16;
+    h->n_local = n_local;
+    h->id_base = id_base;
+    return LRX_OK;
+}
+
+int lrx_set_postings(lrx_handle* h, const uint64_t* dev_term_ptr, const void* dev_postings,
+                     const uint32_t* dev_doc_len, const double* dev_idf, int64_t n_terms,
+                     int64_t nnz, double avgdl, double k1, double b) {
+    if (h == nullptr) return fail(nullptr, LRX_E_ARG, "lrx_set_postings: null handle");
+    std::lock_guard<std::mutex> g(h->mu);
+    if (n_terms < 0 || nnz < 0) return fail(h, LRX_E_ARG, "lrx_set_postings: negative size");
+    if (dev_term_ptr == nullptr || dev_idf == nullptr || (nnz > 0 && dev_postings == nullptr) ||
+        (h->n_local > 0 && dev_doc_len == nullptr))
+        return fail(h, LRX_E_ARG, "lrx_set_postings: null pointer");
+    if (!(avgdl > 0.0)) return fail(h, LRX_E_ARG, "lrx_set_postings: avgdl must be > 0");
+    h->term_ptr = dev_term_ptr;
+    h->postings = dev_postings;
+    h->doc_len = dev_doc_len;
+    h->idf = dev_idf;
+    h->n_terms = n_terms;
+    h->nnz = nnz;
+    h->avgdl = avgdl;
+    h->k1 = k1;
+    h->b = b;
+    return LRX_OK;
+}
+
+static int check_dense(lrx_handle* h, const char* fn, int B, int K) {
+    if (h->x == nullptr && h->n_local > 0) return fail(h, LRX_E_STATE, "%s: corpus not set", fn);
+    if (B < 1 || B > LRX_MAX_BATCH) return fail(h, LRX_E_ARG, "%s: B must be in [1,%d]", fn, LRX_MAX_BATCH);
+    if (K < 1 || K > LRX_MAX_DEPTH) return fail(h, LRX_E_ARG, "%s: K must be in [1,%d]", fn, LRX_MAX_DEPTH);
+    return LRX_OK;
+}
+
+int lrx_dense_topk_ex(lrx_handle* h, const void* dev_q_fp16, int32_t B, int32_t K, int32_t width,
+                      double* dev_exact, float* dev_D, int64_t* dev_I, int32_t* dev_flags) {
+    if (h == nullptr) return fail(nullptr, LRX_E_ARG, "lrx_dense_topk: null handle");
+    std::lock_guard<std::mutex> g(h->mu);
+    int rc = check_dense(h, "lrx_dense_topk", B, K);
+    if (rc != LRX_OK) return rc;
+    if (dev_q_fp16 == nullptr || dev_exact == nullptr || dev_D == nullptr || dev_I == nullptr ||
+        dev_flags == nullptr)
+        return fail(h, LRX_E_ARG, "lrx_dense_topk: null pointer");
+    if (width <= 0) width = dense_default_width(K);
+    if (width < K || width > 512 || (width & (width - 1)) != 0)
+        return fail(h, LRX_E_ARG, "lrx_dense_topk: width must be a power of two in [K,512]");
+    LRX_CUDA(h, cudaSetDevice(h->device));
+    LRX_CUDA(h, launch_dense_topk(h, dev_q_fp16, B, K, width, dev_exact, dev_D, dev_I, dev_flags));
+    return LRX_OK;
+}
+
+int lrx_dense_topk(lrx_handle* h, const void* dev_q_fp16, int32_t B, int32_t K, double* dev_exact,
+                   float* dev_D, int64_t* dev_I, int32_t* dev_flags) {
+    return lrx_dense_topk_ex(h, dev_q_fp16, B, K, 0, dev_exact, dev_D, dev_I, dev_flags);
+}
+
+int lrx_dense_at(lrx_handle* h, const void* dev_q_fp16, int32_t B, const int64_t* dev_ids,
+                 int32_t n, double* dev_out) {
+    if (h == nullptr) return fail(nullptr, LRX_E_ARG, "lrx_dense_at: null handle");
+    std::lock_guard<std::mutex> g(h->mu);
+    if (h->x == nullptr && h->n_local > 0) return fail(h, LRX_E_STATE, "lrx_dense_at: corpus not set");
+    if (B < 1 || B > LRX_MAX_BATCH || n < 0) return fail(h, LRX_E_ARG, "lrx_dense_at: bad B/n");
+    if (dev_q_fp16 == nullptr || (n > 0 && (dev_ids == nullptr || dev_out == nullptr)))
+        return fail(h, LRX_E_ARG, "lrx_dense_at: null pointer");
+    LRX_CUDA(h, cudaSetDevice(h->device));
+    LRX_CUDA(h, launch_dense_at(h, dev_q_fp16, B, dev_ids, n, dev_out));
+    return LRX_OK;
+}
+
+int lrx_bm25(lrx_handle* h, const int32_t* dev_q_terms, const int32_t* dev_q_ptr, int32_t B,
+             const int64_t* dev_cand_ids, int32_t n_cand, double* dev_cand_scores, double* dev_max,
+             int32_t K, double* dev_top_scores, int64_t* dev_top_ids) {
+    if (h == nullptr) return fail(nullptr, LRX_E_ARG, "lrx_bm25: null handle");
+    std::lock_guard<std::mutex> g(h->mu);
+    if (h->term_ptr == nullptr) return fail(h, LRX_E_STATE, "lrx_bm25: postings not set");
+    if (B < 1 || B > LRX_MAX_BATCH) return fail(h, LRX_E_ARG, "lrx_bm25: B must be in [1,%d]", LRX_MAX_BATCH);
+    if (K < 0 || K > LRX_MAX_DEPTH) return fail(h, LRX_E_ARG, "lrx_bm25: K must be in [0,%d]", LRX_MAX_DEPTH);
+    if (n_cand < 0) return fail(h, LRX_E_ARG, "lrx_bm25: n_cand < 0");
+    if (dev_q_ptr == nullptr || dev_max == nullptr ||
+        (n_cand > 0 && (dev_cand_ids == nullptr || dev_cand_scores == nullptr)) ||
+        (K > 0 && (dev_top_scores == nullptr || dev_top_ids == nullptr)))
+        return fail(h, LRX_E_ARG, "lrx_bm25: null pointer");
+    LRX_CUDA(h, cudaSetDevice(h->device));
+    LRX_CUDA(h, launch_bm25(h, dev_q_terms, dev_q_ptr, B, dev_cand_ids, n_cand, dev_cand_scores,
+                            dev_max, K, dev_top_scores, dev_top_ids));
+    return LRX_OK;
+}
+
+// scratch carved out of ws_misc for one lrx_search_local call
+struct LocalScratch {
+    double* dense_exact;
+    float* dense_D;
+    int64_t* dense_I;
+    double* dense_bm;
+    double* bm_scores;
+    int64_t* bm_ids;
+    double* bm_dense;
+};
+
+static int search_local_locked(lrx_handle* h, const void* q, const int32_t* q_terms,
+                               const int32_t* q_ptr, int B, int k, int mode, int width,
+                               lrx_record* records, double* maxbm, int32_t* flags) {
+    const int K = 2 * k;   // index.search(query_vector, k * 2)  (retrieval_engine.py:64)
+    int rc = check_dense(h, "lrx_search_local", B, K);
+    if (rc != LRX_OK) return rc;
+    if (h->term_ptr == nullptr) return fail(h, LRX_E_STATE, "lrx_search_local: postings not set");
+    if (mode != LRX_FUSE_LINEAR && mode != LRX_FUSE_RRF)
+        return fail(h, LRX_E_ARG, "lrx_search_local: unknown fusion mode %d", mode);
+    if (width <= 0) width = dense_default_width(K);
+    if (width < K || width > 512 || (width & (width - 1)) != 0)
+        return fail(h, LRX_E_ARG, "lrx_search_local: width must be a power of two in [2k,512]");
+    const size_t n = (size_t)B * K;
+    const size_t need = n * (5 * sizeof(double) + 2 * sizeof(int64_t)) + 1024;
+    LRX_CUDA(h, ensure_ws(&h->ws_misc, &h->ws_misc_bytes, need));
+    LocalScratch s;
+    char* p = (char*)h->ws_misc;
+    s.dense_exact = (double*)p; p += n * sizeof(double);
+    s.dense_bm = (double*)p;    p += n * sizeof(double);
+    s.bm_scores = (double*)p;   p += n * sizeof(double);
+    s.bm_dense = (double*)p;    p += n * sizeof(double);
+    s.dense_I = (int64_t*)p;    p += n * sizeof(int64_t);
+    s.bm_ids = (int64_t*)p;     p += n * sizeof(int64_t);
+    s.dense_D = (float*)p;
+    LRX_CUDA(h, launch_dense_topk(h, q, B, K, width, s.dense_exact, s.dense_D, s.dense_I, flags));
+    const int Kb = (mode == LRX_FUSE_RRF) ? K : 0;
+    LRX_CUDA(h, launch_bm25(h, q_terms, q_ptr, B, s.dense_I, K, s.dense_bm, maxbm, Kb, s.bm_scores,
+                            s.bm_ids));
+    if (mode == LRX_FUSE_RRF) LRX_CUDA(h, launch_dense_at(h, q, B, s.bm_ids, K, s.bm_dense));
+    LRX_CUDA(h, launch_pack_records(h, B, K, mode, s.dense_exact, s.dense_I, s.dense_bm, s.bm_scores,
+                                    s.bm_ids, s.bm_dense, records));
+    return LRX_OK;
+}
+
+int lrx_search_local(lrx_handle* h, const void* dev_q_fp16, const int32_t* dev_q_terms,
+                     const int32_t* dev_q_ptr, int32_t B, int32_t k, int32_t mode, int32_t width,
+                     lrx_record* dev_records, double* dev_maxbm25, int32_t* dev_flags) {
+    if (h == nullptr) return fail(nullptr, LRX_E_ARG, "lrx_search_local: null handle");
+    std::lock_guard<std::mutex> g(h->mu);
+    if (dev_q_fp16 == nullptr || dev_q_ptr == nullptr || dev_records == nullptr ||
+        dev_maxbm25 == nullptr || dev_flags == nullptr)
+        return fail(h, LRX_E_ARG, "lrx_search_local: null pointer");
+    LRX_CUDA(h, cudaSetDevice(h->device));
+    return search_local_locked(h, dev_q_fp16, dev_q_terms, dev_q_ptr, B, k, mode, width, dev_records,
+                               dev_maxbm25, dev_flags);
+}
+
+static int search_finish_locked(lrx_handle* h, const lrx_record* rec_all, const double* max_all,
+                                const int32_t* flags_all, int64_t shard_stride, int world, int B,
+                                int k, int mode,
+                                const double* weights, int64_t* ids, double* score, double* sem,
+                                double* kw, int32_t* status) {
+    const int K = 2 * k;
+    if (world < 1 || world * K > 2048)
+        return fail(h, LRX_E_ARG, "lrx_search_finish: world*2k must be in [1,2048]");
+    if (B < 1 || B > LRX_MAX_BATCH || k < 1 || K > LRX_MAX_DEPTH)
+        return fail(h, LRX_E_ARG, "lrx_search_finish: bad B/k");
+    LRX_CUDA(h, launch_fuse(h, rec_all, max_all, flags_all, shard_stride, world, B, K, k, mode,
+                            weights, ids, score, sem, kw, status));
+    return LRX_OK;
+}
+
+int lrx_search_finish(lrx_handle* h, const lrx_record* dev_records_all, const double* dev_max_all,
+                      const int32_t* dev_flags_all, int32_t world, int32_t B, int32_t k,
+                      int32_t mode, const double* dev_weights, int64_t* dev_ids, double* dev_score,
+                      double* dev_sem, double* dev_kw, int32_t* dev_status) {
+    if (h == nullptr) return fail(nullptr, LRX_E_ARG, "lrx_search_finish: null handle");
+    std::lock_guard<std::mutex> g(h->mu);
+    if (dev_records_all == nullptr || dev_max_all == nullptr || dev_ids == nullptr ||
+        dev_score == nullptr || dev_sem == nullptr || dev_kw == nullptr || dev_status == nullptr ||
+        (mode == LRX_FUSE_LINEAR && dev_weights == nullptr))
+        return fail(h, LRX_E_ARG, "lrx_search_finish: null pointer");
+    LRX_CUDA(h, cudaSetDevice(h->device));
+    return search_finish_locked(h, dev_records_all, dev_max_all, dev_flags_all, 0, world, B, k, mode,
+                                dev_weights, dev_ids, dev_score, dev_sem, dev_kw, dev_status);
+}
+
+// ---- packed form: one contiguous block per shard = one all-gather per batch
+static void packed_layout(int B, int k, size_t* o_max, size_t* o_flags, size_t* total) {
+    const size_t rec = (size_t)B * 2 * (2 * k) * sizeof(lrx_record);
+    *o_max = rec;
+    *o_flags = rec + (size_t)B * sizeof(double);
+    *total = align_up(*o_flags + (size_t)B * sizeof(int32_t), 16);
+}
+
+int64_t lrx_packed_bytes(int32_t B, int32_t k) {
+    if (B < 1 || k < 1) return 0;
+    size_t a, b, t;
+    packed_layout(B, k, &a, &b, &t);
+    return (int64_t)t;
+}
+
+int lrx_search_local_packed(lrx_handle* h, const void* dev_q_fp16, const int32_t* dev_q_terms,
+                            const int32_t* dev_q_ptr, int32_t B, int32_t k, int32_t mode,
+                            int32_t width, void* dev_packed) {
+    if (h == nullptr) return fail(nullptr, LRX_E_ARG, "lrx_search_local_packed: null handle");
+    std::lock_guard<std::mutex> g(h->mu);
+    if (dev_q_fp16 == nullptr || dev_q_ptr == nullptr || dev_packed == nullptr)
+        return fail(h, LRX_E_ARG, "lrx_search_local_packed: null pointer");
+    if (B < 1 || k < 1) return fail(h, LRX_E_ARG, "lrx_search_local_packed: bad B/k");
+    size_t o_max, o_flags, total;
+    packed_layout(B, k, &o_max, &o_flags, &total);
+    LRX_CUDA(h, cudaSetDevice(h->device));
+    char* p = (char*)dev_packed;
+    return search_local_locked(h, dev_q_fp16, dev_q_terms, dev_q_ptr, B, k, mode, width,
+                               (lrx_record*)p, (double*)(p + o_max), (int32_t*)(p + o_flags));
+}
+
+int lrx_search_finish_packed(lrx_handle* h, const void* dev_packed_all, int32_t world, int32_t B,
+                             int32_t k, int32_t mode, const double* dev_weights, int64_t* dev_ids,
+                             double* dev_score, double* dev_sem, double* dev_kw,
+                             int32_t* dev_status) {
+    if (h == nullptr) return fail(nullptr, LRX_E_ARG, "lrx_search_finish_packed: null handle");
+    std::lock_guard<std::mutex> g(h->mu);
+    if (dev_packed_all == nullptr || dev_ids == nullptr || dev_score == nullptr ||
+        dev_sem == nullptr || dev_kw == nullptr || dev_status == nullptr ||
+        (mode == LRX_FUSE_LINEAR && dev_weights == nullptr))
+        return fail(h, LRX_E_ARG, "lrx_search_finish_packed: null pointer");
+    if (B < 1 || k < 1) return fail(h, LRX_E_ARG, "lrx_search_finish_packed: bad B/k");
+    size_t o_max, o_flags, total;
+    packed_layout(B, k, &o_max, &o_flags, &total);
+    LRX_CUDA(h, cudaSetDevice(h->device));
+    const char* p = (const char*)dev_packed_all;
+    return search_finish_locked(h, (const lrx_record*)p, (const double*)(p + o_max),
+                                (const int32_t*)(p + o_flags), (int64_t)total, world, B, k, mode,
+                                dev_weights, dev_ids, dev_score, dev_sem, dev_kw, dev_status);
+}
+
+int lrx_search_batch_host(lrx_handle* h, const void* host_q_fp16, const int32_t* host_q_terms,
+                          const int32_t* host_q_ptr, const double* host_weights, int32_t B,
+                          int32_t k, int32_t mode, int64_t* host_ids, double* host_score,
+                          double* host_sem, double* host_kw) {
+    if (h == nullptr) return fail(nullptr, LRX_E_ARG, "lrx_search_batch_host: null handle");
+    std::lock_guard<std::mutex> g(h->mu);
+    if (host_q_fp16 == nullptr || host_q_ptr == nullptr || host_weights == nullptr ||
+        host_ids == nullptr || host_score == nullptr || host_sem == nullptr || host_kw == nullptr)
+        return fail(h, LRX_E_ARG, "lrx_search_batch_host: null pointer");
+    if (B < 1 || B > LRX_MAX_BATCH) return fail(h, LRX_E_ARG, "lrx_search_batch_host: bad B");
+    if (k < 1 || 2 * k > LRX_MAX_DEPTH) return fail(h, LRX_E_ARG, "lrx_search_batch_host: bad k");
+    if (h->world != 1)
+        return fail(h, LRX_E_STATE, "lrx_search_batch_host: handle is a shard (world=%d); use "
+                                    "lrx_search_local / all-gather / lrx_search_finish", h->world);
+    const int nt = host_q_ptr[B];
+    if (nt < 0 || host_q_ptr[0] != 0) return fail(h, LRX_E_ARG, "lrx_search_batch_host: bad q_ptr");
+    if (nt > 0 && host_q_terms == nullptr) return fail(h, LRX_E_ARG, "lrx_search_batch_host: null terms");
+    for (int b = 0; b < B; ++b)
+        if (host_q_ptr[b + 1] < host_q_ptr[b] || host_q_ptr[b + 1] - host_q_ptr[b] > LRX_MAX_QUERY_TERMS)
+            return fail(h, LRX_E_ARG, "lrx_search_batch_host: query %d has more than %d terms", b,
+                        LRX_MAX_QUERY_TERMS);
+    LRX_CUDA(h, cudaSetDevice(h->device));
+    const int K = 2 * k;
+    // ---- staging layout (same offsets on host and device)
+    size_t off = 0;
+    const size_t o_q = off;       off = align_up(off + (size_t)B * kRowBytes, 256);
+    const size_t o_w = off;       off = align_up(off + (size_t)B * sizeof(double), 256);
+    const size_t o_ptr = off;     off = align_up(off + (size_t)(B + 1) * sizeof(int32_t), 256);
+    const size_t o_terms = off;   off = align_up(off + (size_t)(nt > 0 ? nt : 1) * sizeof(int32_t), 256);
+    const size_t in_bytes = off;
+    const size_t o_ids = off;     off = align_up(off + (size_t)B * k * sizeof(int64_t), 256);
+    const size_t o_score = off;   off = align_up(off + (size_t)B * k * sizeof(double), 256);
+    const size_t o_sem = off;     off = align_up(off + (size_t)B * k * sizeof(double), 256);
+    const size_t o_kw = off;      off = align_up(off + (size_t)B * k * sizeof(double), 256);
+    const size_t o_status = off;  off = align_up(off + (size_t)B * sizeof(int32_t), 256);
+    const size_t out_bytes = off - in_bytes;
+    const size_t o_rec = off;     off = align_up(off + (size_t)B * 2 * K * sizeof(lrx_record), 256);
+    const size_t o_max = off;     off = align_up(off + (size_t)B * sizeof(double), 256);
+    const size_t o_flags = off;   off = align_up(off + (size_t)B * sizeof(int32_t), 256);
+    const size_t total = off;
+    if (h->ws_host_bytes < total) {
+        if (h->ws_host != nullptr) cudaFreeHost(h->ws_host);
+        h->ws_host = nullptr;
+        h->ws_host_bytes = 0;
+        LRX_CUDA(h, cudaMallocHost(&h->ws_host, total * 2));
+        h->ws_host_bytes = total * 2;
+    }
+    LRX_CUDA(h, ensure_ws(&h->ws_io, &h->ws_io_bytes, total));
+    char* hp = (char*)h->ws_host;
+    char* dp = (char*)h->ws_io;
+    memcpy(hp + o_q, host_q_fp16, (size_t)B * kRowBytes);
+    memcpy(hp + o_w, host_weights, (size_t)B * sizeof(double));
+    memcpy(hp + o_ptr, host_q_ptr, (size_t)(B + 1) * sizeof(int32_t));
+    if (nt > 0) memcpy(hp + o_terms, host_q_terms, (size_t)nt * sizeof(int32_t));
+    LRX_CUDA(h, cudaMemcpyAsync(dp, hp, in_bytes, cudaMemcpyHostToDevice, h->stream));
+
+    int width = dense_default_width(K);
+    for (;;) {
+        int rc = search_local_locked(h, dp + o_q, (const int32_t*)(dp + o_terms),
+                                     (const int32_t*)(dp + o_ptr), B, k, mode, width,
+                                     (lrx_record*)(dp + o_rec), (double*)(dp + o_max),
+                                     (int32_t*)(dp + o_flags));
+        if (rc != LRX_OK) return rc;
+        rc = search_finish_locked(h, (const lrx_record*)(dp + o_rec), (const double*)(dp + o_max),
+                                  (const int32_t*)(dp + o_flags), 0, 1, B, k, mode,
+                                  (const double*)(dp + o_w), (int64_t*)(dp + o_ids),
+                                  (double*)(dp + o_score), (double*)(dp + o_sem),
+                                  (double*)(dp + o_kw), (int32_t*)(dp + o_status));
+        if (rc != LRX_OK) return rc;
+        LRX_CUDA(h, cudaMemcpyAsync(hp + in_bytes, dp + in_bytes, out_bytes, cudaMemcpyDeviceToHost,
+                                    h->stream));
+        LRX_CUDA(h, cudaStreamSynchronize(h->stream));
+        bool ambiguous = false;
+        const int32_t* st = (const int32_t*)(hp + o_status);
+        for (int b = 0; b < B; ++b) ambiguous |= (st[b] != 0);
+        if (!ambiguous) break;
+        if (width >= 512)
+            return fail(h, LRX_E_AMBIGUOUS,
+                        "dense candidates are not separable at width 512 (more than ~500 rows "
+                        "within the fp32 error band of the 2k-th score)");
+        width *= 2;   // rare: widen the candidate list and rerun
+    }
+    memcpy(host_ids, hp + o_ids, (size_t)B * k * sizeof(int64_t));
+    memcpy(host_score, hp + o_score, (size_t)B * k * sizeof(double));
+    memcpy(host_sem, hp + o_sem, (size_t)B * k * sizeof(double));
+    memcpy(host_kw, hp + o_kw, (size_t)B * k * sizeof(double));
+    return LRX_OK;
+}
+
+}  // extern "C"

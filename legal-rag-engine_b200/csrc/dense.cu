@@ -1,0 +1,457 @@
+// K2a: flat inner-product scan of the fp16 chunk matrix fused with top-k select.
+//
+// Replaces faiss IndexFlatIP.search (reference: src/retrieval/retrieval_engine.py:64)
+// for small query batches (the B <= 4 sub-queries of one fan-out).
+//
+// Three kernels:
+//   dense_scan_kernel   HBM-bound: streams the [n,384] fp16 matrix once through a
+//                       4-stage shared-memory ring filled by 1-D bulk async copies
+//                       (TMA engine, mbarrier byte counting), scores NQ queries per
+//                       row with fp32 FFMA (fp16 x fp16 products are exact in fp32),
+//                       and keeps a per-CTA top-`width` candidate list in shared
+//                       memory (threshold test in registers; block-wide bitonic
+//                       prune only when the buffer fills).  Scores never touch HBM.
+//   merge_keys_kernel   one CTA per query merges the per-CTA lists.
+//   dense_rescore_kernel re-scores the `width` survivors EXACTLY in float64 (exact
+//                       and order independent, see oracle/flat_ip.py), orders them by
+//                       (score desc, id asc), emits the best K and the guard flag.
+//
+// Algorithmic HBM bytes per launch of dense_scan_kernel: n_local * 768.
+#include "common.cuh"
+#include "handle.h"
+
+namespace lrx {
+
+constexpr int kScanThreads = 512;
+constexpr int kTileRows = 64;                      // 4 rows per warp per tile
+constexpr int kTileBytes = kTileRows * kRowBytes;  // 49152
+constexpr int kStages = 4;
+constexpr int kCap = 1024;                         // candidate buffer entries per query
+constexpr int kMaxWidth = 512;                     // max per-CTA list length
+
+struct ScanSmem {
+    // ring first (16-byte aligned bulk-copy destinations)
+    unsigned char ring[kStages][kTileBytes];
+    uint64_t full[kStages];
+    int count[4];
+    uint32_t tau[4];
+    uint64_t keys[1];   // [NQ][kCap], sized at launch
+};
+
+template <int NQ>
+__device__ __forceinline__ void scan_prune(uint64_t* keys, int* count, uint32_t* tau, int width,
+                                           int tid) {
+    // pad unused slots with the empty key, sort all NQ buffers at once, keep `width`
+#pragma unroll
+    for (int q = 0; q < NQ; ++q) {
+        const int n = count[q];
+        for (int i = tid; i < kCap; i += kScanThreads)
+            if (i >= n) keys[q * kCap + i] = 0ull;
+    }
+    __syncthreads();
+    block_bitonic_sort_desc<uint64_t>(keys, kCap, NQ, kCap, tid, kScanThreads);
+    if (tid < NQ) {
+        const int c = min(count[tid], width);
+        count[tid] = c;
+        if (c == width) tau[tid] = (uint32_t)(keys[tid * kCap + width - 1] >> 32);
+    }
+    __syncthreads();
+}
+
+template <int NQ>
+__global__ void __launch_bounds__(kScanThreads, 1)
+dense_scan_kernel(const unsigned char* __restrict__ x, int64_t n_rows,
+                  const __half* __restrict__ q, int n_q, int width,
+                  uint64_t* __restrict__ part /* [grid][NQ][width] */) {
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    ScanSmem& sm = *reinterpret_cast<ScanSmem*>(smem_raw);
+    uint64_t* keys = sm.keys;
+
+    const int tid = threadIdx.x;
+    const int lane = tid & 31;
+    const int warp = tid >> 5;
+
+    constexpr int NV = 4 * NQ;                                   // (row, query) values per warp pass
+    constexpr int LOGV = (NQ == 4) ? 4 : (NQ == 2) ? 3 : 2;     // halving steps
+    constexpr int kRepl = 1 << (5 - LOGV);                       // lanes sharing one result
+
+    const int64_t n_tiles = (n_rows + kTileRows - 1) / kTileRows;
+    const int64_t my_tiles =
+        (n_tiles > (int64_t)blockIdx.x) ? (n_tiles - blockIdx.x + gridDim.x - 1) / gridDim.x : 0;
+
+    if (tid == 0) {
+        for (int s = 0; s < kStages; ++s) mbar_init(&sm.full[s], 1);
+        fence_barrier_init();
+    }
+    if (tid < 4) {
+        sm.count[tid] = 0;
+        sm.tau[tid] = 0u;   // ordinal 0: every finite score passes
+    }
+    __syncthreads();
+
+    auto issue = [&](int64_t it, int s) {
+        const int64_t tile = (int64_t)blockIdx.x + it * gridDim.x;
+        const int64_t row0 = tile * kTileRows;
+        const int rows = (int)min((int64_t)kTileRows, n_rows - row0);
+        const uint32_t bytes = (uint32_t)rows * kRowBytes;
+        mbar_arrive_expect_tx(&sm.full[s], bytes);
+        bulk_g2s(sm.ring[s], x + row0 * kRowBytes, bytes, &sm.full[s]);
+    };
+    if (tid == 0) {
+        for (int s = 0; s < kStages && s < my_tiles; ++s) issue(s, s);
+    }
+
+    // This lane's 12 query elements per query: halves j*128 + lane*4 + {0..3}, j = 0..2
+    float qf[NQ][12];
+#pragma unroll
+    for (int qi = 0; qi < NQ; ++qi) {
+#pragma unroll
+        for (int j = 0; j < 3; ++j) {
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+                const int col = j * 128 + lane * 4 + e;
+                qf[qi][j * 4 + e] = (qi < n_q) ? __half2float(q[qi * kDim + col]) : 0.f;
+            }
+        }
+    }
+
+    for (int64_t it = 0; it < my_tiles; ++it) {
+        const int s = (int)(it % kStages);
+        const uint32_t parity = (uint32_t)((it / kStages) & 1);
+        const int64_t tile = (int64_t)blockIdx.x + it * gridDim.x;
+        const int64_t row0 = tile * kTileRows;
+        const int rows = (int)min((int64_t)kTileRows, n_rows - row0);
+
+        mbar_wait(&sm.full[s], parity);
+
+        // ---- score 4 rows x NQ queries per warp
+        float acc[NV];
+#pragma unroll
+        for (int i = 0; i < NV; ++i) acc[i] = 0.f;
+        const int r0 = warp * 4;
+#pragma unroll
+        for (int r = 0; r < 4; ++r) {
+            const uint2* rowp = reinterpret_cast<const uint2*>(sm.ring[s] + (r0 + r) * kRowBytes);
+#pragma unroll
+            for (int j = 0; j < 3; ++j) {
+                const uint2 v = rowp[j * 32 + lane];
+                const float2 a = __half22float2(*reinterpret_cast<const __half2*>(&v.x));
+                const float2 b = __half22float2(*reinterpret_cast<const __half2*>(&v.y));
+#pragma unroll
+                for (int qi = 0; qi < NQ; ++qi) {
+                    float t = acc[r * NQ + qi];
+                    t = fmaf(a.x, qf[qi][j * 4 + 0], t);
+                    t = fmaf(a.y, qf[qi][j * 4 + 1], t);
+                    t = fmaf(b.x, qf[qi][j * 4 + 2], t);
+                    t = fmaf(b.y, qf[qi][j * 4 + 3], t);
+                    acc[r * NQ + qi] = t;
+                }
+            }
+        }
+        // ---- reduce-scatter across the warp: one shuffle per output value.
+        //      Same tree for every (row, query) -> identical rows give identical bits.
+#pragma unroll
+        for (int st = 0; st < LOGV; ++st) {
+            const int lb = 16 >> st;
+            const int half = NV >> (st + 1);
+            const bool up = (lane & lb) != 0;
+#pragma unroll
+            for (int i = 0; i < half; ++i) {
+                const float send = up ? acc[i] : acc[i + half];
+                const float keep = up ? acc[i + half] : acc[i];
+                acc[i] = keep + __shfl_xor_sync(0xffffffffu, send, lb);
+            }
+        }
+#pragma unroll
+        for (int lb = (16 >> LOGV); lb > 0; lb >>= 1)
+            acc[0] += __shfl_xor_sync(0xffffffffu, acc[0], lb);
+
+        // ---- threshold test in registers; rare append to the shared buffer
+        {
+            const int idx = lane >> (5 - LOGV);
+            const int r = idx / NQ;
+            const int qi = idx - r * NQ;
+            const int row_in_tile = r0 + r;
+            if ((lane & (kRepl - 1)) == 0 && row_in_tile < rows && qi < n_q) {
+                const uint32_t o = f32_ord(acc[0]);
+                if (o >= sm.tau[qi]) {
+                    const int pos = atomicAdd(&sm.count[qi], 1);
+                    keys[qi * kCap + pos] =
+                        ((uint64_t)o << 32) | (uint32_t)(~(uint32_t)(row0 + row_in_tile));
+                }
+            }
+        }
+        // ---- block barrier: frees the stage, decides pruning uniformly
+        bool need = false;
+#pragma unroll
+        for (int qi = 0; qi < NQ; ++qi) need |= (sm.count[qi] > kCap - kTileRows);
+        const int any = __syncthreads_or(need ? 1 : 0);
+        if (tid == 0 && it + kStages < my_tiles) issue(it + kStages, s);
+        if (any) scan_prune<NQ>(keys, sm.count, sm.tau, width, tid);
+    }
+
+    // ---- final: sorted per-CTA lists out
+    __syncthreads();
+    scan_prune<NQ>(keys, sm.count, sm.tau, width, tid);
+    for (int i = tid; i < NQ * width; i += kScanThreads) {
+        const int qi = i / width;
+        const int j = i - qi * width;
+        const uint64_t k = (j < sm.count[qi]) ? keys[qi * kCap + j] : 0ull;
+        part[((size_t)blockIdx.x * NQ + qi) * width + j] = k;
+    }
+}
+
+// ---------------------------------------------------------------------------
+// Merge `n_lists` sorted key lists (each `width` long, 0-padded) of query
+// blockIdx.x into the best `width` keys.  Generic threshold-buffer select.
+constexpr int kMergeThreads = 1024;
+constexpr int kMergeCap = 4096;
+
+template <typename KeyT>
+__global__ void __launch_bounds__(kMergeThreads, 1)
+merge_keys_kernel(const KeyT* __restrict__ part, int n_lists, int list_stride /* in lists */,
+                  int width, KeyT* __restrict__ out /* [nq][width] */) {
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    KeyT* buf = reinterpret_cast<KeyT*>(smem_raw);
+    __shared__ int count;
+    __shared__ KeyT tau;
+    const int qi = blockIdx.x;
+    const int tid = threadIdx.x;
+    if (tid == 0) {
+        count = 0;
+        tau = 0;
+    }
+    __syncthreads();
+    const int64_t total = (int64_t)n_lists * width;
+    auto prune = [&]() {
+        const int n = count;
+        for (int i = tid; i < kMergeCap; i += kMergeThreads)
+            if (i >= n) buf[i] = 0;
+        __syncthreads();
+        block_bitonic_sort_desc<KeyT>(buf, kMergeCap, 1, kMergeCap, tid, kMergeThreads);
+        if (tid == 0) {
+            const int c = min(count, width);
+            count = c;
+            if (c == width) tau = buf[width - 1];
+        }
+        __syncthreads();
+    };
+    for (int64_t base = 0; base < total; base += kMergeThreads) {
+        const int64_t e = base + tid;
+        if (e < total) {
+            // column-major over the lists: best entries of every list first
+            const int pos = (int)(e / n_lists);
+            const int list = (int)(e - (int64_t)pos * n_lists);
+            const KeyT k = part[((size_t)list * list_stride + qi) * width + pos];
+            if (k != 0 && k > tau) {
+                const int p = atomicAdd(&count, 1);
+                buf[p] = k;
+            }
+        }
+        const int any = __syncthreads_or(count > kMergeCap - kMergeThreads ? 1 : 0);
+        if (any) prune();
+    }
+    __syncthreads();
+    prune();
+    for (int i = tid; i < width; i += kMergeThreads)
+        out[(size_t)qi * width + i] = (i < count) ? buf[i] : (KeyT)0;
+}
+
+template __global__ void merge_keys_kernel<uint64_t>(const uint64_t*, int, int, int, uint64_t*);
+template __global__ void merge_keys_kernel<u128>(const u128*, int, int, int, u128*);
+
+cudaError_t launch_merge_u64(cudaStream_t st, const uint64_t* part, int n_lists, int list_stride,
+                             int width, int nq, uint64_t* out) {
+    merge_keys_kernel<uint64_t><<<nq, kMergeThreads, kMergeCap * sizeof(uint64_t), st>>>(
+        part, n_lists, list_stride, width, out);
+    return cudaGetLastError();
+}
+cudaError_t launch_merge_u128(cudaStream_t st, const void* part, int n_lists, int list_stride,
+                              int width, int nq, void* out) {
+    static bool attr = false;
+    if (!attr) {
+        cudaFuncSetAttribute(merge_keys_kernel<u128>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                             (int)(kMergeCap * sizeof(u128)));
+        attr = true;
+    }
+    merge_keys_kernel<u128><<<nq, kMergeThreads, kMergeCap * sizeof(u128), st>>>(
+        (const u128*)part, n_lists, list_stride, width, (u128*)out);
+    return cudaGetLastError();
+}
+
+// ---------------------------------------------------------------------------
+// Exact float64 inner product of one fp16 row with one fp16 query, by a warp.
+__device__ __forceinline__ double warp_exact_dot(const unsigned char* __restrict__ x, int64_t row,
+                                                 const __half* __restrict__ qv, int lane) {
+    const uint2* rowp = reinterpret_cast<const uint2*>(x + row * kRowBytes);
+    const uint2* qp = reinterpret_cast<const uint2*>(qv);
+    double acc = 0.0;
+#pragma unroll
+    for (int j = 0; j < 3; ++j) {
+        const uint2 v = rowp[j * 32 + lane];
+        const uint2 w = qp[j * 32 + lane];
+        const float2 a = __half22float2(*reinterpret_cast<const __half2*>(&v.x));
+        const float2 b = __half22float2(*reinterpret_cast<const __half2*>(&v.y));
+        const float2 c = __half22float2(*reinterpret_cast<const __half2*>(&w.x));
+        const float2 d = __half22float2(*reinterpret_cast<const __half2*>(&w.y));
+        acc = fma((double)a.x, (double)c.x, acc);
+        acc = fma((double)a.y, (double)c.y, acc);
+        acc = fma((double)b.x, (double)d.x, acc);
+        acc = fma((double)b.y, (double)d.y, acc);
+    }
+#pragma unroll
+    for (int lb = 16; lb > 0; lb >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, lb);
+    return acc;
+}
+
+constexpr int kRescoreThreads = 256;
+
+__global__ void __launch_bounds__(kRescoreThreads)
+dense_rescore_kernel(const unsigned char* __restrict__ x, int64_t n_rows, int64_t id_base,
+                     const __half* __restrict__ q, const uint64_t* __restrict__ merged, int width,
+                     int K, double eps, double* __restrict__ out_exact, float* __restrict__ out_D,
+                     int64_t* __restrict__ out_I, int32_t* __restrict__ out_flag) {
+    __shared__ u128 keys[kMaxWidth];
+    const int qi = blockIdx.x;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int wp2 = next_pow2(width);
+    for (int j = warp; j < wp2; j += kRescoreThreads / 32) {
+        u128 key = 0;
+        if (j < width) {
+            const uint64_t k = merged[(size_t)qi * width + j];
+            if (k != 0ull) {
+                const uint32_t row = key64_row(k);
+                const double e = warp_exact_dot(x, row, q + (size_t)qi * kDim, lane);
+                key = make_key128(e, row);
+            }
+        }
+        if (lane == 0) keys[j] = key;
+    }
+    __syncthreads();
+    block_bitonic_sort_desc<u128>(keys, wp2, 1, wp2, tid, kRescoreThreads);
+    for (int j = tid; j < K; j += kRescoreThreads) {
+        const u128 key = (j < wp2) ? keys[j] : (u128)0;
+        const size_t o = (size_t)qi * K + j;
+        if (key != 0) {
+            const double e = key128_score(key);
+            out_exact[o] = e;
+            out_D[o] = (float)e;
+            out_I[o] = id_base + (int64_t)key128_row(key);
+        } else {
+            out_exact[o] = -INFINITY;
+            out_D[o] = -3.4028234663852886e38f;
+            out_I[o] = -1;
+        }
+    }
+    if (tid == 0) {
+        int flag = 0;
+        if (n_rows > width) {
+            // rows outside the candidate list have fp32 score <= s_last, hence exact
+            // score <= s_last + eps; they must lose strictly to the K-th exact score.
+            const uint64_t last = merged[(size_t)qi * width + width - 1];
+            const int kk = (K < width) ? K : width;
+            const u128 kth = keys[kk - 1];
+            if (last == 0ull || kth == 0 || K > width) {
+                flag = 1;
+            } else {
+                const double s_last = (double)key64_score(last);
+                flag = (s_last + eps < key128_score(kth)) ? 0 : 1;
+            }
+        }
+        out_flag[qi] = flag;
+    }
+}
+
+// exact scores at given global ids; one warp per (query, id)
+__global__ void dense_at_kernel(const unsigned char* __restrict__ x, int64_t n_rows,
+                                int64_t id_base, const __half* __restrict__ q,
+                                const int64_t* __restrict__ ids, int n, double* __restrict__ out) {
+    const int qi = blockIdx.y;
+    const int lane = threadIdx.x & 31;
+    const int j = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    if (j >= n) return;
+    const int64_t id = ids[(size_t)qi * n + j];
+    const int64_t row = id - id_base;
+    double e = -INFINITY;
+    if (id >= 0 && row >= 0 && row < n_rows) e = warp_exact_dot(x, row, q + (size_t)qi * kDim, lane);
+    if (lane == 0) out[(size_t)qi * n + j] = e;
+}
+
+// ---------------------------------------------------------------------------
+static size_t scan_smem_bytes(int nq) {
+    return offsetof(ScanSmem, keys) + (size_t)nq * kCap * sizeof(uint64_t);
+}
+
+int dense_scan_grid(const lrx_handle* h) {
+    const int64_t n_tiles = (h->n_local + kTileRows - 1) / kTileRows;
+    return (int)((n_tiles < h->num_sms) ? (n_tiles > 0 ? n_tiles : 1) : h->num_sms);
+}
+
+template <int NQ>
+static cudaError_t launch_scan(lrx_handle* h, const __half* q, int n_q, int width, uint64_t* part,
+                               int grid) {
+    static bool attr = false;
+    const size_t smem = scan_smem_bytes(NQ);
+    if (!attr) {
+        cudaError_t e = cudaFuncSetAttribute(dense_scan_kernel<NQ>,
+                                             cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return e;
+        attr = true;
+    }
+    prof_begin(h, 0);
+    dense_scan_kernel<NQ><<<grid, kScanThreads, smem, h->stream>>>(
+        (const unsigned char*)h->x, h->n_local, q, n_q, width, part);
+    prof_end(h, 0);
+    h->launches++;
+    return cudaGetLastError();
+}
+
+int dense_default_width(int K) {
+    int w = next_pow2(K + 32);
+    if (w < 64) w = 64;
+    return w;
+}
+
+cudaError_t launch_dense_topk(lrx_handle* h, const void* qv, int B, int K, int width,
+                              double* exact, float* D, int64_t* I, int32_t* flags) {
+    const int grid = dense_scan_grid(h);
+    cudaError_t e;
+    // per-CTA lists for up to 4 queries per pass, merged lists for all B
+    e = ensure_ws(&h->ws_dense_part, &h->ws_dense_part_bytes,
+                  (size_t)grid * 4 * width * sizeof(uint64_t));
+    if (e != cudaSuccess) return e;
+    e = ensure_ws(&h->ws_dense_merged, &h->ws_dense_merged_bytes,
+                  (size_t)B * width * sizeof(uint64_t));
+    if (e != cudaSuccess) return e;
+    uint64_t* part = (uint64_t*)h->ws_dense_part;
+    uint64_t* merged = (uint64_t*)h->ws_dense_merged;
+    const __half* q = (const __half*)qv;
+    for (int b0 = 0; b0 < B; b0 += 4) {
+        const int nq = (B - b0 < 4) ? (B - b0) : 4;
+        const int NQ = (nq > 2) ? 4 : nq;
+        if (NQ == 4) e = launch_scan<4>(h, q + (size_t)b0 * kDim, nq, width, part, grid);
+        else if (NQ == 2) e = launch_scan<2>(h, q + (size_t)b0 * kDim, nq, width, part, grid);
+        else e = launch_scan<1>(h, q + (size_t)b0 * kDim, nq, width, part, grid);
+        if (e != cudaSuccess) return e;
+        e = launch_merge_u64(h->stream, part, grid, NQ, width, nq, merged + (size_t)b0 * width);
+        h->launches++;
+        if (e != cudaSuccess) return e;
+    }
+    dense_rescore_kernel<<<B, kRescoreThreads, 0, h->stream>>>(
+        (const unsigned char*)h->x, h->n_local, h->id_base, q, merged, width, K, kDenseEps, exact,
+        D, I, flags);
+    h->launches++;
+    return cudaGetLastError();
+}
+
+cudaError_t launch_dense_at(lrx_handle* h, const void* q, int B, const int64_t* ids, int n,
+                            double* out) {
+    if (n <= 0 || B <= 0) return cudaSuccess;
+    dim3 grid((n + 3) / 4, B);
+    dense_at_kernel<<<grid, 128, 0, h->stream>>>((const unsigned char*)h->x, h->n_local,
+                                                 h->id_base, (const __half*)q, ids, n, out);
+    h->launches++;
+    return cudaGetLastError();
+}
+
+}  // namespace lrx

@@ -1,0 +1,251 @@
+// K4: cross-shard merge of candidate records + score fusion.
+//
+// linear : reference src/retrieval/retrieval_engine.py:71-96, operation for
+//          operation in float64 (no FMA contraction) -- candidates are the dense
+//          top-2k only, semantic = float32-rounded inner product, keyword =
+//          bm25/max_bm25, stable descending sort (ties keep flat-IP order).
+// rrf    : README.md:39,82-83 (no upstream code): sum of 1/(60+rank) over the dense
+//          and BM25 lists, order (rrf desc, id asc).  See oracle/fusion.py.
+//
+// One CTA per sub-query; every shard runs the same deterministic merge on the
+// all-gathered records, so the result is replicated bit for bit.
+#include "common.cuh"
+#include "handle.h"
+
+namespace lrx {
+
+constexpr int kFuseThreads = 256;
+constexpr int kFuseMaxIn = 2048;   // world * K records per list
+constexpr int kFuseMaxK = LRX_MAX_DEPTH;
+
+__global__ void pack_records_kernel(int B, int K, int mode, const double* __restrict__ dense_exact,
+                                    const int64_t* __restrict__ dense_ids,
+                                    const double* __restrict__ dense_bm25,
+                                    const double* __restrict__ bm_scores,
+                                    const int64_t* __restrict__ bm_ids,
+                                    const double* __restrict__ bm_dense,
+                                    lrx_record* __restrict__ records) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= B * K) return;
+    const int b = i / K, j = i - b * K;
+    lrx_record r0;
+    r0.id = dense_ids[i];
+    r0.dense = dense_exact[i];
+    r0.bm25 = (r0.id >= 0) ? dense_bm25[i] : 0.0;
+    records[((size_t)b * 2 + 0) * K + j] = r0;
+    lrx_record r1;
+    if (mode == LRX_FUSE_RRF && bm_ids[i] >= 0) {
+        r1.id = bm_ids[i];
+        r1.dense = bm_dense[i];
+        r1.bm25 = bm_scores[i];
+    } else {
+        r1.id = -1;
+        r1.dense = -INFINITY;
+        r1.bm25 = 0.0;
+    }
+    records[((size_t)b * 2 + 1) * K + j] = r1;
+}
+
+// key = order image (64) | ~id (32) | source slot (32): sorts by (value desc, id asc)
+__device__ __forceinline__ u128 rec_key(double v, int64_t id, uint32_t src) {
+    return ((u128)f64_ord(v) << 64) | ((u128)(uint32_t)(~(uint32_t)id) << 32) | (u128)src;
+}
+
+__global__ void __launch_bounds__(kFuseThreads)
+fuse_kernel(const lrx_record* __restrict__ rec_all, const double* __restrict__ max_all,
+            const int32_t* __restrict__ flags_all, int64_t shard_stride /* bytes; 0 = dense */,
+            int world, int B, int K, int k, int mode,
+            const double* __restrict__ weights, int64_t* __restrict__ out_ids,
+            double* __restrict__ out_score, double* __restrict__ out_sem,
+            double* __restrict__ out_kw, int32_t* __restrict__ out_status) {
+    extern __shared__ __align__(16) unsigned char fuse_dyn[];
+    u128* keys = reinterpret_cast<u128*>(fuse_dyn);   // [kFuseMaxIn]
+    __shared__ lrx_record dsel[kFuseMaxK];      // global dense top-K
+    __shared__ lrx_record ssel[kFuseMaxK];      // global BM25 top-K (rrf)
+    __shared__ double fscore[2 * kFuseMaxK];
+    __shared__ int n_dense, n_sparse;
+    const int b = blockIdx.x;
+    const int tid = threadIdx.x;
+    const int n_in = world * K;
+    const int np2 = next_pow2(n_in);
+
+    // max_bm25 = max(scores) if max(scores) > 0 else 1.0   (retrieval_engine.py:74)
+    double maxbm = 0.0;
+    int status = 0;
+    for (int w = 0; w < world; ++w) {
+        const double* mw = shard_stride
+            ? reinterpret_cast<const double*>(reinterpret_cast<const char*>(max_all) + w * shard_stride)
+            : max_all + (size_t)w * B;
+        maxbm = fmax(maxbm, mw[b]);
+        if (flags_all != nullptr) {
+            const int32_t* fw = shard_stride
+                ? reinterpret_cast<const int32_t*>(reinterpret_cast<const char*>(flags_all) + w * shard_stride)
+                : flags_all + (size_t)w * B;
+            status |= fw[b];
+        }
+    }
+    if (!(maxbm > 0.0)) maxbm = 1.0;
+
+    auto rec_at = [&](int list, int src) -> const lrx_record& {
+        const int w = src / K, j = src - w * K;
+        const lrx_record* rw = shard_stride
+            ? reinterpret_cast<const lrx_record*>(reinterpret_cast<const char*>(rec_all) + w * shard_stride)
+            : rec_all + (size_t)w * B * 2 * K;
+        return rw[((size_t)b * 2 + list) * K + j];
+    };
+
+    // ---- global dense list: merge the shards' sorted lists
+    for (int i = tid; i < np2; i += kFuseThreads) {
+        u128 key = 0;
+        if (i < n_in) {
+            const lrx_record& r = rec_at(0, i);
+            if (r.id >= 0) key = rec_key(r.dense, r.id, (uint32_t)i);
+        }
+        keys[i] = key;
+    }
+    __syncthreads();
+    block_bitonic_sort_desc<u128>(keys, np2, 1, np2, tid, kFuseThreads);
+    if (tid == 0) {
+        int n = 0;
+        while (n < K && n < np2 && keys[n] != 0) ++n;
+        n_dense = n;
+    }
+    __syncthreads();
+    for (int j = tid; j < n_dense; j += kFuseThreads) dsel[j] = rec_at(0, (int)(uint32_t)keys[j]);
+    __syncthreads();
+    const int nd = n_dense;
+
+    int n_out = 0;
+    if (mode == LRX_FUSE_LINEAR) {
+        const double w = weights[b];
+        const double one_m_w = __dsub_rn(1.0, w);
+        const int kp2 = next_pow2(K);
+        __syncthreads();
+        for (int j = tid; j < kp2; j += kFuseThreads) {
+            u128 key = 0;
+            if (j < nd) {
+                const double sem = (double)__double2float_rn(dsel[j].dense);   // float(dist)
+                const double kw = __ddiv_rn(dsel[j].bm25, maxbm);
+                const double s = __dadd_rn(__dmul_rn(sem, one_m_w), __dmul_rn(kw, w));
+                fscore[j] = s;
+                // stable descending sort: ties keep flat-IP order j
+                key = ((u128)f64_ord(s) << 64) | ((u128)(uint32_t)(~(uint32_t)j) << 32) | (u128)(uint32_t)j;
+            }
+            keys[j] = key;
+        }
+        __syncthreads();
+        block_bitonic_sort_desc<u128>(keys, kp2, 1, kp2, tid, kFuseThreads);
+        n_out = min(k, nd);
+        for (int i = tid; i < k; i += kFuseThreads) {
+            const size_t o = (size_t)b * k + i;
+            if (i < n_out) {
+                const int j = (int)(uint32_t)keys[i];
+                out_ids[o] = dsel[j].id;
+                out_score[o] = fscore[j];
+                out_sem[o] = (double)__double2float_rn(dsel[j].dense);
+                out_kw[o] = __ddiv_rn(dsel[j].bm25, maxbm);
+            } else {
+                out_ids[o] = -1;
+                out_score[o] = 0.0;
+                out_sem[o] = 0.0;
+                out_kw[o] = 0.0;
+            }
+        }
+    } else {
+        // ---- global BM25 list
+        __syncthreads();
+        for (int i = tid; i < np2; i += kFuseThreads) {
+            u128 key = 0;
+            if (i < n_in) {
+                const lrx_record& r = rec_at(1, i);
+                if (r.id >= 0) key = rec_key(r.bm25, r.id, (uint32_t)i);
+            }
+            keys[i] = key;
+        }
+        __syncthreads();
+        block_bitonic_sort_desc<u128>(keys, np2, 1, np2, tid, kFuseThreads);
+        if (tid == 0) {
+            int n = 0;
+            while (n < K && n < np2 && keys[n] != 0) ++n;
+            n_sparse = n;
+        }
+        __syncthreads();
+        for (int j = tid; j < n_sparse; j += kFuseThreads) ssel[j] = rec_at(1, (int)(uint32_t)keys[j]);
+        for (int j = tid; j < 2 * kFuseMaxK; j += kFuseThreads) fscore[j] = -1.0;   // empty
+        __syncthreads();
+        const int ns = n_sparse;
+        // dense term first: 0.0 + 1/(60 + rank)
+        for (int j = tid; j < nd; j += kFuseThreads)
+            fscore[j] = __dadd_rn(0.0, __ddiv_rn(1.0, 60.0 + (double)(j + 1)));
+        __syncthreads();
+        for (int r = tid; r < ns; r += kFuseThreads) {
+            const double term = __ddiv_rn(1.0, 60.0 + (double)(r + 1));
+            int hit = -1;
+            for (int j = 0; j < nd; ++j)
+                if (dsel[j].id == ssel[r].id) hit = j;
+            if (hit >= 0) fscore[hit] = __dadd_rn(fscore[hit], term);      // unique hit per r
+            else fscore[kFuseMaxK + r] = __dadd_rn(0.0, term);
+        }
+        __syncthreads();
+        const int tot = 2 * kFuseMaxK;   // power of two
+        for (int i = tid; i < tot; i += kFuseThreads) {
+            u128 key = 0;
+            if (fscore[i] > 0.0) {
+                const int64_t id = (i < kFuseMaxK) ? dsel[i].id : ssel[i - kFuseMaxK].id;
+                key = rec_key(fscore[i], id, (uint32_t)i);
+            }
+            keys[i] = key;
+        }
+        __syncthreads();
+        block_bitonic_sort_desc<u128>(keys, tot, 1, tot, tid, kFuseThreads);
+        for (int i = tid; i < k; i += kFuseThreads) {
+            const size_t o = (size_t)b * k + i;
+            const u128 key = (i < tot) ? keys[i] : (u128)0;
+            if (key != 0) {
+                const int src = (int)(uint32_t)key;
+                const lrx_record& r = (src < kFuseMaxK) ? dsel[src] : ssel[src - kFuseMaxK];
+                out_ids[o] = r.id;
+                out_score[o] = fscore[src];
+                out_sem[o] = (double)__double2float_rn(r.dense);
+                out_kw[o] = __ddiv_rn(r.bm25, maxbm);
+            } else {
+                out_ids[o] = -1;
+                out_score[o] = 0.0;
+                out_sem[o] = 0.0;
+                out_kw[o] = 0.0;
+            }
+        }
+    }
+    if (tid == 0) out_status[b] = status;
+}
+
+cudaError_t launch_pack_records(lrx_handle* h, int B, int K, int mode, const double* dense_exact,
+                                const int64_t* dense_ids, const double* dense_bm25,
+                                const double* bm_scores, const int64_t* bm_ids,
+                                const double* bm_dense, lrx_record* records) {
+    const int n = B * K;
+    pack_records_kernel<<<(n + 255) / 256, 256, 0, h->stream>>>(
+        B, K, mode, dense_exact, dense_ids, dense_bm25, bm_scores, bm_ids, bm_dense, records);
+    h->launches++;
+    return cudaGetLastError();
+}
+
+cudaError_t launch_fuse(lrx_handle* h, const lrx_record* records_all, const double* max_all,
+                        const int32_t* flags_all, int64_t shard_stride, int world, int B, int K,
+                        int k, int mode, const double* weights, int64_t* ids, double* score,
+                        double* sem, double* kw, int32_t* status) {
+    static bool attr = false;
+    if (!attr) {
+        cudaError_t e = cudaFuncSetAttribute(fuse_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                             (int)(kFuseMaxIn * sizeof(u128)));
+        if (e != cudaSuccess) return e;
+        attr = true;
+    }
+    if (world * K > kFuseMaxIn || K > kFuseMaxK) return cudaErrorInvalidValue;
+    fuse_kernel<<<B, kFuseThreads, kFuseMaxIn * sizeof(u128), h->stream>>>(records_all, max_all, flags_all, shard_stride, world, B, K, k,
+                                                   mode, weights, ids, score, sem, kw, status);
+    h->launches++;
+    return cudaGetLastError();
+}
+
+}  // namespace lrx

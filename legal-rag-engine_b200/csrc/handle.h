@@ -1,0 +1,89 @@
+// Internal: the handle behind include/lrx.h and the host-side launchers each
+// .cu file exports to api.cu.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include <mutex>
+#include <string>
+#include <vector>
+
+#include "../../include/lrx.h"
+
+struct lrx_handle {
+    int device = 0;
+    int num_sms = 0;
+    int rank = 0, world = 1;
+    cudaStream_t stream = 0;
+    std::mutex mu;
+    std::string err;
+    int64_t launches = 0;
+
+    // optional per-kernel timing (bench.py's roofline figure): CUDA event pairs
+    // recorded on the launch stream around the two streaming kernels
+    bool prof = false;
+    std::vector<cudaEvent_t> prof_ev[2];   // [0] dense_scan_kernel, [1] bm25_scan_kernel
+
+    // corpus (caller-owned)
+    const void* x = nullptr;      // fp16 [n_local, 384]
+    int64_t n_local = 0, id_base = 0;
+
+    // postings (caller-owned)
+    const uint64_t* term_ptr = nullptr;
+    const void* postings = nullptr;
+    const uint32_t* doc_len = nullptr;
+    const double* idf = nullptr;
+    int64_t n_terms = 0, nnz = 0;
+    double avgdl = 0, k1 = 1.5, b = 0.75;
+
+    // workspaces (handle-owned, grown on demand)
+    void* ws_dense_part = nullptr;   size_t ws_dense_part_bytes = 0;    // per-CTA key lists
+    void* ws_dense_merged = nullptr; size_t ws_dense_merged_bytes = 0;  // [B][width] keys
+    void* ws_bm_part = nullptr;      size_t ws_bm_part_bytes = 0;       // per-chunk key lists
+    void* ws_bm_max = nullptr;       size_t ws_bm_max_bytes = 0;        // per-CTA max
+    void* ws_misc = nullptr;         size_t ws_misc_bytes = 0;          // search_local scratch
+    void* ws_host = nullptr;         size_t ws_host_bytes = 0;          // pinned staging
+    void* ws_io = nullptr;           size_t ws_io_bytes = 0;            // device staging
+};
+
+namespace lrx {
+
+// Fast-pass score error bound used by the exactness guard:
+// |fp32 scan score - exact| <= 17 roundings * 2^-24 * sum|x_i q_i| <= 1.02e-6
+// for L2-normalised rows; doubled for margin.
+constexpr double kDenseEps = 2.1e-6;
+
+constexpr int kDim = LRX_DIM;
+constexpr int kRowBytes = LRX_DIM * 2;
+
+// dense.cu
+int dense_scan_grid(const lrx_handle* h);
+int dense_default_width(int K);
+cudaError_t launch_dense_topk(lrx_handle* h, const void* q, int B, int K, int width,
+                              double* exact, float* D, int64_t* I, int32_t* flags);
+cudaError_t launch_dense_at(lrx_handle* h, const void* q, int B, const int64_t* ids, int n,
+                            double* out);
+
+// bm25.cu
+cudaError_t launch_bm25(lrx_handle* h, const int32_t* q_terms, const int32_t* q_ptr, int B,
+                        const int64_t* cand_ids, int n_cand, double* cand_scores, double* out_max,
+                        int K, double* top_scores, int64_t* top_ids);
+
+// fuse.cu
+cudaError_t launch_pack_records(lrx_handle* h, int B, int K, int mode, const double* dense_exact,
+                                const int64_t* dense_ids, const double* dense_bm25,
+                                const double* bm_scores, const int64_t* bm_ids,
+                                const double* bm_dense, lrx_record* records);
+cudaError_t launch_fuse(lrx_handle* h, const lrx_record* records_all, const double* max_all,
+                        const int32_t* flags_all, int64_t shard_stride, int world, int B, int K,
+                        int k, int mode, const double* weights, int64_t* ids, double* score,
+                        double* sem, double* kw, int32_t* status);
+
+// profiling hooks (no-ops unless lrx_profile_enable(h, 1))
+void prof_begin(lrx_handle* h, int which);
+void prof_end(lrx_handle* h, int which);
+
+// shared helper: grow a device workspace
+cudaError_t ensure_ws(void** p, size_t* have, size_t need);
+
+}  // namespace lrx

@@ -1,0 +1,210 @@
+"""One GPU shard of the hybrid index: torch owns the device memory, the C ABI
+(include/lrx.h) runs the kernels.  Thin, typed wrappers; no arithmetic here."""
+from __future__ import annotations
+
+import ctypes as C
+from typing import Optional, Sequence
+
+import numpy as np
+import torch
+
+from . import _lib
+from ._lib import LRX_DIM, LRX_FUSE_LINEAR, LRX_FUSE_RRF, RECORD_BYTES
+
+FUSION = {"linear": LRX_FUSE_LINEAR, "rrf": LRX_FUSE_RRF}
+
+
+def _ptr(t: Optional[torch.Tensor]):
+    return C.c_void_p(t.data_ptr()) if t is not None else C.c_void_p(0)
+
+
+class DeviceIndex:
+    def __init__(self, device: int = 0, rank: int = 0, world: int = 1):
+        if not torch.cuda.is_available():
+            raise RuntimeError("DeviceIndex needs a CUDA device: this engine has no CPU fallback")
+        self.lib = _lib.load()
+        self.device = torch.device("cuda", device)
+        self.rank, self.world = rank, world
+        cfg = _lib.lrx_config(device, LRX_DIM, rank, world)
+        h = C.c_void_p()
+        _lib.check(self.lib.lrx_open(C.byref(cfg), C.byref(h)))
+        self.h = h
+        self.x = None
+        self.n_local = 0
+        self.id_base = 0
+        self._post = None
+        self.use_current_stream()
+
+    def close(self):
+        if getattr(self, "h", None) is not None and self.h:
+            self.lib.lrx_close(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def _ck(self, rc):
+        _lib.check(rc, self.h)
+
+    def use_current_stream(self):
+        """Bind the library to torch's current stream on this device."""
+        s = torch.cuda.current_stream(self.device).cuda_stream
+        self._ck(self.lib.lrx_set_stream(self.h, C.c_void_p(s)))
+
+    # ------------------------------------------------------------- residency
+    def set_corpus(self, x: torch.Tensor, id_base: int = 0):
+        assert x.dtype == torch.float16 and x.is_cuda and x.is_contiguous()
+        assert x.dim() == 2 and x.shape[1] == LRX_DIM
+        self.x, self.n_local, self.id_base = x, int(x.shape[0]), int(id_base)
+        self._ck(self.lib.lrx_set_corpus(self.h, _ptr(x), self.n_local, self.id_base, LRX_DIM))
+
+    def set_postings(self, term_ptr, postings, doc_len, idf, avgdl: float, k1: float = 1.5,
+                     b: float = 0.75):
+        """term_ptr int64/uint64 [V+1]; postings int32/uint32 [nnz,2]; doc_len int32/uint32 [n];
+        idf float64 [V] -- torch CUDA tensors or numpy arrays (uploaded)."""
+        def dev(a, dt):
+            if isinstance(a, np.ndarray):
+                if a.dtype == np.uint64:
+                    a = a.view(np.int64)
+                elif a.dtype == np.uint32:
+                    a = a.view(np.int32)
+                a = torch.from_numpy(np.ascontiguousarray(a))
+            return a.to(self.device, dtype=dt).contiguous()
+        tp = dev(term_ptr, torch.int64)
+        po = dev(postings, torch.int32)
+        dl = dev(doc_len, torch.int32)
+        idf_t = dev(idf, torch.float64)
+        if po.numel() == 0:
+            po = torch.zeros((1, 2), dtype=torch.int32, device=self.device)
+        if dl.numel() == 0:
+            dl = torch.zeros(1, dtype=torch.int32, device=self.device)
+        nnz = int(tp[-1].item())
+        self._post = (tp, po, dl, idf_t)
+        self.n_terms = int(tp.numel() - 1)
+        self._ck(self.lib.lrx_set_postings(self.h, _ptr(tp), _ptr(po), _ptr(dl), _ptr(idf_t),
+                                           self.n_terms, nnz, float(avgdl), float(k1), float(b)))
+
+    # ---------------------------------------------------------------- stages
+    def dense_topk(self, q: torch.Tensor, K: int, width: int = 0):
+        assert q.dtype == torch.float16 and q.is_cuda and q.is_contiguous()
+        B = int(q.shape[0])
+        exact = torch.empty((B, K), dtype=torch.float64, device=self.device)
+        D = torch.empty((B, K), dtype=torch.float32, device=self.device)
+        I = torch.empty((B, K), dtype=torch.int64, device=self.device)
+        flags = torch.empty(B, dtype=torch.int32, device=self.device)
+        self._ck(self.lib.lrx_dense_topk_ex(self.h, _ptr(q), B, K, width, _ptr(exact), _ptr(D),
+                                            _ptr(I), _ptr(flags)))
+        return exact, D, I, flags
+
+    def dense_at(self, q: torch.Tensor, ids: torch.Tensor):
+        B, n = int(ids.shape[0]), int(ids.shape[1])
+        out = torch.empty((B, n), dtype=torch.float64, device=self.device)
+        self._ck(self.lib.lrx_dense_at(self.h, _ptr(q), B, _ptr(ids.contiguous()), n, _ptr(out)))
+        return out
+
+    def bm25(self, q_terms: torch.Tensor, q_ptr: torch.Tensor, cand_ids: Optional[torch.Tensor] = None,
+             K: int = 0):
+        """Returns (cand_scores [B,n] or None, max [B], top_scores [B,K], top_ids [B,K])."""
+        B = int(q_ptr.numel() - 1)
+        n = int(cand_ids.shape[1]) if cand_ids is not None else 0
+        cs = torch.empty((B, n), dtype=torch.float64, device=self.device) if n else None
+        mx = torch.empty(B, dtype=torch.float64, device=self.device)
+        ts = torch.empty((B, max(K, 1)), dtype=torch.float64, device=self.device)
+        ti = torch.empty((B, max(K, 1)), dtype=torch.int64, device=self.device)
+        if q_terms.numel() == 0:
+            q_terms = torch.zeros(1, dtype=torch.int32, device=self.device)
+        self._ck(self.lib.lrx_bm25(self.h, _ptr(q_terms), _ptr(q_ptr), B,
+                                   _ptr(cand_ids.contiguous() if n else None), n, _ptr(cs), _ptr(mx),
+                                   K, _ptr(ts), _ptr(ti)))
+        return cs, mx, ts[:, :K], ti[:, :K]
+
+    def search_local(self, q, q_terms, q_ptr, k: int, mode: int, width: int = 0):
+        """K2 + K3 on this shard -> (records uint8 [B,2,2k,24], maxbm25 [B], flags [B])."""
+        B = int(q.shape[0])
+        K = 2 * k
+        rec = torch.empty((B, 2, K, RECORD_BYTES), dtype=torch.uint8, device=self.device)
+        mx = torch.empty(B, dtype=torch.float64, device=self.device)
+        flags = torch.empty(B, dtype=torch.int32, device=self.device)
+        if q_terms.numel() == 0:
+            q_terms = torch.zeros(1, dtype=torch.int32, device=self.device)
+        self._ck(self.lib.lrx_search_local(self.h, _ptr(q), _ptr(q_terms), _ptr(q_ptr), B, k, mode,
+                                           width, _ptr(rec), _ptr(mx), _ptr(flags)))
+        return rec, mx, flags
+
+    def search_finish(self, rec_all, max_all, flags_all, world: int, B: int, k: int, mode: int,
+                      weights: torch.Tensor):
+        ids = torch.empty((B, k), dtype=torch.int64, device=self.device)
+        score = torch.empty((B, k), dtype=torch.float64, device=self.device)
+        sem = torch.empty((B, k), dtype=torch.float64, device=self.device)
+        kw = torch.empty((B, k), dtype=torch.float64, device=self.device)
+        status = torch.empty(B, dtype=torch.int32, device=self.device)
+        self._ck(self.lib.lrx_search_finish(self.h, _ptr(rec_all), _ptr(max_all), _ptr(flags_all),
+                                            world, B, k, mode, _ptr(weights), _ptr(ids), _ptr(score),
+                                            _ptr(sem), _ptr(kw), _ptr(status)))
+        return ids, score, sem, kw, status
+
+    # ------------------------------------------------ packed form (one all-gather)
+    def packed_bytes(self, B: int, k: int) -> int:
+        return int(self.lib.lrx_packed_bytes(B, k))
+
+    def search_local_packed(self, q, q_terms, q_ptr, k: int, mode: int, out: torch.Tensor,
+                            width: int = 0):
+        """K2 + K3 on this shard into `out` (uint8 [packed_bytes]) -- the all-gather unit."""
+        B = int(q.shape[0])
+        self._ck(self.lib.lrx_search_local_packed(self.h, _ptr(q), _ptr(q_terms), _ptr(q_ptr), B, k,
+                                                  mode, width, _ptr(out)))
+        return out
+
+    def search_finish_packed(self, packed_all, world: int, B: int, k: int, mode: int, weights, outs):
+        """K4 on the gathered [world][packed] buffer; outs = (ids, score, sem, kw, status)."""
+        ids, score, sem, kw, status = outs
+        self._ck(self.lib.lrx_search_finish_packed(self.h, _ptr(packed_all), world, B, k, mode,
+                                                   _ptr(weights), _ptr(ids), _ptr(score), _ptr(sem),
+                                                   _ptr(kw), _ptr(status)))
+        return outs
+
+    def alloc_outputs(self, B: int, k: int):
+        return (torch.empty((B, k), dtype=torch.int64, device=self.device),
+                torch.empty((B, k), dtype=torch.float64, device=self.device),
+                torch.empty((B, k), dtype=torch.float64, device=self.device),
+                torch.empty((B, k), dtype=torch.float64, device=self.device),
+                torch.empty(B, dtype=torch.int32, device=self.device))
+
+    # ----------------------------------------------------- whole search, host
+    def search_batch_host(self, q_fp16: np.ndarray, term_lists: Sequence[Sequence[int]], k: int,
+                          weights: Sequence[float], fusion: str = "linear"):
+        """Host buffers in, host buffers out (H2D + kernels + D2H inside the call).
+        Returns (ids int64 [B,k], score, semantic, keyword float64 [B,k])."""
+        q_fp16 = np.ascontiguousarray(q_fp16, dtype=np.float16)
+        B = q_fp16.shape[0]
+        ptr = np.zeros(B + 1, dtype=np.int32)
+        for i, t in enumerate(term_lists):
+            ptr[i + 1] = ptr[i] + len(t)
+        terms = np.fromiter((int(x) for t in term_lists for x in t), dtype=np.int32, count=int(ptr[-1]))
+        if terms.size == 0:
+            terms = np.zeros(1, dtype=np.int32)
+        w = np.ascontiguousarray(weights, dtype=np.float64)
+        ids = np.empty((B, k), dtype=np.int64)
+        score = np.empty((B, k), dtype=np.float64)
+        sem = np.empty((B, k), dtype=np.float64)
+        kw = np.empty((B, k), dtype=np.float64)
+        vp = lambda a: a.ctypes.data_as(C.c_void_p)
+        self._ck(self.lib.lrx_search_batch_host(self.h, vp(q_fp16), vp(terms), vp(ptr), vp(w), B, k,
+                                                FUSION[fusion], vp(ids), vp(score), vp(sem), vp(kw)))
+        return ids, score, sem, kw
+
+    def profile(self, on: bool):
+        self._ck(self.lib.lrx_profile_enable(self.h, 1 if on else 0))
+
+    def profile_read(self, which: int):
+        """(summed device ms, launches) of kernel `which` (0 dense scan, 1 BM25 scan)."""
+        ms, n = C.c_double(), C.c_int64()
+        self._ck(self.lib.lrx_profile_read(self.h, which, C.byref(ms), C.byref(n)))
+        return ms.value, n.value
+
+    @property
+    def launches(self) -> int:
+        return int(self.lib.lrx_launch_count(self.h))

@@ -1,0 +1,250 @@
+"""Parity of the CUDA path (through the C ABI) with the CPU oracle: bit-exact ids,
+scores and fused order.  Runs on the B200 box (`-m gpu`)."""
+import numpy as np
+import pytest
+import torch
+
+from oracle import bm25 as obm25
+from oracle import flat_ip
+from oracle.search import OracleIndex
+
+from legal_rag_engine_b200 import synth
+from legal_rag_engine_b200.bm25_index import BM25Index, tokenize
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def dev():
+    from legal_rag_engine_b200.device_index import DeviceIndex
+    d = DeviceIndex(0)
+    yield d
+    d.close()
+
+
+def _csr_of(idx: BM25Index):
+    return obm25.BM25OkapiCSR.from_postings(idx.n_docs, idx.doc_len, idx.term_ptr.astype(np.int64),
+                                            idx.postings[:, 0], idx.postings[:, 1])
+
+
+def _set_postings(dev, idx: BM25Index):
+    dev.set_postings(idx.term_ptr, idx.postings, idx.doc_len, idx.idf, idx.avgdl, idx.k1, idx.b)
+
+
+def _cuda(a, dt=None):
+    t = torch.from_numpy(np.ascontiguousarray(a)).cuda()
+    return t if dt is None else t.to(dt)
+
+
+# ------------------------------------------------------------------ K2 dense
+@pytest.mark.parametrize("n", [1, 5, 63, 64, 65, 1000, 20011, 300000])
+@pytest.mark.parametrize("B", [1, 2, 3, 4, 7])
+def test_dense_topk_matches_oracle(dev, n, B):
+    x = synth.host_vectors(n, seed=100 + n, dup_frac=0.01)
+    q = synth.host_queries(B, seed=7 + B)
+    if n > 10:
+        q[0] = synth.host_planted_queries(x, [n // 3], seed=1)[0]
+    dev.set_corpus(_cuda(x), id_base=1000)
+    s = flat_ip.exact_scores(x, q)
+    for K in (1, 20, 200):
+        Eo, Do, Io = flat_ip.topk_from_scores(s, K, id_base=1000)
+        E, D, I, flags = dev.dense_topk(_cuda(q), K)
+        assert flags.cpu().numpy().sum() == 0
+        np.testing.assert_array_equal(I.cpu().numpy(), Io)
+        np.testing.assert_array_equal(E.cpu().numpy(), Eo)        # exact float64, bit for bit
+        np.testing.assert_array_equal(D.cpu().numpy(), Do)
+    if n > 10:
+        assert I[0, 0].item() == 1000 + n // 3 or s[0].argmax() != n // 3
+
+
+def test_dense_topk_exact_duplicates_order_by_id(dev):
+    x = synth.host_vectors(5000, seed=5, dup_frac=0.0)
+    x[10:40] = x[4000]                       # 31 identical rows
+    q = synth.host_planted_queries(x, [4000], seed=2)
+    dev.set_corpus(_cuda(x), 0)
+    E, D, I, flags = dev.dense_topk(_cuda(q), 20)
+    assert flags.item() == 0
+    Eo, Do, Io = flat_ip.topk_from_scores(flat_ip.exact_scores(x, q), 20)
+    np.testing.assert_array_equal(I.cpu().numpy(), Io)
+    assert I[0, :20].tolist() == list(range(10, 30))
+
+
+def test_dense_guard_flags_unseparable_candidates(dev):
+    # 600 identical rows tie at the top: width 64 cannot prove exactness -> flag set
+    x = synth.host_vectors(4000, seed=6, dup_frac=0.0)
+    x[100:700] = x[0]
+    q = synth.host_planted_queries(x, [0], seed=3)
+    dev.set_corpus(_cuda(x), 0)
+    E, D, I, flags = dev.dense_topk(_cuda(q), 20, width=64)
+    assert flags.item() == 1
+
+
+def test_dense_at(dev):
+    x = synth.host_vectors(3000, seed=8)
+    q = synth.host_queries(2, seed=9)
+    dev.set_corpus(_cuda(x), 500)
+    ids = np.array([[500, 3499, 499, -1, 3500, 777], [1000, 1001, 1002, 1003, 1004, 1005]], dtype=np.int64)
+    out = dev.dense_at(_cuda(q), _cuda(ids)).cpu().numpy()
+    s = flat_ip.exact_scores(x, q)
+    for b in range(2):
+        for j, i in enumerate(ids[b]):
+            if 500 <= i < 3500:
+                assert out[b, j] == s[b, i - 500]
+            else:
+                assert out[b, j] == -np.inf
+
+
+# ------------------------------------------------------------------- K3 bm25
+def _check_bm25(dev, idx, csr, term_lists, id_base=0, K=20, n_cand=16, seed=0):
+    rng = np.random.default_rng(seed)
+    B = len(term_lists)
+    ptr = np.zeros(B + 1, dtype=np.int32)
+    for i, t in enumerate(term_lists):
+        ptr[i + 1] = ptr[i] + len(t)
+    terms = np.array([x for t in term_lists for x in t] or [0], dtype=np.int32)
+    cand = rng.integers(id_base - 2, id_base + idx.n_docs + 2, size=(B, n_cand)).astype(np.int64)
+    cand[:, 0] = -1
+    cs, mx, ts, ti = dev.bm25(_cuda(terms), _cuda(ptr), _cuda(cand), K)
+    cs, mx, ts, ti = cs.cpu().numpy(), mx.cpu().numpy(), ts.cpu().numpy(), ti.cpu().numpy()
+    for b in range(B):
+        s = csr.get_scores_ids(term_lists[b])
+        pos = s[s > 0]
+        assert mx[b] == (pos.max() if len(pos) else 0.0)
+        for j in range(n_cand):
+            i = cand[b, j] - id_base
+            want = s[i] if (cand[b, j] >= 0 and 0 <= i < idx.n_docs) else 0.0
+            assert cs[b, j] == want                        # bit for bit
+        so, io = obm25.topk_positive(s, K, id_base)
+        np.testing.assert_array_equal(ti[b, :len(io)], io)
+        np.testing.assert_array_equal(ts[b, :len(io)], so)
+        assert (ti[b, len(io):] == -1).all()
+
+
+def test_bm25_real_corpus_bit_exact(dev, legal_texts, reference_queries):
+    idx = BM25Index.from_texts(legal_texts)
+    csr = obm25.BM25OkapiCSR.from_corpus([obm25.tokenize(t) for t in legal_texts])
+    dev.set_corpus(_cuda(synth.host_vectors(idx.n_docs, seed=1)), 0)
+    _set_postings(dev, idx)
+    lists = [idx.term_ids(tokenize(q)) for q in reference_queries]
+    _check_bm25(dev, idx, csr, lists, K=20)
+    _check_bm25(dev, idx, csr, lists[:4], K=200)
+    _check_bm25(dev, idx, csr, lists[:3], K=0)
+
+
+@pytest.mark.parametrize("n,vocab", [(1, 10), (2047, 300), (2048, 300), (16385, 1000), (120000, 5000)])
+def test_bm25_synthetic_bit_exact(dev, n, vocab):
+    idx = synth.host_bm25(n, seed=n, vocab=vocab)
+    csr = _csr_of(idx)
+    dev.set_corpus(_cuda(synth.host_vectors(n, seed=2)), 77)
+    _set_postings(dev, idx)
+    terms, ptr = synth.host_query_terms(5, 8, seed=n + 1, vocab=vocab)
+    lists = [terms[ptr[b]:ptr[b + 1]].tolist() for b in range(5)]
+    lists[1] = lists[1] + [lists[1][0], -1, lists[1][0]]      # repeats + OOV
+    lists[4] = []
+    _check_bm25(dev, idx, csr, lists, id_base=77, K=20, seed=n)
+
+
+# -------------------------------------------------- K4/K5 whole search, host API
+def _oracle_search(x, csr, q, lists, k, weights, fusion):
+    oi = OracleIndex(x, csr)
+    return oi.search_batch_vec(q, lists, k, weights, fusion)
+
+
+def _assert_results(got, want, k):
+    ids, score, sem, kw = got
+    for b, res in enumerate(want):
+        assert ids[b, :len(res)].tolist() == [r[0] for r in res]
+        assert (ids[b, len(res):] == -1).all()
+        for j, r in enumerate(res):
+            assert score[b, j] == r[1] and sem[b, j] == r[2] and kw[b, j] == r[3]
+
+
+@pytest.mark.parametrize("fusion", ["linear", "rrf"])
+@pytest.mark.parametrize("n", [7, 3000, 70000])
+def test_search_batch_host_matches_oracle(dev, n, fusion):
+    x = synth.host_vectors(n, seed=n + 1, dup_frac=0.01)
+    idx = synth.host_bm25(n, seed=n + 2, vocab=3000)
+    csr = _csr_of(idx)
+    dev.set_corpus(_cuda(x), 0)
+    _set_postings(dev, idx)
+    B = 4
+    q = synth.host_queries(B, seed=n + 3)
+    q[1] = synth.host_planted_queries(x, [n // 2], seed=4)[0]
+    terms, ptr = synth.host_query_terms(B, 8, seed=n + 4, vocab=3000)
+    lists = [terms[ptr[b]:ptr[b + 1]].tolist() for b in range(B)]
+    lists[2] = [-1, -1]                                        # all out-of-vocabulary
+    weights = [0.5, 0.6, 0.5, 0.6]
+    for k in (1, 5, 10):
+        want = _oracle_search(x, csr, q, lists, k, weights, fusion)
+        got = dev.search_batch_host(q, lists, k, weights, fusion)
+        _assert_results(got, want, k)
+
+
+def test_real_corpus_hybrid_search(dev, legal_texts, reference_queries):
+    """Config C1 minus the encoder: real BM25 side, seeded stand-in vectors."""
+    idx = BM25Index.from_texts(legal_texts)
+    csr = obm25.BM25OkapiCSR.from_corpus([obm25.tokenize(t) for t in legal_texts])
+    x = synth.host_vectors(idx.n_docs, seed=42, dup_frac=0.004)
+    dev.set_corpus(_cuda(x), 0)
+    _set_postings(dev, idx)
+    qs = reference_queries[:8]
+    q = synth.host_planted_queries(x, list(range(100, 100 + len(qs))), seed=5, noise=0.5)
+    lists = [idx.term_ids(tokenize(s)) for s in qs]
+    weights = [0.6 if "procedure" in s.lower() else 0.5 for s in qs]
+    for fusion in ("linear", "rrf"):
+        want = _oracle_search(x, csr, q, lists, 10, weights, fusion)
+        got = dev.search_batch_host(q, lists, 10, weights, fusion)
+        _assert_results(got, want, 10)
+
+
+# ------------------------------------------------------ shards on one GPU
+@pytest.mark.parametrize("fusion", ["linear", "rrf"])
+def test_two_shards_merge_equals_unsharded(fusion):
+    """Emulates the all-gather on one GPU: two shard handles, records concatenated,
+    lrx_search_finish on the union == the unsharded oracle."""
+    from legal_rag_engine_b200.device_index import DeviceIndex, FUSION
+    n, cut = 50000, 21000
+    x = synth.host_vectors(n, seed=31, dup_frac=0.01)
+    idx = synth.host_bm25(n, seed=32, vocab=3000)
+    csr = _csr_of(idx)
+    B, k = 4, 10
+    q = synth.host_queries(B, seed=33)
+    terms, ptr = synth.host_query_terms(B, 8, seed=34, vocab=3000)
+    lists = [terms[ptr[b]:ptr[b + 1]].tolist() for b in range(B)]
+    weights = [0.5, 0.6, 0.5, 0.6]
+    shards = []
+    for r, (lo, hi) in enumerate([(0, cut), (cut, n)]):
+        d = DeviceIndex(0, rank=r, world=2)
+        d.set_corpus(_cuda(x[lo:hi]), lo)
+        sh = idx.shard(lo, hi)
+        d.set_postings(sh.term_ptr, sh.postings, sh.doc_len, sh.idf, sh.avgdl)
+        shards.append(d)
+    recs, maxes, flags = [], [], []
+    for d in shards:
+        r, m, f = d.search_local(_cuda(q), _cuda(terms), _cuda(ptr), k, FUSION[fusion])
+        recs.append(r); maxes.append(m); flags.append(f)
+    rec_all, max_all, flags_all = torch.stack(recs), torch.stack(maxes), torch.stack(flags)
+    out = shards[0].search_finish(rec_all, max_all, flags_all, 2, B, k, FUSION[fusion],
+                                  _cuda(np.array(weights)))
+    ids, score, sem, kw, status = [t.cpu().numpy() for t in out]
+    assert status.sum() == 0
+    want = _oracle_search(x, csr, q, lists, k, weights, fusion)
+    _assert_results((ids, score, sem, kw), want, k)
+    for d in shards:
+        d.close()
+
+
+def test_one_million_rows(dev):
+    """Config C3 size: 1 M x 384, batch 1 and 4, top-20 -- still bit-exact."""
+    n = 1_000_000
+    x = synth.host_vectors(n, seed=1234)
+    q = synth.host_queries(4, seed=4321)
+    dev.set_corpus(_cuda(x), 0)
+    s = flat_ip.exact_scores(x, q)
+    Eo, Do, Io = flat_ip.topk_from_scores(s, 20)
+    E, D, I, flags = dev.dense_topk(_cuda(q), 20)
+    assert flags.sum().item() == 0
+    np.testing.assert_array_equal(I.cpu().numpy(), Io)
+    np.testing.assert_array_equal(E.cpu().numpy(), Eo)
+    E1, D1, I1, f1 = dev.dense_topk(_cuda(q[:1]), 20)
+    np.testing.assert_array_equal(I1.cpu().numpy(), Io[:1])
