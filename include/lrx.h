@@ -81,11 +81,18 @@ const char* lrx_version(void);
 int lrx_set_corpus(lrx_handle* h, const void* dev_x_fp16, int64_t n_local, int64_t id_base,
                    int32_t dim);
 /* Term-major CSR postings restricted to this shard's documents, doc ids LOCAL and
- * ascending within a term.  dev_postings: nnz pairs {u32 doc_local, u32 tf}.
- * idf/avgdl/k1/b are the GLOBAL BM25Okapi statistics (rank_bm25 semantics). */
+ * ascending within a term.  dev_postings: nnz 16-byte entries {u32 doc_local, u32 tf,
+ * f64 impact}, 16-byte aligned, where
+ *   impact = tf*(k1+1) / (tf + k1*(1 - b + b*len(doc)/avgdl))
+ * is the query-independent BM25Okapi factor in float64 (lrx_bm25_build_impacts fills it
+ * from doc/tf, the document lengths and the GLOBAL avgdl).  dev_idf: GLOBAL idf per
+ * term (rank_bm25 semantics: epsilon floor applied).  Replaces pickle.load(bm25.pkl). */
 int lrx_set_postings(lrx_handle* h, const uint64_t* dev_term_ptr, const void* dev_postings,
-                     const uint32_t* dev_doc_len, const double* dev_idf, int64_t n_terms,
-                     int64_t nnz, double avgdl, double k1, double b);
+                     const double* dev_idf, int64_t n_terms, int64_t nnz);
+/* Index build (create_vector_store.py:60-61, the BM25Okapi constructor): fills the
+ * `impact` field of nnz postings in place, with rank_bm25's float64 operation order. */
+int lrx_bm25_build_impacts(lrx_handle* h, void* dev_postings, int64_t nnz,
+                           const uint32_t* dev_doc_len, double avgdl, double k1, double b);
 
 /* ---- stage kernels (device pointers) ----------------------------------- */
 /* K2: replaces IndexFlatIP.search(x, K)  (retrieval_engine.py:64).

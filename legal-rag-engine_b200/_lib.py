@@ -56,7 +56,8 @@ _SIGNATURES = {
     "lrx_set_stream": (C.c_int, [_vp, _vp]),
     "lrx_version": (C.c_char_p, []),
     "lrx_set_corpus": (C.c_int, [_vp, _vp, _i64, _i64, _i32]),
-    "lrx_set_postings": (C.c_int, [_vp, _vp, _vp, _vp, _vp, _i64, _i64, _f64, _f64, _f64]),
+    "lrx_set_postings": (C.c_int, [_vp, _vp, _vp, _vp, _i64, _i64]),
+    "lrx_bm25_build_impacts": (C.c_int, [_vp, _vp, _i64, _vp, _f64, _f64, _f64]),
     "lrx_dense_topk": (C.c_int, [_vp, _vp, _i32, _i32, _vp, _vp, _vp, _vp]),
     "lrx_dense_topk_ex": (C.c_int, [_vp, _vp, _i32, _i32, _i32, _vp, _vp, _vp, _vp]),
     "lrx_dense_at": (C.c_int, [_vp, _vp, _i32, _vp, _i32, _vp]),

@@ -104,6 +104,12 @@ int lrx_open(const lrx_config* cfg, lrx_handle** out) {
     h->num_sms = prop.multiProcessorCount;
     h->rank = cfg->rank;
     h->world = cfg->world > 0 ? cfg->world : 1;
+    if (cudaStreamCreateWithFlags(&h->aux, cudaStreamNonBlocking) != cudaSuccess ||
+        cudaEventCreateWithFlags(&h->ev_fork, cudaEventDisableTiming) != cudaSuccess ||
+        cudaEventCreateWithFlags(&h->ev_join, cudaEventDisableTiming) != cudaSuccess) {
+        delete h;
+        return fail(nullptr, LRX_E_CUDA, "lrx_open: cannot create side stream / events");
+    }
     *out = h;
     return LRX_OK;
 }
@@ -117,6 +123,9 @@ int lrx_close(lrx_handle* h) {
     for (void* p : ws)
         if (p != nullptr) cudaFree(p);
     if (h->ws_host != nullptr) cudaFreeHost(h->ws_host);
+    if (h->aux) cudaStreamDestroy(h->aux);
+    if (h->ev_fork) cudaEventDestroy(h->ev_fork);
+    if (h->ev_join) cudaEventDestroy(h->ev_join);
     delete h;
     return LRX_OK;
 }
@@ -179,24 +188,33 @@ int lrx_set_corpus(lrx_handle* h, const void* dev_x_fp16, int64_t n_local, int64
 }
 
 int lrx_set_postings(lrx_handle* h, const uint64_t* dev_term_ptr, const void* dev_postings,
-                     const uint32_t* dev_doc_len, const double* dev_idf, int64_t n_terms,
-                     int64_t nnz, double avgdl, double k1, double b) {
+                     const double* dev_idf, int64_t n_terms, int64_t nnz) {
     if (h == nullptr) return fail(nullptr, LRX_E_ARG, "lrx_set_postings: null handle");
     std::lock_guard<std::mutex> g(h->mu);
     if (n_terms < 0 || nnz < 0) return fail(h, LRX_E_ARG, "lrx_set_postings: negative size");
-    if (dev_term_ptr == nullptr || dev_idf == nullptr || (nnz > 0 && dev_postings == nullptr) ||
-        (h->n_local > 0 && dev_doc_len == nullptr))
+    if (dev_term_ptr == nullptr || dev_idf == nullptr || (nnz > 0 && dev_postings == nullptr))
         return fail(h, LRX_E_ARG, "lrx_set_postings: null pointer");
-    if (!(avgdl > 0.0)) return fail(h, LRX_E_ARG, "lrx_set_postings: avgdl must be > 0");
+    if (((uintptr_t)dev_postings & 15) != 0)
+        return fail(h, LRX_E_ARG, "lrx_set_postings: postings must be 16-byte aligned");
     h->term_ptr = dev_term_ptr;
     h->postings = dev_postings;
-    h->doc_len = dev_doc_len;
     h->idf = dev_idf;
     h->n_terms = n_terms;
     h->nnz = nnz;
-    h->avgdl = avgdl;
-    h->k1 = k1;
-    h->b = b;
+    return LRX_OK;
+}
+
+int lrx_bm25_build_impacts(lrx_handle* h, void* dev_postings, int64_t nnz,
+                           const uint32_t* dev_doc_len, double avgdl, double k1, double b) {
+    if (h == nullptr) return fail(nullptr, LRX_E_ARG, "lrx_bm25_build_impacts: null handle");
+    std::lock_guard<std::mutex> g(h->mu);
+    if (nnz < 0 || (nnz > 0 && (dev_postings == nullptr || dev_doc_len == nullptr)))
+        return fail(h, LRX_E_ARG, "lrx_bm25_build_impacts: bad argument");
+    if (!(avgdl > 0.0)) return fail(h, LRX_E_ARG, "lrx_bm25_build_impacts: avgdl must be > 0");
+    if (((uintptr_t)dev_postings & 15) != 0)
+        return fail(h, LRX_E_ARG, "lrx_bm25_build_impacts: postings must be 16-byte aligned");
+    LRX_CUDA(h, cudaSetDevice(h->device));
+    LRX_CUDA(h, launch_bm25_impacts(h, dev_postings, nnz, dev_doc_len, avgdl, k1, b));
     return LRX_OK;
 }
 
@@ -296,10 +314,16 @@ static int search_local_locked(lrx_handle* h, const void* q, const int32_t* q_te
     s.dense_I = (int64_t*)p;    p += n * sizeof(int64_t);
     s.bm_ids = (int64_t*)p;     p += n * sizeof(int64_t);
     s.dense_D = (float*)p;
+    // fork: tile bounds of every query token (needs only the query) on the side stream
+    LRX_CUDA(h, cudaEventRecord(h->ev_fork, h->stream));
+    LRX_CUDA(h, cudaStreamWaitEvent(h->aux, h->ev_fork, 0));
+    LRX_CUDA(h, launch_bm25_bounds(h, q_terms, q_ptr, B, h->aux));
+    LRX_CUDA(h, cudaEventRecord(h->ev_join, h->aux));
     LRX_CUDA(h, launch_dense_topk(h, q, B, K, width, s.dense_exact, s.dense_D, s.dense_I, flags));
+    LRX_CUDA(h, cudaStreamWaitEvent(h->stream, h->ev_join, 0));   // join
     const int Kb = (mode == LRX_FUSE_RRF) ? K : 0;
-    LRX_CUDA(h, launch_bm25(h, q_terms, q_ptr, B, s.dense_I, K, s.dense_bm, maxbm, Kb, s.bm_scores,
-                            s.bm_ids));
+    LRX_CUDA(h, launch_bm25_scan(h, q_terms, q_ptr, B, s.dense_I, K, s.dense_bm, maxbm, Kb,
+                                 s.bm_scores, s.bm_ids));
     if (mode == LRX_FUSE_RRF) LRX_CUDA(h, launch_dense_at(h, q, B, s.bm_ids, K, s.bm_dense));
     LRX_CUDA(h, launch_pack_records(h, B, K, mode, s.dense_exact, s.dense_I, s.dense_bm, s.bm_scores,
                                     s.bm_ids, s.bm_dense, records));

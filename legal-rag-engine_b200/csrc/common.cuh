@@ -46,10 +46,9 @@ __device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
 // Bounded wait: a pipeline bug traps (surfaces as a CUDA error) instead of
 // hanging the GPU box.
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
-    if (mbar_try_wait(bar, parity)) return;
-    const long long t0 = clock64();
+    uint32_t spins = 0;
     while (!mbar_try_wait(bar, parity)) {
-        if (clock64() - t0 > 6000000000LL) __trap();   // ~3 s at 2 GHz
+        if (++spins > (1u << 24)) __trap();   // each failed try_wait already sleeps in HW
     }
 }
 // 1-D bulk async copy global -> shared (TMA engine, no tensor map), completion
@@ -115,6 +114,28 @@ __device__ __forceinline__ void block_bitonic_sort_desc(KeyT* keys, int n, int n
                 }
             }
             __syncthreads();
+        }
+    }
+}
+
+// Descending bitonic sort of n (power of two) keys in shared memory by ONE warp:
+// ordering between stages is a __syncwarp, no block barrier.
+template <typename KeyT>
+__device__ __forceinline__ void warp_bitonic_sort_desc(KeyT* keys, int n, int lane) {
+    const int half = n >> 1;
+    for (int k = 2; k <= n; k <<= 1) {
+        for (int j = k >> 1; j > 0; j >>= 1) {
+            for (int u = lane; u < half; u += 32) {
+                const int i = ((u & ~(j - 1)) << 1) | (u & (j - 1));
+                const int p = i | j;
+                const KeyT a = keys[i], b = keys[p];
+                const bool desc = ((i & k) == 0);
+                if (desc ? (a < b) : (a > b)) {
+                    keys[i] = b;
+                    keys[p] = a;
+                }
+            }
+            __syncwarp();
         }
     }
 }

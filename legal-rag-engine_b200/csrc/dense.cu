@@ -201,83 +201,9 @@ dense_scan_kernel(const unsigned char* __restrict__ x, int64_t n_rows,
     }
 }
 
-// ---------------------------------------------------------------------------
-// Merge `n_lists` sorted key lists (each `width` long, 0-padded) of query
-// blockIdx.x into the best `width` keys.  Generic threshold-buffer select.
-constexpr int kMergeThreads = 1024;
-constexpr int kMergeCap = 4096;
-
-template <typename KeyT>
-__global__ void __launch_bounds__(kMergeThreads, 1)
-merge_keys_kernel(const KeyT* __restrict__ part, int n_lists, int list_stride /* in lists */,
-                  int width, KeyT* __restrict__ out /* [nq][width] */) {
-    extern __shared__ __align__(128) unsigned char smem_raw[];
-    KeyT* buf = reinterpret_cast<KeyT*>(smem_raw);
-    __shared__ int count;
-    __shared__ KeyT tau;
-    const int qi = blockIdx.x;
-    const int tid = threadIdx.x;
-    if (tid == 0) {
-        count = 0;
-        tau = 0;
-    }
-    __syncthreads();
-    const int64_t total = (int64_t)n_lists * width;
-    auto prune = [&]() {
-        const int n = count;
-        for (int i = tid; i < kMergeCap; i += kMergeThreads)
-            if (i >= n) buf[i] = 0;
-        __syncthreads();
-        block_bitonic_sort_desc<KeyT>(buf, kMergeCap, 1, kMergeCap, tid, kMergeThreads);
-        if (tid == 0) {
-            const int c = min(count, width);
-            count = c;
-            if (c == width) tau = buf[width - 1];
-        }
-        __syncthreads();
-    };
-    for (int64_t base = 0; base < total; base += kMergeThreads) {
-        const int64_t e = base + tid;
-        if (e < total) {
-            // column-major over the lists: best entries of every list first
-            const int pos = (int)(e / n_lists);
-            const int list = (int)(e - (int64_t)pos * n_lists);
-            const KeyT k = part[((size_t)list * list_stride + qi) * width + pos];
-            if (k != 0 && k > tau) {
-                const int p = atomicAdd(&count, 1);
-                buf[p] = k;
-            }
-        }
-        const int any = __syncthreads_or(count > kMergeCap - kMergeThreads ? 1 : 0);
-        if (any) prune();
-    }
-    __syncthreads();
-    prune();
-    for (int i = tid; i < width; i += kMergeThreads)
-        out[(size_t)qi * width + i] = (i < count) ? buf[i] : (KeyT)0;
-}
-
-template __global__ void merge_keys_kernel<uint64_t>(const uint64_t*, int, int, int, uint64_t*);
-template __global__ void merge_keys_kernel<u128>(const u128*, int, int, int, u128*);
-
+// merge.cu
 cudaError_t launch_merge_u64(cudaStream_t st, const uint64_t* part, int n_lists, int list_stride,
-                             int width, int nq, uint64_t* out) {
-    merge_keys_kernel<uint64_t><<<nq, kMergeThreads, kMergeCap * sizeof(uint64_t), st>>>(
-        part, n_lists, list_stride, width, out);
-    return cudaGetLastError();
-}
-cudaError_t launch_merge_u128(cudaStream_t st, const void* part, int n_lists, int list_stride,
-                              int width, int nq, void* out) {
-    static bool attr = false;
-    if (!attr) {
-        cudaFuncSetAttribute(merge_keys_kernel<u128>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                             (int)(kMergeCap * sizeof(u128)));
-        attr = true;
-    }
-    merge_keys_kernel<u128><<<nq, kMergeThreads, kMergeCap * sizeof(u128), st>>>(
-        (const u128*)part, n_lists, list_stride, width, (u128*)out);
-    return cudaGetLastError();
-}
+                             int width, int nq, uint64_t* out);
 
 // ---------------------------------------------------------------------------
 // Exact float64 inner product of one fp16 row with one fp16 query, by a warp.
@@ -315,20 +241,51 @@ dense_rescore_kernel(const unsigned char* __restrict__ x, int64_t n_rows, int64_
     const int qi = blockIdx.x;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int wp2 = next_pow2(width);
-    for (int j = warp; j < wp2; j += kRescoreThreads / 32) {
-        u128 key = 0;
-        if (j < width) {
-            const uint64_t k = merged[(size_t)qi * width + j];
-            if (k != 0ull) {
-                const uint32_t row = key64_row(k);
-                const double e = warp_exact_dot(x, row, q + (size_t)qi * kDim, lane);
-                key = make_key128(e, row);
-            }
+    constexpr int kWarps = kRescoreThreads / 32;
+    // each warp: 4 candidates per pass, their 12 row loads issued before any reduction
+    for (int j0 = warp * 4; j0 < wp2; j0 += kWarps * 4) {
+        uint64_t kk[4];
+        uint2 rv[4][3];
+#pragma unroll
+        for (int c = 0; c < 4; ++c) {
+            const int j = j0 + c;
+            kk[c] = (j < width) ? merged[(size_t)qi * width + j] : 0ull;
         }
-        if (lane == 0) keys[j] = key;
+#pragma unroll
+        for (int c = 0; c < 4; ++c) {
+            const uint2* rowp = reinterpret_cast<const uint2*>(
+                x + (int64_t)(kk[c] ? key64_row(kk[c]) : 0u) * kRowBytes);
+#pragma unroll
+            for (int s = 0; s < 3; ++s)
+                rv[c][s] = (kk[c] && n_rows > 0) ? rowp[s * 32 + lane] : make_uint2(0u, 0u);
+        }
+        const uint2* qp = reinterpret_cast<const uint2*>(q + (size_t)qi * kDim);
+        uint2 qv[3];
+#pragma unroll
+        for (int s = 0; s < 3; ++s) qv[s] = qp[s * 32 + lane];
+#pragma unroll
+        for (int c = 0; c < 4; ++c) {
+            double acc = 0.0;
+#pragma unroll
+            for (int s = 0; s < 3; ++s) {
+                const float2 a = __half22float2(*reinterpret_cast<const __half2*>(&rv[c][s].x));
+                const float2 b = __half22float2(*reinterpret_cast<const __half2*>(&rv[c][s].y));
+                const float2 e = __half22float2(*reinterpret_cast<const __half2*>(&qv[s].x));
+                const float2 f = __half22float2(*reinterpret_cast<const __half2*>(&qv[s].y));
+                acc = fma((double)a.x, (double)e.x, acc);
+                acc = fma((double)a.y, (double)e.y, acc);
+                acc = fma((double)b.x, (double)f.x, acc);
+                acc = fma((double)b.y, (double)f.y, acc);
+            }
+#pragma unroll
+            for (int lb = 16; lb > 0; lb >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, lb);
+            if (lane == 0 && j0 + c < wp2)
+                keys[j0 + c] = kk[c] ? make_key128(acc, key64_row(kk[c])) : (u128)0;
+        }
     }
     __syncthreads();
-    block_bitonic_sort_desc<u128>(keys, wp2, 1, wp2, tid, kRescoreThreads);
+    if (warp == 0) warp_bitonic_sort_desc<u128>(keys, wp2, lane);
+    __syncthreads();
     for (int j = tid; j < K; j += kRescoreThreads) {
         const u128 key = (j < wp2) ? keys[j] : (u128)0;
         const size_t o = (size_t)qi * K + j;

@@ -8,13 +8,14 @@
 //          and BM25 lists, order (rrf desc, id asc).  See oracle/fusion.py.
 //
 // One CTA per sub-query; every shard runs the same deterministic merge on the
-// all-gathered records, so the result is replicated bit for bit.
+// all-gathered records, so the result is replicated bit for bit.  All sorts are
+// small (<= world*2k keys), so one warp sorts in shared memory without block barriers.
 #include "common.cuh"
 #include "handle.h"
 
 namespace lrx {
 
-constexpr int kFuseThreads = 256;
+constexpr int kFuseThreads = 128;
 constexpr int kFuseMaxIn = 2048;   // world * K records per list
 constexpr int kFuseMaxK = LRX_MAX_DEPTH;
 
@@ -51,6 +52,21 @@ __device__ __forceinline__ u128 rec_key(double v, int64_t id, uint32_t src) {
     return ((u128)f64_ord(v) << 64) | ((u128)(uint32_t)(~(uint32_t)id) << 32) | (u128)src;
 }
 
+// Sort `n` keys (padded with 0 to a power of two) descending: one warp, or the block
+// when there are more than 1024.  Block-uniform; returns synced.
+__device__ __forceinline__ void fuse_sort(u128* keys, int n, int tid) {
+    const int p2 = max(32, next_pow2(n));
+    __syncthreads();
+    for (int i = n + tid; i < p2; i += kFuseThreads) keys[i] = 0;
+    __syncthreads();
+    if (p2 <= 1024) {
+        if (tid < 32) warp_bitonic_sort_desc<u128>(keys, p2, tid);
+        __syncthreads();
+    } else {
+        block_bitonic_sort_desc<u128>(keys, p2, 1, p2, tid, kFuseThreads);
+    }
+}
+
 __global__ void __launch_bounds__(kFuseThreads)
 fuse_kernel(const lrx_record* __restrict__ rec_all, const double* __restrict__ max_all,
             const int32_t* __restrict__ flags_all, int64_t shard_stride /* bytes; 0 = dense */,
@@ -67,7 +83,6 @@ fuse_kernel(const lrx_record* __restrict__ rec_all, const double* __restrict__ m
     const int b = blockIdx.x;
     const int tid = threadIdx.x;
     const int n_in = world * K;
-    const int np2 = next_pow2(n_in);
 
     // max_bm25 = max(scores) if max(scores) > 0 else 1.0   (retrieval_engine.py:74)
     double maxbm = 0.0;
@@ -95,19 +110,14 @@ fuse_kernel(const lrx_record* __restrict__ rec_all, const double* __restrict__ m
     };
 
     // ---- global dense list: merge the shards' sorted lists
-    for (int i = tid; i < np2; i += kFuseThreads) {
-        u128 key = 0;
-        if (i < n_in) {
-            const lrx_record& r = rec_at(0, i);
-            if (r.id >= 0) key = rec_key(r.dense, r.id, (uint32_t)i);
-        }
-        keys[i] = key;
+    for (int i = tid; i < n_in; i += kFuseThreads) {
+        const lrx_record& r = rec_at(0, i);
+        keys[i] = (r.id >= 0) ? rec_key(r.dense, r.id, (uint32_t)i) : (u128)0;
     }
-    __syncthreads();
-    block_bitonic_sort_desc<u128>(keys, np2, 1, np2, tid, kFuseThreads);
+    fuse_sort(keys, n_in, tid);
     if (tid == 0) {
         int n = 0;
-        while (n < K && n < np2 && keys[n] != 0) ++n;
+        while (n < K && n < n_in && keys[n] != 0) ++n;
         n_dense = n;
     }
     __syncthreads();
@@ -115,27 +125,19 @@ fuse_kernel(const lrx_record* __restrict__ rec_all, const double* __restrict__ m
     __syncthreads();
     const int nd = n_dense;
 
-    int n_out = 0;
     if (mode == LRX_FUSE_LINEAR) {
         const double w = weights[b];
         const double one_m_w = __dsub_rn(1.0, w);
-        const int kp2 = next_pow2(K);
-        __syncthreads();
-        for (int j = tid; j < kp2; j += kFuseThreads) {
-            u128 key = 0;
-            if (j < nd) {
-                const double sem = (double)__double2float_rn(dsel[j].dense);   // float(dist)
-                const double kw = __ddiv_rn(dsel[j].bm25, maxbm);
-                const double s = __dadd_rn(__dmul_rn(sem, one_m_w), __dmul_rn(kw, w));
-                fscore[j] = s;
-                // stable descending sort: ties keep flat-IP order j
-                key = ((u128)f64_ord(s) << 64) | ((u128)(uint32_t)(~(uint32_t)j) << 32) | (u128)(uint32_t)j;
-            }
-            keys[j] = key;
+        for (int j = tid; j < nd; j += kFuseThreads) {
+            const double sem = (double)__double2float_rn(dsel[j].dense);   // float(dist)
+            const double kw = __ddiv_rn(dsel[j].bm25, maxbm);
+            const double s = __dadd_rn(__dmul_rn(sem, one_m_w), __dmul_rn(kw, w));
+            fscore[j] = s;
+            // stable descending sort: ties keep flat-IP order j
+            keys[j] = ((u128)f64_ord(s) << 64) | ((u128)(uint32_t)(~(uint32_t)j) << 32) | (u128)(uint32_t)j;
         }
-        __syncthreads();
-        block_bitonic_sort_desc<u128>(keys, kp2, 1, kp2, tid, kFuseThreads);
-        n_out = min(k, nd);
+        fuse_sort(keys, nd, tid);
+        const int n_out = min(k, nd);
         for (int i = tid; i < k; i += kFuseThreads) {
             const size_t o = (size_t)b * k + i;
             if (i < n_out) {
@@ -153,30 +155,24 @@ fuse_kernel(const lrx_record* __restrict__ rec_all, const double* __restrict__ m
         }
     } else {
         // ---- global BM25 list
-        __syncthreads();
-        for (int i = tid; i < np2; i += kFuseThreads) {
-            u128 key = 0;
-            if (i < n_in) {
-                const lrx_record& r = rec_at(1, i);
-                if (r.id >= 0) key = rec_key(r.bm25, r.id, (uint32_t)i);
-            }
-            keys[i] = key;
+        for (int i = tid; i < n_in; i += kFuseThreads) {
+            const lrx_record& r = rec_at(1, i);
+            keys[i] = (r.id >= 0) ? rec_key(r.bm25, r.id, (uint32_t)i) : (u128)0;
         }
-        __syncthreads();
-        block_bitonic_sort_desc<u128>(keys, np2, 1, np2, tid, kFuseThreads);
+        fuse_sort(keys, n_in, tid);
         if (tid == 0) {
             int n = 0;
-            while (n < K && n < np2 && keys[n] != 0) ++n;
+            while (n < K && n < n_in && keys[n] != 0) ++n;
             n_sparse = n;
         }
         __syncthreads();
         for (int j = tid; j < n_sparse; j += kFuseThreads) ssel[j] = rec_at(1, (int)(uint32_t)keys[j]);
-        for (int j = tid; j < 2 * kFuseMaxK; j += kFuseThreads) fscore[j] = -1.0;   // empty
         __syncthreads();
         const int ns = n_sparse;
-        // dense term first: 0.0 + 1/(60 + rank)
-        for (int j = tid; j < nd; j += kFuseThreads)
-            fscore[j] = __dadd_rn(0.0, __ddiv_rn(1.0, 60.0 + (double)(j + 1)));
+        // union slots: [0, nd) dense entries, [nd, nd + ns) BM25 entries (unused when the
+        // document is already in the dense list).  Dense term first: 0.0 + 1/(60 + rank).
+        for (int j = tid; j < nd + ns; j += kFuseThreads)
+            fscore[j] = (j < nd) ? __dadd_rn(0.0, __ddiv_rn(1.0, 60.0 + (double)(j + 1))) : -1.0;
         __syncthreads();
         for (int r = tid; r < ns; r += kFuseThreads) {
             const double term = __ddiv_rn(1.0, 60.0 + (double)(r + 1));
@@ -184,26 +180,24 @@ fuse_kernel(const lrx_record* __restrict__ rec_all, const double* __restrict__ m
             for (int j = 0; j < nd; ++j)
                 if (dsel[j].id == ssel[r].id) hit = j;
             if (hit >= 0) fscore[hit] = __dadd_rn(fscore[hit], term);      // unique hit per r
-            else fscore[kFuseMaxK + r] = __dadd_rn(0.0, term);
+            else fscore[nd + r] = __dadd_rn(0.0, term);
         }
         __syncthreads();
-        const int tot = 2 * kFuseMaxK;   // power of two
-        for (int i = tid; i < tot; i += kFuseThreads) {
+        for (int i = tid; i < nd + ns; i += kFuseThreads) {
             u128 key = 0;
             if (fscore[i] > 0.0) {
-                const int64_t id = (i < kFuseMaxK) ? dsel[i].id : ssel[i - kFuseMaxK].id;
+                const int64_t id = (i < nd) ? dsel[i].id : ssel[i - nd].id;
                 key = rec_key(fscore[i], id, (uint32_t)i);
             }
             keys[i] = key;
         }
-        __syncthreads();
-        block_bitonic_sort_desc<u128>(keys, tot, 1, tot, tid, kFuseThreads);
+        fuse_sort(keys, nd + ns, tid);
         for (int i = tid; i < k; i += kFuseThreads) {
             const size_t o = (size_t)b * k + i;
-            const u128 key = (i < tot) ? keys[i] : (u128)0;
+            const u128 key = (i < nd + ns) ? keys[i] : (u128)0;
             if (key != 0) {
                 const int src = (int)(uint32_t)key;
-                const lrx_record& r = (src < kFuseMaxK) ? dsel[src] : ssel[src - kFuseMaxK];
+                const lrx_record& r = (src < nd) ? dsel[src] : ssel[src - nd];
                 out_ids[o] = r.id;
                 out_score[o] = fscore[src];
                 out_sem[o] = (double)__double2float_rn(r.dense);
@@ -242,8 +236,9 @@ cudaError_t launch_fuse(lrx_handle* h, const lrx_record* records_all, const doub
         attr = true;
     }
     if (world * K > kFuseMaxIn || K > kFuseMaxK) return cudaErrorInvalidValue;
-    fuse_kernel<<<B, kFuseThreads, kFuseMaxIn * sizeof(u128), h->stream>>>(records_all, max_all, flags_all, shard_stride, world, B, K, k,
-                                                   mode, weights, ids, score, sem, kw, status);
+    fuse_kernel<<<B, kFuseThreads, kFuseMaxIn * sizeof(u128), h->stream>>>(
+        records_all, max_all, flags_all, shard_stride, world, B, K, k, mode, weights, ids, score,
+        sem, kw, status);
     h->launches++;
     return cudaGetLastError();
 }

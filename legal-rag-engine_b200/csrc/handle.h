@@ -15,6 +15,10 @@ struct lrx_handle {
     int num_sms = 0;
     int rank = 0, world = 1;
     cudaStream_t stream = 0;
+    // side stream + fork/join events: the BM25 bounds kernel (query-only) runs in the
+    // shadow of the dense scan
+    cudaStream_t aux = nullptr;
+    cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
     std::mutex mu;
     std::string err;
     int64_t launches = 0;
@@ -31,10 +35,8 @@ struct lrx_handle {
     // postings (caller-owned)
     const uint64_t* term_ptr = nullptr;
     const void* postings = nullptr;
-    const uint32_t* doc_len = nullptr;
     const double* idf = nullptr;
     int64_t n_terms = 0, nnz = 0;
-    double avgdl = 0, k1 = 1.5, b = 0.75;
 
     // workspaces (handle-owned, grown on demand)
     void* ws_dense_part = nullptr;   size_t ws_dense_part_bytes = 0;    // per-CTA key lists
@@ -68,6 +70,14 @@ cudaError_t launch_dense_at(lrx_handle* h, const void* q, int B, const int64_t* 
 cudaError_t launch_bm25(lrx_handle* h, const int32_t* q_terms, const int32_t* q_ptr, int B,
                         const int64_t* cand_ids, int n_cand, double* cand_scores, double* out_max,
                         int K, double* top_scores, int64_t* top_ids);
+
+cudaError_t launch_bm25_bounds(lrx_handle* h, const int32_t* q_terms, const int32_t* q_ptr, int B,
+                               cudaStream_t st);
+cudaError_t launch_bm25_scan(lrx_handle* h, const int32_t* q_terms, const int32_t* q_ptr, int B,
+                             const int64_t* cand_ids, int n_cand, double* cand_scores,
+                             double* out_max, int K, double* top_scores, int64_t* top_ids);
+cudaError_t launch_bm25_impacts(lrx_handle* h, void* postings, int64_t nnz, const uint32_t* doc_len,
+                                double avgdl, double k1, double b);
 
 // fuse.cu
 cudaError_t launch_pack_records(lrx_handle* h, int B, int K, int mode, const double* dense_exact,

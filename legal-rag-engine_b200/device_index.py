@@ -63,8 +63,10 @@ class DeviceIndex:
 
     def set_postings(self, term_ptr, postings, doc_len, idf, avgdl: float, k1: float = 1.5,
                      b: float = 0.75):
-        """term_ptr int64/uint64 [V+1]; postings int32/uint32 [nnz,2]; doc_len int32/uint32 [n];
-        idf float64 [V] -- torch CUDA tensors or numpy arrays (uploaded)."""
+        """Make the BM25 postings resident.  term_ptr int64/uint64 [V+1]; postings
+        int32/uint32 [nnz,2] = (local doc, tf); doc_len int32/uint32 [n]; idf float64 [V]
+        (GLOBAL statistics) -- torch CUDA tensors or numpy arrays (uploaded).  The 16-byte
+        scoring layout {doc, tf, f64 impact} is built on the device (index-build step)."""
         def dev(a, dt):
             if isinstance(a, np.ndarray):
                 if a.dtype == np.uint64:
@@ -77,15 +79,21 @@ class DeviceIndex:
         po = dev(postings, torch.int32)
         dl = dev(doc_len, torch.int32)
         idf_t = dev(idf, torch.float64)
-        if po.numel() == 0:
-            po = torch.zeros((1, 2), dtype=torch.int32, device=self.device)
+        nnz = int(tp[-1].item())
+        assert po.shape[0] == nnz, (po.shape, nnz)
         if dl.numel() == 0:
             dl = torch.zeros(1, dtype=torch.int32, device=self.device)
-        nnz = int(tp[-1].item())
-        self._post = (tp, po, dl, idf_t)
+        p16 = torch.zeros((max(nnz, 1), 4), dtype=torch.int32, device=self.device)
+        if nnz:
+            p16[:nnz, :2] = po
+        del po
+        self._ck(self.lib.lrx_bm25_build_impacts(self.h, _ptr(p16), nnz, _ptr(dl), float(avgdl),
+                                                 float(k1), float(b)))
+        self._post = (tp, p16, idf_t)
+        self.doc_len = dl
         self.n_terms = int(tp.numel() - 1)
-        self._ck(self.lib.lrx_set_postings(self.h, _ptr(tp), _ptr(po), _ptr(dl), _ptr(idf_t),
-                                           self.n_terms, nnz, float(avgdl), float(k1), float(b)))
+        self._ck(self.lib.lrx_set_postings(self.h, _ptr(tp), _ptr(p16), _ptr(idf_t), self.n_terms,
+                                           nnz))
 
     # ---------------------------------------------------------------- stages
     def dense_topk(self, q: torch.Tensor, K: int, width: int = 0):
