@@ -144,6 +144,21 @@ def test_bm25_synthetic_bit_exact(dev, n, vocab):
     _check_bm25(dev, idx, csr, lists, id_base=77, K=20, seed=n)
 
 
+def test_bm25_massive_ties(dev):
+    """Thousands of documents with EXACTLY the same score: the list is decided by id."""
+    n = 6000
+    docs = [["common", f"u{i}"] for i in range(n)]
+    docs[4000] = ["common", "common", "u4000"]           # one clear winner
+    idx = BM25Index.from_token_lists(docs)
+    csr = obm25.BM25OkapiCSR.from_corpus(docs)
+    assert csr.idf[csr.vocab["common"]] > 0              # floored idf: epsilon * mean idf
+    dev.set_corpus(_cuda(synth.host_vectors(n, seed=3)), 10)
+    _set_postings(dev, idx)
+    lists = [idx.term_ids(["common"]), idx.term_ids(["common", "u17", "common"]), idx.term_ids(["u5"])]
+    for K in (20, 200):
+        _check_bm25(dev, idx, csr, lists, id_base=10, K=K, seed=K)
+
+
 # -------------------------------------------------- K4/K5 whole search, host API
 def _oracle_search(x, csr, q, lists, k, weights, fusion):
     oi = OracleIndex(x, csr)
