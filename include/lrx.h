@@ -94,6 +94,48 @@ int lrx_set_postings(lrx_handle* h, const uint64_t* dev_term_ptr, const void* de
 int lrx_bm25_build_impacts(lrx_handle* h, void* dev_postings, int64_t nnz,
                            const uint32_t* dev_doc_len, double avgdl, double k1, double b);
 
+/* ---- K1: encoder (replaces SentenceTransformer("all-MiniLM-L6-v2").encode followed by
+ *      faiss.normalize_L2; retrieval_engine.py:28,61-62, create_vector_store.py:33-34,45,51) --
+ * Weights: DEVICE pointers to float32 tensors in the HuggingFace BertModel state_dict layout
+ * (nn.Linear weight = [out, in]); the library packs its own fp16 copies, so the caller may
+ * free them when lrx_set_encoder_weights returns.  Fixed architecture: hidden 384, 12 heads,
+ * FFN 1536, 6 layers, LayerNorm eps 1e-12, exact-erf GELU, token type 0. */
+#define LRX_BERT_LAYERS 6
+typedef struct lrx_bert_layer {
+    const float *wq, *bq, *wk, *bk, *wv, *bv;   /* attention.self.{query,key,value}  [384,384],[384] */
+    const float *wo, *bo;                       /* attention.output.dense           [384,384],[384] */
+    const float *ln1_g, *ln1_b;                 /* attention.output.LayerNorm       [384]           */
+    const float *w1, *b1;                       /* intermediate.dense               [1536,384],[1536] */
+    const float *w2, *b2;                       /* output.dense                     [384,1536],[384] */
+    const float *ln2_g, *ln2_b;                 /* output.LayerNorm                 [384]           */
+} lrx_bert_layer;
+typedef struct lrx_bert_weights {
+    int32_t vocab_size;        /* 30522 for all-MiniLM-L6-v2 */
+    int32_t max_positions;     /* 512 */
+    const float* word_emb;     /* embeddings.word_embeddings        [vocab, 384] */
+    const float* pos_emb;      /* embeddings.position_embeddings    [max_positions, 384] */
+    const float* type_emb;     /* embeddings.token_type_embeddings  [2, 384] (row 0 used) */
+    const float *emb_ln_g, *emb_ln_b;
+    lrx_bert_layer layers[LRX_BERT_LAYERS];
+} lrx_bert_weights;
+int lrx_set_encoder_weights(lrx_handle* h, const lrx_bert_weights* w);
+/* dev_ids int32 [B,S] WordPiece ids ([CLS] ... [SEP], 0-padded), dev_lens int32 [B] = number of
+ * attended tokens per sequence (the attention mask is a prefix mask, as the tokenizer emits).
+ * Outputs (either may be NULL): float32 [B,384] and fp16 [B,384] unit vectors (the fp16 copy is
+ * the query operand of lrx_dense_topk / lrx_search_*). */
+int lrx_encode(lrx_handle* h, const int32_t* dev_ids, const int32_t* dev_lens, int32_t B, int32_t S,
+               float* dev_out_f32, void* dev_out_f16);
+/* Host-buffer form: H2D of ids/lens, the forward pass, D2H of the embeddings, synchronised. */
+int lrx_encode_host(lrx_handle* h, const int32_t* host_ids, const int32_t* host_lens, int32_t B,
+                    int32_t S, float* host_out_f32);
+/* The tensor-core GEMM stage on its own: out[M,N] = epi(A[M,K] * W[N,K]^T), fp16 row-major
+ * operands, fp32 accumulation.  epi: 0 +bias -> fp16, 1 +bias, GELU(erf) -> fp16,
+ * 2 +bias +residual, LayerNorm (N == 384) -> fp16, 3 raw accumulators -> float32.
+ * K % 64 == 0, N % 128 == 0. */
+int lrx_gemm_f16(lrx_handle* h, const void* dev_a, const void* dev_w, int32_t M, int32_t N, int32_t K,
+                 int32_t epi, const float* dev_bias, const void* dev_residual,
+                 const float* dev_gamma, const float* dev_beta, float eps, void* dev_out);
+
 /* ---- stage kernels (device pointers) ----------------------------------- */
 /* K2: replaces IndexFlatIP.search(x, K)  (retrieval_engine.py:64).
  * dev_q_fp16 [B,384]; outputs [B,K]: exact float64 score, float32 D, int64 I,

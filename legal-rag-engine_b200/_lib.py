@@ -36,6 +36,20 @@ class lrx_record(C.Structure):
     _fields_ = [("id", C.c_int64), ("dense", C.c_double), ("bm25", C.c_double)]
 
 
+_fp = C.c_void_p   # device pointers to float32 tensors
+
+
+class lrx_bert_layer(C.Structure):
+    _fields_ = [(n, _fp) for n in ("wq", "bq", "wk", "bk", "wv", "bv", "wo", "bo", "ln1_g", "ln1_b",
+                                   "w1", "b1", "w2", "b2", "ln2_g", "ln2_b")]
+
+
+class lrx_bert_weights(C.Structure):
+    _fields_ = [("vocab_size", C.c_int32), ("max_positions", C.c_int32),
+                ("word_emb", _fp), ("pos_emb", _fp), ("type_emb", _fp),
+                ("emb_ln_g", _fp), ("emb_ln_b", _fp), ("layers", lrx_bert_layer * 6)]
+
+
 RECORD_BYTES = C.sizeof(lrx_record)
 assert RECORD_BYTES == 24
 
@@ -58,6 +72,11 @@ _SIGNATURES = {
     "lrx_set_corpus": (C.c_int, [_vp, _vp, _i64, _i64, _i32]),
     "lrx_set_postings": (C.c_int, [_vp, _vp, _vp, _vp, _i64, _i64]),
     "lrx_bm25_build_impacts": (C.c_int, [_vp, _vp, _i64, _vp, _f64, _f64, _f64]),
+    "lrx_set_encoder_weights": (C.c_int, [_vp, C.POINTER(lrx_bert_weights)]),
+    "lrx_encode": (C.c_int, [_vp, _vp, _vp, _i32, _i32, _vp, _vp]),
+    "lrx_encode_host": (C.c_int, [_vp, _vp, _vp, _i32, _i32, _vp]),
+    "lrx_gemm_f16": (C.c_int, [_vp, _vp, _vp, _i32, _i32, _i32, _i32, _vp, _vp, _vp, _vp, C.c_float,
+                               _vp]),
     "lrx_dense_topk": (C.c_int, [_vp, _vp, _i32, _i32, _vp, _vp, _vp, _vp]),
     "lrx_dense_topk_ex": (C.c_int, [_vp, _vp, _i32, _i32, _i32, _vp, _vp, _vp, _vp]),
     "lrx_dense_at": (C.c_int, [_vp, _vp, _i32, _vp, _i32, _vp]),

@@ -122,6 +122,7 @@ int lrx_close(lrx_handle* h) {
                   h->ws_io};
     for (void* p : ws)
         if (p != nullptr) cudaFree(p);
+    encoder_free(h);
     if (h->ws_host != nullptr) cudaFreeHost(h->ws_host);
     if (h->aux) cudaStreamDestroy(h->aux);
     if (h->ev_fork) cudaEventDestroy(h->ev_fork);
@@ -215,6 +216,82 @@ int lrx_bm25_build_impacts(lrx_handle* h, void* dev_postings, int64_t nnz,
         return fail(h, LRX_E_ARG, "lrx_bm25_build_impacts: postings must be 16-byte aligned");
     LRX_CUDA(h, cudaSetDevice(h->device));
     LRX_CUDA(h, launch_bm25_impacts(h, dev_postings, nnz, dev_doc_len, avgdl, k1, b));
+    return LRX_OK;
+}
+
+int lrx_set_encoder_weights(lrx_handle* h, const lrx_bert_weights* w) {
+    if (h == nullptr) return fail(nullptr, LRX_E_ARG, "lrx_set_encoder_weights: null handle");
+    std::lock_guard<std::mutex> g(h->mu);
+    if (w == nullptr) return fail(h, LRX_E_ARG, "lrx_set_encoder_weights: null weights");
+    if (w->vocab_size < 1 || w->max_positions < 1)
+        return fail(h, LRX_E_ARG, "lrx_set_encoder_weights: bad vocab_size / max_positions");
+    const float* top[] = {w->word_emb, w->pos_emb, w->type_emb, w->emb_ln_g, w->emb_ln_b};
+    for (const float* p : top)
+        if (p == nullptr) return fail(h, LRX_E_ARG, "lrx_set_encoder_weights: null embedding tensor");
+    for (int l = 0; l < LRX_BERT_LAYERS; ++l) {
+        const lrx_bert_layer& s = w->layers[l];
+        const float* ps[] = {s.wq, s.bq, s.wk, s.bk, s.wv, s.bv, s.wo, s.bo, s.ln1_g, s.ln1_b,
+                             s.w1, s.b1, s.w2, s.b2, s.ln2_g, s.ln2_b};
+        for (const float* p : ps)
+            if (p == nullptr)
+                return fail(h, LRX_E_ARG, "lrx_set_encoder_weights: null tensor in layer %d", l);
+    }
+    LRX_CUDA(h, cudaSetDevice(h->device));
+    LRX_CUDA(h, encoder_set_weights(h, w));
+    return LRX_OK;
+}
+
+static int check_encode(lrx_handle* h, const char* fn, int B, int S) {
+    if (h->encoder == nullptr) return fail(h, LRX_E_STATE, "%s: encoder weights not set", fn);
+    if (B < 1 || B > (1 << 20)) return fail(h, LRX_E_ARG, "%s: B must be in [1, 2^20]", fn);
+    if (S < 1 || S > 512) return fail(h, LRX_E_ARG, "%s: S must be in [1,512]", fn);
+    return LRX_OK;
+}
+
+int lrx_encode(lrx_handle* h, const int32_t* dev_ids, const int32_t* dev_lens, int32_t B, int32_t S,
+               float* dev_out_f32, void* dev_out_f16) {
+    if (h == nullptr) return fail(nullptr, LRX_E_ARG, "lrx_encode: null handle");
+    std::lock_guard<std::mutex> g(h->mu);
+    int rc = check_encode(h, "lrx_encode", B, S);
+    if (rc != LRX_OK) return rc;
+    if (dev_ids == nullptr || dev_lens == nullptr || (dev_out_f32 == nullptr && dev_out_f16 == nullptr))
+        return fail(h, LRX_E_ARG, "lrx_encode: null pointer");
+    LRX_CUDA(h, cudaSetDevice(h->device));
+    LRX_CUDA(h, encoder_forward(h, dev_ids, dev_lens, B, S, dev_out_f32, dev_out_f16));
+    return LRX_OK;
+}
+
+int lrx_encode_host(lrx_handle* h, const int32_t* host_ids, const int32_t* host_lens, int32_t B,
+                    int32_t S, float* host_out_f32) {
+    if (h == nullptr) return fail(nullptr, LRX_E_ARG, "lrx_encode_host: null handle");
+    std::lock_guard<std::mutex> g(h->mu);
+    int rc = check_encode(h, "lrx_encode_host", B, S);
+    if (rc != LRX_OK) return rc;
+    if (host_ids == nullptr || host_lens == nullptr || host_out_f32 == nullptr)
+        return fail(h, LRX_E_ARG, "lrx_encode_host: null pointer");
+    LRX_CUDA(h, cudaSetDevice(h->device));
+    LRX_CUDA(h, encoder_forward_host(h, host_ids, host_lens, B, S, host_out_f32));
+    return LRX_OK;
+}
+
+int lrx_gemm_f16(lrx_handle* h, const void* dev_a, const void* dev_w, int32_t M, int32_t N, int32_t K,
+                 int32_t epi, const float* dev_bias, const void* dev_residual,
+                 const float* dev_gamma, const float* dev_beta, float eps, void* dev_out) {
+    if (h == nullptr) return fail(nullptr, LRX_E_ARG, "lrx_gemm_f16: null handle");
+    std::lock_guard<std::mutex> g(h->mu);
+    if (M < 1 || N < 128 || N % 128 != 0 || K < 64 || K % 64 != 0)
+        return fail(h, LRX_E_ARG, "lrx_gemm_f16: need M >= 1, N %% 128 == 0, K %% 64 == 0");
+    if (epi < 0 || epi > 3 || (epi == 2 && N != 384))
+        return fail(h, LRX_E_ARG, "lrx_gemm_f16: bad epilogue (LayerNorm needs N == 384)");
+    if (dev_a == nullptr || dev_w == nullptr || dev_out == nullptr ||
+        (epi != 3 && dev_bias == nullptr) ||
+        (epi == 2 && (dev_residual == nullptr || dev_gamma == nullptr || dev_beta == nullptr)))
+        return fail(h, LRX_E_ARG, "lrx_gemm_f16: null pointer");
+    if ((((uintptr_t)dev_a | (uintptr_t)dev_w | (uintptr_t)dev_out) & 15) != 0)
+        return fail(h, LRX_E_ARG, "lrx_gemm_f16: operands must be 16-byte aligned");
+    LRX_CUDA(h, cudaSetDevice(h->device));
+    LRX_CUDA(h, gemm_f16_adhoc(h, dev_a, dev_w, M, N, K, epi, dev_bias, dev_residual, dev_gamma,
+                               dev_beta, eps, dev_out));
     return LRX_OK;
 }
 
@@ -465,7 +542,8 @@ int lrx_search_batch_host(lrx_handle* h, const void* host_q_fp16, const int32_t*
     const size_t o_flags = off;   off = align_up(off + (size_t)B * sizeof(int32_t), 256);
     const size_t total = off;
     if (h->ws_host_bytes < total) {
-        if (h->ws_host != nullptr) cudaFreeHost(h->ws_host);
+        encoder_free(h);
+    if (h->ws_host != nullptr) cudaFreeHost(h->ws_host);
         h->ws_host = nullptr;
         h->ws_host_bytes = 0;
         LRX_CUDA(h, cudaMallocHost(&h->ws_host, total * 2));

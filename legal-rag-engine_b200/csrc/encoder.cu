@@ -1,0 +1,553 @@
+// K1: all-MiniLM-L6-v2 forward = SentenceTransformer.encode + faiss.normalize_L2
+// (reference: src/retrieval/retrieval_engine.py:61-62, create_vector_store.py:45,51).
+//
+//   BertEmbeddings   word[id] + position[s] + token_type[0], LayerNorm(eps 1e-12)
+//   6 x BertLayer    QKV projection (tc_gemm, +bias) -> 12-head attention (this file)
+//                    -> output projection + residual + LayerNorm (tc_gemm, fused epilogue)
+//                    -> FFN up + exact-erf GELU (tc_gemm) -> FFN down + residual + LayerNorm
+//   Pooling          sum(h * mask) / max(sum(mask), 1e-9)
+//   Normalize        x / max(||x||_2, 1e-12)      (sentence-transformers Normalize module)
+//   normalize_L2     x * (1 / sqrt(||x||^2))      (faiss, applied again by the reference)
+//
+// Activations are fp16 [tokens, width] row-major in handle-owned workspaces, processed in
+// chunks of whole sequences sized so one chunk's working set stays L2-resident; all
+// statistics (LayerNorm, softmax, pooling, norms) are fp32.
+#include <cmath>
+#include <cstring>
+
+#include "handle.h"
+#include "tc.cuh"
+
+namespace lrx {
+
+constexpr int kHidden = 384;
+constexpr int kHeads = 12;
+constexpr int kHeadDim = 32;
+constexpr int kFfn = 1536;
+constexpr int kQkv = 3 * kHidden;
+constexpr int kLayers = 6;
+constexpr float kLnEps = 1e-12f;
+
+// tc_gemm.cu
+cudaError_t make_tmap_f16(CUtensorMap* out, const void* ptr, int64_t rows, int64_t cols, int64_t ld,
+                          int box_rows);
+cudaError_t launch_tc_gemm(lrx_handle* h, const CUtensorMap& ta, const CUtensorMap& tb, int M, int N,
+                           int K, int epi, const float* bias, const __half* residual, int ld_res,
+                           const float* gamma, const float* beta, float eps, void* out, int ld_out);
+
+struct EncLayer {
+    __half* wqkv;   // [1152, 384]
+    __half* wo;     // [384, 384]
+    __half* w1;     // [1536, 384]
+    __half* w2;     // [384, 1536]
+    float *bqkv, *bo, *b1, *b2, *ln1_g, *ln1_b, *ln2_g, *ln2_b;
+    CUtensorMap t_wqkv, t_wo, t_w1, t_w2;
+};
+
+struct Encoder {
+    int vocab = 0, max_pos = 0;
+    float *word = nullptr, *pos = nullptr, *type0 = nullptr, *eln_g = nullptr, *eln_b = nullptr;
+    EncLayer L[kLayers];
+    void* blob = nullptr;      // one allocation holding every packed weight
+    // activation workspaces for `cap` tokens
+    int64_t cap = 0;
+    void* act = nullptr;
+    __half *x = nullptr, *x1 = nullptr, *qkv = nullptr, *ctx = nullptr, *ff = nullptr;
+    CUtensorMap t_x, t_x1, t_ctx, t_ff;
+    void* io = nullptr;        // host-form staging (ids, lens, out)
+    size_t io_bytes = 0;
+    void* io_host = nullptr;
+    size_t io_host_bytes = 0;
+};
+
+// ------------------------------------------------------------ weight packing
+__global__ void f32_to_f16_kernel(const float* __restrict__ src, __half* __restrict__ dst, int64_t n) {
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n;
+         i += (int64_t)gridDim.x * blockDim.x)
+        dst[i] = __float2half_rn(src[i]);
+}
+
+// ---------------------------------------------------------------- embeddings
+// one warp per token; lane owns columns j*128 + lane*4 + {0..3}, j = 0..2
+__global__ void __launch_bounds__(256)
+embed_ln_kernel(const int32_t* __restrict__ ids, int64_t n_tokens, int S, int vocab, int max_pos,
+                const float* __restrict__ word, const float* __restrict__ pos,
+                const float* __restrict__ type0, const float* __restrict__ g,
+                const float* __restrict__ b, __half* __restrict__ out) {
+    const int lane = threadIdx.x & 31;
+    const int64_t tok = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    if (tok >= n_tokens) return;
+    int id = ids[tok];
+    id = (id < 0 || id >= vocab) ? 0 : id;
+    int s = (int)(tok % S);
+    s = (s >= max_pos) ? max_pos - 1 : s;
+    float v[12];
+    float sum = 0.f;
+#pragma unroll
+    for (int j = 0; j < 3; ++j) {
+        const int c = j * 128 + lane * 4;
+        const float4 w = __ldg(reinterpret_cast<const float4*>(word + (size_t)id * kHidden + c));
+        const float4 p = __ldg(reinterpret_cast<const float4*>(pos + (size_t)s * kHidden + c));
+        const float4 t = __ldg(reinterpret_cast<const float4*>(type0 + c));
+        v[4 * j + 0] = w.x + p.x + t.x;
+        v[4 * j + 1] = w.y + p.y + t.y;
+        v[4 * j + 2] = w.z + p.z + t.z;
+        v[4 * j + 3] = w.w + p.w + t.w;
+        sum += v[4 * j] + v[4 * j + 1] + v[4 * j + 2] + v[4 * j + 3];
+    }
+#pragma unroll
+    for (int lb = 16; lb > 0; lb >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, lb);
+    const float mean = sum * (1.0f / kHidden);
+    float var = 0.f;
+#pragma unroll
+    for (int i = 0; i < 12; ++i) {
+        const float d = v[i] - mean;
+        var = fmaf(d, d, var);
+    }
+#pragma unroll
+    for (int lb = 16; lb > 0; lb >>= 1) var += __shfl_xor_sync(0xffffffffu, var, lb);
+    const float rstd = 1.0f / sqrtf(var * (1.0f / kHidden) + kLnEps);
+#pragma unroll
+    for (int j = 0; j < 3; ++j) {
+        const int c = j * 128 + lane * 4;
+        const float4 gg = __ldg(reinterpret_cast<const float4*>(g + c));
+        const float4 bb = __ldg(reinterpret_cast<const float4*>(b + c));
+        const __half2 h0 = __floats2half2_rn((v[4 * j + 0] - mean) * rstd * gg.x + bb.x,
+                                             (v[4 * j + 1] - mean) * rstd * gg.y + bb.y);
+        const __half2 h1 = __floats2half2_rn((v[4 * j + 2] - mean) * rstd * gg.z + bb.z,
+                                             (v[4 * j + 3] - mean) * rstd * gg.w + bb.w);
+        uint2 u;
+        u.x = *reinterpret_cast<const uint32_t*>(&h0);
+        u.y = *reinterpret_cast<const uint32_t*>(&h1);
+        *reinterpret_cast<uint2*>(out + tok * kHidden + c) = u;
+    }
+}
+
+// ----------------------------------------------------------------- attention
+// One CTA per (head, sequence): K and V^T of the head staged in shared memory, each warp
+// owns 16-query tiles; scores and P*V on mma.sync m16n8k16 (fp16 in, fp32 accumulate),
+// online softmax over 64-key blocks in fp32.  Keys >= len are masked out; query rows
+// >= len (padding) produce zeros.
+constexpr int kAttnThreads = 256;
+constexpr int kKPad = 40;    // halves per K row in smem (32 + 8: conflict-free fragment loads)
+
+__device__ __forceinline__ void mma16816(float (&d)[4], const uint32_t (&a)[4], uint32_t b0,
+                                         uint32_t b1) {
+    asm volatile(
+        "mma.sync.aligned.m16n8k16.row.col.f32.f16.f16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, "
+        "{%0,%1,%2,%3};"
+        : "+f"(d[0]), "+f"(d[1]), "+f"(d[2]), "+f"(d[3])
+        : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
+}
+__device__ __forceinline__ uint32_t pack_h2(float a, float b) {
+    const __half2 h = __floats2half2_rn(a, b);
+    return *reinterpret_cast<const uint32_t*>(&h);
+}
+
+__global__ void __launch_bounds__(kAttnThreads)
+attention_kernel(const __half* __restrict__ qkv, const int32_t* __restrict__ lens, int S,
+                 __half* __restrict__ ctx) {
+    extern __shared__ __align__(16) unsigned char attn_raw[];
+    const int head = blockIdx.x;
+    const int seq = blockIdx.y;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int g = lane >> 2, t = lane & 3;
+    int len = lens[seq];
+    len = len < 0 ? 0 : (len > S ? S : len);
+    const int Sk = (len + 63) & ~63;                 // staged keys (multiple of 64)
+    const int vt_ld = Sk + 8;                        // halves per V^T row
+    __half* sK = reinterpret_cast<__half*>(attn_raw);            // [Sk][kKPad]
+    __half* sVt = sK + (size_t)Sk * kKPad;                        // [32][vt_ld]
+    const __half* base = qkv + (size_t)seq * S * kQkv + head * kHeadDim;
+
+    // ---- stage K (row-major, padded) and V^T; rows >= len are zero
+    for (int i = tid; i < Sk * 4; i += kAttnThreads) {
+        const int s = i >> 2, part = i & 3;          // 4 x 16-byte parts per 64-byte row
+        uint4 kv = make_uint4(0, 0, 0, 0), vv = make_uint4(0, 0, 0, 0);
+        if (s < len) {
+            kv = __ldg(reinterpret_cast<const uint4*>(base + (size_t)s * kQkv + kHidden) + part);
+            vv = __ldg(reinterpret_cast<const uint4*>(base + (size_t)s * kQkv + 2 * kHidden) + part);
+        }
+        *reinterpret_cast<uint4*>(sK + s * kKPad + part * 8) = kv;
+        const __half* vh = reinterpret_cast<const __half*>(&vv);
+#pragma unroll
+        for (int e = 0; e < 8; ++e) sVt[(part * 8 + e) * vt_ld + s] = vh[e];
+    }
+    __syncthreads();
+
+    const float scale = 0.17677669529663687f;        // 1 / sqrt(32)
+    const int n_qtiles = (S + 15) >> 4;
+    for (int qt = warp; qt < n_qtiles; qt += kAttnThreads / 32) {
+        const int q0 = qt * 16;
+        const int r0 = q0 + g, r1 = q0 + g + 8;
+        __half* o0 = ctx + ((size_t)seq * S + r0) * kHidden + head * kHeadDim;
+        __half* o1 = ctx + ((size_t)seq * S + r1) * kHidden + head * kHeadDim;
+        if (q0 >= len) {                              // padding tile: zeros
+#pragma unroll
+            for (int nd = 0; nd < 4; ++nd) {
+                if (r0 < S) *reinterpret_cast<uint32_t*>(o0 + nd * 8 + 2 * t) = 0u;
+                if (r1 < S) *reinterpret_cast<uint32_t*>(o1 + nd * 8 + 2 * t) = 0u;
+            }
+            continue;
+        }
+        // Q fragments (A operand), two k-steps over d = 0..31
+        uint32_t qa[2][4];
+#pragma unroll
+        for (int ks = 0; ks < 2; ++ks) {
+            const __half* q0p = base + (size_t)r0 * kQkv + ks * 16 + 2 * t;
+            const __half* q1p = base + (size_t)r1 * kQkv + ks * 16 + 2 * t;
+            qa[ks][0] = (r0 < S) ? __ldg(reinterpret_cast<const uint32_t*>(q0p)) : 0u;
+            qa[ks][1] = (r1 < S) ? __ldg(reinterpret_cast<const uint32_t*>(q1p)) : 0u;
+            qa[ks][2] = (r0 < S) ? __ldg(reinterpret_cast<const uint32_t*>(q0p + 8)) : 0u;
+            qa[ks][3] = (r1 < S) ? __ldg(reinterpret_cast<const uint32_t*>(q1p + 8)) : 0u;
+        }
+        float m0 = -INFINITY, m1 = -INFINITY, l0 = 0.f, l1 = 0.f;
+        float o[4][4];
+#pragma unroll
+        for (int nd = 0; nd < 4; ++nd)
+#pragma unroll
+            for (int i = 0; i < 4; ++i) o[nd][i] = 0.f;
+
+        for (int kb = 0; kb < Sk; kb += 64) {
+            float sc[8][4];
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+#pragma unroll
+                for (int i = 0; i < 4; ++i) sc[j][i] = 0.f;
+                const __half* kp = sK + (kb + j * 8 + g) * kKPad + 2 * t;
+#pragma unroll
+                for (int ks = 0; ks < 2; ++ks) {
+                    const uint32_t b0 = *reinterpret_cast<const uint32_t*>(kp + ks * 16);
+                    const uint32_t b1 = *reinterpret_cast<const uint32_t*>(kp + ks * 16 + 8);
+                    mma16816(sc[j], qa[ks], b0, b1);
+                }
+            }
+            // scale + mask + block max
+            float bm0 = -INFINITY, bm1 = -INFINITY;
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+                const int key = kb + j * 8 + 2 * t;
+                sc[j][0] = (key < len) ? sc[j][0] * scale : -INFINITY;
+                sc[j][1] = (key + 1 < len) ? sc[j][1] * scale : -INFINITY;
+                sc[j][2] = (key < len) ? sc[j][2] * scale : -INFINITY;
+                sc[j][3] = (key + 1 < len) ? sc[j][3] * scale : -INFINITY;
+                bm0 = fmaxf(bm0, fmaxf(sc[j][0], sc[j][1]));
+                bm1 = fmaxf(bm1, fmaxf(sc[j][2], sc[j][3]));
+            }
+            bm0 = fmaxf(bm0, __shfl_xor_sync(0xffffffffu, bm0, 1));
+            bm0 = fmaxf(bm0, __shfl_xor_sync(0xffffffffu, bm0, 2));
+            bm1 = fmaxf(bm1, __shfl_xor_sync(0xffffffffu, bm1, 1));
+            bm1 = fmaxf(bm1, __shfl_xor_sync(0xffffffffu, bm1, 2));
+            const float mn0 = fmaxf(m0, bm0), mn1 = fmaxf(m1, bm1);   // finite: key kb < len
+            const float a0 = expf(m0 - mn0), a1 = expf(m1 - mn1);
+            m0 = mn0; m1 = mn1;
+            float ps0 = 0.f, ps1 = 0.f;
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+                sc[j][0] = expf(sc[j][0] - mn0);
+                sc[j][1] = expf(sc[j][1] - mn0);
+                sc[j][2] = expf(sc[j][2] - mn1);
+                sc[j][3] = expf(sc[j][3] - mn1);
+                ps0 += sc[j][0] + sc[j][1];
+                ps1 += sc[j][2] + sc[j][3];
+            }
+            l0 = l0 * a0 + ps0;
+            l1 = l1 * a1 + ps1;
+#pragma unroll
+            for (int nd = 0; nd < 4; ++nd) {
+                o[nd][0] *= a0; o[nd][1] *= a0;
+                o[nd][2] *= a1; o[nd][3] *= a1;
+            }
+            // O += P * V   (P from the score fragments, V^T from shared memory)
+#pragma unroll
+            for (int kk = 0; kk < 4; ++kk) {
+                uint32_t pa[4];
+                pa[0] = pack_h2(sc[2 * kk][0], sc[2 * kk][1]);
+                pa[1] = pack_h2(sc[2 * kk][2], sc[2 * kk][3]);
+                pa[2] = pack_h2(sc[2 * kk + 1][0], sc[2 * kk + 1][1]);
+                pa[3] = pack_h2(sc[2 * kk + 1][2], sc[2 * kk + 1][3]);
+#pragma unroll
+                for (int nd = 0; nd < 4; ++nd) {
+                    const __half* vp = sVt + (nd * 8 + g) * vt_ld + kb + kk * 16 + 2 * t;
+                    const uint32_t b0 = *reinterpret_cast<const uint32_t*>(vp);
+                    const uint32_t b1 = *reinterpret_cast<const uint32_t*>(vp + 8);
+                    mma16816(o[nd], pa, b0, b1);
+                }
+            }
+        }
+        // row sums across the quad, normalise, store
+        l0 += __shfl_xor_sync(0xffffffffu, l0, 1);
+        l0 += __shfl_xor_sync(0xffffffffu, l0, 2);
+        l1 += __shfl_xor_sync(0xffffffffu, l1, 1);
+        l1 += __shfl_xor_sync(0xffffffffu, l1, 2);
+        const float i0 = 1.0f / l0, i1 = 1.0f / l1;
+#pragma unroll
+        for (int nd = 0; nd < 4; ++nd) {
+            if (r0 < S)
+                *reinterpret_cast<uint32_t*>(o0 + nd * 8 + 2 * t) =
+                    (r0 < len) ? pack_h2(o[nd][0] * i0, o[nd][1] * i0) : 0u;
+            if (r1 < S)
+                *reinterpret_cast<uint32_t*>(o1 + nd * 8 + 2 * t) =
+                    (r1 < len) ? pack_h2(o[nd][2] * i1, o[nd][3] * i1) : 0u;
+        }
+    }
+}
+
+// ------------------------------------------------------------------- pooling
+// One CTA (128 threads x 3 columns) per sequence: masked mean, Normalize, normalize_L2.
+__device__ __forceinline__ float block_sum_128(float v, float* red) {
+#pragma unroll
+    for (int lb = 16; lb > 0; lb >>= 1) v += __shfl_xor_sync(0xffffffffu, v, lb);
+    __syncthreads();
+    if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = v;
+    __syncthreads();
+    return red[0] + red[1] + red[2] + red[3];
+}
+
+__global__ void __launch_bounds__(128)
+pool_normalize_kernel(const __half* __restrict__ x, const int32_t* __restrict__ lens, int S,
+                      float* __restrict__ out_f32, __half* __restrict__ out_f16) {
+    __shared__ float red[4];
+    const int seq = blockIdx.x;
+    const int tid = threadIdx.x;
+    int len = lens[seq];
+    len = len < 0 ? 0 : (len > S ? S : len);
+    float acc[3] = {0.f, 0.f, 0.f};
+    const __half* p = x + (size_t)seq * S * kHidden;
+    for (int s = 0; s < len; ++s) {
+#pragma unroll
+        for (int j = 0; j < 3; ++j) acc[j] += __half2float(p[(size_t)s * kHidden + j * 128 + tid]);
+    }
+    const float denom = fmaxf((float)len, 1e-9f);          // torch.clamp(sum_mask, min=1e-9)
+    float sq = 0.f;
+#pragma unroll
+    for (int j = 0; j < 3; ++j) {
+        acc[j] = acc[j] / denom;
+        sq = fmaf(acc[j], acc[j], sq);
+    }
+    sq = block_sum_128(sq, red);
+    const float nrm = fmaxf(sqrtf(sq), 1e-12f);            // F.normalize(p=2, eps=1e-12)
+    float sq2 = 0.f;
+#pragma unroll
+    for (int j = 0; j < 3; ++j) {
+        acc[j] = acc[j] / nrm;
+        sq2 = fmaf(acc[j], acc[j], sq2);
+    }
+    sq2 = block_sum_128(sq2, red);
+    if (sq2 > 0.f) {                                       // faiss.normalize_L2
+        const float inv = 1.0f / sqrtf(sq2);
+#pragma unroll
+        for (int j = 0; j < 3; ++j) acc[j] *= inv;
+    }
+#pragma unroll
+    for (int j = 0; j < 3; ++j) {
+        const size_t o = (size_t)seq * kHidden + j * 128 + tid;
+        if (out_f32 != nullptr) out_f32[o] = acc[j];
+        if (out_f16 != nullptr) out_f16[o] = __float2half_rn(acc[j]);
+    }
+}
+
+// ------------------------------------------------------------------ host side
+static size_t rup(size_t v, size_t a) { return (v + a - 1) / a * a; }
+
+void encoder_free(lrx_handle* h) {
+    Encoder* e = (Encoder*)h->encoder;
+    if (e == nullptr) return;
+    if (e->blob) cudaFree(e->blob);
+    if (e->act) cudaFree(e->act);
+    if (e->io) cudaFree(e->io);
+    if (e->io_host) cudaFreeHost(e->io_host);
+    delete e;
+    h->encoder = nullptr;
+}
+
+static cudaError_t conv(cudaStream_t st, const float* src, __half* dst, int64_t n) {
+    f32_to_f16_kernel<<<256, 256, 0, st>>>(src, dst, n);
+    return cudaGetLastError();
+}
+
+#define ENC_CK(expr)                          \
+    do {                                      \
+        cudaError_t _e = (expr);              \
+        if (_e != cudaSuccess) return _e;     \
+    } while (0)
+
+cudaError_t encoder_set_weights(lrx_handle* h, const lrx_bert_weights* w) {
+    encoder_free(h);
+    Encoder* e = new Encoder();
+    h->encoder = e;
+    e->vocab = w->vocab_size;
+    e->max_pos = w->max_positions;
+    // ---- one blob: fp32 tables + per-layer fp16 matrices + fp32 vectors
+    size_t off = 0;
+    auto take = [&](size_t bytes) { size_t o = off; off = rup(off + bytes, 256); return o; };
+    const size_t o_word = take((size_t)e->vocab * kHidden * 4);
+    const size_t o_pos = take((size_t)e->max_pos * kHidden * 4);
+    const size_t o_type = take(kHidden * 4);
+    const size_t o_eg = take(kHidden * 4), o_eb = take(kHidden * 4);
+    size_t o_l[kLayers][12];
+    for (int l = 0; l < kLayers; ++l) {
+        o_l[l][0] = take((size_t)kQkv * kHidden * 2);
+        o_l[l][1] = take((size_t)kHidden * kHidden * 2);
+        o_l[l][2] = take((size_t)kFfn * kHidden * 2);
+        o_l[l][3] = take((size_t)kHidden * kFfn * 2);
+        o_l[l][4] = take(kQkv * 4);
+        o_l[l][5] = take(kHidden * 4);
+        o_l[l][6] = take(kFfn * 4);
+        o_l[l][7] = take(kHidden * 4);
+        for (int i = 8; i < 12; ++i) o_l[l][i] = take(kHidden * 4);
+    }
+    ENC_CK(cudaMalloc(&e->blob, off));
+    char* B = (char*)e->blob;
+    cudaStream_t st = h->stream;
+    auto cpy = [&](size_t o, const float* src, size_t n) {
+        return cudaMemcpyAsync(B + o, src, n * 4, cudaMemcpyDeviceToDevice, st);
+    };
+    e->word = (float*)(B + o_word); ENC_CK(cpy(o_word, w->word_emb, (size_t)e->vocab * kHidden));
+    e->pos = (float*)(B + o_pos);   ENC_CK(cpy(o_pos, w->pos_emb, (size_t)e->max_pos * kHidden));
+    e->type0 = (float*)(B + o_type); ENC_CK(cpy(o_type, w->type_emb, kHidden));
+    e->eln_g = (float*)(B + o_eg);  ENC_CK(cpy(o_eg, w->emb_ln_g, kHidden));
+    e->eln_b = (float*)(B + o_eb);  ENC_CK(cpy(o_eb, w->emb_ln_b, kHidden));
+    for (int l = 0; l < kLayers; ++l) {
+        const lrx_bert_layer& s = w->layers[l];
+        EncLayer& d = e->L[l];
+        d.wqkv = (__half*)(B + o_l[l][0]);
+        d.wo = (__half*)(B + o_l[l][1]);
+        d.w1 = (__half*)(B + o_l[l][2]);
+        d.w2 = (__half*)(B + o_l[l][3]);
+        d.bqkv = (float*)(B + o_l[l][4]);
+        d.bo = (float*)(B + o_l[l][5]);
+        d.b1 = (float*)(B + o_l[l][6]);
+        d.b2 = (float*)(B + o_l[l][7]);
+        d.ln1_g = (float*)(B + o_l[l][8]);
+        d.ln1_b = (float*)(B + o_l[l][9]);
+        d.ln2_g = (float*)(B + o_l[l][10]);
+        d.ln2_b = (float*)(B + o_l[l][11]);
+        const int64_t hh = (int64_t)kHidden * kHidden;
+        ENC_CK(conv(st, s.wq, d.wqkv, hh));
+        ENC_CK(conv(st, s.wk, d.wqkv + hh, hh));
+        ENC_CK(conv(st, s.wv, d.wqkv + 2 * hh, hh));
+        ENC_CK(conv(st, s.wo, d.wo, hh));
+        ENC_CK(conv(st, s.w1, d.w1, (int64_t)kFfn * kHidden));
+        ENC_CK(conv(st, s.w2, d.w2, (int64_t)kHidden * kFfn));
+        ENC_CK(cpy(o_l[l][4], s.bq, kHidden));
+        ENC_CK(cpy(o_l[l][4] + kHidden * 4, s.bk, kHidden));
+        ENC_CK(cpy(o_l[l][4] + 2 * kHidden * 4, s.bv, kHidden));
+        ENC_CK(cpy(o_l[l][5], s.bo, kHidden));
+        ENC_CK(cpy(o_l[l][6], s.b1, kFfn));
+        ENC_CK(cpy(o_l[l][7], s.b2, kHidden));
+        ENC_CK(cpy(o_l[l][8], s.ln1_g, kHidden));
+        ENC_CK(cpy(o_l[l][9], s.ln1_b, kHidden));
+        ENC_CK(cpy(o_l[l][10], s.ln2_g, kHidden));
+        ENC_CK(cpy(o_l[l][11], s.ln2_b, kHidden));
+        ENC_CK(make_tmap_f16(&d.t_wqkv, d.wqkv, kQkv, kHidden, kHidden, 128));
+        ENC_CK(make_tmap_f16(&d.t_wo, d.wo, kHidden, kHidden, kHidden, 128));
+        ENC_CK(make_tmap_f16(&d.t_w1, d.w1, kFfn, kHidden, kHidden, 128));
+        ENC_CK(make_tmap_f16(&d.t_w2, d.w2, kHidden, kFfn, kFfn, 128));
+    }
+    h->launches += 6 * kLayers;
+    return cudaStreamSynchronize(st);   // the caller may free its fp32 copies on return
+}
+
+static cudaError_t encoder_reserve(Encoder* e, int64_t tokens) {
+    if (tokens <= e->cap) return cudaSuccess;
+    if (e->act) { ENC_CK(cudaFree(e->act)); e->act = nullptr; e->cap = 0; }
+    const int64_t cap = (int64_t)rup((size_t)tokens, 128);
+    size_t off = 0;
+    auto take = [&](size_t bytes) { size_t o = off; off = rup(off + bytes, 1024); return o; };
+    const size_t o_x = take((size_t)cap * kHidden * 2), o_x1 = take((size_t)cap * kHidden * 2);
+    const size_t o_qkv = take((size_t)cap * kQkv * 2), o_ctx = take((size_t)cap * kHidden * 2);
+    const size_t o_ff = take((size_t)cap * kFfn * 2);
+    ENC_CK(cudaMalloc(&e->act, off));
+    ENC_CK(cudaMemset(e->act, 0, off));
+    char* A = (char*)e->act;
+    e->x = (__half*)(A + o_x); e->x1 = (__half*)(A + o_x1); e->qkv = (__half*)(A + o_qkv);
+    e->ctx = (__half*)(A + o_ctx); e->ff = (__half*)(A + o_ff);
+    ENC_CK(make_tmap_f16(&e->t_x, e->x, cap, kHidden, kHidden, 128));
+    ENC_CK(make_tmap_f16(&e->t_x1, e->x1, cap, kHidden, kHidden, 128));
+    ENC_CK(make_tmap_f16(&e->t_ctx, e->ctx, cap, kHidden, kHidden, 128));
+    ENC_CK(make_tmap_f16(&e->t_ff, e->ff, cap, kFfn, kFfn, 128));
+    e->cap = cap;
+    return cudaSuccess;
+}
+
+// tokens per chunk: ~7.7 KB of activations per token; 8192 tokens = 63 MB, L2-resident
+constexpr int64_t kChunkTokens = 8192;
+
+cudaError_t encoder_forward(lrx_handle* h, const int32_t* ids, const int32_t* lens, int B, int S,
+                            float* out_f32, void* out_f16) {
+    Encoder* e = (Encoder*)h->encoder;
+    int seq_per_chunk = (int)(kChunkTokens / S);
+    if (seq_per_chunk < 1) seq_per_chunk = 1;
+    if (seq_per_chunk > B) seq_per_chunk = B;
+    ENC_CK(encoder_reserve(e, (int64_t)seq_per_chunk * S));
+    static bool attr = false;
+    if (!attr) {
+        ENC_CK(cudaFuncSetAttribute(attention_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                    96 * 1024));
+        attr = true;
+    }
+    cudaStream_t st = h->stream;
+    for (int b0 = 0; b0 < B; b0 += seq_per_chunk) {
+        const int nb = (B - b0 < seq_per_chunk) ? (B - b0) : seq_per_chunk;
+        const int64_t T = (int64_t)nb * S;
+        const int32_t* cid = ids + (size_t)b0 * S;
+        const int32_t* clen = lens + b0;
+        embed_ln_kernel<<<(unsigned)((T + 7) / 8), 256, 0, st>>>(cid, T, S, e->vocab, e->max_pos, e->word,
+                                                                 e->pos, e->type0, e->eln_g, e->eln_b, e->x);
+        h->launches++;
+        ENC_CK(cudaGetLastError());
+        const int Sk = (S + 63) & ~63;
+        const size_t attn_smem = (size_t)Sk * kKPad * 2 + (size_t)kHeadDim * (Sk + 8) * 2;
+        for (int l = 0; l < kLayers; ++l) {
+            EncLayer& L = e->L[l];
+            ENC_CK(launch_tc_gemm(h, e->t_x, L.t_wqkv, (int)T, kQkv, kHidden, 0, L.bqkv, nullptr, 0,
+                                  nullptr, nullptr, 0.f, e->qkv, kQkv));
+            attention_kernel<<<dim3(kHeads, nb), kAttnThreads, attn_smem, st>>>(e->qkv, clen, S, e->ctx);
+            h->launches++;
+            ENC_CK(cudaGetLastError());
+            ENC_CK(launch_tc_gemm(h, e->t_ctx, L.t_wo, (int)T, kHidden, kHidden, 2, L.bo, e->x, kHidden,
+                                  L.ln1_g, L.ln1_b, kLnEps, e->x1, kHidden));
+            ENC_CK(launch_tc_gemm(h, e->t_x1, L.t_w1, (int)T, kFfn, kHidden, 1, L.b1, nullptr, 0,
+                                  nullptr, nullptr, 0.f, e->ff, kFfn));
+            ENC_CK(launch_tc_gemm(h, e->t_ff, L.t_w2, (int)T, kHidden, kFfn, 2, L.b2, e->x1, kHidden,
+                                  L.ln2_g, L.ln2_b, kLnEps, e->x, kHidden));
+        }
+        pool_normalize_kernel<<<nb, 128, 0, st>>>(
+            e->x, clen, S, out_f32 ? out_f32 + (size_t)b0 * kHidden : nullptr,
+            out_f16 ? (__half*)out_f16 + (size_t)b0 * kHidden : nullptr);
+        h->launches++;
+        ENC_CK(cudaGetLastError());
+    }
+    return cudaSuccess;
+}
+
+cudaError_t encoder_forward_host(lrx_handle* h, const int32_t* host_ids, const int32_t* host_lens,
+                                 int B, int S, float* host_out) {
+    Encoder* e = (Encoder*)h->encoder;
+    const size_t b_ids = rup((size_t)B * S * 4, 256), b_len = rup((size_t)B * 4, 256);
+    const size_t b_out = rup((size_t)B * kHidden * 4, 256);
+    const size_t total = b_ids + b_len + b_out;
+    if (e->io_bytes < total) {
+        if (e->io) cudaFree(e->io);
+        if (e->io_host) cudaFreeHost(e->io_host);
+        e->io = nullptr; e->io_host = nullptr; e->io_bytes = 0;
+        ENC_CK(cudaMalloc(&e->io, total * 2));
+        ENC_CK(cudaMallocHost(&e->io_host, total * 2));
+        e->io_bytes = total * 2;
+    }
+    char* hp = (char*)e->io_host;
+    char* dp = (char*)e->io;
+    memcpy(hp, host_ids, (size_t)B * S * 4);
+    memcpy(hp + b_ids, host_lens, (size_t)B * 4);
+    ENC_CK(cudaMemcpyAsync(dp, hp, b_ids + b_len, cudaMemcpyHostToDevice, h->stream));
+    ENC_CK(encoder_forward(h, (const int32_t*)dp, (const int32_t*)(dp + b_ids), B, S,
+                           (float*)(dp + b_ids + b_len), nullptr));
+    ENC_CK(cudaMemcpyAsync(hp + b_ids + b_len, dp + b_ids + b_len, (size_t)B * kHidden * 4,
+                           cudaMemcpyDeviceToHost, h->stream));
+    ENC_CK(cudaStreamSynchronize(h->stream));
+    memcpy(host_out, hp + b_ids + b_len, (size_t)B * kHidden * 4);
+    return cudaSuccess;
+}
+
+}  // namespace lrx

@@ -46,6 +46,9 @@ struct lrx_handle {
     void* ws_misc = nullptr;         size_t ws_misc_bytes = 0;          // search_local scratch
     void* ws_host = nullptr;         size_t ws_host_bytes = 0;          // pinned staging
     void* ws_io = nullptr;           size_t ws_io_bytes = 0;            // device staging
+
+    // K1 encoder state (packed weights, activation workspaces, tensor maps): encoder.cu
+    void* encoder = nullptr;
 };
 
 namespace lrx {
@@ -88,6 +91,18 @@ cudaError_t launch_fuse(lrx_handle* h, const lrx_record* records_all, const doub
                         const int32_t* flags_all, int64_t shard_stride, int world, int B, int K,
                         int k, int mode, const double* weights, int64_t* ids, double* score,
                         double* sem, double* kw, int32_t* status);
+
+// encoder.cu
+cudaError_t encoder_set_weights(lrx_handle* h, const lrx_bert_weights* w);
+cudaError_t encoder_forward(lrx_handle* h, const int32_t* ids, const int32_t* lens, int B, int S,
+                            float* out_f32, void* out_f16);
+cudaError_t encoder_forward_host(lrx_handle* h, const int32_t* host_ids, const int32_t* host_lens,
+                                 int B, int S, float* host_out);
+void encoder_free(lrx_handle* h);
+// tc_gemm.cu
+cudaError_t gemm_f16_adhoc(lrx_handle* h, const void* a, const void* w, int M, int N, int K, int epi,
+                           const float* bias, const void* residual, const float* gamma,
+                           const float* beta, float eps, void* out);
 
 // profiling hooks (no-ops unless lrx_profile_enable(h, 1))
 void prof_begin(lrx_handle* h, int which);

@@ -204,6 +204,20 @@ class DeviceIndex:
                                                 FUSION[fusion], vp(ids), vp(score), vp(sem), vp(kw)))
         return ids, score, sem, kw
 
+    # ------------------------------------------------------ K1 stage: GEMM
+    def gemm_f16(self, a: torch.Tensor, w: torch.Tensor, epi: int = 3, bias=None, residual=None,
+                 gamma=None, beta=None, eps: float = 1e-12):
+        """out[M,N] = epi(a[M,K] @ w[N,K]^T) on the tensor cores (lrx_gemm_f16)."""
+        assert a.dtype == torch.float16 and w.dtype == torch.float16
+        assert a.is_contiguous() and w.is_contiguous()
+        M, K = a.shape
+        N = w.shape[0]
+        out = torch.empty((M, N), dtype=torch.float32 if epi == 3 else torch.float16,
+                          device=self.device)
+        self._ck(self.lib.lrx_gemm_f16(self.h, _ptr(a), _ptr(w), M, N, K, epi, _ptr(bias),
+                                       _ptr(residual), _ptr(gamma), _ptr(beta), float(eps), _ptr(out)))
+        return out
+
     def profile(self, on: bool):
         self._ck(self.lib.lrx_profile_enable(self.h, 1 if on else 0))
 

@@ -84,6 +84,52 @@ def host_query_terms(b: int, n_terms: int = 8, seed: int = 999, vocab: int = VOC
     return t, ptr
 
 
+# ------------------------------------------------------------------ encoder
+BERT = dict(vocab=30522, hidden=384, layers=6, heads=12, ffn=1536, max_pos=512)
+
+
+def bert_state_dict(seed: int = 42, std: float = 0.02, vocab: int = BERT["vocab"],
+                    ln_jitter: float = 0.0):
+    """Seeded random weights in HuggingFace ``BertModel`` state_dict naming (float32 numpy):
+    N(0, std^2) matrices/biases, LayerNorm gamma 1 / beta 0.  ``ln_jitter`` > 0
+    perturbs gamma/beta so the affine part of every LayerNorm is exercised too."""
+    rng = np.random.default_rng(seed)
+    H, F = BERT["hidden"], BERT["ffn"]
+    n = lambda *shape: (rng.standard_normal(shape, dtype=np.float32) * np.float32(std))
+
+    def ln(prefix, sd):
+        sd[prefix + ".weight"] = (1.0 + ln_jitter * rng.standard_normal(H)).astype(np.float32)
+        sd[prefix + ".bias"] = (ln_jitter * rng.standard_normal(H)).astype(np.float32)
+
+    sd = {"embeddings.word_embeddings.weight": n(vocab, H),
+          "embeddings.position_embeddings.weight": n(BERT["max_pos"], H),
+          "embeddings.token_type_embeddings.weight": n(2, H)}
+    ln("embeddings.LayerNorm", sd)
+    for l in range(BERT["layers"]):
+        p = f"encoder.layer.{l}."
+        for name, (o, i) in (("attention.self.query", (H, H)), ("attention.self.key", (H, H)),
+                             ("attention.self.value", (H, H)), ("attention.output.dense", (H, H)),
+                             ("intermediate.dense", (F, H)), ("output.dense", (H, F))):
+            sd[p + name + ".weight"] = n(o, i)
+            sd[p + name + ".bias"] = n(o)
+        ln(p + "attention.output.LayerNorm", sd)
+        ln(p + "output.LayerNorm", sd)
+    return sd
+
+
+def token_batch(b: int, s: int, seed: int = 7, vocab: int = BERT["vocab"], full: bool = False):
+    """ids int32 [b,s] ([CLS]=101 ... [SEP]=102, 0-padded, body ids uniform in [1000, vocab))
+    and lens int32 [b]: full length when ``full`` else uniform in [2, s]."""
+    rng = np.random.default_rng(seed)
+    lens = np.full(b, s, dtype=np.int32) if full else rng.integers(2, s + 1, size=b).astype(np.int32)
+    ids = rng.integers(1000, vocab, size=(b, s)).astype(np.int32)
+    ids[:, 0] = 101
+    for i, n_ in enumerate(lens):
+        ids[i, n_ - 1] = 102
+        ids[i, n_:] = 0
+    return ids, lens
+
+
 # ------------------------------------------------------------------- device
 def device_vectors(n: int, device, seed: int = 1234, dup_frac: float = 0.001, dim: int = DIM,
                    chunk: int = 1 << 20):
