@@ -200,6 +200,15 @@ int lrx_search_batch_host(lrx_handle* h, const void* host_q_fp16, const int32_t*
                           int32_t k, int32_t mode, int64_t* host_ids, double* host_score,
                           double* host_sem, double* host_kw);
 
+/* The whole of RetrievalEngine.search for a batch of query STRINGS already tokenised on the host
+ * (world == 1): H2D of WordPiece ids [B,S] + lens [B] and of the BM25 term ids, K1 (encoder) ->
+ * K2 -> K3 -> K4, D2H of the fused results, synchronised.  Replaces retrieval_engine.py:59-96
+ * end to end; `search_batch` with B = 4 is the orchestrator fan-out (orchestrator.py:38-62). */
+int lrx_search_text_host(lrx_handle* h, const int32_t* host_tok_ids, const int32_t* host_tok_lens,
+                         int32_t S, const int32_t* host_q_terms, const int32_t* host_q_ptr,
+                         const double* host_weights, int32_t B, int32_t k, int32_t mode,
+                         int64_t* host_ids, double* host_score, double* host_sem, double* host_kw);
+
 /* Number of kernels launched by this handle since lrx_open (bench.py's gpu_launches). */
 int64_t lrx_launch_count(const lrx_handle* h);
 

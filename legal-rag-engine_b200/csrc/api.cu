@@ -501,27 +501,26 @@ int lrx_search_finish_packed(lrx_handle* h, const void* dev_packed_all, int32_t 
                                 dev_weights, dev_ids, dev_score, dev_sem, dev_kw, dev_status);
 }
 
-int lrx_search_batch_host(lrx_handle* h, const void* host_q_fp16, const int32_t* host_q_terms,
-                          const int32_t* host_q_ptr, const double* host_weights, int32_t B,
-                          int32_t k, int32_t mode, int64_t* host_ids, double* host_score,
-                          double* host_sem, double* host_kw) {
-    if (h == nullptr) return fail(nullptr, LRX_E_ARG, "lrx_search_batch_host: null handle");
-    std::lock_guard<std::mutex> g(h->mu);
-    if (host_q_fp16 == nullptr || host_q_ptr == nullptr || host_weights == nullptr ||
-        host_ids == nullptr || host_score == nullptr || host_sem == nullptr || host_kw == nullptr)
-        return fail(h, LRX_E_ARG, "lrx_search_batch_host: null pointer");
-    if (B < 1 || B > LRX_MAX_BATCH) return fail(h, LRX_E_ARG, "lrx_search_batch_host: bad B");
-    if (k < 1 || 2 * k > LRX_MAX_DEPTH) return fail(h, LRX_E_ARG, "lrx_search_batch_host: bad k");
+// Shared body of the two host-buffer entry points: the query vectors either come from the
+// host as fp16 (host_q_fp16) or are produced on the device by the encoder from token ids.
+static int search_host_locked(lrx_handle* h, const char* fn, const void* host_q_fp16,
+                              const int32_t* host_ids, const int32_t* host_lens, int S,
+                              const int32_t* host_q_terms, const int32_t* host_q_ptr,
+                              const double* host_weights, int32_t B, int32_t k, int32_t mode,
+                              int64_t* host_ids_out, double* host_score, double* host_sem,
+                              double* host_kw) {
+    if (B < 1 || B > LRX_MAX_BATCH) return fail(h, LRX_E_ARG, "%s: B must be in [1,%d]", fn, LRX_MAX_BATCH);
+    if (k < 1 || 2 * k > LRX_MAX_DEPTH) return fail(h, LRX_E_ARG, "%s: k must be in [1,%d]", fn, LRX_MAX_DEPTH / 2);
     if (h->world != 1)
-        return fail(h, LRX_E_STATE, "lrx_search_batch_host: handle is a shard (world=%d); use "
-                                    "lrx_search_local / all-gather / lrx_search_finish", h->world);
+        return fail(h, LRX_E_STATE, "%s: handle is a shard (world=%d); use lrx_search_local / "
+                                    "all-gather / lrx_search_finish", fn, h->world);
     const int nt = host_q_ptr[B];
-    if (nt < 0 || host_q_ptr[0] != 0) return fail(h, LRX_E_ARG, "lrx_search_batch_host: bad q_ptr");
-    if (nt > 0 && host_q_terms == nullptr) return fail(h, LRX_E_ARG, "lrx_search_batch_host: null terms");
+    if (nt < 0 || host_q_ptr[0] != 0) return fail(h, LRX_E_ARG, "%s: bad q_ptr", fn);
+    if (nt > 0 && host_q_terms == nullptr) return fail(h, LRX_E_ARG, "%s: null terms", fn);
     for (int b = 0; b < B; ++b)
         if (host_q_ptr[b + 1] < host_q_ptr[b] || host_q_ptr[b + 1] - host_q_ptr[b] > LRX_MAX_QUERY_TERMS)
-            return fail(h, LRX_E_ARG, "lrx_search_batch_host: query %d has more than %d terms", b,
-                        LRX_MAX_QUERY_TERMS);
+            return fail(h, LRX_E_ARG, "%s: query %d has more than %d terms", fn, b, LRX_MAX_QUERY_TERMS);
+    const bool encode = (host_q_fp16 == nullptr);
     LRX_CUDA(h, cudaSetDevice(h->device));
     const int K = 2 * k;
     // ---- staging layout (same offsets on host and device)
@@ -530,6 +529,8 @@ int lrx_search_batch_host(lrx_handle* h, const void* host_q_fp16, const int32_t*
     const size_t o_w = off;       off = align_up(off + (size_t)B * sizeof(double), 256);
     const size_t o_ptr = off;     off = align_up(off + (size_t)(B + 1) * sizeof(int32_t), 256);
     const size_t o_terms = off;   off = align_up(off + (size_t)(nt > 0 ? nt : 1) * sizeof(int32_t), 256);
+    const size_t o_tok = off;     off = align_up(off + (encode ? (size_t)B * S * sizeof(int32_t) : 0), 256);
+    const size_t o_len = off;     off = align_up(off + (encode ? (size_t)B * sizeof(int32_t) : 0), 256);
     const size_t in_bytes = off;
     const size_t o_ids = off;     off = align_up(off + (size_t)B * k * sizeof(int64_t), 256);
     const size_t o_score = off;   off = align_up(off + (size_t)B * k * sizeof(double), 256);
@@ -542,8 +543,7 @@ int lrx_search_batch_host(lrx_handle* h, const void* host_q_fp16, const int32_t*
     const size_t o_flags = off;   off = align_up(off + (size_t)B * sizeof(int32_t), 256);
     const size_t total = off;
     if (h->ws_host_bytes < total) {
-        encoder_free(h);
-    if (h->ws_host != nullptr) cudaFreeHost(h->ws_host);
+        if (h->ws_host != nullptr) cudaFreeHost(h->ws_host);
         h->ws_host = nullptr;
         h->ws_host_bytes = 0;
         LRX_CUDA(h, cudaMallocHost(&h->ws_host, total * 2));
@@ -552,11 +552,18 @@ int lrx_search_batch_host(lrx_handle* h, const void* host_q_fp16, const int32_t*
     LRX_CUDA(h, ensure_ws(&h->ws_io, &h->ws_io_bytes, total));
     char* hp = (char*)h->ws_host;
     char* dp = (char*)h->ws_io;
-    memcpy(hp + o_q, host_q_fp16, (size_t)B * kRowBytes);
+    if (!encode) memcpy(hp + o_q, host_q_fp16, (size_t)B * kRowBytes);
     memcpy(hp + o_w, host_weights, (size_t)B * sizeof(double));
     memcpy(hp + o_ptr, host_q_ptr, (size_t)(B + 1) * sizeof(int32_t));
     if (nt > 0) memcpy(hp + o_terms, host_q_terms, (size_t)nt * sizeof(int32_t));
+    if (encode) {
+        memcpy(hp + o_tok, host_ids, (size_t)B * S * sizeof(int32_t));
+        memcpy(hp + o_len, host_lens, (size_t)B * sizeof(int32_t));
+    }
     LRX_CUDA(h, cudaMemcpyAsync(dp, hp, in_bytes, cudaMemcpyHostToDevice, h->stream));
+    if (encode)   // K1: token ids -> fp16 unit query vectors, straight into the K2 operand slot
+        LRX_CUDA(h, encoder_forward(h, (const int32_t*)(dp + o_tok), (const int32_t*)(dp + o_len), B, S,
+                                    nullptr, dp + o_q));
 
     int width = dense_default_width(K);
     for (;;) {
@@ -584,11 +591,42 @@ int lrx_search_batch_host(lrx_handle* h, const void* host_q_fp16, const int32_t*
                         "within the fp32 error band of the 2k-th score)");
         width *= 2;   // rare: widen the candidate list and rerun
     }
-    memcpy(host_ids, hp + o_ids, (size_t)B * k * sizeof(int64_t));
+    memcpy(host_ids_out, hp + o_ids, (size_t)B * k * sizeof(int64_t));
     memcpy(host_score, hp + o_score, (size_t)B * k * sizeof(double));
     memcpy(host_sem, hp + o_sem, (size_t)B * k * sizeof(double));
     memcpy(host_kw, hp + o_kw, (size_t)B * k * sizeof(double));
     return LRX_OK;
+}
+
+int lrx_search_batch_host(lrx_handle* h, const void* host_q_fp16, const int32_t* host_q_terms,
+                          const int32_t* host_q_ptr, const double* host_weights, int32_t B,
+                          int32_t k, int32_t mode, int64_t* host_ids, double* host_score,
+                          double* host_sem, double* host_kw) {
+    if (h == nullptr) return fail(nullptr, LRX_E_ARG, "lrx_search_batch_host: null handle");
+    std::lock_guard<std::mutex> g(h->mu);
+    if (host_q_fp16 == nullptr || host_q_ptr == nullptr || host_weights == nullptr ||
+        host_ids == nullptr || host_score == nullptr || host_sem == nullptr || host_kw == nullptr)
+        return fail(h, LRX_E_ARG, "lrx_search_batch_host: null pointer");
+    return search_host_locked(h, "lrx_search_batch_host", host_q_fp16, nullptr, nullptr, 0,
+                              host_q_terms, host_q_ptr, host_weights, B, k, mode, host_ids,
+                              host_score, host_sem, host_kw);
+}
+
+int lrx_search_text_host(lrx_handle* h, const int32_t* host_tok_ids, const int32_t* host_tok_lens,
+                         int32_t S, const int32_t* host_q_terms, const int32_t* host_q_ptr,
+                         const double* host_weights, int32_t B, int32_t k, int32_t mode,
+                         int64_t* host_ids, double* host_score, double* host_sem, double* host_kw) {
+    if (h == nullptr) return fail(nullptr, LRX_E_ARG, "lrx_search_text_host: null handle");
+    std::lock_guard<std::mutex> g(h->mu);
+    if (host_tok_ids == nullptr || host_tok_lens == nullptr || host_q_ptr == nullptr ||
+        host_weights == nullptr || host_ids == nullptr || host_score == nullptr ||
+        host_sem == nullptr || host_kw == nullptr)
+        return fail(h, LRX_E_ARG, "lrx_search_text_host: null pointer");
+    if (h->encoder == nullptr) return fail(h, LRX_E_STATE, "lrx_search_text_host: encoder weights not set");
+    if (S < 1 || S > 512) return fail(h, LRX_E_ARG, "lrx_search_text_host: S must be in [1,512]");
+    return search_host_locked(h, "lrx_search_text_host", nullptr, host_tok_ids, host_tok_lens, S,
+                              host_q_terms, host_q_ptr, host_weights, B, k, mode, host_ids,
+                              host_score, host_sem, host_kw);
 }
 
 }  // extern "C"

@@ -1,0 +1,87 @@
+"""The drop-in boundary on the GPU: create_vector_store + RetrievalEngine.search /
+search_batch on the reference's own corpus (legal_chunks.json) and query strings, checked
+bit for bit against the CPU oracle downstream of the embeddings (the embeddings themselves
+are checked against the fp32 oracle here on a sample and in test_gpu_encoder.py)."""
+import json
+
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def built(tmp_path_factory, legal_chunks):
+    from legal_rag_engine_b200 import synth
+    from legal_rag_engine_b200.engine import RetrievalEngine, create_vector_store
+    d = tmp_path_factory.mktemp("store")
+    src = d / "legal_chunks.json"
+    src.write_text(json.dumps(legal_chunks), encoding="utf-8")
+    sd = synth.bert_state_dict(42, 0.05, ln_jitter=0.1)
+    create_vector_store(str(src), str(d / "vs"), encoder_state_dict=sd)
+    eng = RetrievalEngine(str(d / "vs"), encoder_state_dict=sd)
+    yield eng, sd, d / "vs"
+    eng.close()
+
+
+def _oracle(eng):
+    from oracle import bm25 as obm25
+    from oracle.search import OracleIndex
+    b = eng.bm25
+    csr = obm25.BM25OkapiCSR(b.n_docs, b.doc_len, b.term_ptr.astype(np.int64), b.postings[:, 0],
+                             b.postings[:, 1], vocab=b.vocab)
+    return OracleIndex(eng._x.cpu().numpy(), csr), csr
+
+
+def test_store_embeddings_match_fp32_oracle(built, legal_texts):
+    eng, sd, vs = built
+    from oracle import encoder as oenc
+    xh = np.load(vs / "vectors.f16.npy")
+    assert xh.shape == (len(legal_texts), 384)
+    tok = eng.model.tokenizer
+    for i in [0, 1, 17, 500, 2619]:
+        ids = np.asarray([tok.encode(legal_texts[i], 256)], dtype=np.int32)
+        want = oenc.encode_ids(sd, ids, np.array([ids.shape[1]]))[0].astype(np.float64)
+        got = xh[i].astype(np.float64)
+        assert got @ want / np.linalg.norm(got) / np.linalg.norm(want) >= 0.9999
+
+
+@pytest.mark.parametrize("fusion", ["linear", "rrf"])
+def test_search_matches_oracle(built, reference_queries, fusion):
+    eng, sd, _ = built
+    oracle, csr = _oracle(eng)
+    from oracle.bm25 import tokenize
+    for q in reference_queries:
+        for k, w in ((5, 0.5), (10, 0.6)):
+            got = eng.search(q, k=k, hybrid_weight=w, fusion=fusion)
+            qh = eng.encode([q]).astype(np.float16)[0]
+            want = oracle.search_vec(qh, csr.term_ids(tokenize(q)), k, w, fusion)
+            assert len(got) == len(want) <= k
+            for r, (i, score, sem, kw) in zip(got, want):
+                assert set(r) == {"chunk", "score", "semantic", "keyword"}
+                assert r["chunk"] is eng.chunks[i]          # the metadata dict object itself
+                assert r["score"] == score and r["semantic"] == sem and r["keyword"] == kw
+                assert isinstance(r["score"], float) and "text" in r["chunk"]
+            assert [r["score"] for r in got] == sorted((r["score"] for r in got), reverse=True)
+
+
+def test_search_batch_equals_sequential_search(built):
+    eng, _, _ = built
+    from legal_rag_engine_b200.engine import fanout_queries, merge_fanout
+    qs, ws = fanout_queries("I was robbed at knife point, what should I do?", "victim_distress",
+                            ["robbery"], "procedure")
+    assert len(qs) == 4
+    batch = eng.search_batch(qs, k=5, hybrid_weights=ws)
+    single = [eng.search(q, k=5, hybrid_weight=w) for q, w in zip(qs, ws)]
+    strip = lambda rs: [(r["chunk"]["canonical_header"], r["score"], r["semantic"], r["keyword"]) for r in rs]
+    assert [strip(r) for r in batch] == [strip(r) for r in single]
+    merged = merge_fanout(batch)
+    heads = [r["chunk"]["canonical_header"] for r in merged]
+    assert len(heads) == len(set(heads)) and len(merged) <= 20
+
+
+def test_small_k_and_bad_fusion(built):
+    eng, _, _ = built
+    assert len(eng.search("zero fir", k=3)) == 3
+    with pytest.raises(KeyError):
+        eng.search("zero fir", fusion="nope")
