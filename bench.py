@@ -245,17 +245,13 @@ def run_ours(args):
     t_dev = torch.from_numpy(th).to(device)
     ptr_dev = torch.from_numpy(ptr_h).to(device)
     w_dev = torch.tensor(WEIGHTS, dtype=torch.float64, device=device)
-    pb = dev.packed_bytes(N_SUB, K_TOP)
-    packed = torch.empty(pb, dtype=torch.uint8, device=device)
-    packed_all = torch.empty(pb * world, dtype=torch.uint8, device=device) if world > 1 else packed
-    outs = dev.alloc_outputs(N_SUB, K_TOP)
+    from legal_rag_engine_b200.sharding import ShardedSearcher
+    searcher = ShardedSearcher(dev)            # K2+K3 local -> one all-gather -> K4
+    packed, packed_all, outs = searcher.buffers(N_SUB, K_TOP)
 
     def step(i):
         p = i % POOL
-        dev.search_local_packed(q_dev[p], t_dev[p], ptr_dev, K_TOP, mode, packed)
-        if world > 1:
-            dist.all_gather_into_tensor(packed_all, packed)
-        dev.search_finish_packed(packed_all, world, N_SUB, K_TOP, mode, w_dev, outs)
+        searcher.search(q_dev[p], t_dev[p], ptr_dev, K_TOP, mode, w_dev)
 
     def barrier():
         if world > 1:
@@ -311,9 +307,7 @@ def run_ours(args):
             p = i % POOL
             qd.copy_(pin_q[p], non_blocking=True)
             td.copy_(pin_t[p], non_blocking=True)
-            dev.search_local_packed(qd, td, ptr_dev, K_TOP, mode, packed)
-            dist.all_gather_into_tensor(packed_all, packed)
-            dev.search_finish_packed(packed_all, world, N_SUB, K_TOP, mode, w_dev, outs)
+            searcher.search(qd, td, ptr_dev, K_TOP, mode, w_dev)
             for o, po in zip(outs[:4], pin_out):
                 po.copy_(o, non_blocking=True)
             torch.cuda.current_stream().synchronize()
