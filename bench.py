@@ -336,9 +336,9 @@ def run_ours(args):
     peak_src = "measured (MEASURED_PEAKS.json hbm_gbs)" if "hbm_gbs" in peaks else "fallback 6650 GB/s"
     scan_bytes = n_local * 768
     scan_gbs = scan_bytes / (scan_ms / max(scan_n, 1) * 1e-3) / 1e9 if scan_ms > 0 else 0.0
-    # BM25 kernel: sum over query tokens of df_local * 16 B ({doc, tf, f64 impact}),
+    # BM25 kernel: sum over query tokens of df_local * 8 B ({u32 doc, u16 tf, u16 len}),
     # averaged over the pool
-    bm_bytes = float(np.mean([df_local[th[p]].sum() * 16 for p in range(POOL)]))
+    bm_bytes = float(np.mean([df_local[th[p]].sum() * 8 for p in range(POOL)]))
     bm_gbs = bm_bytes / (bm_ms / max(bm_n, 1) * 1e-3) / 1e9 if bm_ms > 0 else 0.0
 
     if rank == 0:

@@ -81,18 +81,22 @@ const char* lrx_version(void);
 int lrx_set_corpus(lrx_handle* h, const void* dev_x_fp16, int64_t n_local, int64_t id_base,
                    int32_t dim);
 /* Term-major CSR postings restricted to this shard's documents, doc ids LOCAL and
- * ascending within a term.  dev_postings: nnz 16-byte entries {u32 doc_local, u32 tf,
- * f64 impact}, 16-byte aligned, where
- *   impact = tf*(k1+1) / (tf + k1*(1 - b + b*len(doc)/avgdl))
- * is the query-independent BM25Okapi factor in float64 (lrx_bm25_build_impacts fills it
- * from doc/tf, the document lengths and the GLOBAL avgdl).  dev_idf: GLOBAL idf per
- * term (rank_bm25 semantics: epsilon floor applied).  Replaces pickle.load(bm25.pkl). */
+ * ascending within a term.  dev_postings: nnz 8-byte entries {u32 doc_local, u16 tf,
+ * u16 doc_len} (lrx_bm25_build_postings fills them from (doc, tf) pairs and the document
+ * lengths), 16-byte aligned and readable up to nnz rounded up to an even count (the scan
+ * moves 16-byte units).  The query-independent BM25Okapi factor
+ *   impact(tf, len) = tf*(k1+1) / (tf + k1*(1 - b + b*len/avgdl))          (float64)
+ * is looked up in a handle-owned table built here from the GLOBAL avgdl with rank_bm25's
+ * float64 operation order.  dev_idf: GLOBAL idf per term (rank_bm25 semantics: epsilon
+ * floor applied).  max_doc_len <= 65535.  Replaces pickle.load(bm25.pkl). */
 int lrx_set_postings(lrx_handle* h, const uint64_t* dev_term_ptr, const void* dev_postings,
-                     const double* dev_idf, int64_t n_terms, int64_t nnz);
-/* Index build (create_vector_store.py:60-61, the BM25Okapi constructor): fills the
- * `impact` field of nnz postings in place, with rank_bm25's float64 operation order. */
-int lrx_bm25_build_impacts(lrx_handle* h, void* dev_postings, int64_t nnz,
-                           const uint32_t* dev_doc_len, double avgdl, double k1, double b);
+                     const double* dev_idf, int64_t n_terms, int64_t nnz, double avgdl, double k1,
+                     double b, int32_t max_doc_len);
+/* Index build (create_vector_store.py:60-61, the BM25Okapi constructor's per-document
+ * frequency tables): dev_doc_tf = nnz pairs {u32 doc_local, u32 tf} in CSR order ->
+ * dev_postings_out (nnz x 8 bytes).  LRX_E_ARG if a tf or a length exceeds 65535. */
+int lrx_bm25_build_postings(lrx_handle* h, const uint32_t* dev_doc_tf, int64_t nnz,
+                            const uint32_t* dev_doc_len, void* dev_postings_out);
 
 /* ---- K1: encoder (replaces SentenceTransformer("all-MiniLM-L6-v2").encode followed by
  *      faiss.normalize_L2; retrieval_engine.py:28,61-62, create_vector_store.py:33-34,45,51) --

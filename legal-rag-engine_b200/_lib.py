@@ -70,8 +70,8 @@ _SIGNATURES = {
     "lrx_set_stream": (C.c_int, [_vp, _vp]),
     "lrx_version": (C.c_char_p, []),
     "lrx_set_corpus": (C.c_int, [_vp, _vp, _i64, _i64, _i32]),
-    "lrx_set_postings": (C.c_int, [_vp, _vp, _vp, _vp, _i64, _i64]),
-    "lrx_bm25_build_impacts": (C.c_int, [_vp, _vp, _i64, _vp, _f64, _f64, _f64]),
+    "lrx_set_postings": (C.c_int, [_vp, _vp, _vp, _vp, _i64, _i64, _f64, _f64, _f64, _i32]),
+    "lrx_bm25_build_postings": (C.c_int, [_vp, _vp, _i64, _vp, _vp]),
     "lrx_set_encoder_weights": (C.c_int, [_vp, C.POINTER(lrx_bert_weights)]),
     "lrx_encode": (C.c_int, [_vp, _vp, _vp, _i32, _i32, _vp, _vp]),
     "lrx_encode_host": (C.c_int, [_vp, _vp, _vp, _i32, _i32, _vp]),

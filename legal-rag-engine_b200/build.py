@@ -46,14 +46,21 @@ def needs_build() -> bool:
 
 
 def build_library(force: bool = False, verbose: bool = False) -> Path:
-    if not force and not needs_build():
+    """LRX_EXTRA_NVCC (extra flags, e.g. -DNAME=value) and LRX_ONLY (comma-separated source
+    names to recompile, the other objects being reused) serve kernel tuning runs."""
+    extra = os.environ.get("LRX_EXTRA_NVCC", "").split()
+    only = [s for s in os.environ.get("LRX_ONLY", "").split(",") if s]
+    if not force and not needs_build() and not extra and not only:
         return LIB
     nvcc = _nvcc()
     objs = []
     log = []
     for src in sources():
         obj = src.with_suffix(".o")
-        cmd = [nvcc, *NVCC_FLAGS, "-c", str(src), "-o", str(obj)]
+        if only and src.name not in only and obj.exists():
+            objs.append(str(obj))
+            continue
+        cmd = [nvcc, *NVCC_FLAGS, *extra, "-c", str(src), "-o", str(obj)]
         r = subprocess.run(cmd, capture_output=True, text=True)
         log.append(f"$ {' '.join(cmd)}\n{r.stdout}{r.stderr}")
         if r.returncode != 0:

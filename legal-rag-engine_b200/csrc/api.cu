@@ -119,7 +119,7 @@ int lrx_close(lrx_handle* h) {
     cudaSetDevice(h->device);
     cudaDeviceSynchronize();
     void* ws[] = {h->ws_dense_part, h->ws_dense_merged, h->ws_bm_part, h->ws_bm_max, h->ws_misc,
-                  h->ws_io};
+                  h->ws_io, h->bm_lut};
     for (void* p : ws)
         if (p != nullptr) cudaFree(p);
     encoder_free(h);
@@ -189,7 +189,8 @@ int lrx_set_corpus(lrx_handle* h, const void* dev_x_fp16, int64_t n_local, int64
 }
 
 int lrx_set_postings(lrx_handle* h, const uint64_t* dev_term_ptr, const void* dev_postings,
-                     const double* dev_idf, int64_t n_terms, int64_t nnz) {
+                     const double* dev_idf, int64_t n_terms, int64_t nnz, double avgdl, double k1,
+                     double b, int32_t max_doc_len) {
     if (h == nullptr) return fail(nullptr, LRX_E_ARG, "lrx_set_postings: null handle");
     std::lock_guard<std::mutex> g(h->mu);
     if (n_terms < 0 || nnz < 0) return fail(h, LRX_E_ARG, "lrx_set_postings: negative size");
@@ -197,6 +198,12 @@ int lrx_set_postings(lrx_handle* h, const uint64_t* dev_term_ptr, const void* de
         return fail(h, LRX_E_ARG, "lrx_set_postings: null pointer");
     if (((uintptr_t)dev_postings & 15) != 0)
         return fail(h, LRX_E_ARG, "lrx_set_postings: postings must be 16-byte aligned");
+    if (!(avgdl > 0.0)) return fail(h, LRX_E_ARG, "lrx_set_postings: avgdl must be > 0");
+    if (max_doc_len < 0 || max_doc_len > 65535)
+        return fail(h, LRX_E_ARG, "lrx_set_postings: max_doc_len must be in [0,65535] "
+                                  "(the 8-byte posting stores the document length in 16 bits)");
+    LRX_CUDA(h, cudaSetDevice(h->device));
+    LRX_CUDA(h, launch_bm25_lut(h, avgdl, k1, b, max_doc_len));
     h->term_ptr = dev_term_ptr;
     h->postings = dev_postings;
     h->idf = dev_idf;
@@ -205,17 +212,21 @@ int lrx_set_postings(lrx_handle* h, const uint64_t* dev_term_ptr, const void* de
     return LRX_OK;
 }
 
-int lrx_bm25_build_impacts(lrx_handle* h, void* dev_postings, int64_t nnz,
-                           const uint32_t* dev_doc_len, double avgdl, double k1, double b) {
-    if (h == nullptr) return fail(nullptr, LRX_E_ARG, "lrx_bm25_build_impacts: null handle");
+int lrx_bm25_build_postings(lrx_handle* h, const uint32_t* dev_doc_tf, int64_t nnz,
+                            const uint32_t* dev_doc_len, void* dev_postings_out) {
+    if (h == nullptr) return fail(nullptr, LRX_E_ARG, "lrx_bm25_build_postings: null handle");
     std::lock_guard<std::mutex> g(h->mu);
-    if (nnz < 0 || (nnz > 0 && (dev_postings == nullptr || dev_doc_len == nullptr)))
-        return fail(h, LRX_E_ARG, "lrx_bm25_build_impacts: bad argument");
-    if (!(avgdl > 0.0)) return fail(h, LRX_E_ARG, "lrx_bm25_build_impacts: avgdl must be > 0");
-    if (((uintptr_t)dev_postings & 15) != 0)
-        return fail(h, LRX_E_ARG, "lrx_bm25_build_impacts: postings must be 16-byte aligned");
+    if (nnz < 0 || (nnz > 0 && (dev_doc_tf == nullptr || dev_doc_len == nullptr ||
+                                dev_postings_out == nullptr)))
+        return fail(h, LRX_E_ARG, "lrx_bm25_build_postings: bad argument");
+    if ((((uintptr_t)dev_postings_out | (uintptr_t)dev_doc_tf) & 7) != 0)
+        return fail(h, LRX_E_ARG, "lrx_bm25_build_postings: buffers must be 8-byte aligned");
     LRX_CUDA(h, cudaSetDevice(h->device));
-    LRX_CUDA(h, launch_bm25_impacts(h, dev_postings, nnz, dev_doc_len, avgdl, k1, b));
+    int overflow = 0;
+    LRX_CUDA(h, launch_bm25_pack(h, dev_doc_tf, nnz, dev_doc_len, dev_postings_out, &overflow));
+    if (overflow)
+        return fail(h, LRX_E_ARG, "lrx_bm25_build_postings: a term frequency or document length "
+                                  "exceeds 65535 (16-bit posting fields)");
     return LRX_OK;
 }
 

@@ -37,6 +37,10 @@ struct lrx_handle {
     const void* postings = nullptr;
     const double* idf = nullptr;
     int64_t n_terms = 0, nnz = 0;
+    // BM25 impact table [8][bm_lut_ld] (handle-owned) and the constants behind it
+    void* bm_lut = nullptr;          size_t bm_lut_bytes = 0;
+    int bm_lut_ld = 0;
+    double bm_avgdl = 0.0, bm_k1 = 1.5, bm_b = 0.75;
 
     // workspaces (handle-owned, grown on demand)
     void* ws_dense_part = nullptr;   size_t ws_dense_part_bytes = 0;    // per-CTA key lists
@@ -79,8 +83,9 @@ cudaError_t launch_bm25_bounds(lrx_handle* h, const int32_t* q_terms, const int3
 cudaError_t launch_bm25_scan(lrx_handle* h, const int32_t* q_terms, const int32_t* q_ptr, int B,
                              const int64_t* cand_ids, int n_cand, double* cand_scores,
                              double* out_max, int K, double* top_scores, int64_t* top_ids);
-cudaError_t launch_bm25_impacts(lrx_handle* h, void* postings, int64_t nnz, const uint32_t* doc_len,
-                                double avgdl, double k1, double b);
+cudaError_t launch_bm25_pack(lrx_handle* h, const uint32_t* doc_tf, int64_t nnz, const uint32_t* doc_len,
+                             void* out, int* host_overflow);
+cudaError_t launch_bm25_lut(lrx_handle* h, double avgdl, double k1, double b, int max_len);
 
 // fuse.cu
 cudaError_t launch_pack_records(lrx_handle* h, int B, int K, int mode, const double* dense_exact,

@@ -65,8 +65,8 @@ class DeviceIndex:
                      b: float = 0.75):
         """Make the BM25 postings resident.  term_ptr int64/uint64 [V+1]; postings
         int32/uint32 [nnz,2] = (local doc, tf); doc_len int32/uint32 [n]; idf float64 [V]
-        (GLOBAL statistics) -- torch CUDA tensors or numpy arrays (uploaded).  The 16-byte
-        scoring layout {doc, tf, f64 impact} is built on the device (index-build step)."""
+        (GLOBAL statistics) -- torch CUDA tensors or numpy arrays (uploaded).  The 8-byte
+        scoring layout {doc, u16 tf, u16 len} is built on the device (index-build step)."""
         def dev(a, dt):
             if isinstance(a, np.ndarray):
                 if a.dtype == np.uint64:
@@ -83,17 +83,15 @@ class DeviceIndex:
         assert po.shape[0] == nnz, (po.shape, nnz)
         if dl.numel() == 0:
             dl = torch.zeros(1, dtype=torch.int32, device=self.device)
-        p16 = torch.zeros((max(nnz, 1), 4), dtype=torch.int32, device=self.device)
-        if nnz:
-            p16[:nnz, :2] = po
+        max_len = int(dl.max().item())
+        p8 = torch.zeros((nnz + 2, 2), dtype=torch.int32, device=self.device)   # 8 B / posting, padded
+        self._ck(self.lib.lrx_bm25_build_postings(self.h, _ptr(po), nnz, _ptr(dl), _ptr(p8)))
         del po
-        self._ck(self.lib.lrx_bm25_build_impacts(self.h, _ptr(p16), nnz, _ptr(dl), float(avgdl),
-                                                 float(k1), float(b)))
-        self._post = (tp, p16, idf_t)
+        self._post = (tp, p8, idf_t)
         self.doc_len = dl
         self.n_terms = int(tp.numel() - 1)
-        self._ck(self.lib.lrx_set_postings(self.h, _ptr(tp), _ptr(p16), _ptr(idf_t), self.n_terms,
-                                           nnz))
+        self._ck(self.lib.lrx_set_postings(self.h, _ptr(tp), _ptr(p8), _ptr(idf_t), self.n_terms, nnz,
+                                           float(avgdl), float(k1), float(b), max_len))
 
     # ---------------------------------------------------------------- stages
     def dense_topk(self, q: torch.Tensor, K: int, width: int = 0):
