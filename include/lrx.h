@@ -151,6 +151,13 @@ int lrx_dense_topk(lrx_handle* h, const void* dev_q_fp16, int32_t B, int32_t K,
 int lrx_dense_topk_ex(lrx_handle* h, const void* dev_q_fp16, int32_t B, int32_t K,
                       int32_t width, double* dev_exact, float* dev_D, int64_t* dev_I,
                       int32_t* dev_flags);
+/* K2b: the same search for LARGE batches (B up to 4096; FAISS's BLAS regime, nq >= 20) on the
+ * tensor cores: two tcgen05 GEMM passes (tile maxima -> per-query threshold; candidates above
+ * it) + exact float64 re-score.  Same outputs and ordering as lrx_dense_topk.  stride: pass 1
+ * samples every stride-th 256-row tile (0 = automatic).  dev_flags[b] = 1: more than 512
+ * candidates survived for query b -- rerun with stride 1. */
+int lrx_dense_topk_batched(lrx_handle* h, const void* dev_q_fp16, int32_t B, int32_t K, int32_t stride,
+                           double* dev_exact, float* dev_D, int64_t* dev_I, int32_t* dev_flags);
 /* Exact inner products at given global ids (ids outside the shard or -1 -> -inf). */
 int lrx_dense_at(lrx_handle* h, const void* dev_q_fp16, int32_t B, const int64_t* dev_ids,
                  int32_t n, double* dev_out);

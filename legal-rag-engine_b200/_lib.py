@@ -79,6 +79,7 @@ _SIGNATURES = {
                                _vp]),
     "lrx_dense_topk": (C.c_int, [_vp, _vp, _i32, _i32, _vp, _vp, _vp, _vp]),
     "lrx_dense_topk_ex": (C.c_int, [_vp, _vp, _i32, _i32, _i32, _vp, _vp, _vp, _vp]),
+    "lrx_dense_topk_batched": (C.c_int, [_vp, _vp, _i32, _i32, _i32, _vp, _vp, _vp, _vp]),
     "lrx_dense_at": (C.c_int, [_vp, _vp, _i32, _vp, _i32, _vp]),
     "lrx_bm25": (C.c_int, [_vp, _vp, _vp, _i32, _vp, _i32, _vp, _vp, _i32, _vp, _vp]),
     "lrx_search_local": (C.c_int, [_vp, _vp, _vp, _vp, _i32, _i32, _i32, _i32, _vp, _vp, _vp]),

@@ -335,6 +335,22 @@ int lrx_dense_topk(lrx_handle* h, const void* dev_q_fp16, int32_t B, int32_t K, 
     return lrx_dense_topk_ex(h, dev_q_fp16, B, K, 0, dev_exact, dev_D, dev_I, dev_flags);
 }
 
+int lrx_dense_topk_batched(lrx_handle* h, const void* dev_q_fp16, int32_t B, int32_t K, int32_t stride,
+                           double* dev_exact, float* dev_D, int64_t* dev_I, int32_t* dev_flags) {
+    if (h == nullptr) return fail(nullptr, LRX_E_ARG, "lrx_dense_topk_batched: null handle");
+    std::lock_guard<std::mutex> g(h->mu);
+    if (h->x == nullptr || h->n_local < 1) return fail(h, LRX_E_STATE, "lrx_dense_topk_batched: corpus not set");
+    if (B < 1 || B > 4096) return fail(h, LRX_E_ARG, "lrx_dense_topk_batched: B must be in [1,4096]");
+    if (K < 1 || K > LRX_MAX_DEPTH) return fail(h, LRX_E_ARG, "lrx_dense_topk_batched: K must be in [1,%d]", LRX_MAX_DEPTH);
+    if (stride < 0) return fail(h, LRX_E_ARG, "lrx_dense_topk_batched: stride < 0");
+    if (dev_q_fp16 == nullptr || dev_exact == nullptr || dev_D == nullptr || dev_I == nullptr ||
+        dev_flags == nullptr || ((uintptr_t)dev_q_fp16 & 15) != 0)
+        return fail(h, LRX_E_ARG, "lrx_dense_topk_batched: null or misaligned pointer");
+    LRX_CUDA(h, cudaSetDevice(h->device));
+    LRX_CUDA(h, launch_dense_topk_batched(h, dev_q_fp16, B, K, stride, dev_exact, dev_D, dev_I, dev_flags));
+    return LRX_OK;
+}
+
 int lrx_dense_at(lrx_handle* h, const void* dev_q_fp16, int32_t B, const int64_t* dev_ids,
                  int32_t n, double* dev_out) {
     if (h == nullptr) return fail(nullptr, LRX_E_ARG, "lrx_dense_at: null handle");

@@ -1,0 +1,375 @@
+// K2b: flat inner-product top-K for LARGE query batches (B = 64 ... 4096) on the tensor cores.
+//
+// Replaces faiss IndexFlatIP.search(x, K) for nq >= 20, where FAISS switches from its
+// per-query scan to BLAS sgemm blocks (reference call site: src/retrieval/retrieval_engine.py:64;
+// config C3, B = 1024).  scores[B, N] = Q[B,384] * X[N,384]^T never exists in HBM: the GEMM
+// tiles live in TMEM and are reduced on the way out.
+//
+// Two tensor-core passes with the same persistent kernel (dense_tc_kernel<PASS>):
+//   pass 1  over every `stride`-th 256-row tile: per (query, 32-row chunk) the MAXIMUM score.
+//           The K-th largest chunk maximum T[q] (tilemax_kth_kernel) is a lower bound of the
+//           K-th best score: K distinct rows reach it.
+//   pass 2  over all tiles: every (query, row) with score >= T[q] - slack is appended to the
+//           query's candidate list (global atomics; a few hundred per query).
+// dense_rescore_list_kernel then re-scores the candidates EXACTLY in float64 (oracle/flat_ip.py),
+// orders them by (score desc, id asc) and emits the best K.  With slack = 2 * kTcEps a row that
+// was not appended is strictly below the K-th best exact score, so the result is bit-exact; the
+// only failure mode is a candidate list overflow (flag -> caller reruns with stride 1).
+//
+// Kernel shape (one CTA per SM, 192 threads, warp-specialised like tc_gemm.cu):
+//   A operand = 128 queries x 384, loaded once by TMA and RESIDENT in shared memory (96 KB);
+//   B operand = 256 chunk rows x 64 per stage, 3-stage TMA ring (SWIZZLE_128B);
+//   tcgen05.mma cta_group::1 kind::f16, UMMA 128 x 256 x 16, fp32 accumulators in TMEM,
+//   DOUBLE-BUFFERED (2 x 256 columns) so the epilogue of tile i overlaps the MMAs of tile i+1;
+//   epilogue thread = query (TMEM lane): tcgen05.ld 32 columns at a time, running max / compare.
+// CTA c serves query tile (c % n_mt) and walks chunk tiles (c / n_mt), (c / n_mt) + G, ... so the
+// n_mt CTAs that need the same chunk tile touch it at about the same time (one HBM read, L2 hits).
+//
+// Roofline: tensor pipe.  flops per launch = 2 * B_padded * 384 * rows scanned.
+#include <cfloat>
+
+#include "handle.h"
+#include "tc.cuh"
+
+namespace lrx {
+
+cudaError_t make_tmap_f16(CUtensorMap* out, const void* ptr, int64_t rows, int64_t cols, int64_t ld,
+                          int box_rows);
+
+constexpr int kDbQ = 128;             // queries per CTA (UMMA M)
+constexpr int kDbN = 256;             // chunk rows per tile (UMMA N)
+constexpr int kDbK = 64;              // halves per k-block (128 B, one swizzle row)
+constexpr int kDbKB = kDim / kDbK;    // 6 k-blocks
+constexpr int kDbStages = 3;
+constexpr int kDbABytes = kDbQ * kDbK * 2;    // 16 KB per k-block of the query tile
+constexpr int kDbBBytes = kDbN * kDbK * 2;    // 32 KB per stage
+constexpr int kDbThreads = 192;
+constexpr size_t kDbSmem = (size_t)kDbKB * kDbABytes + (size_t)kDbStages * kDbBBytes + 1024 + 256;
+constexpr int kDbCap = 512;           // candidates kept per query
+// |tensor-core fp32 score - exact| for unit fp16 vectors: 384 exact products accumulated in
+// fp32 (possibly truncating) in 24 instructions -> well below 1e-5
+constexpr float kTcEps = 1e-5f;
+
+struct DbParams {
+    int B;                 // valid queries
+    int64_t n_rows;
+    int n_tiles;           // ceil(n_rows / 256)
+    int n_mt;              // query tiles
+    int stride;            // pass 1: every stride-th tile
+    float* tilemax;        // [n_mt*128][n_samp]       (pass 1 out)
+    int n_samp;
+    const float* thr;      // [n_mt*128]               (pass 2 in)
+    int* cnt;              // [n_mt*128]
+    uint64_t* cand;        // [n_mt*128][kDbCap] keys (f32 image << 32 | ~row)
+};
+
+template <int PASS>
+__global__ void __launch_bounds__(kDbThreads, 1)
+dense_tc_kernel(const __grid_constant__ CUtensorMap tma_q, const __grid_constant__ CUtensorMap tma_x,
+                const DbParams P) {
+    extern __shared__ unsigned char db_raw[];
+    unsigned char* base = reinterpret_cast<unsigned char*>(
+        (reinterpret_cast<uintptr_t>(db_raw) + 1023) & ~(uintptr_t)1023);
+    unsigned char* sA = base;
+    unsigned char* sB = base + kDbKB * kDbABytes;
+    uint64_t* full = reinterpret_cast<uint64_t*>(sB + kDbStages * kDbBBytes);
+    uint64_t* empty = full + kDbStages;
+    uint64_t* a_full = empty + kDbStages;
+    uint64_t* t_full = a_full + 1;       // [2] accumulator ready
+    uint64_t* t_empty = t_full + 2;      // [2] accumulator drained
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(t_empty + 2);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int m_tile = blockIdx.x % P.n_mt;
+    const int group = blockIdx.x / P.n_mt;
+    const int n_groups = gridDim.x / P.n_mt;
+    const int step = (PASS == 1) ? P.stride : 1;
+    // this CTA's tiles: t = (group + i * n_groups) * step
+    const int n_units = (P.n_tiles + step - 1) / step;
+    const int my_units = (n_units > group) ? (n_units - group + n_groups - 1) / n_groups : 0;
+
+    if (warp == 4 && lane == 0) {
+        tma_prefetch_desc(&tma_q);
+        tma_prefetch_desc(&tma_x);
+        for (int s = 0; s < kDbStages; ++s) {
+            mbar_init(&full[s], 1);
+            mbar_init(&empty[s], 1);
+        }
+        mbar_init(a_full, 1);
+        for (int b = 0; b < 2; ++b) {
+            mbar_init(&t_full[b], 1);
+            mbar_init(&t_empty[b], 4);
+        }
+        fence_barrier_init();
+    }
+    if (warp == 5) {
+        tmem_alloc(tmem_slot, 512);
+        tmem_relinquish();
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    if (warp == 4) {
+        if (lane == 0) {
+            // the query tile, once
+            mbar_arrive_expect_tx(a_full, (uint32_t)(kDbKB * kDbABytes));
+            for (int kb = 0; kb < kDbKB; ++kb)
+                tma_load_2d(sA + kb * kDbABytes, &tma_q, kb * kDbK, m_tile * kDbQ, a_full);
+            uint32_t it = 0;
+            for (int u = 0; u < my_units; ++u) {
+                const int tile = (group + u * n_groups) * step;
+                for (int kb = 0; kb < kDbKB; ++kb, ++it) {
+                    const int s = (int)(it % kDbStages);
+                    const uint32_t ph = (it / kDbStages) & 1u;
+                    mbar_wait(&empty[s], ph ^ 1u);
+                    mbar_arrive_expect_tx(&full[s], (uint32_t)kDbBBytes);
+                    tma_load_2d(sB + s * kDbBBytes, &tma_x, kb * kDbK, tile * kDbN, &full[s]);
+                }
+            }
+        }
+    } else if (warp == 5) {
+        if (lane == 0) {
+            constexpr uint32_t idesc = umma_idesc_f16(kDbQ, kDbN);
+            mbar_wait(a_full, 0);
+            uint32_t it = 0;
+            for (int u = 0; u < my_units; ++u) {
+                const int buf = u & 1;
+                const uint32_t use = (uint32_t)(u >> 1);
+                mbar_wait(&t_empty[buf], (use & 1u) ^ 1u);     // epilogue drained this buffer
+                tc_fence_after();
+                for (int kb = 0; kb < kDbKB; ++kb, ++it) {
+                    const int s = (int)(it % kDbStages);
+                    const uint32_t ph = (it / kDbStages) & 1u;
+                    mbar_wait(&full[s], ph);
+                    tc_fence_after();
+                    const uint32_t a_addr = smem_u32(sA + kb * kDbABytes);
+                    const uint32_t b_addr = smem_u32(sB + s * kDbBBytes);
+#pragma unroll
+                    for (int k = 0; k < kDbK / 16; ++k)
+                        umma_f16(tmem_base + buf * kDbN, umma_desc_sw128(a_addr + k * 32),
+                                 umma_desc_sw128(b_addr + k * 32), idesc, (kb > 0 || k > 0) ? 1u : 0u);
+                    umma_commit(&empty[s]);
+                }
+                umma_commit(&t_full[buf]);
+            }
+        }
+    } else {
+        // ===== epilogue: thread = query
+        const int ql = warp * 32 + lane;
+        const int q = m_tile * kDbQ + ql;
+        const bool q_ok = q < P.B;
+        const uint32_t trow = tmem_base + ((uint32_t)(warp * 32) << 16);
+        float thr = 0.f;
+        if (PASS == 2) thr = q_ok ? P.thr[q] : FLT_MAX;
+        uint32_t r[32];
+        for (int u = 0; u < my_units; ++u) {
+            const int buf = u & 1;
+            const uint32_t use = (uint32_t)(u >> 1);
+            const int tile = (group + u * n_groups) * step;
+            const int64_t row0 = (int64_t)tile * kDbN;
+            const int valid = (int)min((int64_t)kDbN, P.n_rows - row0);
+            mbar_wait(&t_full[buf], use & 1u);
+            tc_fence_after();
+            for (int c = 0; c < kDbN; c += 32) {
+                tmem_ld32(trow + buf * kDbN + c, r);
+                tmem_wait_ld();
+                if (PASS == 1) {
+                    // maximum of every 32-row chunk: 8 samples per tile for the threshold
+                    float mx = -FLT_MAX;
+#pragma unroll
+                    for (int j = 0; j < 32; ++j)
+                        if (c + j < valid) mx = fmaxf(mx, __uint_as_float(r[j]));
+                    P.tilemax[(size_t)q * P.n_samp + (size_t)(tile / step) * (kDbN / 32) + (c >> 5)] = mx;
+                } else {
+#pragma unroll
+                    for (int j = 0; j < 32; ++j) {
+                        const float sc = __uint_as_float(r[j]);
+                        if (sc >= thr && c + j < valid) {
+                            const int slot = atomicAdd(P.cnt + q, 1);
+                            if (slot < kDbCap)
+                                P.cand[(size_t)q * kDbCap + slot] = make_key64(sc, (uint32_t)(row0 + c + j));
+                        }
+                    }
+                }
+            }
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&t_empty[buf]);
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 5) {
+        tc_fence_after();
+        tmem_dealloc(tmem_base, 512);
+    }
+}
+
+// T[q] = (K-th largest tile maximum) - slack; -FLT_MAX when fewer than K tiles were sampled.
+// One CTA per query, bitonic sort in shared memory (n_samp <= 16384).
+__global__ void __launch_bounds__(256)
+tilemax_kth_kernel(const float* __restrict__ tilemax, int n_samp, int K, float slack,
+                   float* __restrict__ thr, int* __restrict__ cnt) {
+    extern __shared__ uint32_t tm_keys[];
+    const int q = blockIdx.x, tid = threadIdx.x;
+    const int p2 = next_pow2(max(n_samp, 2));
+    for (int i = tid; i < p2; i += 256)
+        tm_keys[i] = (i < n_samp) ? f32_ord(tilemax[(size_t)q * n_samp + i]) : 0u;
+    __syncthreads();
+    block_bitonic_sort_desc<uint32_t>(tm_keys, p2, 1, p2, tid, 256);
+    if (tid == 0) {
+        thr[q] = (K <= n_samp) ? ord_f32(tm_keys[K - 1]) - slack : -FLT_MAX;
+        cnt[q] = 0;
+    }
+}
+
+// Exact float64 re-score of a query's (unsorted) candidate list, best K out.
+constexpr int kRlThreads = 256;
+__global__ void __launch_bounds__(kRlThreads)
+dense_rescore_list_kernel(const unsigned char* __restrict__ x, int64_t id_base,
+                          const __half* __restrict__ q, const uint64_t* __restrict__ cand,
+                          const int* __restrict__ cnt, int K, double* __restrict__ out_exact,
+                          float* __restrict__ out_D, int64_t* __restrict__ out_I,
+                          int32_t* __restrict__ out_flag) {
+    __shared__ u128 keys[kDbCap];
+    const int qi = blockIdx.x;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int total = cnt[qi];
+    const int n = min(total, kDbCap);
+    const uint2* qp = reinterpret_cast<const uint2*>(q + (size_t)qi * kDim);
+    uint2 qv[3];
+#pragma unroll
+    for (int s = 0; s < 3; ++s) qv[s] = qp[s * 32 + lane];
+    for (int j = warp; j < kDbCap; j += kRlThreads / 32) {
+        u128 key = 0;
+        if (j < n) {
+            const uint32_t row = key64_row(cand[(size_t)qi * kDbCap + j]);
+            const uint2* rowp = reinterpret_cast<const uint2*>(x + (int64_t)row * kRowBytes);
+            double acc = 0.0;
+#pragma unroll
+            for (int s = 0; s < 3; ++s) {
+                const uint2 v = rowp[s * 32 + lane];
+                const float2 a = __half22float2(*reinterpret_cast<const __half2*>(&v.x));
+                const float2 b = __half22float2(*reinterpret_cast<const __half2*>(&v.y));
+                const float2 e = __half22float2(*reinterpret_cast<const __half2*>(&qv[s].x));
+                const float2 f = __half22float2(*reinterpret_cast<const __half2*>(&qv[s].y));
+                acc = fma((double)a.x, (double)e.x, acc);
+                acc = fma((double)a.y, (double)e.y, acc);
+                acc = fma((double)b.x, (double)f.x, acc);
+                acc = fma((double)b.y, (double)f.y, acc);
+            }
+#pragma unroll
+            for (int lb = 16; lb > 0; lb >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, lb);
+            key = make_key128(acc, row);
+        }
+        if (lane == 0) keys[j] = key;
+    }
+    __syncthreads();
+    block_bitonic_sort_desc<u128>(keys, kDbCap, 1, kDbCap, tid, kRlThreads);
+    for (int j = tid; j < K; j += kRlThreads) {
+        const u128 key = (j < kDbCap) ? keys[j] : (u128)0;
+        const size_t o = (size_t)qi * K + j;
+        if (key != 0) {
+            const double e = key128_score(key);
+            out_exact[o] = e;
+            out_D[o] = (float)e;
+            out_I[o] = id_base + (int64_t)key128_row(key);
+        } else {
+            out_exact[o] = -INFINITY;
+            out_D[o] = -3.4028234663852886e38f;
+            out_I[o] = -1;
+        }
+    }
+    if (tid == 0) out_flag[qi] = (total > kDbCap) ? 1 : 0;
+}
+
+int dense_batched_max_stride(int64_t n_rows, int K) {
+    // keep at least 16K sampled 32-row chunks so T is a tight bound
+    const int64_t n_tiles = (n_rows + kDbN - 1) / kDbN;
+    int s = (int)(n_tiles * (kDbN / 32) / (16 * (int64_t)K));
+    if (s < 1) s = 1;
+    if (s > 8) s = 8;
+    return s;
+}
+
+cudaError_t launch_dense_topk_batched(lrx_handle* h, const void* q, int B, int K, int stride,
+                                      double* exact, float* D, int64_t* I, int32_t* flags) {
+    static bool attr = false;
+    cudaError_t e;
+    if (!attr) {
+        e = cudaFuncSetAttribute(dense_tc_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kDbSmem);
+        if (e != cudaSuccess) return e;
+        e = cudaFuncSetAttribute(dense_tc_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kDbSmem);
+        if (e != cudaSuccess) return e;
+        e = cudaFuncSetAttribute(tilemax_kth_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 65536);
+        if (e != cudaSuccess) return e;
+        attr = true;
+    }
+    const int64_t n = h->n_local;
+    const int n_tiles = (int)((n + kDbN - 1) / kDbN);
+    const int n_mt = (B + kDbQ - 1) / kDbQ;
+    const int Bp = n_mt * kDbQ;
+    if (stride < 1) stride = dense_batched_max_stride(n, K);
+    constexpr int kChunks = kDbN / 32;
+    int n_samp = (n_tiles + stride - 1) / stride * kChunks;
+    if (n_samp > 16384) {                      // shared-memory sort limit of tilemax_kth_kernel
+        stride = (n_tiles * kChunks + 16383) / 16384;
+        n_samp = (n_tiles + stride - 1) / stride * kChunks;
+    }
+    if (n_samp < K) {
+        // tiny corpus for this K: no useful threshold -- the streaming kernel, 64 queries a time
+        for (int b0 = 0; b0 < B; b0 += LRX_MAX_BATCH) {
+            const int nb = (B - b0 < LRX_MAX_BATCH) ? (B - b0) : LRX_MAX_BATCH;
+            e = launch_dense_topk(h, (const __half*)q + (size_t)b0 * kDim, nb, K, dense_default_width(K),
+                                  exact + (size_t)b0 * K, D + (size_t)b0 * K, I + (size_t)b0 * K, flags + b0);
+            if (e != cudaSuccess) return e;
+        }
+        return cudaSuccess;
+    }
+    int grid = (h->num_sms / n_mt) * n_mt;
+    if (grid < n_mt) grid = n_mt;
+    // workspace: tilemax | thr | cnt | cand
+    size_t off = 0;
+    auto take = [&](size_t bytes) { size_t o = off; off = (off + bytes + 255) / 256 * 256; return o; };
+    const size_t o_tm = take((size_t)Bp * n_samp * sizeof(float));
+    const size_t o_thr = take((size_t)Bp * sizeof(float));
+    const size_t o_cnt = take((size_t)Bp * sizeof(int));
+    const size_t o_cand = take((size_t)Bp * kDbCap * sizeof(uint64_t));
+    e = ensure_ws(&h->ws_dense_part, &h->ws_dense_part_bytes, off);
+    if (e != cudaSuccess) return e;
+    char* W = (char*)h->ws_dense_part;
+    CUtensorMap tq, tx;
+    e = make_tmap_f16(&tq, q, B, kDim, kDim, kDbQ);
+    if (e != cudaSuccess) return e;
+    e = make_tmap_f16(&tx, h->x, n, kDim, kDim, kDbN);
+    if (e != cudaSuccess) return e;
+    DbParams P;
+    P.B = B; P.n_rows = n; P.n_tiles = n_tiles; P.n_mt = n_mt; P.stride = stride;
+    P.tilemax = (float*)(W + o_tm); P.n_samp = n_samp; P.thr = (const float*)(W + o_thr);
+    P.cnt = (int*)(W + o_cnt); P.cand = (uint64_t*)(W + o_cand);
+    prof_begin(h, 0);
+    dense_tc_kernel<1><<<grid, kDbThreads, kDbSmem, h->stream>>>(tq, tx, P);
+    prof_end(h, 0);
+    h->launches++;
+    e = cudaGetLastError();
+    if (e != cudaSuccess) return e;
+    tilemax_kth_kernel<<<Bp, 256, (size_t)next_pow2(n_samp > 2 ? n_samp : 2) * sizeof(uint32_t), h->stream>>>(
+        P.tilemax, n_samp, K, 2.0f * kTcEps, (float*)(W + o_thr), P.cnt);
+    h->launches++;
+    e = cudaGetLastError();
+    if (e != cudaSuccess) return e;
+    prof_begin(h, 0);
+    dense_tc_kernel<2><<<grid, kDbThreads, kDbSmem, h->stream>>>(tq, tx, P);
+    prof_end(h, 0);
+    h->launches++;
+    e = cudaGetLastError();
+    if (e != cudaSuccess) return e;
+    dense_rescore_list_kernel<<<B, kRlThreads, 0, h->stream>>>(
+        (const unsigned char*)h->x, h->id_base, (const __half*)q, P.cand, P.cnt, K, exact, D, I, flags);
+    h->launches++;
+    return cudaGetLastError();
+}
+
+}  // namespace lrx

@@ -73,6 +73,10 @@ cudaError_t launch_dense_topk(lrx_handle* h, const void* q, int B, int K, int wi
 cudaError_t launch_dense_at(lrx_handle* h, const void* q, int B, const int64_t* ids, int n,
                             double* out);
 
+// dense_batched.cu
+cudaError_t launch_dense_topk_batched(lrx_handle* h, const void* q, int B, int K, int stride,
+                                      double* exact, float* D, int64_t* I, int32_t* flags);
+
 // bm25.cu
 cudaError_t launch_bm25(lrx_handle* h, const int32_t* q_terms, const int32_t* q_ptr, int B,
                         const int64_t* cand_ids, int n_cand, double* cand_scores, double* out_max,

@@ -105,6 +105,18 @@ class DeviceIndex:
                                             _ptr(I), _ptr(flags)))
         return exact, D, I, flags
 
+    def dense_topk_batched(self, q: torch.Tensor, K: int, stride: int = 0):
+        """K2b: tensor-core path for large batches (B up to 4096).  Same outputs as dense_topk."""
+        assert q.dtype == torch.float16 and q.is_cuda and q.is_contiguous()
+        B = int(q.shape[0])
+        exact = torch.empty((B, K), dtype=torch.float64, device=self.device)
+        D = torch.empty((B, K), dtype=torch.float32, device=self.device)
+        I = torch.empty((B, K), dtype=torch.int64, device=self.device)
+        flags = torch.empty(B, dtype=torch.int32, device=self.device)
+        self._ck(self.lib.lrx_dense_topk_batched(self.h, _ptr(q), B, K, stride, _ptr(exact), _ptr(D),
+                                                 _ptr(I), _ptr(flags)))
+        return exact, D, I, flags
+
     def dense_at(self, q: torch.Tensor, ids: torch.Tensor):
         B, n = int(ids.shape[0]), int(ids.shape[1])
         out = torch.empty((B, n), dtype=torch.float64, device=self.device)

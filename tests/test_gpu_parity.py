@@ -263,3 +263,43 @@ def test_one_million_rows(dev):
     np.testing.assert_array_equal(E.cpu().numpy(), Eo)
     E1, D1, I1, f1 = dev.dense_topk(_cuda(q[:1]), 20)
     np.testing.assert_array_equal(I1.cpu().numpy(), Io[:1])
+
+
+# ------------------------------------------------ K2b: tensor-core batched scoring
+@pytest.mark.parametrize("n,B,K", [(300, 5, 20), (1000, 64, 20), (20011, 130, 10), (300000, 256, 20),
+                                   (100000, 1024, 200)])
+def test_dense_topk_batched_matches_oracle(dev, n, B, K):
+    x = synth.host_vectors(n, seed=n + 7, dup_frac=0.01)
+    q = synth.host_queries(B, seed=B + n)
+    q[0] = x[n // 2]                                   # a planted exact hit
+    dev.set_corpus(_cuda(x), 1000)
+    E, D, I, flags = dev.dense_topk_batched(_cuda(q), K)
+    if int(flags.sum().item()) != 0:                   # candidate overflow -> exhaustive pass 1
+        E, D, I, flags = dev.dense_topk_batched(_cuda(q), K, stride=1)
+    assert int(flags.sum().item()) == 0
+    s = flat_ip.exact_scores(x, q)
+    Eo, Do, Io = flat_ip.topk_from_scores(s, K, id_base=1000)
+    np.testing.assert_array_equal(I.cpu().numpy(), Io)
+    np.testing.assert_array_equal(E.cpu().numpy(), Eo)
+    np.testing.assert_array_equal(D.cpu().numpy(), Do)
+
+
+def test_dense_topk_batched_one_million_rows_b1024(dev):
+    """Config C3: 1 M x 384, query batch 1024, top-20 -- bit-exact against the oracle on a sample
+    of the queries, and against the small-batch kernel on all of them."""
+    n, B, K = 1_000_000, 1024, 20
+    x = synth.host_vectors(n, seed=1234)
+    q = synth.host_queries(B, seed=4321)
+    dev.set_corpus(_cuda(x), 0)
+    E, D, I, flags = dev.dense_topk_batched(_cuda(q), K)
+    assert int(flags.sum().item()) == 0
+    pick = [0, 1, 511, 1023]
+    s = flat_ip.exact_scores(x, q[pick])
+    Eo, _, Io = flat_ip.topk_from_scores(s, K)
+    np.testing.assert_array_equal(I.cpu().numpy()[pick], Io)
+    np.testing.assert_array_equal(E.cpu().numpy()[pick], Eo)
+    for b0 in range(0, 64, 4):                         # K2a on the first 64 queries
+        E2, _, I2, f2 = dev.dense_topk(_cuda(q[b0:b0 + 4]), K)
+        assert int(f2.sum().item()) == 0
+        np.testing.assert_array_equal(I.cpu().numpy()[b0:b0 + 4], I2.cpu().numpy())
+        np.testing.assert_array_equal(E.cpu().numpy()[b0:b0 + 4], E2.cpu().numpy())
