@@ -27,6 +27,9 @@ constexpr int kFfn = 1536;
 constexpr int kQkv = 3 * kHidden;
 constexpr int kLayers = 6;
 constexpr float kLnEps = 1e-12f;
+// tokens per chunk: 148 row tiles of 128 = one full wave of the LayerNorm GEMMs (whose tile is
+// the whole 384-wide row); ~7.7 KB of activations per token, consecutive kernels hit in L2
+constexpr int64_t kChunkTokens = 148 * 128;
 
 // tc_gemm.cu
 cudaError_t make_tmap_f16(CUtensorMap* out, const void* ptr, int64_t rows, int64_t cols, int64_t ld,
@@ -34,6 +37,7 @@ cudaError_t make_tmap_f16(CUtensorMap* out, const void* ptr, int64_t rows, int64
 cudaError_t launch_tc_gemm(lrx_handle* h, const CUtensorMap& ta, const CUtensorMap& tb, int M, int N,
                            int K, int epi, const float* bias, const __half* residual, int ld_res,
                            const float* gamma, const float* beta, float eps, void* out, int ld_out);
+int gemm_box_rows_w(int num_sms, int M, int N, int K, int epi);
 
 struct EncLayer {
     __half* wqkv;   // [1152, 384]
@@ -41,7 +45,8 @@ struct EncLayer {
     __half* w1;     // [1536, 384]
     __half* w2;     // [384, 1536]
     float *bqkv, *bo, *b1, *b2, *ln1_g, *ln1_b, *ln2_g, *ln2_b;
-    CUtensorMap t_wqkv, t_wo, t_w1, t_w2;
+    // W tensor maps for the two launch plans: [0] small batches, [1] full waves (clusters)
+    CUtensorMap t_wqkv[2], t_wo[2], t_w1[2], t_w2[2];
 };
 
 struct Encoder {
@@ -440,10 +445,17 @@ cudaError_t encoder_set_weights(lrx_handle* h, const lrx_bert_weights* w) {
         ENC_CK(cpy(o_l[l][9], s.ln1_b, kHidden));
         ENC_CK(cpy(o_l[l][10], s.ln2_g, kHidden));
         ENC_CK(cpy(o_l[l][11], s.ln2_b, kHidden));
-        ENC_CK(make_tmap_f16(&d.t_wqkv, d.wqkv, kQkv, kHidden, kHidden, 128));
-        ENC_CK(make_tmap_f16(&d.t_wo, d.wo, kHidden, kHidden, kHidden, 128));
-        ENC_CK(make_tmap_f16(&d.t_w1, d.w1, kFfn, kHidden, kHidden, 128));
-        ENC_CK(make_tmap_f16(&d.t_w2, d.w2, kHidden, kFfn, kFfn, 128));
+        for (int pl = 0; pl < 2; ++pl) {
+            const int Mp = pl ? (int)kChunkTokens : 128;
+            ENC_CK(make_tmap_f16(&d.t_wqkv[pl], d.wqkv, kQkv, kHidden, kHidden,
+                                 gemm_box_rows_w(h->num_sms, Mp, kQkv, kHidden, 0)));
+            ENC_CK(make_tmap_f16(&d.t_wo[pl], d.wo, kHidden, kHidden, kHidden,
+                                 gemm_box_rows_w(h->num_sms, Mp, kHidden, kHidden, 2)));
+            ENC_CK(make_tmap_f16(&d.t_w1[pl], d.w1, kFfn, kHidden, kHidden,
+                                 gemm_box_rows_w(h->num_sms, Mp, kFfn, kHidden, 1)));
+            ENC_CK(make_tmap_f16(&d.t_w2[pl], d.w2, kHidden, kFfn, kFfn,
+                                 gemm_box_rows_w(h->num_sms, Mp, kHidden, kFfn, 2)));
+        }
     }
     h->launches += 6 * kLayers;
     return cudaStreamSynchronize(st);   // the caller may free its fp32 copies on return
@@ -471,8 +483,6 @@ static cudaError_t encoder_reserve(Encoder* e, int64_t tokens) {
     return cudaSuccess;
 }
 
-// tokens per chunk: ~7.7 KB of activations per token; 8192 tokens = 63 MB, L2-resident
-constexpr int64_t kChunkTokens = 8192;
 
 cudaError_t encoder_forward(lrx_handle* h, const int32_t* ids, const int32_t* lens, int B, int S,
                             float* out_f32, void* out_f16) {
@@ -499,18 +509,20 @@ cudaError_t encoder_forward(lrx_handle* h, const int32_t* ids, const int32_t* le
         ENC_CK(cudaGetLastError());
         const int Sk = (S + 63) & ~63;
         const size_t attn_smem = (size_t)Sk * kKPad * 2 + (size_t)kHeadDim * (Sk + 8) * 2;
+        // which W tensor-map set matches the plan the GEMM launcher picks for this many rows
+        const int pl = ((int)((T + 127) / 128) >= h->num_sms / 2) ? 1 : 0;
         for (int l = 0; l < kLayers; ++l) {
             EncLayer& L = e->L[l];
-            ENC_CK(launch_tc_gemm(h, e->t_x, L.t_wqkv, (int)T, kQkv, kHidden, 0, L.bqkv, nullptr, 0,
+            ENC_CK(launch_tc_gemm(h, e->t_x, L.t_wqkv[pl], (int)T, kQkv, kHidden, 0, L.bqkv, nullptr, 0,
                                   nullptr, nullptr, 0.f, e->qkv, kQkv));
             attention_kernel<<<dim3(kHeads, nb), kAttnThreads, attn_smem, st>>>(e->qkv, clen, S, e->ctx);
             h->launches++;
             ENC_CK(cudaGetLastError());
-            ENC_CK(launch_tc_gemm(h, e->t_ctx, L.t_wo, (int)T, kHidden, kHidden, 2, L.bo, e->x, kHidden,
+            ENC_CK(launch_tc_gemm(h, e->t_ctx, L.t_wo[pl], (int)T, kHidden, kHidden, 2, L.bo, e->x, kHidden,
                                   L.ln1_g, L.ln1_b, kLnEps, e->x1, kHidden));
-            ENC_CK(launch_tc_gemm(h, e->t_x1, L.t_w1, (int)T, kFfn, kHidden, 1, L.b1, nullptr, 0,
+            ENC_CK(launch_tc_gemm(h, e->t_x1, L.t_w1[pl], (int)T, kFfn, kHidden, 1, L.b1, nullptr, 0,
                                   nullptr, nullptr, 0.f, e->ff, kFfn));
-            ENC_CK(launch_tc_gemm(h, e->t_ff, L.t_w2, (int)T, kHidden, kFfn, 2, L.b2, e->x1, kHidden,
+            ENC_CK(launch_tc_gemm(h, e->t_ff, L.t_w2[pl], (int)T, kHidden, kFfn, 2, L.b2, e->x1, kHidden,
                                   L.ln2_g, L.ln2_b, kLnEps, e->x, kHidden));
         }
         pool_normalize_kernel<<<nb, 128, 0, st>>>(

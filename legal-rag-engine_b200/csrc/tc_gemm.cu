@@ -29,9 +29,13 @@
 
 namespace lrx {
 
+#ifndef LRX_GEMM_CLUSTER
+#define LRX_GEMM_CLUSTER 2
+#endif
 constexpr int kBM = 128;
 constexpr int kBK = 64;
-constexpr int kGemmThreads = 192;
+constexpr int kEpiWarps = 8;                      // two per TMEM lane quarter: column halves
+constexpr int kGemmThreads = (kEpiWarps + 2) * 32;   // + TMA producer warp + MMA warp
 constexpr int kABytes = kBM * kBK * 2;   // 16 KB
 
 struct GemmEpi {
@@ -45,18 +49,48 @@ struct GemmEpi {
     float eps;
 };
 
-template <int BN>
+constexpr int kAResKB = 6;                        // k-blocks of a RESIDENT A tile (K = 384)
+
+// ARES: the 128 x 384 A tile of the CTA's row block stays in shared memory (96 KB) while the CTA
+// walks the n-blocks, so only W streams through the ring (K == 384 GEMMs); otherwise A and W
+// both stream (K = 1536).
+// CS: cluster size along M.  The CS CTAs of a cluster need the same W tile at the same time: each
+// loads 1/CS of it and MULTICASTS it to all, so L2 sees one request per cluster instead of one per
+// CTA (the W tiles are the hot spot: every CTA of the grid reads the same few hundred lines).
+template <int BN, bool ARES, int CS>
 struct GemmCfg {
-    static constexpr int kStages = (BN >= 256) ? 3 : 3;
+    static constexpr int kBoxB = (CS > 1) ? BN / CS : ((BN > 256) ? 128 : BN);   // rows per TMA box of W
     static constexpr int kBBytes = BN * kBK * 2;
-    static constexpr int kStageBytes = kABytes + kBBytes;
-    static constexpr int kTmemCols = (BN <= 128) ? 128 : (BN <= 256 ? 256 : 512);
-    static constexpr size_t kSmem = (size_t)kStages * kStageBytes + 1024 /*align*/ + 256 /*barriers*/;
+    static constexpr int kStageBytes = (ARES ? 0 : kABytes) + kBBytes;
+    static constexpr int kResBytes = ARES ? kAResKB * kABytes : 0;
+    static constexpr int kStagesRaw = (192 * 1024 - kResBytes) / kStageBytes;
+    static constexpr int kStages = kStagesRaw > 8 ? 8 : kStagesRaw;
+    static constexpr int kAcc = (2 * BN <= 512) ? 2 : 1;              // TMEM accumulator buffers
+    static constexpr int kTmemCols = (kAcc * BN <= 128) ? 128 : (kAcc * BN <= 256 ? 256 : 512);
+    // + bias (2 x BN) / gamma / beta / LayerNorm partial sums staged for the epilogue
+    static constexpr int kParamBytes = 2 * BN * 4 + 2 * 384 * 4 + 2 * 2 * 128 * 4 + 2048 * 8 /*GELU table*/;
+    static constexpr size_t kSmem = (size_t)kResBytes + (size_t)kStages * kStageBytes + 1024 /*align*/ + 256 /*barriers*/ + kParamBytes;
 };
 
+// exact-erf GELU (builds the interpolation table)
 __device__ __forceinline__ float gelu_erf(float x) {
     return 0.5f * x * (1.0f + erff(x * 0.70710678118654752440f));
 }
+// The epilogue's GELU: table of (value, slope) pairs on [-8, 8] in steps of 1/128, linear
+// interpolation (error <= h^2/8 * max|gelu''| < 1e-5, far inside the fp16 rounding of the output);
+// index and fraction come from a magic-number add -- no conversion or MUFU instruction, so the
+// epilogue keeps up with the tensor pipe.  Outside the table GELU(x) = x (x > 8) or -0 (x < -8).
+constexpr int kGeluN = 2048;
+__device__ __forceinline__ float gelu_lut(const float2* __restrict__ lut, float x) {
+    const float xc = fminf(fmaxf(x, -8.0f), 8.0f - 1.0f / 256.0f);
+    const float t = fmaf(xc, 128.0f, 1024.0f);                 // [0, 2048)
+    const float m = t - 0.5f + 12582912.0f;                    // 1.5 * 2^23: low bits = floor(t)
+    const int i = __float_as_int(m) & (kGeluN - 1);
+    const float fr = t - (m - 12582912.0f);
+    const float2 e = lut[i];
+    return fmaf(e.y, fr, e.x) + fmaxf(x - 8.0f, 0.0f);
+}
+__device__ __forceinline__ void epi_bar() { asm volatile("bar.sync 1, 256;" ::: "memory"); }
 
 __device__ __forceinline__ void store_row32_f16(__half* dst, const float (&v)[32]) {
     uint4* d4 = reinterpret_cast<uint4*>(dst);
@@ -75,177 +109,354 @@ __device__ __forceinline__ void store_row32_f16(__half* dst, const float (&v)[32
     }
 }
 
-template <int BN, int EPI>
+// Persistent: CTA c owns output tiles c, c + grid, ... (n-block fastest, so CTAs running side by
+// side share the A rows in L2).  The shared-memory ring flows across tiles; with two TMEM
+// accumulators (BN <= 256) the epilogue of tile i overlaps the MMAs of tile i + 1.
+template <int BN, int EPI, bool ARES, int CS>
 __global__ void __launch_bounds__(kGemmThreads, 1)
 tc_gemm_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ CUtensorMap tma_b,
-               int num_k_blocks, GemmEpi ep) {
-    using Cfg = GemmCfg<BN>;
+               int num_k_blocks, int m_tiles, int n_tiles, GemmEpi ep) {
+    using Cfg = GemmCfg<BN, ARES, CS>;
+    constexpr uint16_t kMask = (uint16_t)((1u << CS) - 1u);
+    const uint32_t crank = (CS > 1) ? cluster_ctarank() : 0u;
     constexpr int kStages = Cfg::kStages;
+    constexpr int kAcc = Cfg::kAcc;
     extern __shared__ unsigned char gemm_smem_raw[];
     unsigned char* base = reinterpret_cast<unsigned char*>(
         (reinterpret_cast<uintptr_t>(gemm_smem_raw) + 1023) & ~(uintptr_t)1023);
-    unsigned char* sA = base;
-    unsigned char* sB = base + kStages * kABytes;
-    uint64_t* full = reinterpret_cast<uint64_t*>(base + kStages * Cfg::kStageBytes);
+    unsigned char* sA = base;                                        // ARES: [6][16 KB]; else [stages][16 KB]
+    unsigned char* sB = base + (ARES ? Cfg::kResBytes : kStages * kABytes);
+    unsigned char* sEnd = base + Cfg::kResBytes + kStages * Cfg::kStageBytes;
+    uint64_t* full = reinterpret_cast<uint64_t*>(sEnd);
     uint64_t* empty = full + kStages;
-    uint64_t* tmem_full = empty + kStages;
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tmem_full + 1);
+    uint64_t* t_full = empty + kStages;      // [kAcc] accumulator complete
+    uint64_t* t_empty = t_full + 2;          // [kAcc] accumulator drained by the epilogue
+    uint64_t* a_full = t_empty + 2;          // ARES: resident A tile landed
+    uint64_t* a_empty = a_full + 1;          // ARES: every MMA of the row block has read it
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(a_empty + 1);
+    float* s_bias = reinterpret_cast<float*>(sEnd + 256);                                 // [2][BN]
+    float* s_gamma = s_bias + 2 * BN;                                                     // [384]
+    float* s_beta = s_gamma + 384;                                                        // [384]
+    float* s_part = s_beta + 384;                                                         // [2][2][128]
+    const float2* s_gelu = reinterpret_cast<const float2*>(s_part + 2 * 2 * 128);        // [2048] (EPI 1)
 
     const int warp = threadIdx.x >> 5;
     const int lane = threadIdx.x & 31;
-    const int m_blk = blockIdx.x;
-    const int n_blk = blockIdx.y;
+    const int total_tiles = m_tiles * n_tiles;
+    constexpr int kProducerWarp = kEpiWarps, kMmaWarp = kEpiWarps + 1;
 
-    if (warp == 4 && lane == 0) {
+    if (warp == kProducerWarp && lane == 0) {
         tma_prefetch_desc(&tma_a);
         tma_prefetch_desc(&tma_b);
         for (int s = 0; s < kStages; ++s) {
             mbar_init(&full[s], 1);
-            mbar_init(&empty[s], 1);
+            mbar_init(&empty[s], CS);          // released by the MMA warp of every CTA of the cluster
         }
-        mbar_init(tmem_full, 1);
+        for (int b = 0; b < 2; ++b) {
+            mbar_init(&t_full[b], 1);
+            mbar_init(&t_empty[b], kEpiWarps);
+        }
+        mbar_init(a_full, 1);
+        mbar_init(a_empty, 1);
         fence_barrier_init();
     }
-    if (warp == 5) {
+    if (warp == kMmaWarp) {
         tmem_alloc(tmem_slot, Cfg::kTmemCols);
         tmem_relinquish();
     }
     tc_fence_before();
     __syncthreads();
+    if (CS > 1) cluster_sync_all();            // peers' barriers are initialised before any multicast
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
 
-    if (warp == 4) {
+    if (warp == kProducerWarp) {
         // ===== TMA producer
         if (lane == 0) {
-            for (int kb = 0; kb < num_k_blocks; ++kb) {
-                const int s = kb % kStages;
-                const uint32_t ph = (uint32_t)(kb / kStages) & 1u;
-                mbar_wait(&empty[s], ph ^ 1u);
-                mbar_arrive_expect_tx(&full[s], (uint32_t)Cfg::kStageBytes);
-                tma_load_2d(sA + s * kABytes, &tma_a, kb * kBK, m_blk * kBM, &full[s]);
+            uint32_t it = 0;
+            if (ARES) {
+                int mi = 0;
+                for (int m_blk = blockIdx.x; m_blk < m_tiles; m_blk += gridDim.x, ++mi) {
+                    mbar_wait(a_empty, ((uint32_t)mi & 1u) ^ 1u);     // previous row block retired
+                    mbar_arrive_expect_tx(a_full, (uint32_t)Cfg::kResBytes);
+                    for (int kb = 0; kb < kAResKB; ++kb)
+                        tma_load_2d(sA + kb * kABytes, &tma_a, kb * kBK, m_blk * kBM, a_full);
+                    for (int n_blk = 0; n_blk < n_tiles; ++n_blk) {
+                        for (int kb = 0; kb < kAResKB; ++kb, ++it) {
+                            const int s = (int)(it % kStages);
+                            const uint32_t ph = (it / kStages) & 1u;
+                            mbar_wait(&empty[s], ph ^ 1u);
+                            mbar_arrive_expect_tx(&full[s], (uint32_t)Cfg::kStageBytes);
+                            if (CS > 1) {
+                                tma_load_2d_mc(sB + s * Cfg::kBBytes + crank * (Cfg::kBoxB * kBK * 2), &tma_b,
+                                               kb * kBK, n_blk * BN + (int)crank * Cfg::kBoxB, &full[s], kMask);
+                            } else {
 #pragma unroll
-                for (int nb = 0; nb < BN / 128; ++nb)
-                    tma_load_2d(sB + s * Cfg::kBBytes + nb * (128 * kBK * 2), &tma_b, kb * kBK,
-                                n_blk * BN + nb * 128, &full[s]);
+                                for (int nb = 0; nb < BN / Cfg::kBoxB; ++nb)
+                                    tma_load_2d(sB + s * Cfg::kBBytes + nb * (Cfg::kBoxB * kBK * 2), &tma_b,
+                                                kb * kBK, n_blk * BN + nb * Cfg::kBoxB, &full[s]);
+                            }
+                        }
+                    }
+                }
+            } else {
+                for (int tile = blockIdx.x; tile < total_tiles; tile += gridDim.x) {
+                    const int m_blk = tile / n_tiles, n_blk = tile - m_blk * n_tiles;
+                    for (int kb = 0; kb < num_k_blocks; ++kb, ++it) {
+                        const int s = (int)(it % kStages);
+                        const uint32_t ph = (it / kStages) & 1u;
+                        mbar_wait(&empty[s], ph ^ 1u);
+                        mbar_arrive_expect_tx(&full[s], (uint32_t)Cfg::kStageBytes);
+                        tma_load_2d(sA + s * kABytes, &tma_a, kb * kBK, m_blk * kBM, &full[s]);
+                        if (CS > 1) {
+                            tma_load_2d_mc(sB + s * Cfg::kBBytes + crank * (Cfg::kBoxB * kBK * 2), &tma_b,
+                                           kb * kBK, n_blk * BN + (int)crank * Cfg::kBoxB, &full[s], kMask);
+                        } else {
+#pragma unroll
+                            for (int nb = 0; nb < BN / Cfg::kBoxB; ++nb)
+                                tma_load_2d(sB + s * Cfg::kBBytes + nb * (Cfg::kBoxB * kBK * 2), &tma_b, kb * kBK,
+                                            n_blk * BN + nb * Cfg::kBoxB, &full[s]);
+                        }
+                    }
+                }
             }
         }
-    } else if (warp == 5) {
+    } else if (warp == kMmaWarp) {
         // ===== MMA issuer (one lane)
         if (lane == 0) {
             constexpr int N0 = (BN > 256) ? 256 : BN;
             constexpr int N1 = BN - N0;
             constexpr uint32_t idesc0 = umma_idesc_f16(kBM, N0);
             constexpr uint32_t idesc1 = umma_idesc_f16(kBM, N1 > 0 ? N1 : 16);
-            for (int kb = 0; kb < num_k_blocks; ++kb) {
-                const int s = kb % kStages;
-                const uint32_t ph = (uint32_t)(kb / kStages) & 1u;
-                mbar_wait(&full[s], ph);
-                tc_fence_after();
-                const uint32_t a_addr = smem_u32(sA + s * kABytes);
-                const uint32_t b_addr = smem_u32(sB + s * Cfg::kBBytes);
-#pragma unroll
-                for (int k = 0; k < kBK / 16; ++k) {
-                    const uint64_t ad = umma_desc_sw128(a_addr + k * 32);
-                    const uint64_t bd = umma_desc_sw128(b_addr + k * 32);
-                    const uint32_t acc = (kb > 0 || k > 0) ? 1u : 0u;
-                    umma_f16(tmem_base, ad, bd, idesc0, acc);
-                    if (N1 > 0) {
-                        const uint64_t bd1 = umma_desc_sw128(b_addr + N0 * 128 + k * 32);
-                        umma_f16(tmem_base + N0, ad, bd1, idesc1, acc);
-                    }
+            uint32_t it = 0;
+            int u = 0;
+            // tiles in the order the producer feeds them: ARES -> row block by row block
+            const int n_mine = ARES ? ((m_tiles > (int)blockIdx.x) ? (m_tiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x : 0) * n_tiles
+                                    : ((total_tiles > (int)blockIdx.x) ? (total_tiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x : 0);
+            for (; u < n_mine; ++u) {
+                const int buf = u % kAcc;
+                const uint32_t use = (uint32_t)(u / kAcc);
+                if (ARES && (u % n_tiles) == 0) {
+                    mbar_wait(a_full, (uint32_t)(u / n_tiles) & 1u);
+                    tc_fence_after();
                 }
-                umma_commit(&empty[s]);                       // smem slot free when the MMAs retire
-                if (kb == num_k_blocks - 1) umma_commit(tmem_full);   // accumulator complete
+                mbar_wait(&t_empty[buf], (use & 1u) ^ 1u);    // epilogue has drained this accumulator
+                tc_fence_after();
+                const uint32_t tacc = tmem_base + buf * BN;
+                for (int kb = 0; kb < num_k_blocks; ++kb, ++it) {
+                    const int s = (int)(it % kStages);
+                    const uint32_t ph = (it / kStages) & 1u;
+                    mbar_wait(&full[s], ph);
+                    tc_fence_after();
+                    const uint32_t a_addr = smem_u32(sA + (ARES ? kb : s) * kABytes);
+                    const uint32_t b_addr = smem_u32(sB + s * Cfg::kBBytes);
+#pragma unroll
+                    for (int k = 0; k < kBK / 16; ++k) {
+                        const uint64_t ad = umma_desc_sw128(a_addr + k * 32);
+                        const uint64_t bd = umma_desc_sw128(b_addr + k * 32);
+                        const uint32_t acc = (kb > 0 || k > 0) ? 1u : 0u;
+                        umma_f16(tacc, ad, bd, idesc0, acc);
+                        if (N1 > 0) {
+                            const uint64_t bd1 = umma_desc_sw128(b_addr + N0 * 128 + k * 32);
+                            umma_f16(tacc + N0, ad, bd1, idesc1, acc);
+                        }
+                    }
+                    if (CS > 1) umma_commit_mc(&empty[s], kMask);   // slot free in every CTA of the cluster
+                    else umma_commit(&empty[s]);              // smem slot free when the MMAs retire
+                }
+                umma_commit(&t_full[buf]);                    // accumulator complete
+                if (ARES && (u % n_tiles) == n_tiles - 1) umma_commit(a_empty);   // A tile may be replaced
             }
         }
     } else {
-        // ===== epilogue: thread = output row = TMEM lane
-        mbar_wait(tmem_full, 0);
-        tc_fence_after();
-        const int row = warp * 32 + lane;
-        const int64_t grow = (int64_t)m_blk * kBM + row;
-        const bool ok = grow < ep.M;
-        const uint32_t trow = tmem_base + ((uint32_t)(warp * 32) << 16);
-        const int n0 = n_blk * BN;
-        uint32_t r[32];
-        float v[32];
-        if (EPI == 3) {
-            float* out = reinterpret_cast<float*>(ep.out) + grow * ep.ld_out + n0;
-            for (int c = 0; c < BN; c += 32) {
-                tmem_ld32(trow + c, r);
+        // ===== epilogue: 8 warps; thread = output row (TMEM lane 32*(warp&3)+lane), column half
+        //       (warp >> 2).  Per-column parameters are staged in shared memory (float4 broadcast
+        //       loads instead of one global load per element).
+        const int quarter = warp & 3, half = warp >> 2;
+        const int et = threadIdx.x;                      // 0..255
+        constexpr int HB = BN / 2;                       // columns per half
+        if (EPI == 1) {
+            float2* g = const_cast<float2*>(s_gelu);
+            for (int i = et; i < kGeluN; i += 256) {
+                const float x0 = (float)(i - 1024) * (1.0f / 128.0f), x1 = x0 + 1.0f / 128.0f;
+                const float g0 = gelu_erf(x0), g1 = gelu_erf(x1);
+                g[i] = make_float2(g0, g1 - g0);
+            }
+            epi_bar();
+        }
+        if (EPI == 2) {
+            for (int i = et; i < 384; i += 256) {
+                s_gamma[i] = ep.gamma[i];
+                s_beta[i] = ep.beta[i];
+                s_bias[i] = ep.bias[i];
+            }
+            epi_bar();
+        }
+        const int n_mine = ARES ? ((m_tiles > (int)blockIdx.x) ? (m_tiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x : 0) * n_tiles
+                                : ((total_tiles > (int)blockIdx.x) ? (total_tiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x : 0);
+        for (int u = 0; u < n_mine; ++u) {
+            int m_blk, n_blk;
+            if (ARES) {
+                m_blk = blockIdx.x + (u / n_tiles) * gridDim.x;
+                n_blk = u % n_tiles;
+            } else {
+                const int tile = blockIdx.x + u * gridDim.x;
+                m_blk = tile / n_tiles;
+                n_blk = tile - m_blk * n_tiles;
+            }
+            const int buf = u % kAcc;
+            const uint32_t use = (uint32_t)(u / kAcc);
+            const int n0 = n_blk * BN;
+            float* bias = s_bias + (EPI == 2 ? 0 : (u & 1) * BN);
+            if (EPI == 0 || EPI == 1) {
+                for (int i = et; i < BN; i += 256) bias[i] = ep.bias[n0 + i];
+                epi_bar();
+            }
+            mbar_wait(&t_full[buf], use & 1u);
+            tc_fence_after();
+            const int row = quarter * 32 + lane;
+            const int64_t grow = (int64_t)m_blk * kBM + row;
+            const bool ok = grow < ep.M;
+            const uint32_t trow = tmem_base + ((uint32_t)(quarter * 32) << 16) + buf * BN + half * HB;
+            const int cb = half * HB;                    // first column of this thread's half
+            float v[32];
+            // TMEM loads are software-pipelined: the load of chunk c + 1 is in flight while
+            // chunk c is processed (tcgen05.wait::ld comes after the math).
+            constexpr int NCH = HB / 32;
+            uint32_t rb[2][32];
+            if (EPI == 3) {
+                float* out = reinterpret_cast<float*>(ep.out) + grow * ep.ld_out + n0 + cb;
+                tmem_ld32(trow, rb[0]);
                 tmem_wait_ld();
-                if (ok) {
-                    float4* o4 = reinterpret_cast<float4*>(out + c);
 #pragma unroll
-                    for (int j = 0; j < 8; ++j)
-                        o4[j] = make_float4(__uint_as_float(r[4 * j]), __uint_as_float(r[4 * j + 1]),
-                                            __uint_as_float(r[4 * j + 2]), __uint_as_float(r[4 * j + 3]));
+                for (int ch = 0; ch < NCH; ++ch) {
+                    if (ch + 1 < NCH) tmem_ld32(trow + (ch + 1) * 32, rb[(ch + 1) & 1]);
+                    const uint32_t(&r)[32] = rb[ch & 1];
+                    if (ok) {
+                        float4* o4 = reinterpret_cast<float4*>(out + ch * 32);
+#pragma unroll
+                        for (int j = 0; j < 8; ++j)
+                            o4[j] = make_float4(__uint_as_float(r[4 * j]), __uint_as_float(r[4 * j + 1]),
+                                                __uint_as_float(r[4 * j + 2]), __uint_as_float(r[4 * j + 3]));
+                    }
+                    tmem_wait_ld();
+                }
+            } else if (EPI == 0 || EPI == 1) {
+                __half* out = reinterpret_cast<__half*>(ep.out) + grow * ep.ld_out + n0 + cb;
+                tmem_ld32(trow, rb[0]);
+                tmem_wait_ld();
+#pragma unroll
+                for (int ch = 0; ch < NCH; ++ch) {
+                    if (ch + 1 < NCH) tmem_ld32(trow + (ch + 1) * 32, rb[(ch + 1) & 1]);
+                    const uint32_t(&r)[32] = rb[ch & 1];
+                    const int c = ch * 32;
+#pragma unroll
+                    for (int j4 = 0; j4 < 8; ++j4) {
+                        const float4 bb = *reinterpret_cast<const float4*>(bias + cb + c + 4 * j4);
+                        const float x0 = __uint_as_float(r[4 * j4 + 0]) + bb.x;
+                        const float x1 = __uint_as_float(r[4 * j4 + 1]) + bb.y;
+                        const float x2 = __uint_as_float(r[4 * j4 + 2]) + bb.z;
+                        const float x3 = __uint_as_float(r[4 * j4 + 3]) + bb.w;
+                        v[4 * j4 + 0] = (EPI == 1) ? gelu_lut(s_gelu, x0) : x0;
+                        v[4 * j4 + 1] = (EPI == 1) ? gelu_lut(s_gelu, x1) : x1;
+                        v[4 * j4 + 2] = (EPI == 1) ? gelu_lut(s_gelu, x2) : x2;
+                        v[4 * j4 + 3] = (EPI == 1) ? gelu_lut(s_gelu, x3) : x3;
+                    }
+                    if (ok) store_row32_f16(out + c, v);
+                    tmem_wait_ld();
+                }
+            } else {
+                // bias + residual, LayerNorm over the whole row (BN == N == 384): each thread owns
+                // half a row, the two halves exchange their partial sums through shared memory
+                const __half* res = ep.residual + grow * ep.ld_res + cb;
+                float* part = s_part + (u & 1) * 2 * 2 * 128;       // [stat][half][row]
+                float sum = 0.f;
+                uint4 rq[2][4];                                      // residual chunk, same pipeline
+                auto ldres = [&](int ch, uint4 (&dst)[4]) {
+#pragma unroll
+                    for (int i = 0; i < 4; ++i)
+                        dst[i] = ok ? __ldg(reinterpret_cast<const uint4*>(res + ch * 32) + i) : make_uint4(0, 0, 0, 0);
+                };
+                ldres(0, rq[0]);
+                tmem_ld32(trow, rb[0]);
+                tmem_wait_ld();
+#pragma unroll
+                for (int ch = 0; ch < NCH; ++ch) {
+                    if (ch + 1 < NCH) {
+                        ldres(ch + 1, rq[(ch + 1) & 1]);
+                        tmem_ld32(trow + (ch + 1) * 32, rb[(ch + 1) & 1]);
+                    }
+                    uint32_t(&r)[32] = rb[ch & 1];
+                    const int c = ch * 32;
+                    const __half2* rh = reinterpret_cast<const __half2*>(rq[ch & 1]);
+#pragma unroll
+                    for (int j4 = 0; j4 < 8; ++j4) {
+                        const float4 bb = *reinterpret_cast<const float4*>(bias + cb + c + 4 * j4);
+                        const float2 f0 = __half22float2(rh[2 * j4]), f1 = __half22float2(rh[2 * j4 + 1]);
+                        const float x0 = __uint_as_float(r[4 * j4 + 0]) + bb.x + f0.x;
+                        const float x1 = __uint_as_float(r[4 * j4 + 1]) + bb.y + f0.y;
+                        const float x2 = __uint_as_float(r[4 * j4 + 2]) + bb.z + f1.x;
+                        const float x3 = __uint_as_float(r[4 * j4 + 3]) + bb.w + f1.y;
+                        sum += (x0 + x1) + (x2 + x3);
+                        r[4 * j4 + 0] = __float_as_uint(x0);
+                        r[4 * j4 + 1] = __float_as_uint(x1);
+                        r[4 * j4 + 2] = __float_as_uint(x2);
+                        r[4 * j4 + 3] = __float_as_uint(x3);
+                    }
+                    tmem_wait_ld();                       // chunk ch + 1 has landed ...
+                    tmem_st32(trow + c, r);               // ... before this buffer's registers are reused
+                }
+                part[half * 128 + row] = sum;
+                tmem_wait_st();
+                epi_bar();
+                const float mean = (part[row] + part[128 + row]) * (1.0f / BN);
+                float var = 0.f;
+                tmem_ld32(trow, rb[0]);
+                tmem_wait_ld();
+#pragma unroll
+                for (int ch = 0; ch < NCH; ++ch) {
+                    if (ch + 1 < NCH) tmem_ld32(trow + (ch + 1) * 32, rb[(ch + 1) & 1]);
+                    const uint32_t(&r)[32] = rb[ch & 1];
+#pragma unroll
+                    for (int j = 0; j < 32; ++j) {
+                        const float d = __uint_as_float(r[j]) - mean;
+                        var = fmaf(d, d, var);
+                    }
+                    tmem_wait_ld();
+                }
+                part[256 + half * 128 + row] = var;
+                epi_bar();
+                const float rstd = 1.0f / sqrtf((part[256 + row] + part[256 + 128 + row]) * (1.0f / BN) + ep.eps);
+                __half* out = reinterpret_cast<__half*>(ep.out) + grow * ep.ld_out + cb;
+                tmem_ld32(trow, rb[0]);
+                tmem_wait_ld();
+#pragma unroll
+                for (int ch = 0; ch < NCH; ++ch) {
+                    if (ch + 1 < NCH) tmem_ld32(trow + (ch + 1) * 32, rb[(ch + 1) & 1]);
+                    const uint32_t(&r)[32] = rb[ch & 1];
+                    const int c = ch * 32;
+#pragma unroll
+                    for (int j4 = 0; j4 < 8; ++j4) {
+                        const float4 gg = *reinterpret_cast<const float4*>(s_gamma + cb + c + 4 * j4);
+                        const float4 be = *reinterpret_cast<const float4*>(s_beta + cb + c + 4 * j4);
+                        v[4 * j4 + 0] = (__uint_as_float(r[4 * j4 + 0]) - mean) * rstd * gg.x + be.x;
+                        v[4 * j4 + 1] = (__uint_as_float(r[4 * j4 + 1]) - mean) * rstd * gg.y + be.y;
+                        v[4 * j4 + 2] = (__uint_as_float(r[4 * j4 + 2]) - mean) * rstd * gg.z + be.z;
+                        v[4 * j4 + 3] = (__uint_as_float(r[4 * j4 + 3]) - mean) * rstd * gg.w + be.w;
+                    }
+                    if (ok) store_row32_f16(out + c, v);
+                    tmem_wait_ld();
                 }
             }
-        } else if (EPI == 0 || EPI == 1) {
-            __half* out = reinterpret_cast<__half*>(ep.out) + grow * ep.ld_out + n0;
-            for (int c = 0; c < BN; c += 32) {
-                tmem_ld32(trow + c, r);
-                tmem_wait_ld();
-#pragma unroll
-                for (int j = 0; j < 32; ++j) {
-                    float x = __uint_as_float(r[j]) + __ldg(ep.bias + n0 + c + j);
-                    v[j] = (EPI == 1) ? gelu_erf(x) : x;
-                }
-                if (ok) store_row32_f16(out + c, v);
-            }
-        } else {
-            // bias + residual, LayerNorm over the whole row (BN == N)
-            const __half* res = ep.residual + grow * ep.ld_res;
-            float sum = 0.f;
-            for (int c = 0; c < BN; c += 32) {
-                tmem_ld32(trow + c, r);
-                uint4 rr[4];
-#pragma unroll
-                for (int i = 0; i < 4; ++i)
-                    rr[i] = ok ? __ldg(reinterpret_cast<const uint4*>(res + c) + i) : make_uint4(0, 0, 0, 0);
-                tmem_wait_ld();
-                const __half2* rh = reinterpret_cast<const __half2*>(rr);
-#pragma unroll
-                for (int j = 0; j < 16; ++j) {
-                    const float2 f = __half22float2(rh[j]);
-                    const float x0 = __uint_as_float(r[2 * j]) + __ldg(ep.bias + c + 2 * j) + f.x;
-                    const float x1 = __uint_as_float(r[2 * j + 1]) + __ldg(ep.bias + c + 2 * j + 1) + f.y;
-                    sum += x0 + x1;
-                    r[2 * j] = __float_as_uint(x0);
-                    r[2 * j + 1] = __float_as_uint(x1);
-                }
-                tmem_st32(trow + c, r);
-            }
-            tmem_wait_st();
-            const float mean = sum * (1.0f / BN);
-            float var = 0.f;
-            for (int c = 0; c < BN; c += 32) {
-                tmem_ld32(trow + c, r);
-                tmem_wait_ld();
-#pragma unroll
-                for (int j = 0; j < 32; ++j) {
-                    const float d = __uint_as_float(r[j]) - mean;
-                    var = fmaf(d, d, var);
-                }
-            }
-            const float rstd = 1.0f / sqrtf(var * (1.0f / BN) + ep.eps);
-            __half* out = reinterpret_cast<__half*>(ep.out) + grow * ep.ld_out;
-            for (int c = 0; c < BN; c += 32) {
-                tmem_ld32(trow + c, r);
-                tmem_wait_ld();
-#pragma unroll
-                for (int j = 0; j < 32; ++j)
-                    v[j] = (__uint_as_float(r[j]) - mean) * rstd * __ldg(ep.gamma + c + j) +
-                           __ldg(ep.beta + c + j);
-                if (ok) store_row32_f16(out + c, v);
-            }
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&t_empty[buf]);        // accumulator may be overwritten
         }
     }
     tc_fence_before();
     __syncthreads();
-    if (warp == 5) {
+    if (CS > 1) cluster_sync_all();            // nobody leaves while a peer may still multicast to it
+    if (warp == kMmaWarp) {
         tc_fence_after();
         tmem_dealloc(tmem_base, Cfg::kTmemCols);
     }
@@ -286,42 +497,93 @@ cudaError_t make_tmap_f16(CUtensorMap* out, const void* ptr, int64_t rows, int64
     return r == CUDA_SUCCESS ? cudaSuccess : cudaErrorInvalidValue;
 }
 
-template <int BN, int EPI>
-static cudaError_t launch_one(cudaStream_t st, const CUtensorMap& ta, const CUtensorMap& tb, int M,
+template <int BN, int EPI, bool ARES, int CS>
+static cudaError_t launch_cfg(lrx_handle* h, const CUtensorMap& ta, const CUtensorMap& tb, int M,
                               int N, int K, const GemmEpi& ep) {
     static bool attr = false;
+    auto kern = tc_gemm_kernel<BN, EPI, ARES, CS>;
+    constexpr size_t smem = GemmCfg<BN, ARES, CS>::kSmem;
     if (!attr) {
-        cudaError_t e = cudaFuncSetAttribute(tc_gemm_kernel<BN, EPI>,
-                                             cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                             (int)GemmCfg<BN>::kSmem);
+        cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) return e;
         attr = true;
     }
-    dim3 grid((M + kBM - 1) / kBM, N / BN);
-    tc_gemm_kernel<BN, EPI><<<grid, kGemmThreads, GemmCfg<BN>::kSmem, st>>>(ta, tb, K / kBK, ep);
-    return cudaGetLastError();
+    int m_tiles = (M + kBM - 1) / kBM;
+    const int n_tiles = N / BN;
+    if (CS > 1) m_tiles = (m_tiles + CS - 1) / CS * CS;     // padded row blocks: loads zero-fill, stores are guarded
+    const int units = ARES ? m_tiles : m_tiles * n_tiles;
+    int grid = units < h->num_sms ? units : h->num_sms;
+    if (CS > 1) grid = grid / CS * CS;
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(grid);
+    cfg.blockDim = dim3(kGemmThreads);
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = h->stream;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeClusterDimension;
+    at[0].val.clusterDim.x = CS;
+    at[0].val.clusterDim.y = 1;
+    at[0].val.clusterDim.z = 1;
+    cfg.attrs = at;
+    cfg.numAttrs = 1;
+    return cudaLaunchKernelEx(&cfg, kern, ta, tb, K / kBK, m_tiles, n_tiles, ep);
+}
+
+// Which variant runs (the W tensor map's box must match: gemm_box_rows_w).
+struct GemmPlan { int bn; bool ares; int cs; };
+GemmPlan gemm_plan(int num_sms, int M, int N, int K, int epi) {
+    GemmPlan p;
+    p.bn = (epi == 2) ? 384 : (N % 256 == 0 ? 256 : (N % 192 == 0 ? 192 : 128));
+    const int m_tiles = (M + kBM - 1) / kBM;
+    const bool big = m_tiles >= num_sms / 2;                 // enough row blocks to fill the SMs
+    p.ares = (K == kAResKB * kBK) && (big || N / p.bn == 1);
+    // clusters need every CTA of a cluster to walk the same n sequence: A-resident (n inner loop),
+    // or a single n-block
+    p.cs = (big && (p.ares || N / p.bn == 1)) ? LRX_GEMM_CLUSTER : 1;
+    return p;
+}
+
+template <int BN, int EPI>
+static cudaError_t launch_one(lrx_handle* h, const CUtensorMap& ta, const CUtensorMap& tb, int M,
+                              int N, int K, const GemmEpi& ep) {
+    const GemmPlan p = gemm_plan(h->num_sms, M, N, K, EPI);
+    if (p.cs > 1) {
+        if (p.ares) return launch_cfg<BN, EPI, true, LRX_GEMM_CLUSTER>(h, ta, tb, M, N, K, ep);
+        return launch_cfg<BN, EPI, false, LRX_GEMM_CLUSTER>(h, ta, tb, M, N, K, ep);
+    }
+    if (p.ares) return launch_cfg<BN, EPI, true, 1>(h, ta, tb, M, N, K, ep);
+    return launch_cfg<BN, EPI, false, 1>(h, ta, tb, M, N, K, ep);
+}
+
+// W-operand TMA box rows for a GEMM of this shape (the plan the launcher will pick)
+int gemm_box_rows_w(int num_sms, int M, int N, int K, int epi) {
+    const GemmPlan p = gemm_plan(num_sms, M, N, K, epi);
+    if (p.cs > 1) return p.bn / p.cs;
+    return p.bn > 256 ? 128 : p.bn;
 }
 
 // epi: 0 bias, 1 bias+GELU, 2 bias+residual+LayerNorm (N must be 384), 3 raw fp32.
+// `tb` must have been built with gemm_box_rows_w(N, epi) rows per box.
 cudaError_t launch_tc_gemm(lrx_handle* h, const CUtensorMap& ta, const CUtensorMap& tb, int M, int N,
                            int K, int epi, const float* bias, const __half* residual, int ld_res,
                            const float* gamma, const float* beta, float eps, void* out, int ld_out) {
     if (M <= 0) return cudaSuccess;
-    if (K % kBK != 0 || N % 128 != 0) return cudaErrorInvalidValue;
+    if (K % kBK != 0 || N % 128 != 0 || epi < 0 || epi > 3) return cudaErrorInvalidValue;
     GemmEpi ep;
     ep.bias = bias; ep.residual = residual; ep.gamma = gamma; ep.beta = beta;
     ep.out = out; ep.ld_out = ld_out; ep.ld_res = ld_res; ep.M = M; ep.eps = eps;
-    cudaError_t e;
-    switch (epi) {
-        case 0: e = launch_one<128, 0>(h->stream, ta, tb, M, N, K, ep); break;
-        case 1: e = launch_one<128, 1>(h->stream, ta, tb, M, N, K, ep); break;
-        case 2:
-            if (N != 384) return cudaErrorInvalidValue;
-            e = launch_one<384, 2>(h->stream, ta, tb, M, N, K, ep);
-            break;
-        case 3: e = launch_one<128, 3>(h->stream, ta, tb, M, N, K, ep); break;
-        default: return cudaErrorInvalidValue;
+    const int bn = gemm_plan(h->num_sms, M, N, K, epi).bn;
+    cudaError_t e = cudaErrorInvalidValue;
+#define LRX_GEMM_CASE(BN_, EPI_) \
+    if (bn == BN_ && epi == EPI_) e = launch_one<BN_, EPI_>(h, ta, tb, M, N, K, ep)
+    if (epi == 2) {
+        if (N != 384) return cudaErrorInvalidValue;
+        e = launch_one<384, 2>(h, ta, tb, M, N, K, ep);
     }
+    LRX_GEMM_CASE(256, 0); LRX_GEMM_CASE(192, 0); LRX_GEMM_CASE(128, 0);
+    LRX_GEMM_CASE(256, 1); LRX_GEMM_CASE(192, 1); LRX_GEMM_CASE(128, 1);
+    LRX_GEMM_CASE(256, 3); LRX_GEMM_CASE(192, 3); LRX_GEMM_CASE(128, 3);
+#undef LRX_GEMM_CASE
     h->launches++;
     return e;
 }
@@ -333,7 +595,7 @@ cudaError_t gemm_f16_adhoc(lrx_handle* h, const void* a, const void* w, int M, i
     CUtensorMap ta, tb;
     cudaError_t e = make_tmap_f16(&ta, a, M, K, K, 128);
     if (e != cudaSuccess) return e;
-    e = make_tmap_f16(&tb, w, N, K, K, 128);
+    e = make_tmap_f16(&tb, w, N, K, K, gemm_box_rows_w(h->num_sms, M, N, K, epi));
     if (e != cudaSuccess) return e;
     return launch_tc_gemm(h, ta, tb, M, N, K, epi, bias, (const __half*)residual, N, gamma, beta, eps,
                           out, N);
