@@ -138,6 +138,13 @@ int lrx_set_stream(lrx_handle* h, void* cuda_stream) {
     return LRX_OK;
 }
 
+int lrx_debug_set_trace(lrx_handle* h, void* dev_int64_128) {
+    if (h == nullptr) return fail(nullptr, LRX_E_ARG, "lrx_debug_set_trace: null handle");
+    std::lock_guard<std::mutex> g(h->mu);
+    h->debug_trace = dev_int64_128;
+    return LRX_OK;
+}
+
 int64_t lrx_launch_count(const lrx_handle* h) { return h ? h->launches : 0; }
 
 int lrx_profile_enable(lrx_handle* h, int32_t on) {
@@ -292,8 +299,8 @@ int lrx_gemm_f16(lrx_handle* h, const void* dev_a, const void* dev_w, int32_t M,
     std::lock_guard<std::mutex> g(h->mu);
     if (M < 1 || N < 128 || N % 128 != 0 || K < 64 || K % 64 != 0)
         return fail(h, LRX_E_ARG, "lrx_gemm_f16: need M >= 1, N %% 128 == 0, K %% 64 == 0");
-    if (epi < 0 || epi > 3 || (epi == 2 && N != 384))
-        return fail(h, LRX_E_ARG, "lrx_gemm_f16: bad epilogue (LayerNorm needs N == 384)");
+    if (epi < 0 || epi > 3 || (epi == 2 && N != 384) || (epi != 3 && N > 1536))
+        return fail(h, LRX_E_ARG, "lrx_gemm_f16: bad epilogue (LayerNorm needs N == 384; epi 0-2 need N <= 1536)");
     if (dev_a == nullptr || dev_w == nullptr || dev_out == nullptr ||
         (epi != 3 && dev_bias == nullptr) ||
         (epi == 2 && (dev_residual == nullptr || dev_gamma == nullptr || dev_beta == nullptr)))

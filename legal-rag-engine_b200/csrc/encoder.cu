@@ -34,9 +34,11 @@ constexpr int64_t kChunkTokens = 148 * 128;
 // tc_gemm.cu
 cudaError_t make_tmap_f16(CUtensorMap* out, const void* ptr, int64_t rows, int64_t cols, int64_t ld,
                           int box_rows);
-cudaError_t launch_tc_gemm(lrx_handle* h, const CUtensorMap& ta, const CUtensorMap& tb, int M, int N,
-                           int K, int epi, const float* bias, const __half* residual, int ld_res,
-                           const float* gamma, const float* beta, float eps, void* out, int ld_out);
+cudaError_t make_tmap_io_f16(CUtensorMap* out, const void* ptr, int64_t rows, int64_t cols, int64_t ld);
+cudaError_t launch_tc_gemm(lrx_handle* h, const CUtensorMap& ta, const CUtensorMap& tb,
+                           const CUtensorMap& tout, const CUtensorMap& tres, int M, int N, int K, int epi,
+                           const float* bias, const float* gamma, const float* beta, float eps,
+                           void* out, int ld_out);
 int gemm_box_rows_w(int num_sms, int M, int N, int K, int epi);
 
 struct EncLayer {
@@ -58,7 +60,8 @@ struct Encoder {
     int64_t cap = 0;
     void* act = nullptr;
     __half *x = nullptr, *x1 = nullptr, *qkv = nullptr, *ctx = nullptr, *ff = nullptr;
-    CUtensorMap t_x, t_x1, t_ctx, t_ff;
+    CUtensorMap t_x, t_x1, t_ctx, t_ff;              // A-operand views (128-row boxes, SWIZZLE_128B)
+    CUtensorMap io_x, io_x1, io_qkv, io_ff;          // epilogue views (32 x 32 boxes, SWIZZLE_64B)
     void* io = nullptr;        // host-form staging (ids, lens, out)
     size_t io_bytes = 0;
     void* io_host = nullptr;
@@ -129,12 +132,14 @@ embed_ln_kernel(const int32_t* __restrict__ ids, int64_t n_tokens, int S, int vo
 }
 
 // ----------------------------------------------------------------- attention
-// One CTA per (head, sequence): K and V^T of the head staged in shared memory, each warp
-// owns 16-query tiles; scores and P*V on mma.sync m16n8k16 (fp16 in, fp32 accumulate),
-// online softmax over 64-key blocks in fp32.  Keys >= len are masked out; query rows
-// >= len (padding) produce zeros.
+// One CTA per (head, sequence): K and V of the head staged row-major in shared memory (80-byte
+// rows: conflict-free ldmatrix), each warp owns 16-query tiles; QK^T and P*V on mma.sync
+// m16n8k16 (fp16 in, fp32 accumulate) with the B fragments fetched by ldmatrix.x4 (V through
+// .trans, so no transposed copy is ever written); online softmax over 64-key blocks in fp32 in
+// the exp2 domain (one MUFU.EX2 per score).  Keys >= len are masked out; query rows >= len
+// (padding) produce zeros.
 constexpr int kAttnThreads = 256;
-constexpr int kKPad = 40;    // halves per K row in smem (32 + 8: conflict-free fragment loads)
+constexpr int kKPad = 40;    // halves per K / V row in smem (32 + 8)
 
 __device__ __forceinline__ void mma16816(float (&d)[4], const uint32_t (&a)[4], uint32_t b0,
                                          uint32_t b1) {
@@ -148,6 +153,19 @@ __device__ __forceinline__ uint32_t pack_h2(float a, float b) {
     const __half2 h = __floats2half2_rn(a, b);
     return *reinterpret_cast<const uint32_t*>(&h);
 }
+__device__ __forceinline__ void ldsm_x4(uint32_t (&r)[4], const void* p) {
+    asm volatile("ldmatrix.sync.aligned.m8n8.x4.shared.b16 {%0,%1,%2,%3}, [%4];"
+                 : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]) : "r"(smem_u32(p)));
+}
+__device__ __forceinline__ void ldsm_x4_t(uint32_t (&r)[4], const void* p) {
+    asm volatile("ldmatrix.sync.aligned.m8n8.x4.trans.shared.b16 {%0,%1,%2,%3}, [%4];"
+                 : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]) : "r"(smem_u32(p)));
+}
+__device__ __forceinline__ float ex2(float x) {
+    float y;
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+    return y;
+}
 
 __global__ void __launch_bounds__(kAttnThreads)
 attention_kernel(const __half* __restrict__ qkv, const int32_t* __restrict__ lens, int S,
@@ -160,33 +178,51 @@ attention_kernel(const __half* __restrict__ qkv, const int32_t* __restrict__ len
     int len = lens[seq];
     len = len < 0 ? 0 : (len > S ? S : len);
     const int Sk = (len + 63) & ~63;                 // staged keys (multiple of 64)
-    const int vt_ld = Sk + 8;                        // halves per V^T row
     __half* sK = reinterpret_cast<__half*>(attn_raw);            // [Sk][kKPad]
-    __half* sVt = sK + (size_t)Sk * kKPad;                        // [32][vt_ld]
+    __half* sV = sK + (size_t)Sk * kKPad;                         // [Sk][kKPad]
     const __half* base = qkv + (size_t)seq * S * kQkv + head * kHeadDim;
 
-    // ---- stage K (row-major, padded) and V^T; rows >= len are zero
+    // ---- stage K and V (row-major, padded) with 16-byte async copies; rows >= len are zero-filled
     for (int i = tid; i < Sk * 4; i += kAttnThreads) {
         const int s = i >> 2, part = i & 3;          // 4 x 16-byte parts per 64-byte row
-        uint4 kv = make_uint4(0, 0, 0, 0), vv = make_uint4(0, 0, 0, 0);
-        if (s < len) {
-            kv = __ldg(reinterpret_cast<const uint4*>(base + (size_t)s * kQkv + kHidden) + part);
-            vv = __ldg(reinterpret_cast<const uint4*>(base + (size_t)s * kQkv + 2 * kHidden) + part);
-        }
-        *reinterpret_cast<uint4*>(sK + s * kKPad + part * 8) = kv;
-        const __half* vh = reinterpret_cast<const __half*>(&vv);
-#pragma unroll
-        for (int e = 0; e < 8; ++e) sVt[(part * 8 + e) * vt_ld + s] = vh[e];
+        const int sr = s < len ? s : 0;
+        const uint32_t nbytes = s < len ? 16u : 0u;
+        const __half* kp = base + (size_t)sr * kQkv + kHidden + part * 8;
+        asm volatile("cp.async.ca.shared.global [%0], [%1], 16, %2;"
+                     ::"r"(smem_u32(sK + s * kKPad + part * 8)), "l"(kp), "r"(nbytes) : "memory");
+        asm volatile("cp.async.ca.shared.global [%0], [%1], 16, %2;"
+                     ::"r"(smem_u32(sV + s * kKPad + part * 8)), "l"(kp + kHidden), "r"(nbytes) : "memory");
     }
-    __syncthreads();
+    asm volatile("cp.async.commit_group;" ::: "memory");
 
-    const float scale = 0.17677669529663687f;        // 1 / sqrt(32)
+    // softmax in the exp2 domain: p = 2^((s - m) * scale * log2(e)), the scale folded into one FFMA
+    const float scale2 = 0.17677669529663687f * 1.4426950408889634f;
+    // ldmatrix lane roles: matrix (lane >> 3), row (lane & 7)
+    const int lm = lane >> 3, lr = lane & 7;
     const int n_qtiles = (S + 15) >> 4;
+    // Q fragments (A operand) of a 16-query tile, two k-steps over d = 0..31
+    uint32_t qa[2][4];
+    auto load_q = [&](int qt) {
+        const int r0 = qt * 16 + g, r1 = r0 + 8;
+#pragma unroll
+        for (int ks = 0; ks < 2; ++ks) {
+            const __half* q0p = base + (size_t)r0 * kQkv + ks * 16 + 2 * t;
+            const __half* q1p = base + (size_t)r1 * kQkv + ks * 16 + 2 * t;
+            qa[ks][0] = (r0 < len) ? __ldg(reinterpret_cast<const uint32_t*>(q0p)) : 0u;
+            qa[ks][1] = (r1 < len) ? __ldg(reinterpret_cast<const uint32_t*>(q1p)) : 0u;
+            qa[ks][2] = (r0 < len) ? __ldg(reinterpret_cast<const uint32_t*>(q0p + 8)) : 0u;
+            qa[ks][3] = (r1 < len) ? __ldg(reinterpret_cast<const uint32_t*>(q1p + 8)) : 0u;
+        }
+    };
+    if (warp < n_qtiles) load_q(warp);               // in flight together with the K / V copies
+    asm volatile("cp.async.wait_all;" ::: "memory");
+    __syncthreads();
     for (int qt = warp; qt < n_qtiles; qt += kAttnThreads / 32) {
         const int q0 = qt * 16;
         const int r0 = q0 + g, r1 = q0 + g + 8;
         __half* o0 = ctx + ((size_t)seq * S + r0) * kHidden + head * kHeadDim;
         __half* o1 = ctx + ((size_t)seq * S + r1) * kHidden + head * kHeadDim;
+        if (qt != warp) load_q(qt);
         if (q0 >= len) {                              // padding tile: zeros
 #pragma unroll
             for (int nd = 0; nd < 4; ++nd) {
@@ -194,17 +230,6 @@ attention_kernel(const __half* __restrict__ qkv, const int32_t* __restrict__ len
                 if (r1 < S) *reinterpret_cast<uint32_t*>(o1 + nd * 8 + 2 * t) = 0u;
             }
             continue;
-        }
-        // Q fragments (A operand), two k-steps over d = 0..31
-        uint32_t qa[2][4];
-#pragma unroll
-        for (int ks = 0; ks < 2; ++ks) {
-            const __half* q0p = base + (size_t)r0 * kQkv + ks * 16 + 2 * t;
-            const __half* q1p = base + (size_t)r1 * kQkv + ks * 16 + 2 * t;
-            qa[ks][0] = (r0 < S) ? __ldg(reinterpret_cast<const uint32_t*>(q0p)) : 0u;
-            qa[ks][1] = (r1 < S) ? __ldg(reinterpret_cast<const uint32_t*>(q1p)) : 0u;
-            qa[ks][2] = (r0 < S) ? __ldg(reinterpret_cast<const uint32_t*>(q0p + 8)) : 0u;
-            qa[ks][3] = (r1 < S) ? __ldg(reinterpret_cast<const uint32_t*>(q1p + 8)) : 0u;
         }
         float m0 = -INFINITY, m1 = -INFINITY, l0 = 0.f, l1 = 0.f;
         float o[4][4];
@@ -219,23 +244,24 @@ attention_kernel(const __half* __restrict__ qkv, const int32_t* __restrict__ len
             for (int j = 0; j < 8; ++j) {
 #pragma unroll
                 for (int i = 0; i < 4; ++i) sc[j][i] = 0.f;
-                const __half* kp = sK + (kb + j * 8 + g) * kKPad + 2 * t;
+                // K rows kb + 8j .. +7, the four 8-wide d blocks: {b0,b1} of k-step 0, then of k-step 1
+                uint32_t kf[4];
+                ldsm_x4(kf, sK + (kb + j * 8 + lr) * kKPad + lm * 8);
+                mma16816(sc[j], qa[0], kf[0], kf[1]);
+                mma16816(sc[j], qa[1], kf[2], kf[3]);
+            }
+            // mask (last block only) + block max, on the raw scores
+            if (kb + 64 > len) {
 #pragma unroll
-                for (int ks = 0; ks < 2; ++ks) {
-                    const uint32_t b0 = *reinterpret_cast<const uint32_t*>(kp + ks * 16);
-                    const uint32_t b1 = *reinterpret_cast<const uint32_t*>(kp + ks * 16 + 8);
-                    mma16816(sc[j], qa[ks], b0, b1);
+                for (int j = 0; j < 8; ++j) {
+                    const int key = kb + j * 8 + 2 * t;
+                    if (key >= len) { sc[j][0] = -INFINITY; sc[j][2] = -INFINITY; }
+                    if (key + 1 >= len) { sc[j][1] = -INFINITY; sc[j][3] = -INFINITY; }
                 }
             }
-            // scale + mask + block max
             float bm0 = -INFINITY, bm1 = -INFINITY;
 #pragma unroll
             for (int j = 0; j < 8; ++j) {
-                const int key = kb + j * 8 + 2 * t;
-                sc[j][0] = (key < len) ? sc[j][0] * scale : -INFINITY;
-                sc[j][1] = (key + 1 < len) ? sc[j][1] * scale : -INFINITY;
-                sc[j][2] = (key < len) ? sc[j][2] * scale : -INFINITY;
-                sc[j][3] = (key + 1 < len) ? sc[j][3] * scale : -INFINITY;
                 bm0 = fmaxf(bm0, fmaxf(sc[j][0], sc[j][1]));
                 bm1 = fmaxf(bm1, fmaxf(sc[j][2], sc[j][3]));
             }
@@ -244,15 +270,16 @@ attention_kernel(const __half* __restrict__ qkv, const int32_t* __restrict__ len
             bm1 = fmaxf(bm1, __shfl_xor_sync(0xffffffffu, bm1, 1));
             bm1 = fmaxf(bm1, __shfl_xor_sync(0xffffffffu, bm1, 2));
             const float mn0 = fmaxf(m0, bm0), mn1 = fmaxf(m1, bm1);   // finite: key kb < len
-            const float a0 = expf(m0 - mn0), a1 = expf(m1 - mn1);
+            const float a0 = ex2((m0 - mn0) * scale2), a1 = ex2((m1 - mn1) * scale2);
             m0 = mn0; m1 = mn1;
+            const float nm0 = -mn0 * scale2, nm1 = -mn1 * scale2;
             float ps0 = 0.f, ps1 = 0.f;
 #pragma unroll
             for (int j = 0; j < 8; ++j) {
-                sc[j][0] = expf(sc[j][0] - mn0);
-                sc[j][1] = expf(sc[j][1] - mn0);
-                sc[j][2] = expf(sc[j][2] - mn1);
-                sc[j][3] = expf(sc[j][3] - mn1);
+                sc[j][0] = ex2(fmaf(sc[j][0], scale2, nm0));
+                sc[j][1] = ex2(fmaf(sc[j][1], scale2, nm0));
+                sc[j][2] = ex2(fmaf(sc[j][2], scale2, nm1));
+                sc[j][3] = ex2(fmaf(sc[j][3], scale2, nm1));
                 ps0 += sc[j][0] + sc[j][1];
                 ps1 += sc[j][2] + sc[j][3];
             }
@@ -263,7 +290,7 @@ attention_kernel(const __half* __restrict__ qkv, const int32_t* __restrict__ len
                 o[nd][0] *= a0; o[nd][1] *= a0;
                 o[nd][2] *= a1; o[nd][3] *= a1;
             }
-            // O += P * V   (P from the score fragments, V^T from shared memory)
+            // O += P * V   (P from the score fragments; V fragments through ldmatrix.trans)
 #pragma unroll
             for (int kk = 0; kk < 4; ++kk) {
                 uint32_t pa[4];
@@ -272,11 +299,12 @@ attention_kernel(const __half* __restrict__ qkv, const int32_t* __restrict__ len
                 pa[2] = pack_h2(sc[2 * kk + 1][0], sc[2 * kk + 1][1]);
                 pa[3] = pack_h2(sc[2 * kk + 1][2], sc[2 * kk + 1][3]);
 #pragma unroll
-                for (int nd = 0; nd < 4; ++nd) {
-                    const __half* vp = sVt + (nd * 8 + g) * vt_ld + kb + kk * 16 + 2 * t;
-                    const uint32_t b0 = *reinterpret_cast<const uint32_t*>(vp);
-                    const uint32_t b1 = *reinterpret_cast<const uint32_t*>(vp + 8);
-                    mma16816(o[nd], pa, b0, b1);
+                for (int np = 0; np < 2; ++np) {
+                    // matrices: (keys 0-7, d block 2np), (keys 8-15, 2np), (keys 0-7, 2np+1), (keys 8-15, 2np+1)
+                    uint32_t vf[4];
+                    ldsm_x4_t(vf, sV + (kb + kk * 16 + (lm & 1) * 8 + lr) * kKPad + (2 * np + (lm >> 1)) * 8);
+                    mma16816(o[2 * np], pa, vf[0], vf[1]);
+                    mma16816(o[2 * np + 1], pa, vf[2], vf[3]);
                 }
             }
         }
@@ -479,6 +507,10 @@ static cudaError_t encoder_reserve(Encoder* e, int64_t tokens) {
     ENC_CK(make_tmap_f16(&e->t_x1, e->x1, cap, kHidden, kHidden, 128));
     ENC_CK(make_tmap_f16(&e->t_ctx, e->ctx, cap, kHidden, kHidden, 128));
     ENC_CK(make_tmap_f16(&e->t_ff, e->ff, cap, kFfn, kFfn, 128));
+    ENC_CK(make_tmap_io_f16(&e->io_x, e->x, cap, kHidden, kHidden));
+    ENC_CK(make_tmap_io_f16(&e->io_x1, e->x1, cap, kHidden, kHidden));
+    ENC_CK(make_tmap_io_f16(&e->io_qkv, e->qkv, cap, kQkv, kQkv));
+    ENC_CK(make_tmap_io_f16(&e->io_ff, e->ff, cap, kFfn, kFfn));
     e->cap = cap;
     return cudaSuccess;
 }
@@ -508,22 +540,22 @@ cudaError_t encoder_forward(lrx_handle* h, const int32_t* ids, const int32_t* le
         h->launches++;
         ENC_CK(cudaGetLastError());
         const int Sk = (S + 63) & ~63;
-        const size_t attn_smem = (size_t)Sk * kKPad * 2 + (size_t)kHeadDim * (Sk + 8) * 2;
+        const size_t attn_smem = (size_t)Sk * kKPad * 2 * 2;
         // which W tensor-map set matches the plan the GEMM launcher picks for this many rows
         const int pl = ((int)((T + 127) / 128) >= h->num_sms / 2) ? 1 : 0;
         for (int l = 0; l < kLayers; ++l) {
             EncLayer& L = e->L[l];
-            ENC_CK(launch_tc_gemm(h, e->t_x, L.t_wqkv[pl], (int)T, kQkv, kHidden, 0, L.bqkv, nullptr, 0,
-                                  nullptr, nullptr, 0.f, e->qkv, kQkv));
+            ENC_CK(launch_tc_gemm(h, e->t_x, L.t_wqkv[pl], e->io_qkv, e->io_qkv, (int)T, kQkv, kHidden, 0,
+                                  L.bqkv, nullptr, nullptr, 0.f, e->qkv, kQkv));
             attention_kernel<<<dim3(kHeads, nb), kAttnThreads, attn_smem, st>>>(e->qkv, clen, S, e->ctx);
             h->launches++;
             ENC_CK(cudaGetLastError());
-            ENC_CK(launch_tc_gemm(h, e->t_ctx, L.t_wo[pl], (int)T, kHidden, kHidden, 2, L.bo, e->x, kHidden,
-                                  L.ln1_g, L.ln1_b, kLnEps, e->x1, kHidden));
-            ENC_CK(launch_tc_gemm(h, e->t_x1, L.t_w1[pl], (int)T, kFfn, kHidden, 1, L.b1, nullptr, 0,
-                                  nullptr, nullptr, 0.f, e->ff, kFfn));
-            ENC_CK(launch_tc_gemm(h, e->t_ff, L.t_w2[pl], (int)T, kHidden, kFfn, 2, L.b2, e->x1, kHidden,
-                                  L.ln2_g, L.ln2_b, kLnEps, e->x, kHidden));
+            ENC_CK(launch_tc_gemm(h, e->t_ctx, L.t_wo[pl], e->io_x1, e->io_x, (int)T, kHidden, kHidden, 2,
+                                  L.bo, L.ln1_g, L.ln1_b, kLnEps, e->x1, kHidden));
+            ENC_CK(launch_tc_gemm(h, e->t_x1, L.t_w1[pl], e->io_ff, e->io_ff, (int)T, kFfn, kHidden, 1,
+                                  L.b1, nullptr, nullptr, 0.f, e->ff, kFfn));
+            ENC_CK(launch_tc_gemm(h, e->t_ff, L.t_w2[pl], e->io_x, e->io_x1, (int)T, kHidden, kFfn, 2,
+                                  L.b2, L.ln2_g, L.ln2_b, kLnEps, e->x, kHidden));
         }
         pool_normalize_kernel<<<nb, 128, 0, st>>>(
             e->x, clen, S, out_f32 ? out_f32 + (size_t)b0 * kHidden : nullptr,

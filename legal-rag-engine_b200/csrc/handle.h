@@ -53,6 +53,7 @@ struct lrx_handle {
 
     // K1 encoder state (packed weights, activation workspaces, tensor maps): encoder.cu
     void* encoder = nullptr;
+    void* debug_trace = nullptr;     // device int64[128]: GEMM timeline of CTA 0 (lrx_debug_set_trace)
 };
 
 namespace lrx {

@@ -47,6 +47,7 @@ struct GemmEpi {
     int ld_out, ld_res;
     int M;                    // valid rows
     float eps;
+    long long* trace;         // optional timeline of CTA 0 (lrx_debug_set_trace), else NULL
 };
 
 constexpr int kAResKB = 6;                        // k-blocks of a RESIDENT A tile (K = 384)
@@ -63,58 +64,98 @@ struct GemmCfg {
     static constexpr int kBBytes = BN * kBK * 2;
     static constexpr int kStageBytes = (ARES ? 0 : kABytes) + kBBytes;
     static constexpr int kResBytes = ARES ? kAResKB * kABytes : 0;
-    static constexpr int kStagesRaw = (192 * 1024 - kResBytes) / kStageBytes;
+    // epilogue side: bias (whole vector, N <= 1536) / gamma / beta / LayerNorm partial sums, and one 2 KB staging
+    // tiles (32 rows x 32 halves, SWIZZLE_64B), two per epilogue warp, for the TMA stores / residual loads
+    static constexpr int kParamBytes = 1536 * 4 + 2 * 384 * 4 + 2 * 2 * 128 * 4;
+    static constexpr int kIoBytes = kEpiWarps * 2 * 2048 + 2048 /*align*/;   // double-buffered
+    static constexpr int kBarBytes = 512;
+    static constexpr int kBudget = 224 * 1024 - 1024 - kBarBytes - kParamBytes - kIoBytes;
+    static constexpr int kStagesRaw = (kBudget - kResBytes) / kStageBytes;
     static constexpr int kStages = kStagesRaw > 8 ? 8 : kStagesRaw;
     static constexpr int kAcc = (2 * BN <= 512) ? 2 : 1;              // TMEM accumulator buffers
     static constexpr int kTmemCols = (kAcc * BN <= 128) ? 128 : (kAcc * BN <= 256 ? 256 : 512);
-    // + bias (2 x BN) / gamma / beta / LayerNorm partial sums staged for the epilogue
-    static constexpr int kParamBytes = 2 * BN * 4 + 2 * 384 * 4 + 2 * 2 * 128 * 4 + 2048 * 8 /*GELU table*/;
-    static constexpr size_t kSmem = (size_t)kResBytes + (size_t)kStages * kStageBytes + 1024 /*align*/ + 256 /*barriers*/ + kParamBytes;
+    static constexpr size_t kSmem = (size_t)kResBytes + (size_t)kStages * kStageBytes + 1024 /*align*/ +
+                                    kBarBytes + kParamBytes + kIoBytes;
 };
 
-// exact-erf GELU (builds the interpolation table)
-__device__ __forceinline__ float gelu_erf(float x) {
-    return 0.5f * x * (1.0f + erff(x * 0.70710678118654752440f));
-}
-// The epilogue's GELU: table of (value, slope) pairs on [-8, 8] in steps of 1/128, linear
-// interpolation (error <= h^2/8 * max|gelu''| < 1e-5, far inside the fp16 rounding of the output);
-// index and fraction come from a magic-number add -- no conversion or MUFU instruction, so the
-// epilogue keeps up with the tensor pipe.  Outside the table GELU(x) = x (x > 8) or -0 (x < -8).
-constexpr int kGeluN = 2048;
-__device__ __forceinline__ float gelu_lut(const float2* __restrict__ lut, float x) {
-    const float xc = fminf(fmaxf(x, -8.0f), 8.0f - 1.0f / 256.0f);
-    const float t = fmaf(xc, 128.0f, 1024.0f);                 // [0, 2048)
-    const float m = t - 0.5f + 12582912.0f;                    // 1.5 * 2^23: low bits = floor(t)
-    const int i = __float_as_int(m) & (kGeluN - 1);
-    const float fr = t - (m - 12582912.0f);
-    const float2 e = lut[i];
-    return fmaf(e.y, fr, e.x) + fmaxf(x - 8.0f, 0.0f);
+// GELU(x) = x * Phi(x), Phi(x) = 0.5 erfc(-x / sqrt 2), with erfc from Abramowitz & Stegun 7.1.26
+// (|error| <= 1.5e-7 on erf): h = 0.5 (a1 t + ... + a5 t^5) exp(-x^2 / 2), t = 1 / (1 + p |x| / sqrt 2),
+// Phi = x >= 0 ? 1 - h : h.  Two elements at a time so that the exponential is ONE packed
+// ex2.approx.f16x2 (its ~2^-11 relative error scales h, which is <= 0.5 and shrinks as x^2 grows:
+// far inside the fp16 rounding of the output); 13 FP32 instructions + 1.5 MUFU per element instead
+// of erff's branchy ~40 -- the epilogue has to keep up with the tensor pipe.
+__device__ __forceinline__ float2 gelu2(float x0, float x1) {
+    constexpr float kP = 0.3275911f * 0.70710678118654752440f;
+    constexpr float kE = -0.5f * 1.4426950408889634f;            // exp(-x^2/2) = 2^(kE x^2)
+    float t0, t1;
+    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(t0) : "f"(fmaf(kP, fabsf(x0), 1.0f)));
+    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(t1) : "f"(fmaf(kP, fabsf(x1), 1.0f)));
+    const __half2 arg = __floats2half2_rn(kE * x0 * x0, kE * x1 * x1);
+    uint32_t eh;
+    asm("ex2.approx.f16x2 %0, %1;" : "=r"(eh) : "r"(*reinterpret_cast<const uint32_t*>(&arg)));
+    const float2 e = __half22float2(*reinterpret_cast<const __half2*>(&eh));
+    float p0 = fmaf(0.5f * 1.061405429f, t0, 0.5f * -1.453152027f);
+    float p1 = fmaf(0.5f * 1.061405429f, t1, 0.5f * -1.453152027f);
+    p0 = fmaf(p0, t0, 0.5f * 1.421413741f);   p1 = fmaf(p1, t1, 0.5f * 1.421413741f);
+    p0 = fmaf(p0, t0, 0.5f * -0.284496736f);  p1 = fmaf(p1, t1, 0.5f * -0.284496736f);
+    p0 = fmaf(p0, t0, 0.5f * 0.254829592f);   p1 = fmaf(p1, t1, 0.5f * 0.254829592f);
+    const float h0 = p0 * t0 * e.x, h1 = p1 * t1 * e.y;
+    return make_float2(x0 * (x0 >= 0.f ? 1.0f - h0 : h0), x1 * (x1 >= 0.f ? 1.0f - h1 : h1));
 }
 __device__ __forceinline__ void epi_bar() { asm volatile("bar.sync 1, 256;" ::: "memory"); }
 
-__device__ __forceinline__ void store_row32_f16(__half* dst, const float (&v)[32]) {
-    uint4* d4 = reinterpret_cast<uint4*>(dst);
+// Staging tile of one epilogue warp: 32 rows x 32 halves (64 B per row) in the SWIZZLE_64B layout
+// of the TMA tensor maps: 16-byte chunk j of row r sits at chunk (j ^ ((r >> 1) & 3)).  Lane r
+// owns row r, so every quarter-warp touches 8 distinct bank groups (conflict-free).
+__device__ __forceinline__ void stage_put_row(unsigned char* tile, int r, const float (&v)[32]) {
 #pragma unroll
-    for (int i = 0; i < 4; ++i) {
-        __half2 h0 = __floats2half2_rn(v[8 * i + 0], v[8 * i + 1]);
-        __half2 h1 = __floats2half2_rn(v[8 * i + 2], v[8 * i + 3]);
-        __half2 h2 = __floats2half2_rn(v[8 * i + 4], v[8 * i + 5]);
-        __half2 h3 = __floats2half2_rn(v[8 * i + 6], v[8 * i + 7]);
+    for (int j = 0; j < 4; ++j) {
+        const __half2 h0 = __floats2half2_rn(v[8 * j + 0], v[8 * j + 1]);
+        const __half2 h1 = __floats2half2_rn(v[8 * j + 2], v[8 * j + 3]);
+        const __half2 h2 = __floats2half2_rn(v[8 * j + 4], v[8 * j + 5]);
+        const __half2 h3 = __floats2half2_rn(v[8 * j + 6], v[8 * j + 7]);
         uint4 u;
-        u.x = *reinterpret_cast<uint32_t*>(&h0);
-        u.y = *reinterpret_cast<uint32_t*>(&h1);
-        u.z = *reinterpret_cast<uint32_t*>(&h2);
-        u.w = *reinterpret_cast<uint32_t*>(&h3);
-        d4[i] = u;
+        u.x = *reinterpret_cast<const uint32_t*>(&h0);
+        u.y = *reinterpret_cast<const uint32_t*>(&h1);
+        u.z = *reinterpret_cast<const uint32_t*>(&h2);
+        u.w = *reinterpret_cast<const uint32_t*>(&h3);
+        *reinterpret_cast<uint4*>(tile + r * 64 + ((j ^ ((r >> 1) & 3)) << 4)) = u;
     }
+}
+__device__ __forceinline__ void stage_get_row(const unsigned char* tile, int r, uint4 (&dst)[4]) {
+#pragma unroll
+    for (int j = 0; j < 4; ++j)
+        dst[j] = *reinterpret_cast<const uint4*>(tile + r * 64 + ((j ^ ((r >> 1) & 3)) << 4));
+}
+// whole warp: publish the staged tile with one TMA store (rows beyond the tensor are clipped)
+__device__ __forceinline__ void stage_store(const CUtensorMap* m, int col, int row, const unsigned char* tile,
+                                            int lane) {
+    fence_proxy_async();            // generic-proxy writes -> visible to the async proxy
+    __syncwarp();
+    if (lane == 0) {
+        tma_store_2d(m, col, row, tile);
+        bulk_commit();
+    }
+}
+// whole warp: every store has read its tile / every store but the latest has
+__device__ __forceinline__ void stage_acquire(int lane) {
+    if (lane == 0) bulk_wait_read();
+    __syncwarp();
+}
+__device__ __forceinline__ void stage_acquire1(int lane) {
+    if (lane == 0) bulk_wait_read1();
+    __syncwarp();
 }
 
 // Persistent: CTA c owns output tiles c, c + grid, ... (n-block fastest, so CTAs running side by
 // side share the A rows in L2).  The shared-memory ring flows across tiles; with two TMEM
 // accumulators (BN <= 256) the epilogue of tile i overlaps the MMAs of tile i + 1.
+#define LRX_TRACE(slot) do { if (ep.trace != nullptr && blockIdx.x == 0) ep.trace[(slot)] = clock64(); } while (0)
+
 template <int BN, int EPI, bool ARES, int CS>
 __global__ void __launch_bounds__(kGemmThreads, 1)
 tc_gemm_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant__ CUtensorMap tma_b,
+               const __grid_constant__ CUtensorMap tma_out, const __grid_constant__ CUtensorMap tma_res,
                int num_k_blocks, int m_tiles, int n_tiles, GemmEpi ep) {
     using Cfg = GemmCfg<BN, ARES, CS>;
     constexpr uint16_t kMask = (uint16_t)((1u << CS) - 1u);
@@ -133,18 +174,21 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
     uint64_t* t_empty = t_full + 2;          // [kAcc] accumulator drained by the epilogue
     uint64_t* a_full = t_empty + 2;          // ARES: resident A tile landed
     uint64_t* a_empty = a_full + 1;          // ARES: every MMA of the row block has read it
-    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(a_empty + 1);
-    float* s_bias = reinterpret_cast<float*>(sEnd + 256);                                 // [2][BN]
-    float* s_gamma = s_bias + 2 * BN;                                                     // [384]
+    uint64_t* r_full = a_empty + 1;          // [kEpiWarps][2] residual chunk landed (LayerNorm epilogue)
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(r_full + 2 * kEpiWarps);
+    float* s_bias = reinterpret_cast<float*>(sEnd + Cfg::kBarBytes);                      // [N <= 1536]
+    float* s_gamma = s_bias + 1536;                                                     // [384]
     float* s_beta = s_gamma + 384;                                                        // [384]
     float* s_part = s_beta + 384;                                                         // [2][2][128]
-    const float2* s_gelu = reinterpret_cast<const float2*>(s_part + 2 * 2 * 128);        // [2048] (EPI 1)
+    unsigned char* s_io = reinterpret_cast<unsigned char*>(
+        (reinterpret_cast<uintptr_t>(s_part + 2 * 2 * 128) + 2047) & ~(uintptr_t)2047);   // [kEpiWarps][2][2 KB]
 
     const int warp = threadIdx.x >> 5;
     const int lane = threadIdx.x & 31;
     const int total_tiles = m_tiles * n_tiles;
     constexpr int kProducerWarp = kEpiWarps, kMmaWarp = kEpiWarps + 1;
 
+    if (threadIdx.x == 0) LRX_TRACE(0);
     if (warp == kProducerWarp && lane == 0) {
         tma_prefetch_desc(&tma_a);
         tma_prefetch_desc(&tma_b);
@@ -158,6 +202,8 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
         }
         mbar_init(a_full, 1);
         mbar_init(a_empty, 1);
+        for (int w = 0; w < 2 * kEpiWarps; ++w) mbar_init(&r_full[w], 1);
+        tma_prefetch_desc(&tma_out);
         fence_barrier_init();
     }
     if (warp == kMmaWarp) {
@@ -169,6 +215,7 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
     if (CS > 1) cluster_sync_all();            // peers' barriers are initialised before any multicast
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
+    if (threadIdx.x == 0) LRX_TRACE(1);
 
     if (warp == kProducerWarp) {
         // ===== TMA producer
@@ -240,14 +287,17 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
                     mbar_wait(a_full, (uint32_t)(u / n_tiles) & 1u);
                     tc_fence_after();
                 }
+                if (u < 8) LRX_TRACE(16 + u * 4 + 0);
                 mbar_wait(&t_empty[buf], (use & 1u) ^ 1u);    // epilogue has drained this accumulator
                 tc_fence_after();
+                if (u < 8) LRX_TRACE(16 + u * 4 + 1);
                 const uint32_t tacc = tmem_base + buf * BN;
                 for (int kb = 0; kb < num_k_blocks; ++kb, ++it) {
                     const int s = (int)(it % kStages);
                     const uint32_t ph = (it / kStages) & 1u;
                     mbar_wait(&full[s], ph);
                     tc_fence_after();
+                    if (u < 8 && kb == 0) LRX_TRACE(16 + u * 4 + 2);
                     const uint32_t a_addr = smem_u32(sA + (ARES ? kb : s) * kABytes);
                     const uint32_t b_addr = smem_u32(sB + s * Cfg::kBBytes);
 #pragma unroll
@@ -265,6 +315,7 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
                     else umma_commit(&empty[s]);              // smem slot free when the MMAs retire
                 }
                 umma_commit(&t_full[buf]);                    // accumulator complete
+                if (u < 8) LRX_TRACE(16 + u * 4 + 3);
                 if (ARES && (u % n_tiles) == n_tiles - 1) umma_commit(a_empty);   // A tile may be replaced
             }
         }
@@ -275,25 +326,21 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
         const int quarter = warp & 3, half = warp >> 2;
         const int et = threadIdx.x;                      // 0..255
         constexpr int HB = BN / 2;                       // columns per half
-        if (EPI == 1) {
-            float2* g = const_cast<float2*>(s_gelu);
-            for (int i = et; i < kGeluN; i += 256) {
-                const float x0 = (float)(i - 1024) * (1.0f / 128.0f), x1 = x0 + 1.0f / 128.0f;
-                const float g0 = gelu_erf(x0), g1 = gelu_erf(x1);
-                g[i] = make_float2(g0, g1 - g0);
-            }
-            epi_bar();
-        }
-        if (EPI == 2) {
-            for (int i = et; i < 384; i += 256) {
-                s_gamma[i] = ep.gamma[i];
-                s_beta[i] = ep.beta[i];
-                s_bias[i] = ep.bias[i];
+        if (EPI != 3) {
+            for (int i = et; i < n_tiles * BN; i += 256) s_bias[i] = ep.bias[i];
+            if (EPI == 2) {
+                for (int i = et; i < 384; i += 256) {
+                    s_gamma[i] = ep.gamma[i];
+                    s_beta[i] = ep.beta[i];
+                }
             }
             epi_bar();
         }
         const int n_mine = ARES ? ((m_tiles > (int)blockIdx.x) ? (m_tiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x : 0) * n_tiles
                                 : ((total_tiles > (int)blockIdx.x) ? (total_tiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x : 0);
+        unsigned char* tile_io = s_io + warp * 4096;      // this warp's two staging tiles
+        uint32_t io_n = 0;                                // stored tiles so far: buffer = io_n & 1
+        uint32_t res_n = 0;                               // residual chunks so far: buffer = res_n & 1
         for (int u = 0; u < n_mine; ++u) {
             int m_blk, n_blk;
             if (ARES) {
@@ -307,13 +354,11 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
             const int buf = u % kAcc;
             const uint32_t use = (uint32_t)(u / kAcc);
             const int n0 = n_blk * BN;
-            float* bias = s_bias + (EPI == 2 ? 0 : (u & 1) * BN);
-            if (EPI == 0 || EPI == 1) {
-                for (int i = et; i < BN; i += 256) bias[i] = ep.bias[n0 + i];
-                epi_bar();
-            }
+            const float* bias = s_bias + n0;
+            if (threadIdx.x == 0 && u < 8) LRX_TRACE(64 + u * 4 + 0);
             mbar_wait(&t_full[buf], use & 1u);
             tc_fence_after();
+            if (threadIdx.x == 0 && u < 8) LRX_TRACE(64 + u * 4 + 1);
             const int row = quarter * 32 + lane;
             const int64_t grow = (int64_t)m_blk * kBM + row;
             const bool ok = grow < ep.M;
@@ -342,7 +387,7 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
                     tmem_wait_ld();
                 }
             } else if (EPI == 0 || EPI == 1) {
-                __half* out = reinterpret_cast<__half*>(ep.out) + grow * ep.ld_out + n0 + cb;
+                const int row_w = m_blk * kBM + quarter * 32;         // first output row of this warp
                 tmem_ld32(trow, rb[0]);
                 tmem_wait_ld();
 #pragma unroll
@@ -357,38 +402,56 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
                         const float x1 = __uint_as_float(r[4 * j4 + 1]) + bb.y;
                         const float x2 = __uint_as_float(r[4 * j4 + 2]) + bb.z;
                         const float x3 = __uint_as_float(r[4 * j4 + 3]) + bb.w;
-                        v[4 * j4 + 0] = (EPI == 1) ? gelu_lut(s_gelu, x0) : x0;
-                        v[4 * j4 + 1] = (EPI == 1) ? gelu_lut(s_gelu, x1) : x1;
-                        v[4 * j4 + 2] = (EPI == 1) ? gelu_lut(s_gelu, x2) : x2;
-                        v[4 * j4 + 3] = (EPI == 1) ? gelu_lut(s_gelu, x3) : x3;
+                        if (EPI == 1) {
+                            const float2 ga = gelu2(x0, x1), gb = gelu2(x2, x3);
+                            v[4 * j4 + 0] = ga.x; v[4 * j4 + 1] = ga.y;
+                            v[4 * j4 + 2] = gb.x; v[4 * j4 + 3] = gb.y;
+                        } else {
+                            v[4 * j4 + 0] = x0; v[4 * j4 + 1] = x1;
+                            v[4 * j4 + 2] = x2; v[4 * j4 + 3] = x3;
+                        }
                     }
-                    if (ok) store_row32_f16(out + c, v);
+                    unsigned char* tb_ = tile_io + (io_n & 1u) * 2048;
+                    ++io_n;
+                    stage_acquire1(lane);                             // the store before last has read it
+                    stage_put_row(tb_, lane, v);
+                    stage_store(&tma_out, n0 + cb + c, row_w, tb_, lane);
                     tmem_wait_ld();
                 }
             } else {
                 // bias + residual, LayerNorm over the whole row (BN == N == 384): each thread owns
                 // half a row, the two halves exchange their partial sums through shared memory
-                const __half* res = ep.residual + grow * ep.ld_res + cb;
+                const int row_w = m_blk * kBM + quarter * 32;
                 float* part = s_part + (u & 1) * 2 * 2 * 128;       // [stat][half][row]
                 float sum = 0.f;
-                uint4 rq[2][4];                                      // residual chunk, same pipeline
-                auto ldres = [&](int ch, uint4 (&dst)[4]) {
-#pragma unroll
-                    for (int i = 0; i < 4; ++i)
-                        dst[i] = ok ? __ldg(reinterpret_cast<const uint4*>(res + ch * 32) + i) : make_uint4(0, 0, 0, 0);
+                // residual chunks come in through the warp's staging tile (TMA, coalesced): chunk
+                // ch + 1 is requested as soon as every lane holds chunk ch in registers
+                // (double-buffered: chunk ch + 1 is in flight while chunk ch is consumed)
+                auto res_request = [&](int ch, uint32_t n) {
+                    if (lane == 0) {
+                        mbar_arrive_expect_tx(&r_full[warp * 2 + (n & 1u)], 2048u);
+                        tma_load_2d(tile_io + (n & 1u) * 2048, &tma_res, cb + ch * 32, row_w,
+                                    &r_full[warp * 2 + (n & 1u)]);
+                    }
                 };
-                ldres(0, rq[0]);
+                stage_acquire(lane);                                 // last tile's output stores have read them
+                res_request(0, res_n);
                 tmem_ld32(trow, rb[0]);
                 tmem_wait_ld();
 #pragma unroll
                 for (int ch = 0; ch < NCH; ++ch) {
+                    uint4 rr[4];
                     if (ch + 1 < NCH) {
-                        ldres(ch + 1, rq[(ch + 1) & 1]);
+                        res_request(ch + 1, res_n + 1);
                         tmem_ld32(trow + (ch + 1) * 32, rb[(ch + 1) & 1]);
                     }
+                    mbar_wait(&r_full[warp * 2 + (res_n & 1u)], (res_n >> 1) & 1u);
+                    stage_get_row(tile_io + (res_n & 1u) * 2048, lane, rr);
+                    ++res_n;
+                    __syncwarp();
                     uint32_t(&r)[32] = rb[ch & 1];
                     const int c = ch * 32;
-                    const __half2* rh = reinterpret_cast<const __half2*>(rq[ch & 1]);
+                    const __half2* rh = reinterpret_cast<const __half2*>(rr);
 #pragma unroll
                     for (int j4 = 0; j4 < 8; ++j4) {
                         const float4 bb = *reinterpret_cast<const float4*>(bias + cb + c + 4 * j4);
@@ -427,7 +490,6 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
                 part[256 + half * 128 + row] = var;
                 epi_bar();
                 const float rstd = 1.0f / sqrtf((part[256 + row] + part[256 + 128 + row]) * (1.0f / BN) + ep.eps);
-                __half* out = reinterpret_cast<__half*>(ep.out) + grow * ep.ld_out + cb;
                 tmem_ld32(trow, rb[0]);
                 tmem_wait_ld();
 #pragma unroll
@@ -444,18 +506,26 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
                         v[4 * j4 + 2] = (__uint_as_float(r[4 * j4 + 2]) - mean) * rstd * gg.z + be.z;
                         v[4 * j4 + 3] = (__uint_as_float(r[4 * j4 + 3]) - mean) * rstd * gg.w + be.w;
                     }
-                    if (ok) store_row32_f16(out + c, v);
+                    unsigned char* tb_ = tile_io + (io_n & 1u) * 2048;
+                    ++io_n;
+                    stage_acquire1(lane);
+                    stage_put_row(tb_, lane, v);
+                    stage_store(&tma_out, cb + c, row_w, tb_, lane);
                     tmem_wait_ld();
                 }
             }
             tc_fence_before();
             __syncwarp();
+            if (threadIdx.x == 0 && u < 8) LRX_TRACE(64 + u * 4 + 2);
             if (lane == 0) mbar_arrive(&t_empty[buf]);        // accumulator may be overwritten
         }
+        stage_acquire(lane);                                  // shared memory outlives its last store
     }
     tc_fence_before();
     __syncthreads();
+    if (threadIdx.x == 0) LRX_TRACE(2);
     if (CS > 1) cluster_sync_all();            // nobody leaves while a peer may still multicast to it
+    if (threadIdx.x == 0) LRX_TRACE(3);
     if (warp == kMmaWarp) {
         tc_fence_after();
         tmem_dealloc(tmem_base, Cfg::kTmemCols);
@@ -497,8 +567,25 @@ cudaError_t make_tmap_f16(CUtensorMap* out, const void* ptr, int64_t rows, int64
     return r == CUDA_SUCCESS ? cudaSuccess : cudaErrorInvalidValue;
 }
 
+// fp16 row-major [rows, cols]: the epilogue's staging-tile view, box = 32 cols x 32 rows,
+// SWIZZLE_64B (TMA stores of outputs, TMA loads of the LayerNorm residual).
+cudaError_t make_tmap_io_f16(CUtensorMap* out, const void* ptr, int64_t rows, int64_t cols, int64_t ld) {
+    PFN_tmapEncodeTiled fn = get_encode_fn();
+    if (fn == nullptr) return cudaErrorNotSupported;
+    if (rows <= 0) rows = 1;
+    cuuint64_t gdim[2] = {(cuuint64_t)cols, (cuuint64_t)rows};
+    cuuint64_t gstride[1] = {(cuuint64_t)ld * 2};
+    cuuint32_t box[2] = {32, 32};
+    cuuint32_t estr[2] = {1, 1};
+    CUresult r = fn(out, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, const_cast<void*>(ptr), gdim, gstride, box,
+                    estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_64B,
+                    CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    return r == CUDA_SUCCESS ? cudaSuccess : cudaErrorInvalidValue;
+}
+
 template <int BN, int EPI, bool ARES, int CS>
-static cudaError_t launch_cfg(lrx_handle* h, const CUtensorMap& ta, const CUtensorMap& tb, int M,
+static cudaError_t launch_cfg(lrx_handle* h, const CUtensorMap& ta, const CUtensorMap& tb,
+                              const CUtensorMap& tout, const CUtensorMap& tres, int M,
                               int N, int K, const GemmEpi& ep) {
     static bool attr = false;
     auto kern = tc_gemm_kernel<BN, EPI, ARES, CS>;
@@ -526,14 +613,14 @@ static cudaError_t launch_cfg(lrx_handle* h, const CUtensorMap& ta, const CUtens
     at[0].val.clusterDim.z = 1;
     cfg.attrs = at;
     cfg.numAttrs = 1;
-    return cudaLaunchKernelEx(&cfg, kern, ta, tb, K / kBK, m_tiles, n_tiles, ep);
+    return cudaLaunchKernelEx(&cfg, kern, ta, tb, tout, tres, K / kBK, m_tiles, n_tiles, ep);
 }
 
 // Which variant runs (the W tensor map's box must match: gemm_box_rows_w).
 struct GemmPlan { int bn; bool ares; int cs; };
 GemmPlan gemm_plan(int num_sms, int M, int N, int K, int epi) {
     GemmPlan p;
-    p.bn = (epi == 2) ? 384 : (N % 256 == 0 ? 256 : (N % 192 == 0 ? 192 : 128));
+    p.bn = (epi == 2) ? 384 : (N % 192 == 0 ? 192 : (N % 256 == 0 ? 256 : 128));
     const int m_tiles = (M + kBM - 1) / kBM;
     const bool big = m_tiles >= num_sms / 2;                 // enough row blocks to fill the SMs
     p.ares = (K == kAResKB * kBK) && (big || N / p.bn == 1);
@@ -544,15 +631,16 @@ GemmPlan gemm_plan(int num_sms, int M, int N, int K, int epi) {
 }
 
 template <int BN, int EPI>
-static cudaError_t launch_one(lrx_handle* h, const CUtensorMap& ta, const CUtensorMap& tb, int M,
+static cudaError_t launch_one(lrx_handle* h, const CUtensorMap& ta, const CUtensorMap& tb,
+                              const CUtensorMap& tout, const CUtensorMap& tres, int M,
                               int N, int K, const GemmEpi& ep) {
     const GemmPlan p = gemm_plan(h->num_sms, M, N, K, EPI);
     if (p.cs > 1) {
-        if (p.ares) return launch_cfg<BN, EPI, true, LRX_GEMM_CLUSTER>(h, ta, tb, M, N, K, ep);
-        return launch_cfg<BN, EPI, false, LRX_GEMM_CLUSTER>(h, ta, tb, M, N, K, ep);
+        if (p.ares) return launch_cfg<BN, EPI, true, LRX_GEMM_CLUSTER>(h, ta, tb, tout, tres, M, N, K, ep);
+        return launch_cfg<BN, EPI, false, LRX_GEMM_CLUSTER>(h, ta, tb, tout, tres, M, N, K, ep);
     }
-    if (p.ares) return launch_cfg<BN, EPI, true, 1>(h, ta, tb, M, N, K, ep);
-    return launch_cfg<BN, EPI, false, 1>(h, ta, tb, M, N, K, ep);
+    if (p.ares) return launch_cfg<BN, EPI, true, 1>(h, ta, tb, tout, tres, M, N, K, ep);
+    return launch_cfg<BN, EPI, false, 1>(h, ta, tb, tout, tres, M, N, K, ep);
 }
 
 // W-operand TMA box rows for a GEMM of this shape (the plan the launcher will pick)
@@ -563,22 +651,26 @@ int gemm_box_rows_w(int num_sms, int M, int N, int K, int epi) {
 }
 
 // epi: 0 bias, 1 bias+GELU, 2 bias+residual+LayerNorm (N must be 384), 3 raw fp32.
-// `tb` must have been built with gemm_box_rows_w(N, epi) rows per box.
-cudaError_t launch_tc_gemm(lrx_handle* h, const CUtensorMap& ta, const CUtensorMap& tb, int M, int N,
-                           int K, int epi, const float* bias, const __half* residual, int ld_res,
-                           const float* gamma, const float* beta, float eps, void* out, int ld_out) {
+// `tb` must have been built with gemm_box_rows_w(...) rows per box; `tout` / `tres` are
+// make_tmap_io_f16 views of the fp16 output / residual (ignored by epi 3 / epi != 2).
+cudaError_t launch_tc_gemm(lrx_handle* h, const CUtensorMap& ta, const CUtensorMap& tb,
+                           const CUtensorMap& tout, const CUtensorMap& tres, int M, int N, int K, int epi,
+                           const float* bias, const float* gamma, const float* beta, float eps,
+                           void* out, int ld_out) {
     if (M <= 0) return cudaSuccess;
     if (K % kBK != 0 || N % 128 != 0 || epi < 0 || epi > 3) return cudaErrorInvalidValue;
+    if (epi != 3 && N > 1536) return cudaErrorInvalidValue;      // bias vector staged whole in smem
     GemmEpi ep;
-    ep.bias = bias; ep.residual = residual; ep.gamma = gamma; ep.beta = beta;
-    ep.out = out; ep.ld_out = ld_out; ep.ld_res = ld_res; ep.M = M; ep.eps = eps;
+    ep.bias = bias; ep.residual = nullptr; ep.gamma = gamma; ep.beta = beta;
+    ep.out = out; ep.ld_out = ld_out; ep.ld_res = 0; ep.M = M; ep.eps = eps;
+    ep.trace = (long long*)h->debug_trace;
     const int bn = gemm_plan(h->num_sms, M, N, K, epi).bn;
     cudaError_t e = cudaErrorInvalidValue;
 #define LRX_GEMM_CASE(BN_, EPI_) \
-    if (bn == BN_ && epi == EPI_) e = launch_one<BN_, EPI_>(h, ta, tb, M, N, K, ep)
+    if (bn == BN_ && epi == EPI_) e = launch_one<BN_, EPI_>(h, ta, tb, tout, tres, M, N, K, ep)
     if (epi == 2) {
         if (N != 384) return cudaErrorInvalidValue;
-        e = launch_one<384, 2>(h, ta, tb, M, N, K, ep);
+        e = launch_one<384, 2>(h, ta, tb, tout, tres, M, N, K, ep);
     }
     LRX_GEMM_CASE(256, 0); LRX_GEMM_CASE(192, 0); LRX_GEMM_CASE(128, 0);
     LRX_GEMM_CASE(256, 1); LRX_GEMM_CASE(192, 1); LRX_GEMM_CASE(128, 1);
@@ -592,13 +684,22 @@ cudaError_t launch_tc_gemm(lrx_handle* h, const CUtensorMap& ta, const CUtensorM
 cudaError_t gemm_f16_adhoc(lrx_handle* h, const void* a, const void* w, int M, int N, int K, int epi,
                            const float* bias, const void* residual, const float* gamma,
                            const float* beta, float eps, void* out) {
-    CUtensorMap ta, tb;
+    CUtensorMap ta, tb, tout, tres;
     cudaError_t e = make_tmap_f16(&ta, a, M, K, K, 128);
     if (e != cudaSuccess) return e;
     e = make_tmap_f16(&tb, w, N, K, K, gemm_box_rows_w(h->num_sms, M, N, K, epi));
     if (e != cudaSuccess) return e;
-    return launch_tc_gemm(h, ta, tb, M, N, K, epi, bias, (const __half*)residual, N, gamma, beta, eps,
-                          out, N);
+    tout = ta;
+    tres = ta;
+    if (epi != 3) {
+        e = make_tmap_io_f16(&tout, out, M, N, N);
+        if (e != cudaSuccess) return e;
+    }
+    if (epi == 2) {
+        e = make_tmap_io_f16(&tres, residual, M, N, N);
+        if (e != cudaSuccess) return e;
+    }
+    return launch_tc_gemm(h, ta, tb, tout, tres, M, N, K, epi, bias, gamma, beta, eps, out, N);
 }
 
 }  // namespace lrx
