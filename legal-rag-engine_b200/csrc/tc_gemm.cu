@@ -65,9 +65,9 @@ struct GemmCfg {
     static constexpr int kStageBytes = (ARES ? 0 : kABytes) + kBBytes;
     static constexpr int kResBytes = ARES ? kAResKB * kABytes : 0;
     // epilogue side: bias (whole vector, N <= 1536) / gamma / beta / LayerNorm partial sums, and one 2 KB staging
-    // tiles (32 rows x 32 halves, SWIZZLE_64B), two per epilogue warp, for the TMA stores / residual loads
+    // tile (32 rows x 32 halves, SWIZZLE_64B) per epilogue warp for the TMA stores / residual loads
     static constexpr int kParamBytes = 1536 * 4 + 2 * 384 * 4 + 2 * 2 * 128 * 4;
-    static constexpr int kIoBytes = kEpiWarps * 2 * 2048 + 2048 /*align*/;   // double-buffered
+    static constexpr int kIoBytes = kEpiWarps * 2048 + 2048 /*align*/;
     static constexpr int kBarBytes = 512;
     static constexpr int kBudget = 224 * 1024 - 1024 - kBarBytes - kParamBytes - kIoBytes;
     static constexpr int kStagesRaw = (kBudget - kResBytes) / kStageBytes;
@@ -338,9 +338,8 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
         }
         const int n_mine = ARES ? ((m_tiles > (int)blockIdx.x) ? (m_tiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x : 0) * n_tiles
                                 : ((total_tiles > (int)blockIdx.x) ? (total_tiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x : 0);
-        unsigned char* tile_io = s_io + warp * 4096;      // this warp's two staging tiles
-        uint32_t io_n = 0;                                // stored tiles so far: buffer = io_n & 1
-        uint32_t res_n = 0;                               // residual chunks so far: buffer = res_n & 1
+        unsigned char* tile_io = s_io + warp * 2048;      // this warp's staging tile
+        uint32_t res_n = 0;                               // residual chunks requested so far (phase)
         for (int u = 0; u < n_mine; ++u) {
             int m_blk, n_blk;
             if (ARES) {
@@ -411,11 +410,9 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
                             v[4 * j4 + 2] = x2; v[4 * j4 + 3] = x3;
                         }
                     }
-                    unsigned char* tb_ = tile_io + (io_n & 1u) * 2048;
-                    ++io_n;
-                    stage_acquire1(lane);                             // the store before last has read it
-                    stage_put_row(tb_, lane, v);
-                    stage_store(&tma_out, n0 + cb + c, row_w, tb_, lane);
+                    stage_acquire(lane);                              // the previous store has read the tile
+                    stage_put_row(tile_io, lane, v);
+                    stage_store(&tma_out, n0 + cb + c, row_w, tile_io, lane);
                     tmem_wait_ld();
                 }
             } else {
@@ -426,29 +423,28 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
                 float sum = 0.f;
                 // residual chunks come in through the warp's staging tile (TMA, coalesced): chunk
                 // ch + 1 is requested as soon as every lane holds chunk ch in registers
-                // (double-buffered: chunk ch + 1 is in flight while chunk ch is consumed)
-                auto res_request = [&](int ch, uint32_t n) {
+                // (chunk ch + 1 is requested as soon as every lane holds chunk ch in registers)
+                auto res_request = [&](int ch) {
                     if (lane == 0) {
-                        mbar_arrive_expect_tx(&r_full[warp * 2 + (n & 1u)], 2048u);
-                        tma_load_2d(tile_io + (n & 1u) * 2048, &tma_res, cb + ch * 32, row_w,
-                                    &r_full[warp * 2 + (n & 1u)]);
+                        mbar_arrive_expect_tx(&r_full[warp], 2048u);
+                        tma_load_2d(tile_io, &tma_res, cb + ch * 32, row_w, &r_full[warp]);
                     }
                 };
-                stage_acquire(lane);                                 // last tile's output stores have read them
-                res_request(0, res_n);
+                stage_acquire(lane);                                 // last tile's output store has read it
+                res_request(0);
                 tmem_ld32(trow, rb[0]);
                 tmem_wait_ld();
 #pragma unroll
                 for (int ch = 0; ch < NCH; ++ch) {
                     uint4 rr[4];
+                    mbar_wait(&r_full[warp], res_n & 1u);
+                    ++res_n;
+                    stage_get_row(tile_io, lane, rr);
+                    __syncwarp();
                     if (ch + 1 < NCH) {
-                        res_request(ch + 1, res_n + 1);
+                        res_request(ch + 1);
                         tmem_ld32(trow + (ch + 1) * 32, rb[(ch + 1) & 1]);
                     }
-                    mbar_wait(&r_full[warp * 2 + (res_n & 1u)], (res_n >> 1) & 1u);
-                    stage_get_row(tile_io + (res_n & 1u) * 2048, lane, rr);
-                    ++res_n;
-                    __syncwarp();
                     uint32_t(&r)[32] = rb[ch & 1];
                     const int c = ch * 32;
                     const __half2* rh = reinterpret_cast<const __half2*>(rr);
@@ -506,11 +502,9 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
                         v[4 * j4 + 2] = (__uint_as_float(r[4 * j4 + 2]) - mean) * rstd * gg.z + be.z;
                         v[4 * j4 + 3] = (__uint_as_float(r[4 * j4 + 3]) - mean) * rstd * gg.w + be.w;
                     }
-                    unsigned char* tb_ = tile_io + (io_n & 1u) * 2048;
-                    ++io_n;
-                    stage_acquire1(lane);
-                    stage_put_row(tb_, lane, v);
-                    stage_store(&tma_out, cb + c, row_w, tb_, lane);
+                    stage_acquire(lane);
+                    stage_put_row(tile_io, lane, v);
+                    stage_store(&tma_out, cb + c, row_w, tile_io, lane);
                     tmem_wait_ld();
                 }
             }
