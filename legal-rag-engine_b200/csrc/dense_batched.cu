@@ -16,12 +16,13 @@
 // was not appended is strictly below the K-th best exact score, so the result is bit-exact; the
 // only failure mode is a candidate list overflow (flag -> caller reruns with stride 1).
 //
-// Kernel shape (one CTA per SM, 192 threads, warp-specialised like tc_gemm.cu):
+// Kernel shape (one CTA per SM, 320 threads, warp-specialised like tc_gemm.cu):
 //   A operand = 128 queries x 384, loaded once by TMA and RESIDENT in shared memory (96 KB);
 //   B operand = 256 chunk rows x 64 per stage, 3-stage TMA ring (SWIZZLE_128B);
 //   tcgen05.mma cta_group::1 kind::f16, UMMA 128 x 256 x 16, fp32 accumulators in TMEM,
 //   DOUBLE-BUFFERED (2 x 256 columns) so the epilogue of tile i overlaps the MMAs of tile i+1;
-//   epilogue thread = query (TMEM lane): tcgen05.ld 32 columns at a time, running max / compare.
+//   8 epilogue warps, thread = (query, column half): pipelined tcgen05.ld of 32 columns, running
+//   max / compare.  CTA pairs (cluster of 2) multicast the chunk tiles to each other.
 // CTA c serves query tile (c % n_mt) and walks chunk tiles (c / n_mt), (c / n_mt) + G, ... so the
 // n_mt CTAs that need the same chunk tile touch it at about the same time (one HBM read, L2 hits).
 //
@@ -43,7 +44,8 @@ constexpr int kDbKB = kDim / kDbK;    // 6 k-blocks
 constexpr int kDbStages = 3;
 constexpr int kDbABytes = kDbQ * kDbK * 2;    // 16 KB per k-block of the query tile
 constexpr int kDbBBytes = kDbN * kDbK * 2;    // 32 KB per stage
-constexpr int kDbThreads = 192;
+constexpr int kDbEpiWarps = 8;          // two per TMEM lane quarter: column halves of a tile
+constexpr int kDbThreads = (kDbEpiWarps + 2) * 32;
 constexpr size_t kDbSmem = (size_t)kDbKB * kDbABytes + (size_t)kDbStages * kDbBBytes + 1024 + 256;
 constexpr int kDbCap = 512;           // candidates kept per query
 // |tensor-core fp32 score - exact| for unit fp16 vectors: 384 exact products accumulated in
@@ -63,10 +65,14 @@ struct DbParams {
     uint64_t* cand;        // [n_mt*128][kDbCap] keys (f32 image << 32 | ~row)
 };
 
-template <int PASS>
+// CS: cluster size.  The CS CTAs of a cluster serve CS different query tiles and walk the SAME chunk
+// tiles: each loads 1/CS of a tile's rows and multicasts them to all (one L2 read per cluster).
+template <int PASS, int CS>
 __global__ void __launch_bounds__(kDbThreads, 1)
 dense_tc_kernel(const __grid_constant__ CUtensorMap tma_q, const __grid_constant__ CUtensorMap tma_x,
                 const DbParams P) {
+    constexpr uint16_t kMask = (uint16_t)((1u << CS) - 1u);
+    const uint32_t crank = (CS > 1) ? cluster_ctarank() : 0u;
     extern __shared__ unsigned char db_raw[];
     unsigned char* base = reinterpret_cast<unsigned char*>(
         (reinterpret_cast<uintptr_t>(db_raw) + 1023) & ~(uintptr_t)1023);
@@ -88,30 +94,32 @@ dense_tc_kernel(const __grid_constant__ CUtensorMap tma_q, const __grid_constant
     const int n_units = (P.n_tiles + step - 1) / step;
     const int my_units = (n_units > group) ? (n_units - group + n_groups - 1) / n_groups : 0;
 
-    if (warp == 4 && lane == 0) {
+    constexpr int kProducerWarp = kDbEpiWarps, kMmaWarp = kDbEpiWarps + 1;
+    if (warp == kProducerWarp && lane == 0) {
         tma_prefetch_desc(&tma_q);
         tma_prefetch_desc(&tma_x);
         for (int s = 0; s < kDbStages; ++s) {
             mbar_init(&full[s], 1);
-            mbar_init(&empty[s], 1);
+            mbar_init(&empty[s], CS);
         }
         mbar_init(a_full, 1);
         for (int b = 0; b < 2; ++b) {
             mbar_init(&t_full[b], 1);
-            mbar_init(&t_empty[b], 4);
+            mbar_init(&t_empty[b], kDbEpiWarps);
         }
         fence_barrier_init();
     }
-    if (warp == 5) {
+    if (warp == kMmaWarp) {
         tmem_alloc(tmem_slot, 512);
         tmem_relinquish();
     }
     tc_fence_before();
     __syncthreads();
+    if (CS > 1) cluster_sync_all();
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
 
-    if (warp == 4) {
+    if (warp == kProducerWarp) {
         if (lane == 0) {
             // the query tile, once
             mbar_arrive_expect_tx(a_full, (uint32_t)(kDbKB * kDbABytes));
@@ -125,11 +133,15 @@ dense_tc_kernel(const __grid_constant__ CUtensorMap tma_q, const __grid_constant
                     const uint32_t ph = (it / kDbStages) & 1u;
                     mbar_wait(&empty[s], ph ^ 1u);
                     mbar_arrive_expect_tx(&full[s], (uint32_t)kDbBBytes);
-                    tma_load_2d(sB + s * kDbBBytes, &tma_x, kb * kDbK, tile * kDbN, &full[s]);
+                    if (CS > 1)
+                        tma_load_2d_mc(sB + s * kDbBBytes + crank * (kDbBBytes / CS), &tma_x, kb * kDbK,
+                                       tile * kDbN + (int)crank * (kDbN / CS), &full[s], kMask);
+                    else
+                        tma_load_2d(sB + s * kDbBBytes, &tma_x, kb * kDbK, tile * kDbN, &full[s]);
                 }
             }
         }
-    } else if (warp == 5) {
+    } else if (warp == kMmaWarp) {
         if (lane == 0) {
             constexpr uint32_t idesc = umma_idesc_f16(kDbQ, kDbN);
             mbar_wait(a_full, 0);
@@ -150,49 +162,62 @@ dense_tc_kernel(const __grid_constant__ CUtensorMap tma_q, const __grid_constant
                     for (int k = 0; k < kDbK / 16; ++k)
                         umma_f16(tmem_base + buf * kDbN, umma_desc_sw128(a_addr + k * 32),
                                  umma_desc_sw128(b_addr + k * 32), idesc, (kb > 0 || k > 0) ? 1u : 0u);
-                    umma_commit(&empty[s]);
+                    if (CS > 1) umma_commit_mc(&empty[s], kMask);
+                    else umma_commit(&empty[s]);
                 }
                 umma_commit(&t_full[buf]);
             }
         }
     } else {
-        // ===== epilogue: thread = query
-        const int ql = warp * 32 + lane;
+        // ===== epilogue: 8 warps; thread = query (TMEM lane 32*(warp&3)+lane), column half (warp>>2)
+        const int quarter = warp & 3, half = warp >> 2;
+        constexpr int HB = kDbN / 2, NCH = HB / 32;
+        const int ql = quarter * 32 + lane;
         const int q = m_tile * kDbQ + ql;
         const bool q_ok = q < P.B;
-        const uint32_t trow = tmem_base + ((uint32_t)(warp * 32) << 16);
+        const uint32_t trow = tmem_base + ((uint32_t)(quarter * 32) << 16) + half * HB;
         float thr = 0.f;
         if (PASS == 2) thr = q_ok ? P.thr[q] : FLT_MAX;
-        uint32_t r[32];
+        uint32_t rb[2][32];
         for (int u = 0; u < my_units; ++u) {
             const int buf = u & 1;
             const uint32_t use = (uint32_t)(u >> 1);
             const int tile = (group + u * n_groups) * step;
-            const int64_t row0 = (int64_t)tile * kDbN;
-            const int valid = (int)min((int64_t)kDbN, P.n_rows - row0);
+            const int64_t row0 = (int64_t)tile * kDbN + half * HB;
+            const int valid = (int)max((int64_t)0, min((int64_t)HB, P.n_rows - row0));
             mbar_wait(&t_full[buf], use & 1u);
             tc_fence_after();
-            for (int c = 0; c < kDbN; c += 32) {
-                tmem_ld32(trow + buf * kDbN + c, r);
-                tmem_wait_ld();
+            tmem_ld32(trow + buf * kDbN, rb[0]);
+            tmem_wait_ld();
+#pragma unroll
+            for (int ch = 0; ch < NCH; ++ch) {
+                if (ch + 1 < NCH) tmem_ld32(trow + buf * kDbN + (ch + 1) * 32, rb[(ch + 1) & 1]);
+                const uint32_t(&r)[32] = rb[ch & 1];
+                const int c = ch * 32;
                 if (PASS == 1) {
                     // maximum of every 32-row chunk: 8 samples per tile for the threshold
                     float mx = -FLT_MAX;
 #pragma unroll
                     for (int j = 0; j < 32; ++j)
                         if (c + j < valid) mx = fmaxf(mx, __uint_as_float(r[j]));
-                    P.tilemax[(size_t)q * P.n_samp + (size_t)(tile / step) * (kDbN / 32) + (c >> 5)] = mx;
+                    P.tilemax[(size_t)q * P.n_samp + (size_t)(tile / step) * (kDbN / 32) + half * NCH + ch] = mx;
                 } else {
+                    float best = -FLT_MAX;
 #pragma unroll
-                    for (int j = 0; j < 32; ++j) {
-                        const float sc = __uint_as_float(r[j]);
-                        if (sc >= thr && c + j < valid) {
-                            const int slot = atomicAdd(P.cnt + q, 1);
-                            if (slot < kDbCap)
-                                P.cand[(size_t)q * kDbCap + slot] = make_key64(sc, (uint32_t)(row0 + c + j));
+                    for (int j = 0; j < 32; ++j) best = fmaxf(best, (c + j < valid) ? __uint_as_float(r[j]) : -FLT_MAX);
+                    if (best >= thr) {                       // rare: some score of the chunk qualifies
+#pragma unroll
+                        for (int j = 0; j < 32; ++j) {
+                            const float sc = __uint_as_float(r[j]);
+                            if (sc >= thr && c + j < valid) {
+                                const int slot = atomicAdd(P.cnt + q, 1);
+                                if (slot < kDbCap)
+                                    P.cand[(size_t)q * kDbCap + slot] = make_key64(sc, (uint32_t)(row0 + c + j));
+                            }
                         }
                     }
                 }
+                tmem_wait_ld();
             }
             tc_fence_before();
             __syncwarp();
@@ -201,7 +226,8 @@ dense_tc_kernel(const __grid_constant__ CUtensorMap tma_q, const __grid_constant
     }
     tc_fence_before();
     __syncthreads();
-    if (warp == 5) {
+    if (CS > 1) cluster_sync_all();
+    if (warp == kMmaWarp) {
         tc_fence_after();
         tmem_dealloc(tmem_base, 512);
     }
@@ -299,17 +325,23 @@ cudaError_t launch_dense_topk_batched(lrx_handle* h, const void* q, int B, int K
     static bool attr = false;
     cudaError_t e;
     if (!attr) {
-        e = cudaFuncSetAttribute(dense_tc_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kDbSmem);
-        if (e != cudaSuccess) return e;
-        e = cudaFuncSetAttribute(dense_tc_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kDbSmem);
-        if (e != cudaSuccess) return e;
+        const void* ks[] = {(const void*)dense_tc_kernel<1, 1>, (const void*)dense_tc_kernel<2, 1>,
+                            (const void*)dense_tc_kernel<1, 2>, (const void*)dense_tc_kernel<2, 2>,
+                            (const void*)dense_tc_kernel<1, 4>, (const void*)dense_tc_kernel<2, 4>};
+        for (const void* k : ks) {
+            e = cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kDbSmem);
+            if (e != cudaSuccess) return e;
+        }
         e = cudaFuncSetAttribute(tilemax_kth_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 65536);
         if (e != cudaSuccess) return e;
         attr = true;
     }
     const int64_t n = h->n_local;
     const int n_tiles = (int)((n + kDbN - 1) / kDbN);
-    const int n_mt = (B + kDbQ - 1) / kDbQ;
+    int n_mt = (B + kDbQ - 1) / kDbQ;
+    // cluster of query tiles sharing every chunk tile (padded query tiles are zero rows)
+    const int cs = (n_mt >= 2) ? 2 : 1;
+    n_mt = (n_mt + cs - 1) / cs * cs;
     const int Bp = n_mt * kDbQ;
     if (stride < 1) stride = dense_batched_max_stride(n, K);
     constexpr int kChunks = kDbN / 32;
@@ -343,17 +375,36 @@ cudaError_t launch_dense_topk_batched(lrx_handle* h, const void* q, int B, int K
     CUtensorMap tq, tx;
     e = make_tmap_f16(&tq, q, B, kDim, kDim, kDbQ);
     if (e != cudaSuccess) return e;
-    e = make_tmap_f16(&tx, h->x, n, kDim, kDim, kDbN);
+    e = make_tmap_f16(&tx, h->x, n, kDim, kDim, kDbN / cs);
     if (e != cudaSuccess) return e;
     DbParams P;
     P.B = B; P.n_rows = n; P.n_tiles = n_tiles; P.n_mt = n_mt; P.stride = stride;
     P.tilemax = (float*)(W + o_tm); P.n_samp = n_samp; P.thr = (const float*)(W + o_thr);
     P.cnt = (int*)(W + o_cnt); P.cand = (uint64_t*)(W + o_cand);
+    auto launch = [&](int pass) -> cudaError_t {
+        cudaLaunchConfig_t cfg = {};
+        cfg.gridDim = dim3(grid);
+        cfg.blockDim = dim3(kDbThreads);
+        cfg.dynamicSmemBytes = kDbSmem;
+        cfg.stream = h->stream;
+        cudaLaunchAttribute at[1];
+        at[0].id = cudaLaunchAttributeClusterDimension;
+        at[0].val.clusterDim.x = cs;
+        at[0].val.clusterDim.y = 1;
+        at[0].val.clusterDim.z = 1;
+        cfg.attrs = at;
+        cfg.numAttrs = 1;
+        if (cs == 4) return pass == 1 ? cudaLaunchKernelEx(&cfg, dense_tc_kernel<1, 4>, tq, tx, P)
+                                      : cudaLaunchKernelEx(&cfg, dense_tc_kernel<2, 4>, tq, tx, P);
+        if (cs == 2) return pass == 1 ? cudaLaunchKernelEx(&cfg, dense_tc_kernel<1, 2>, tq, tx, P)
+                                      : cudaLaunchKernelEx(&cfg, dense_tc_kernel<2, 2>, tq, tx, P);
+        return pass == 1 ? cudaLaunchKernelEx(&cfg, dense_tc_kernel<1, 1>, tq, tx, P)
+                         : cudaLaunchKernelEx(&cfg, dense_tc_kernel<2, 1>, tq, tx, P);
+    };
     prof_begin(h, 0);
-    dense_tc_kernel<1><<<grid, kDbThreads, kDbSmem, h->stream>>>(tq, tx, P);
+    e = launch(1);
     prof_end(h, 0);
     h->launches++;
-    e = cudaGetLastError();
     if (e != cudaSuccess) return e;
     tilemax_kth_kernel<<<Bp, 256, (size_t)next_pow2(n_samp > 2 ? n_samp : 2) * sizeof(uint32_t), h->stream>>>(
         P.tilemax, n_samp, K, 2.0f * kTcEps, (float*)(W + o_thr), P.cnt);
@@ -361,10 +412,9 @@ cudaError_t launch_dense_topk_batched(lrx_handle* h, const void* q, int B, int K
     e = cudaGetLastError();
     if (e != cudaSuccess) return e;
     prof_begin(h, 0);
-    dense_tc_kernel<2><<<grid, kDbThreads, kDbSmem, h->stream>>>(tq, tx, P);
+    e = launch(2);
     prof_end(h, 0);
     h->launches++;
-    e = cudaGetLastError();
     if (e != cudaSuccess) return e;
     dense_rescore_list_kernel<<<B, kRlThreads, 0, h->stream>>>(
         (const unsigned char*)h->x, h->id_base, (const __half*)q, P.cand, P.cnt, K, exact, D, I, flags);
