@@ -43,6 +43,7 @@ def parse():
     ap.add_argument("--rows", type=int, default=10_000_000)
     ap.add_argument("--fusion", default="rrf", choices=["rrf", "linear"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-stages", action="store_true", help="skip the K1 / K2b stage measurements")
     ap.add_argument("--cpu-sample-rows", type=int, default=1_000_000)
     return ap.parse_args()
 
@@ -197,6 +198,80 @@ def workload_config(args):
             "l2": "inputs larger than L2 (>= 0.96 GB matrix shard per GPU streamed every step)"}
 
 
+# --------------------------------------------------- stage measurements (K1, K2b)
+def measure_stages(dev, n_local, peaks):
+    """Tensor-core stages beside the headline (rank 0, N = 1): the encoder at config C2
+    (B = 1024, S = 128, seeded random weights) and batched dense scoring at B = 1024 over the
+    resident shard (config C3's batch).  Roofline = tensor pipe, against the measured bf16 peak."""
+    import torch
+    from legal_rag_engine_b200 import synth
+    from legal_rag_engine_b200.encoder import SentenceEncoder
+    peak_tf = float(peaks.get("bf16_tflops", 1590.0))
+    out = {"peak_tflops": peak_tf,
+           "peak_source": "measured (MEASURED_PEAKS.json bf16_tflops)" if "bf16_tflops" in peaks else "fallback 1590"}
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+
+    enc = SentenceEncoder(dev, state_dict=synth.bert_state_dict(42, 0.02))
+    for S in (128, 256):
+        B = 1024
+        ids, lens = synth.token_batch(B, S, seed=1, full=True)
+        d_ids, d_lens = torch.from_numpy(ids).to(dev.device), torch.from_numpy(lens).to(dev.device)
+        for _ in range(3):
+            enc.encode_ids_device(d_ids, d_lens)
+        torch.cuda.synchronize()
+        ev0.record()
+        for _ in range(5):
+            enc.encode_ids_device(d_ids, d_lens)
+        ev1.record()
+        torch.cuda.synchronize()
+        ms = ev0.elapsed_time(ev1) / 5
+        flop = B * S * (6 * (2 * 384 * 1152 + 2 * 384 * 384 + 2 * 2 * 384 * 1536) + 6 * 4 * S * 384)
+        out[f"encoder_S{S}"] = {"batch": B, "seq_per_s": B / ms * 1e3, "ms": ms, "tflops": flop / ms / 1e9,
+                                "frac": flop / ms / 1e9 / peak_tf, "bound": "tensor",
+                                "flop_per_seq": flop / B}
+
+    B, K = 1024, 2 * K_TOP
+    q = torch.from_numpy(synth.host_queries(B, seed=4321)).to(dev.device)
+    for _ in range(2):
+        res = dev.dense_topk_batched(q, K)
+    torch.cuda.synchronize()
+    overflow = int(res[3].sum().item())
+    dev.profile(True)
+    dev.profile_read(0)
+    ev0.record()
+    for _ in range(3):
+        dev.dense_topk_batched(q, K)
+    ev1.record()
+    torch.cuda.synchronize()
+    ms = ev0.elapsed_time(ev1) / 3
+    kms, kn = dev.profile_read(0)
+    dev.profile(False)
+    tiles = (n_local + 255) // 256
+    stride = max(1, min(8, tiles * 8 // (16 * K)))          # mirrors launch_dense_topk_batched
+    if (tiles + stride - 1) // stride * 8 > 16384:
+        stride = (tiles * 8 + 16383) // 16384
+    flop = 2.0 * B * 384 * n_local * (1 + 1.0 / stride)
+    out["dense_batched"] = {"batch": B, "rows": n_local, "K": K, "queries_per_s": B / ms * 1e3, "ms": ms,
+                            "gemm_ms": kms / 3, "tflops": flop / (kms / 3) / 1e9,
+                            "frac": flop / (kms / 3) / 1e9 / peak_tf, "bound": "tensor",
+                            "candidate_overflow_queries": overflow}
+    return out
+
+
+def scan_traffic_from_profile(n_local):
+    """dram bytes of dense_scan_kernel from the committed ncu --set full capture (profiles/),
+    scaled per row: the kernel reads each row exactly once, so bytes/row is size independent."""
+    try:
+        prof = json.loads((ROOT / "profiles" / "r1_dense_scan_v1_full.json").read_text())
+        for l in prof["launches"]:
+            if "dense_scan_kernel" in l["kernel"] and "traffic_bytes_per_launch" in l:
+                rows = 10_000_000                       # the capture ran the 10 M-row shard
+                return l["traffic_bytes_per_launch"] / rows * n_local
+    except Exception:
+        pass
+    return None
+
+
 # ------------------------------------------------------------------- ours
 def run_ours(args):
     import torch
@@ -348,7 +423,7 @@ def run_ours(args):
             "value": qps, "unit": "queries/s", "n_gpus": world, "steps": args.steps,
             "warmup": max(args.warmup, 3), "ms_per_step": ms / args.steps,
             "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
-            "dtype": "fp16 data, fp32 scan + exact f64 re-score / f64 BM25", "data": "synthetic",
+            "dtype": "f16 matrix, f32 scan + exact f64 re-score; f64 BM25", "data": "synthetic",
             "config": dict(workload_config(args), parallelism=f"row-shard x{world}",
                            rows_per_gpu=n_local, nnz_per_gpu=nnz_local, build_s=round(t_build, 1)),
             "e2e": {"value": e2e_steps / (e2e_ms * 1e-3), "unit": "queries/s",
@@ -358,13 +433,21 @@ def run_ours(args):
             "clocks": clk,
             "roofline": {"bound": "hbm", "kernel": "dense_scan_kernel<4>", "achieved": scan_gbs,
                          "peak": peak, "unit": "GB/s", "frac": scan_gbs / peak, "peak_source": peak_src,
-                         "frac_of_8TBs_nominal": scan_gbs / 8000.0, "traffic": None,
+                         "frac_of_8TBs_nominal": scan_gbs / 8000.0, "traffic": scan_traffic_from_profile(n_local),
+                         "traffic_source": "ncu --set full dram__bytes_read+write per launch at 10 M rows "
+                                           "(profiles/r1_dense_scan_v1_full.json), scaled by rows",
                          "bytes_per_launch": scan_bytes, "ms_per_launch": scan_ms / max(scan_n, 1),
                          "launches_timed": int(scan_n),
                          "share_of_step": (scan_ms / max(scan_n, 1)) * (scan_n / args.steps) / (ms / args.steps)},
-            "bm25_kernel": {"achieved": bm_gbs, "unit": "GB/s", "frac": bm_gbs / peak,
+            "bm25_kernel": {"kernel": "bm25_scan_kernel", "bound": "hbm (issue-bound as measured)",
+                            "achieved": bm_gbs, "unit": "GB/s", "frac": bm_gbs / peak,
                             "bytes_per_launch": bm_bytes, "ms_per_launch": bm_ms / max(bm_n, 1)},
         }
+        if world == 1 and not args.no_stages:
+            try:
+                line["stages"] = measure_stages(dev, n_local, peaks)
+            except Exception as e:                      # a stage problem must not void the headline
+                line["stages"] = {"error": repr(e)}
         if world == 1 and not args.no_cpu_baseline:
             threads = os.cpu_count() or 1
             sec, desc = cpu_reference_step(args.cpu_sample_rows, args.rows, threads, steps=1)

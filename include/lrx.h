@@ -154,7 +154,7 @@ int lrx_dense_topk_ex(lrx_handle* h, const void* dev_q_fp16, int32_t B, int32_t 
 /* K2b: the same search for LARGE batches (B up to 4096; FAISS's BLAS regime, nq >= 20) on the
  * tensor cores: two tcgen05 GEMM passes (tile maxima -> per-query threshold; candidates above
  * it) + exact float64 re-score.  Same outputs and ordering as lrx_dense_topk.  stride: pass 1
- * samples every stride-th 256-row tile (0 = automatic).  dev_flags[b] = 1: more than 512
+ * samples every stride-th 256-row tile (0 = automatic).  dev_flags[b] = 1: more than 1024
  * candidates survived for query b -- rerun with stride 1. */
 int lrx_dense_topk_batched(lrx_handle* h, const void* dev_q_fp16, int32_t B, int32_t K, int32_t stride,
                            double* dev_exact, float* dev_D, int64_t* dev_I, int32_t* dev_flags);

@@ -47,7 +47,7 @@ constexpr int kDbBBytes = kDbN * kDbK * 2;    // 32 KB per stage
 constexpr int kDbEpiWarps = 8;          // two per TMEM lane quarter: column halves of a tile
 constexpr int kDbThreads = (kDbEpiWarps + 2) * 32;
 constexpr size_t kDbSmem = (size_t)kDbKB * kDbABytes + (size_t)kDbStages * kDbBBytes + 1024 + 256;
-constexpr int kDbCap = 512;           // candidates kept per query
+constexpr int kDbCap = 1024;          // candidates kept per query
 // |tensor-core fp32 score - exact| for unit fp16 vectors: 384 exact products accumulated in
 // fp32 (possibly truncating) in 24 instructions -> well below 1e-5
 constexpr float kTcEps = 1e-5f;

@@ -34,7 +34,10 @@ for B in a.B:
     kms, kn = dev.profile_read(0)
     dev.profile(False)
     Bp = (B + 127) // 128 * 128
-    stride = max(1, min(8, ((a.rows + 255) // 256) * 8 // (16 * a.K)))
+    tiles = (a.rows + 255) // 256
+    stride = max(1, min(8, tiles * 8 // (16 * a.K)))
+    if (tiles + stride - 1) // stride * 8 > 16384:
+        stride = (tiles * 8 + 16383) // 16384
     flop = 2.0 * Bp * 384 * a.rows * (1 + 1.0 / stride)
     print(json.dumps({"rows": a.rows, "B": B, "K": a.K, "call_ms": round(ms, 4), "queries_per_s": round(B / ms * 1e3),
                       "gemm_kernels_ms": round(kms / a.iters, 4), "tflops_gemm": round(flop / (kms / a.iters) / 1e9, 1),
