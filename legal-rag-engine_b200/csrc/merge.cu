@@ -15,11 +15,11 @@ constexpr int kMergeCap = 4096;
 
 template <typename KeyT>
 __device__ __forceinline__ void sort_desc_any(KeyT* buf, int n_valid, int tid, int warp, int lane) {
-    // pads to a power of two; warp sort up to 1024 entries, block sort above.  Block-uniform.
+    // pads to a power of two; warp sort up to 128 entries, block sort above.  Block-uniform.
     const int p2 = max(32, next_pow2(n_valid));
     for (int i = n_valid + tid; i < p2; i += kMergeThreads) buf[i] = 0;
     __syncthreads();
-    if (p2 <= 1024) {
+    if (p2 <= 128) {                       // tiny: one warp, no block barriers
         if (warp == 0) warp_bitonic_sort_desc<KeyT>(buf, p2, lane);
         __syncthreads();
     } else {

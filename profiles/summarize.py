@@ -16,7 +16,9 @@ KEEP = [
     "sm__pipe_tensor_cycles_active.avg.pct_of_peak_sustained_active",
     "sm__pipe_tensor_subpipe_hmma_cycles_active.avg.pct_of_peak_sustained_active",
     "sm__inst_executed_pipe_tensor.sum", "sm__inst_executed_pipe_uniform.sum",
-    "launch__registers_per_thread", "launch__occupancy_limit_shared_mem",
+    "launch__registers_per_thread", "launch__occupancy_limit_shared_mem", "launch__cluster_dim_x",
+    "sm__inst_executed_pipe_tc.sum", "sm__inst_executed_pipe_tma.sum", "sm__inst_executed_pipe_tmem.sum",
+    "smsp__issue_active.avg.pct_of_peak_sustained_active",
     "launch__occupancy_limit_registers", "launch__grid_size", "launch__block_size",
     "smsp__inst_executed.sum", "lts__t_sector_hit_rate.pct",
     "l1tex__data_bank_conflicts_pipe_lsu_mem_shared.sum",
@@ -27,13 +29,18 @@ UNIT = {"Gbyte": 1e9, "Mbyte": 1e6, "Kbyte": 1e3, "byte": 1.0, "Tbyte": 1e12,
         "ms": 1e-3, "us": 1e-6, "ns": 1e-9, "s": 1.0}
 
 
-def main(rep, out):
+def main(rep, out, unique=False):
     raw = subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], capture_output=True,
                          text=True, check=True).stdout
     rows = list(csv.reader(io.StringIO(raw)))
     hdr, units = rows[0], rows[1]
     res = []
+    seen = set()
     for r in rows[2:]:
+        if unique:
+            if r[hdr.index("Kernel Name")] in seen:
+                continue
+            seen.add(r[hdr.index("Kernel Name")])
         d = {"kernel": r[hdr.index("Kernel Name")]}
         for k in KEEP:
             if k in hdr:
@@ -57,4 +64,4 @@ def main(rep, out):
 
 
 if __name__ == "__main__":
-    main(sys.argv[1], sys.argv[2])
+    main(sys.argv[1], sys.argv[2], unique="--unique" in sys.argv)
