@@ -40,20 +40,32 @@ struct ScanSmem {
 
 template <int NQ>
 __device__ __forceinline__ void scan_prune(uint64_t* keys, int* count, uint32_t* tau, int width,
-                                           int tid) {
-    // pad unused slots with the empty key, sort all NQ buffers at once, keep `width`
+                                           int tid, unsigned int* tau_g) {
+    // sort only as many slots as are in use (power of two >= the fullest buffer, >= width):
+    // pad the unused ones with the empty key, sort all NQ buffers at once, keep `width`
+    int nmax = width;
+#pragma unroll
+    for (int q = 0; q < NQ; ++q) nmax = max(nmax, count[q]);
+    const int n2 = min(kCap, next_pow2(nmax));
 #pragma unroll
     for (int q = 0; q < NQ; ++q) {
         const int n = count[q];
-        for (int i = tid; i < kCap; i += kScanThreads)
+        for (int i = tid; i < n2; i += kScanThreads)
             if (i >= n) keys[q * kCap + i] = 0ull;
     }
     __syncthreads();
-    block_bitonic_sort_desc<uint64_t>(keys, kCap, NQ, kCap, tid, kScanThreads);
+    block_bitonic_sort_desc<uint64_t>(keys, n2, NQ, kCap, tid, kScanThreads);
     if (tid < NQ) {
         const int c = min(count[tid], width);
         count[tid] = c;
-        if (c == width) tau[tid] = (uint32_t)(keys[tid * kCap + width - 1] >> 32);
+        if (c == width) {
+            // `width` rows of this CTA reach this score: no row below it, anywhere, can be among
+            // the best `width` -- share it with every CTA of the grid (threshold warm-up once
+            // per grid instead of once per CTA)
+            const uint32_t t = max(tau[tid], (uint32_t)(keys[tid * kCap + width - 1] >> 32));
+            tau[tid] = t;
+            atomicMax(tau_g + tid, t);
+        }
     }
     __syncthreads();
 }
@@ -62,7 +74,8 @@ template <int NQ>
 __global__ void __launch_bounds__(kScanThreads, 1)
 dense_scan_kernel(const unsigned char* __restrict__ x, int64_t n_rows,
                   const __half* __restrict__ q, int n_q, int width,
-                  uint64_t* __restrict__ part /* [grid][NQ][width] */) {
+                  uint64_t* __restrict__ part /* [grid][NQ][width] */,
+                  unsigned int* __restrict__ tau_g /* [4] shared thresholds, zero at launch */) {
     extern __shared__ __align__(128) unsigned char smem_raw[];
     ScanSmem& sm = *reinterpret_cast<ScanSmem*>(smem_raw);
     uint64_t* keys = sm.keys;
@@ -187,12 +200,18 @@ dense_scan_kernel(const unsigned char* __restrict__ x, int64_t n_rows,
         for (int qi = 0; qi < NQ; ++qi) need |= (sm.count[qi] > kCap - kTileRows);
         const int any = __syncthreads_or(need ? 1 : 0);
         if (tid == 0 && it + kStages < my_tiles) issue(it + kStages, s);
-        if (any) scan_prune<NQ>(keys, sm.count, sm.tau, width, tid);
+        if (any) scan_prune<NQ>(keys, sm.count, sm.tau, width, tid, tau_g);
+        else if (tid < NQ) {
+            // pick up thresholds published by other CTAs (read by the next tile's tests: the
+            // barrier of the next iteration orders it; a stale value is only conservative)
+            const uint32_t t = *(volatile unsigned int*)(tau_g + tid);
+            if (t > sm.tau[tid]) sm.tau[tid] = t;
+        }
     }
 
     // ---- final: sorted per-CTA lists out
     __syncthreads();
-    scan_prune<NQ>(keys, sm.count, sm.tau, width, tid);
+    scan_prune<NQ>(keys, sm.count, sm.tau, width, tid, tau_g);
     for (int i = tid; i < NQ * width; i += kScanThreads) {
         const int qi = i / width;
         const int j = i - qi * width;
@@ -355,9 +374,13 @@ static cudaError_t launch_scan(lrx_handle* h, const __half* q, int n_q, int widt
         if (e != cudaSuccess) return e;
         attr = true;
     }
+    // shared thresholds live behind the per-CTA lists in the same workspace
+    unsigned int* tau_g = reinterpret_cast<unsigned int*>(part + (size_t)grid * 4 * width);
+    cudaError_t e0 = cudaMemsetAsync(tau_g, 0, 4 * sizeof(unsigned int), h->stream);
+    if (e0 != cudaSuccess) return e0;
     prof_begin(h, 0);
     dense_scan_kernel<NQ><<<grid, kScanThreads, smem, h->stream>>>(
-        (const unsigned char*)h->x, h->n_local, q, n_q, width, part);
+        (const unsigned char*)h->x, h->n_local, q, n_q, width, part, tau_g);
     prof_end(h, 0);
     h->launches++;
     return cudaGetLastError();
@@ -375,7 +398,7 @@ cudaError_t launch_dense_topk(lrx_handle* h, const void* qv, int B, int K, int w
     cudaError_t e;
     // per-CTA lists for up to 4 queries per pass, merged lists for all B
     e = ensure_ws(&h->ws_dense_part, &h->ws_dense_part_bytes,
-                  (size_t)grid * 4 * width * sizeof(uint64_t));
+                  (size_t)grid * 4 * width * sizeof(uint64_t) + 64);
     if (e != cudaSuccess) return e;
     e = ensure_ws(&h->ws_dense_merged, &h->ws_dense_merged_bytes,
                   (size_t)B * width * sizeof(uint64_t));
