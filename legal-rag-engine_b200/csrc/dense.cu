@@ -75,7 +75,10 @@ __global__ void __launch_bounds__(kScanThreads, 1)
 dense_scan_kernel(const unsigned char* __restrict__ x, int64_t n_rows,
                   const __half* __restrict__ q, int n_q, int width,
                   uint64_t* __restrict__ part /* [grid][NQ][width] */,
-                  unsigned int* __restrict__ tau_g /* [4] shared thresholds, zero at launch */) {
+                  unsigned int* __restrict__ tau_g /* [4] shared thresholds, zero at launch */,
+                  long long* __restrict__ trace /* optional clock64 stamps of CTA 0, or NULL */) {
+#define SCAN_TRACE(slot) do { if (trace != nullptr && blockIdx.x == 0 && threadIdx.x == 0) trace[(slot)] = clock64(); } while (0)
+    SCAN_TRACE(0);
     extern __shared__ __align__(128) unsigned char smem_raw[];
     ScanSmem& sm = *reinterpret_cast<ScanSmem*>(smem_raw);
     uint64_t* keys = sm.keys;
@@ -128,7 +131,9 @@ dense_scan_kernel(const unsigned char* __restrict__ x, int64_t n_rows,
         }
     }
 
+    SCAN_TRACE(1);
     for (int64_t it = 0; it < my_tiles; ++it) {
+        if (it < 20 || (it & 15) == 0) SCAN_TRACE(8 + (it < 20 ? (int)it : 20 + (int)(it >> 4)));
         const int s = (int)(it % kStages);
         const uint32_t parity = (uint32_t)((it / kStages) & 1);
         const int64_t tile = (int64_t)blockIdx.x + it * gridDim.x;
@@ -211,6 +216,7 @@ dense_scan_kernel(const unsigned char* __restrict__ x, int64_t n_rows,
 
     // ---- final: sorted per-CTA lists out
     __syncthreads();
+    SCAN_TRACE(2);
     scan_prune<NQ>(keys, sm.count, sm.tau, width, tid, tau_g);
     for (int i = tid; i < NQ * width; i += kScanThreads) {
         const int qi = i / width;
@@ -218,6 +224,8 @@ dense_scan_kernel(const unsigned char* __restrict__ x, int64_t n_rows,
         const uint64_t k = (j < sm.count[qi]) ? keys[qi * kCap + j] : 0ull;
         part[((size_t)blockIdx.x * NQ + qi) * width + j] = k;
     }
+    SCAN_TRACE(3);
+#undef SCAN_TRACE
 }
 
 // merge.cu
@@ -380,7 +388,7 @@ static cudaError_t launch_scan(lrx_handle* h, const __half* q, int n_q, int widt
     if (e0 != cudaSuccess) return e0;
     prof_begin(h, 0);
     dense_scan_kernel<NQ><<<grid, kScanThreads, smem, h->stream>>>(
-        (const unsigned char*)h->x, h->n_local, q, n_q, width, part, tau_g);
+        (const unsigned char*)h->x, h->n_local, q, n_q, width, part, tau_g, (long long*)h->debug_trace);
     prof_end(h, 0);
     h->launches++;
     return cudaGetLastError();
