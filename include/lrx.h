@@ -224,6 +224,12 @@ int lrx_search_text_host(lrx_handle* h, const int32_t* host_tok_ids, const int32
  * tensor-core GEMM launch writes clock64() stamps of its pipeline events there. */
 int lrx_debug_set_trace(lrx_handle* h, void* dev_int64_128);
 
+/* Test hook for K3: the scan divides with the branch-free fast path of the float64 division
+ * (same FMA sequence as the compiler's, without the exponent-range test); this counts the
+ * (tf, len) pairs in [0,n_tf) x [0,n_len) whose BM25 factor differs from the IEEE division. */
+int lrx_debug_bm25_divcheck(lrx_handle* h, double avgdl, double k1, double b, int32_t n_tf,
+                            int32_t n_len, uint64_t* host_mismatches);
+
 /* Number of kernels launched by this handle since lrx_open (bench.py's gpu_launches). */
 int64_t lrx_launch_count(const lrx_handle* h);
 

@@ -145,6 +145,19 @@ int lrx_debug_set_trace(lrx_handle* h, void* dev_int64_128) {
     return LRX_OK;
 }
 
+int lrx_debug_bm25_divcheck(lrx_handle* h, double avgdl, double k1, double b, int32_t n_tf,
+                            int32_t n_len, uint64_t* host_mismatches) {
+    if (h == nullptr) return fail(nullptr, LRX_E_ARG, "lrx_debug_bm25_divcheck: null handle");
+    if (host_mismatches == nullptr || n_tf <= 0 || n_len <= 0 || !(avgdl > 0.0))
+        return fail(h, LRX_E_ARG, "lrx_debug_bm25_divcheck: bad argument");
+    std::lock_guard<std::mutex> g(h->mu);
+    LRX_CUDA(h, cudaSetDevice(h->device));
+    unsigned long long bad = 0;
+    LRX_CUDA(h, launch_bm25_divcheck(h, avgdl, k1, b, n_tf, n_len, &bad));
+    *host_mismatches = bad;
+    return LRX_OK;
+}
+
 int64_t lrx_launch_count(const lrx_handle* h) { return h ? h->launches : 0; }
 
 int lrx_profile_enable(lrx_handle* h, int32_t on) {

@@ -91,6 +91,8 @@ cudaError_t launch_bm25_scan(lrx_handle* h, const int32_t* q_terms, const int32_
 cudaError_t launch_bm25_pack(lrx_handle* h, const uint32_t* doc_tf, int64_t nnz, const uint32_t* doc_len,
                              void* out, int* host_overflow);
 cudaError_t launch_bm25_lut(lrx_handle* h, double avgdl, double k1, double b, int max_len);
+cudaError_t launch_bm25_divcheck(lrx_handle* h, double avgdl, double k1, double b, int n_tf, int n_len,
+                                 unsigned long long* host_mismatches);
 
 // fuse.cu
 cudaError_t launch_pack_records(lrx_handle* h, int B, int K, int mode, const double* dense_exact,

@@ -144,6 +144,35 @@ def test_bm25_synthetic_bit_exact(dev, n, vocab):
     _check_bm25(dev, idx, csr, lists, id_base=77, K=20, seed=n)
 
 
+def test_bm25_long_queries_two_passes(dev):
+    """More than 32 token slots: the scan walks a unit twice (slots 0-31, then 32-63); tokens past
+    LRX_MAX_QUERY_TERMS = 64 are dropped by the library, so the oracle sees 64 too."""
+    n, vocab = 50000, 2000
+    idx = synth.host_bm25(n, seed=5, vocab=vocab)
+    csr = _csr_of(idx)
+    dev.set_corpus(_cuda(synth.host_vectors(n, seed=2)), 0)
+    _set_postings(dev, idx)
+    terms, ptr = synth.host_query_terms(4, 64, seed=11, vocab=vocab)
+    lists = [terms[ptr[b]:ptr[b + 1]].tolist() for b in range(4)]
+    lists[0] = lists[0][:33]
+    lists[1] = lists[1][:32]
+    lists[2] = lists[2][:47] + [-1, lists[2][0], lists[2][40]]
+    _check_bm25(dev, idx, csr, lists, K=20, seed=1)
+
+
+def test_bm25_division_matches_ddiv_rn(dev):
+    """The scan's branch-free float64 division (csrc/bm25.cu okapi_div) gives the bits of the IEEE
+    division for every (tf, len) a posting can hold, at several average lengths."""
+    import ctypes as C
+    for avgdl in (104.35572519083969, 80.0, 1.0, 517.3, 3.0e4):
+        bad = C.c_uint64(123)
+        dev._ck(dev.lib.lrx_debug_bm25_divcheck(dev.h, avgdl, 1.5, 0.75, 4096, 65536, C.byref(bad)))
+        assert bad.value == 0, (avgdl, bad.value)
+    bad = C.c_uint64(123)
+    dev._ck(dev.lib.lrx_debug_bm25_divcheck(dev.h, 104.35572519083969, 1.5, 0.75, 65536, 4096, C.byref(bad)))
+    assert bad.value == 0
+
+
 def test_bm25_massive_ties(dev):
     """Thousands of documents with EXACTLY the same score: the list is decided by id."""
     n = 6000
