@@ -30,7 +30,11 @@ __device__ __forceinline__ void sort_desc_any(KeyT* buf, int n_valid, int tid, i
 template <typename KeyT>
 __global__ void __launch_bounds__(kMergeThreads, 1)
 merge_keys_kernel(const KeyT* __restrict__ part, int n_lists, int list_stride /* in lists */,
-                  int width, KeyT* __restrict__ out /* [nq][width] */) {
+                  const int* __restrict__ q_start /* or NULL */, int width,
+                  KeyT* __restrict__ out /* [nq][width] */) {
+    // two layouts: list l of query qi at part[(l * list_stride + qi) * width] (q_start == NULL:
+    // the same number of lists for every query), or the lists q_start[qi] .. q_start[qi + 1] of a
+    // flat array of lists (K3: warps are split between the queries by work)
     extern __shared__ __align__(128) unsigned char merge_raw[];
     KeyT* buf = reinterpret_cast<KeyT*>(merge_raw);
     __shared__ int count;
@@ -38,8 +42,14 @@ merge_keys_kernel(const KeyT* __restrict__ part, int n_lists, int list_stride /*
     __shared__ KeyT bound;
     const int qi = blockIdx.x;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    int list0 = qi;
+    if (q_start != nullptr) {
+        list0 = q_start[qi];
+        n_lists = q_start[qi + 1] - list0;
+        list_stride = 1;
+    }
     auto key_at = [&](int list, int pos) -> KeyT {
-        return part[((size_t)list * list_stride + qi) * width + pos];
+        return part[((size_t)list * list_stride + list0) * width + pos];
     };
 
     // ---- 1. lower bound from the heads of the lists
@@ -86,17 +96,17 @@ merge_keys_kernel(const KeyT* __restrict__ part, int n_lists, int list_stride /*
         out[(size_t)qi * width + i] = (i < n) ? buf[i] : (KeyT)0;
 }
 
-template __global__ void merge_keys_kernel<uint64_t>(const uint64_t*, int, int, int, uint64_t*);
-template __global__ void merge_keys_kernel<u128>(const u128*, int, int, int, u128*);
+template __global__ void merge_keys_kernel<uint64_t>(const uint64_t*, int, int, const int*, int, uint64_t*);
+template __global__ void merge_keys_kernel<u128>(const u128*, int, int, const int*, int, u128*);
 
 cudaError_t launch_merge_u64(cudaStream_t st, const uint64_t* part, int n_lists, int list_stride,
                              int width, int nq, uint64_t* out) {
     merge_keys_kernel<uint64_t><<<nq, kMergeThreads, kMergeCap * sizeof(uint64_t), st>>>(
-        part, n_lists, list_stride, width, out);
+        part, n_lists, list_stride, nullptr, width, out);
     return cudaGetLastError();
 }
-cudaError_t launch_merge_u128(cudaStream_t st, const void* part, int n_lists, int list_stride,
-                              int width, int nq, void* out) {
+cudaError_t launch_merge_u128(cudaStream_t st, const void* part, const int* q_start, int width,
+                              int nq, void* out) {
     static bool attr = false;
     if (!attr) {
         cudaFuncSetAttribute(merge_keys_kernel<u128>, cudaFuncAttributeMaxDynamicSharedMemorySize,
@@ -104,7 +114,7 @@ cudaError_t launch_merge_u128(cudaStream_t st, const void* part, int n_lists, in
         attr = true;
     }
     merge_keys_kernel<u128><<<nq, kMergeThreads, kMergeCap * sizeof(u128), st>>>(
-        (const u128*)part, n_lists, list_stride, width, (u128*)out);
+        (const u128*)part, 0, 1, q_start, width, (u128*)out);
     return cudaGetLastError();
 }
 
