@@ -98,11 +98,12 @@ __device__ __forceinline__ void block_bitonic_sort_desc(KeyT* keys, int n, int n
                                                         int tid, int nthreads) {
     const int half = n >> 1;
     const int total = half * nbuf;
+    const int lh = 31 - __clz(half);                  // half is a power of two
     for (int k = 2; k <= n; k <<= 1) {
         for (int j = k >> 1; j > 0; j >>= 1) {
             for (int t = tid; t < total; t += nthreads) {
-                const int buf = t / half;
-                const int u = t - buf * half;
+                const int buf = t >> lh;
+                const int u = t & (half - 1);
                 const int i = ((u & ~(j - 1)) << 1) | (u & (j - 1));
                 const int p = i | j;
                 KeyT* kk = keys + (size_t)buf * stride;

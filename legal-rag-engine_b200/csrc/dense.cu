@@ -27,6 +27,9 @@ constexpr int kTileRows = 64;                      // 4 rows per warp per tile
 constexpr int kTileBytes = kTileRows * kRowBytes;  // 49152
 constexpr int kStages = 4;
 constexpr int kCap = 1024;                         // candidate buffer entries per query
+constexpr int kSoftCap = 256;                      // prune once a buffer holds more than this minus a
+                                                   // tile: sorting 256 keys costs ~3 us, 1024 keys ~40 us,
+                                                   // and the threshold tightens 4x per prune either way
 constexpr int kMaxWidth = 512;                     // max per-CTA list length
 
 struct ScanSmem {
@@ -38,23 +41,107 @@ struct ScanSmem {
     uint64_t keys[1];   // [NQ][kCap], sized at launch
 };
 
+// ---- register sorting networks of the fast prune (two keys per lane, 64 keys per warp)
+__device__ __forceinline__ uint64_t shfl_xor_u64(uint64_t v, int m) {
+    const uint32_t lo = __shfl_xor_sync(0xffffffffu, (uint32_t)v, m);
+    const uint32_t hi = __shfl_xor_sync(0xffffffffu, (uint32_t)(v >> 32), m);
+    return ((uint64_t)hi << 32) | lo;
+}
+// one compare-exchange layer over the 64 keys of a warp, element index i = 2 * lane + r,
+// partner i ^ j; `desc` = the pair's first element keeps the larger key
+template <int J>
+__device__ __forceinline__ void warp64_layer(uint64_t& v0, uint64_t& v1, int lane, bool desc0, bool desc1) {
+    if (J == 1) {
+        const uint64_t hi = max(v0, v1), lo = min(v0, v1);
+        v0 = desc0 ? hi : lo;
+        v1 = desc0 ? lo : hi;
+    } else {
+        const int lj = J >> 1;
+        const bool first = (lane & lj) == 0;
+        const uint64_t o0 = shfl_xor_u64(v0, lj), o1 = shfl_xor_u64(v1, lj);
+        v0 = (desc0 == first) ? max(v0, o0) : min(v0, o0);
+        v1 = (desc1 == first) ? max(v1, o1) : min(v1, o1);
+    }
+}
+// bitonic merge of a bitonic 64-key sequence into descending order
+__device__ __forceinline__ void warp64_merge_desc(uint64_t& v0, uint64_t& v1, int lane) {
+    warp64_layer<32>(v0, v1, lane, true, true);
+    warp64_layer<16>(v0, v1, lane, true, true);
+    warp64_layer<8>(v0, v1, lane, true, true);
+    warp64_layer<4>(v0, v1, lane, true, true);
+    warp64_layer<2>(v0, v1, lane, true, true);
+    warp64_layer<1>(v0, v1, lane, true, true);
+}
+// full descending sort of 64 keys
+__device__ __forceinline__ void warp64_sort_desc(uint64_t& v0, uint64_t& v1, int lane) {
+    const int i0 = 2 * lane;
+#define LRX_L(K, J) warp64_layer<J>(v0, v1, lane, ((i0 & K) == 0), (((i0 + 1) & K) == 0))
+    LRX_L(2, 1);
+    LRX_L(4, 2); LRX_L(4, 1);
+    LRX_L(8, 4); LRX_L(8, 2); LRX_L(8, 1);
+    LRX_L(16, 8); LRX_L(16, 4); LRX_L(16, 2); LRX_L(16, 1);
+    LRX_L(32, 16); LRX_L(32, 8); LRX_L(32, 4); LRX_L(32, 2); LRX_L(32, 1);
+#undef LRX_L
+    warp64_merge_desc(v0, v1, lane);
+}
+
 template <int NQ>
 __device__ __forceinline__ void scan_prune(uint64_t* keys, int* count, uint32_t* tau, int width,
                                            int tid, unsigned int* tau_g) {
-    // sort only as many slots as are in use (power of two >= the fullest buffer, >= width):
-    // pad the unused ones with the empty key, sort all NQ buffers at once, keep `width`
     int nmax = width;
 #pragma unroll
     for (int q = 0; q < NQ; ++q) nmax = max(nmax, count[q]);
-    const int n2 = min(kCap, next_pow2(nmax));
+    if (width == 64 && nmax <= 256) {
+        // fast path (the default list width, pruned at the soft cap): four warps per query sort
+        // 64 keys each in registers; the best 64 of two descending runs A, B are the bitonic
+        // sequence max(A[i], B[63 - i]), sorted by one bitonic merge -- two rounds, 4 -> 2 -> 1.
+        const int lane = tid & 31, warp = tid >> 5;
+        const int q = warp & 3, part = warp >> 2;            // 16 warps: (query, quarter)
+        uint64_t* kq = keys + q * kCap;
+        const bool active = q < NQ;
+        const int n = active ? count[q] : 0;
+        uint64_t v0 = 0ull, v1 = 0ull;
+        if (active) {
+            const int i0 = part * 64 + 2 * lane;
+            v0 = (i0 < n) ? kq[i0] : 0ull;
+            v1 = (i0 + 1 < n) ? kq[i0 + 1] : 0ull;
+            warp64_sort_desc(v0, v1, lane);
+        }
+        __syncthreads();                                     // all reads of keys done
 #pragma unroll
-    for (int q = 0; q < NQ; ++q) {
-        const int n = count[q];
-        for (int i = tid; i < n2; i += kScanThreads)
-            if (i >= n) keys[q * kCap + i] = 0ull;
+        for (int round = 0; round < 2; ++round) {
+            const int stride = 1 << round;                   // partner quarter = part ^ stride
+            if (active && (part & ((2 << round) - 1)) == stride) {   // the giving quarter
+                kq[part * 64 + 2 * lane] = v0;
+                kq[part * 64 + 2 * lane + 1] = v1;
+            }
+            __syncthreads();
+            if (active && (part & ((2 << round) - 1)) == 0) {         // the keeping quarter
+                const uint64_t* other = kq + (part + stride) * 64;
+                v0 = max(v0, other[63 - 2 * lane]);
+                v1 = max(v1, other[62 - 2 * lane]);
+                warp64_merge_desc(v0, v1, lane);
+            }
+            __syncthreads();
+        }
+        if (active && part == 0) {
+            kq[2 * lane] = v0;
+            kq[2 * lane + 1] = v1;
+        }
+        __syncthreads();
+    } else {
+        // general path: sort only as many slots as are in use (power of two >= the fullest
+        // buffer, >= width), pad the unused ones with the empty key, all NQ buffers at once
+        const int n2 = min(kCap, next_pow2(nmax));
+#pragma unroll
+        for (int q = 0; q < NQ; ++q) {
+            const int n = count[q];
+            for (int i = tid; i < n2; i += kScanThreads)
+                if (i >= n) keys[q * kCap + i] = 0ull;
+        }
+        __syncthreads();
+        block_bitonic_sort_desc<uint64_t>(keys, n2, NQ, kCap, tid, kScanThreads);
     }
-    __syncthreads();
-    block_bitonic_sort_desc<uint64_t>(keys, n2, NQ, kCap, tid, kScanThreads);
     if (tid < NQ) {
         const int c = min(count[tid], width);
         count[tid] = c;
@@ -91,6 +178,8 @@ dense_scan_kernel(const unsigned char* __restrict__ x, int64_t n_rows,
     constexpr int LOGV = (NQ == 4) ? 4 : (NQ == 2) ? 3 : 2;     // halving steps
     constexpr int kRepl = 1 << (5 - LOGV);                       // lanes sharing one result
 
+    // width <= 128: prune at 256 entries; wider lists keep the full buffer
+    const int soft_cap = (2 * width <= kSoftCap) ? kSoftCap : kCap;
     const int64_t n_tiles = (n_rows + kTileRows - 1) / kTileRows;
     const int64_t my_tiles =
         (n_tiles > (int64_t)blockIdx.x) ? (n_tiles - blockIdx.x + gridDim.x - 1) / gridDim.x : 0;
@@ -202,7 +291,7 @@ dense_scan_kernel(const unsigned char* __restrict__ x, int64_t n_rows,
         // ---- block barrier: frees the stage, decides pruning uniformly
         bool need = false;
 #pragma unroll
-        for (int qi = 0; qi < NQ; ++qi) need |= (sm.count[qi] > kCap - kTileRows);
+        for (int qi = 0; qi < NQ; ++qi) need |= (sm.count[qi] > soft_cap - kTileRows);
         const int any = __syncthreads_or(need ? 1 : 0);
         if (tid == 0 && it + kStages < my_tiles) issue(it + kStages, s);
         if (any) scan_prune<NQ>(keys, sm.count, sm.tau, width, tid, tau_g);

@@ -8,8 +8,8 @@
 //          and BM25 lists, order (rrf desc, id asc).  See oracle/fusion.py.
 //
 // One CTA per sub-query; every shard runs the same deterministic merge on the
-// all-gathered records, so the result is replicated bit for bit.  All sorts are
-// small (<= world*2k keys), so one warp sorts in shared memory without block barriers.
+// all-gathered records, so the result is replicated bit for bit.  The shards' lists arrive
+// sorted, so merging is rank arithmetic (binary searches), not sorting.
 #include "common.cuh"
 #include "handle.h"
 
@@ -52,21 +52,20 @@ __device__ __forceinline__ u128 rec_key(double v, int64_t id, uint32_t src) {
     return ((u128)f64_ord(v) << 64) | ((u128)(uint32_t)(~(uint32_t)id) << 32) | (u128)src;
 }
 
-// Sort `n` keys (padded with 0 to a power of two) descending: one warp, or the block
-// when there are more than 1024.  Block-uniform; returns synced.
-__device__ __forceinline__ void fuse_sort(u128* keys, int n, int tid) {
-    const int p2 = max(32, next_pow2(n));
-    __syncthreads();
-    for (int i = n + tid; i < p2; i += kFuseThreads) keys[i] = 0;
-    __syncthreads();
-    if (p2 <= 1024) {
-        if (tid < 32) warp_bitonic_sort_desc<u128>(keys, p2, tid);
-        __syncthreads();
-    } else {
-        block_bitonic_sort_desc<u128>(keys, p2, 1, p2, tid, kFuseThreads);
+// Number of keys greater than `key` in a DESCENDING run of n keys (empty keys = 0 at its end).
+__device__ __forceinline__ int count_greater_sorted(const u128* run, int n, u128 key) {
+    int lo = 0, hi = n;                  // first position whose key is <= `key`
+    while (lo < hi) {
+        const int mid = (lo + hi) >> 1;
+        if (run[mid] > key) lo = mid + 1; else hi = mid;
     }
+    return lo;
 }
 
+// No sorting networks here: every list that arrives is already sorted per shard (K2's re-score and
+// K3's merge emit (score desc, id asc)), so the rank of a record in the merged order is a sum of
+// binary searches, and the final order of the <= 2K fused scores is a rank by counting.  Keys are
+// unique (they end in the source slot), so ranks are a permutation.
 __global__ void __launch_bounds__(kFuseThreads)
 fuse_kernel(const lrx_record* __restrict__ rec_all, const double* __restrict__ max_all,
             const int32_t* __restrict__ flags_all, int64_t shard_stride /* bytes; 0 = dense */,
@@ -79,10 +78,12 @@ fuse_kernel(const lrx_record* __restrict__ rec_all, const double* __restrict__ m
     __shared__ lrx_record dsel[kFuseMaxK];      // global dense top-K
     __shared__ lrx_record ssel[kFuseMaxK];      // global BM25 top-K (rrf)
     __shared__ double fscore[2 * kFuseMaxK];
-    __shared__ int n_dense, n_sparse;
+    __shared__ int out_slot[2 * kFuseMaxK];     // fused rank -> union slot
+    __shared__ int n_dense, n_sparse, n_fused;
     const int b = blockIdx.x;
     const int tid = threadIdx.x;
     const int n_in = world * K;
+    if (tid == 0) { n_dense = 0; n_sparse = 0; n_fused = 0; }
 
     // max_bm25 = max(scores) if max(scores) > 0 else 1.0   (retrieval_engine.py:74)
     double maxbm = 0.0;
@@ -108,21 +109,43 @@ fuse_kernel(const lrx_record* __restrict__ rec_all, const double* __restrict__ m
             : rec_all + (size_t)w * B * 2 * K;
         return rw[((size_t)b * 2 + list) * K + j];
     };
+    // merged top-K of the shards' sorted lists `list` (0 dense, 1 BM25) into sel[]; count in *n_sel
+    auto merge_lists = [&](int list, lrx_record* sel, int* n_sel) {
+        __syncthreads();                                      // keys[] free
+        for (int i = tid; i < n_in; i += kFuseThreads) {
+            const lrx_record& r = rec_at(list, i);
+            keys[i] = (r.id >= 0) ? rec_key(list ? r.bm25 : r.dense, r.id, (uint32_t)i) : (u128)0;
+        }
+        __syncthreads();
+        for (int i = tid; i < n_in; i += kFuseThreads) {
+            const u128 key = keys[i];
+            if (key == 0) continue;
+            const int w_own = i / K;
+            int rank = i - w_own * K;                         // position in its own sorted run
+            for (int w = 0; w < world && rank < K; ++w)
+                if (w != w_own) rank += count_greater_sorted(keys + w * K, K, key);
+            if (rank < K) {
+                sel[rank] = rec_at(list, i);
+                atomicAdd(n_sel, 1);
+            }
+        }
+        __syncthreads();
+    };
+    // rank by counting of the n keys in keys[]: out_slot[rank] = low 32 bits of the key
+    auto order_keys = [&](int n) {
+        __syncthreads();
+        for (int i = tid; i < n; i += kFuseThreads) {
+            const u128 key = keys[i];
+            if (key == 0) continue;
+            int rank = 0;
+            for (int j = 0; j < n; ++j) rank += (keys[j] > key) ? 1 : 0;
+            out_slot[rank] = (int)(uint32_t)key;
+            atomicAdd(&n_fused, 1);
+        }
+        __syncthreads();
+    };
 
-    // ---- global dense list: merge the shards' sorted lists
-    for (int i = tid; i < n_in; i += kFuseThreads) {
-        const lrx_record& r = rec_at(0, i);
-        keys[i] = (r.id >= 0) ? rec_key(r.dense, r.id, (uint32_t)i) : (u128)0;
-    }
-    fuse_sort(keys, n_in, tid);
-    if (tid == 0) {
-        int n = 0;
-        while (n < K && n < n_in && keys[n] != 0) ++n;
-        n_dense = n;
-    }
-    __syncthreads();
-    for (int j = tid; j < n_dense; j += kFuseThreads) dsel[j] = rec_at(0, (int)(uint32_t)keys[j]);
-    __syncthreads();
+    merge_lists(0, dsel, &n_dense);
     const int nd = n_dense;
 
     if (mode == LRX_FUSE_LINEAR) {
@@ -136,12 +159,12 @@ fuse_kernel(const lrx_record* __restrict__ rec_all, const double* __restrict__ m
             // stable descending sort: ties keep flat-IP order j
             keys[j] = ((u128)f64_ord(s) << 64) | ((u128)(uint32_t)(~(uint32_t)j) << 32) | (u128)(uint32_t)j;
         }
-        fuse_sort(keys, nd, tid);
-        const int n_out = min(k, nd);
+        order_keys(nd);
+        const int n_out = min(k, n_fused);
         for (int i = tid; i < k; i += kFuseThreads) {
             const size_t o = (size_t)b * k + i;
             if (i < n_out) {
-                const int j = (int)(uint32_t)keys[i];
+                const int j = out_slot[i];
                 out_ids[o] = dsel[j].id;
                 out_score[o] = fscore[j];
                 out_sem[o] = (double)__double2float_rn(dsel[j].dense);
@@ -154,20 +177,7 @@ fuse_kernel(const lrx_record* __restrict__ rec_all, const double* __restrict__ m
             }
         }
     } else {
-        // ---- global BM25 list
-        for (int i = tid; i < n_in; i += kFuseThreads) {
-            const lrx_record& r = rec_at(1, i);
-            keys[i] = (r.id >= 0) ? rec_key(r.bm25, r.id, (uint32_t)i) : (u128)0;
-        }
-        fuse_sort(keys, n_in, tid);
-        if (tid == 0) {
-            int n = 0;
-            while (n < K && n < n_in && keys[n] != 0) ++n;
-            n_sparse = n;
-        }
-        __syncthreads();
-        for (int j = tid; j < n_sparse; j += kFuseThreads) ssel[j] = rec_at(1, (int)(uint32_t)keys[j]);
-        __syncthreads();
+        merge_lists(1, ssel, &n_sparse);
         const int ns = n_sparse;
         // union slots: [0, nd) dense entries, [nd, nd + ns) BM25 entries (unused when the
         // document is already in the dense list).  Dense term first: 0.0 + 1/(60 + rank).
@@ -191,12 +201,12 @@ fuse_kernel(const lrx_record* __restrict__ rec_all, const double* __restrict__ m
             }
             keys[i] = key;
         }
-        fuse_sort(keys, nd + ns, tid);
+        order_keys(nd + ns);
+        const int n_out = min(k, n_fused);
         for (int i = tid; i < k; i += kFuseThreads) {
             const size_t o = (size_t)b * k + i;
-            const u128 key = (i < nd + ns) ? keys[i] : (u128)0;
-            if (key != 0) {
-                const int src = (int)(uint32_t)key;
+            if (i < n_out) {
+                const int src = out_slot[i];
                 const lrx_record& r = (src < nd) ? dsel[src] : ssel[src - nd];
                 out_ids[o] = r.id;
                 out_score[o] = fscore[src];
