@@ -15,7 +15,7 @@ from pathlib import Path
 HERE = Path(__file__).resolve().parent
 CSRC = HERE / "csrc"
 LIB = CSRC / "liblrx.so"
-SOURCES = ["api.cu", "dense.cu", "bm25.cu", "fuse.cu", "merge.cu", "tc_gemm.cu", "encoder.cu", "dense_batched.cu"]
+SOURCES = ["api.cu", "dense.cu", "bm25.cu", "fuse.cu", "tc_gemm.cu", "encoder.cu", "dense_batched.cu"]
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a",
     "-O3", "-lineinfo", "-std=c++17",

@@ -448,9 +448,8 @@ static int search_local_locked(lrx_handle* h, const void* q, const int32_t* q_te
     const int Kb = (mode == LRX_FUSE_RRF) ? K : 0;
     LRX_CUDA(h, launch_bm25_scan(h, q_terms, q_ptr, B, s.dense_I, K, s.dense_bm, maxbm, Kb,
                                  s.bm_scores, s.bm_ids));
-    if (mode == LRX_FUSE_RRF) LRX_CUDA(h, launch_dense_at(h, q, B, s.bm_ids, K, s.bm_dense));
     LRX_CUDA(h, launch_pack_records(h, B, K, mode, s.dense_exact, s.dense_I, s.dense_bm, s.bm_scores,
-                                    s.bm_ids, s.bm_dense, records));
+                                    s.bm_ids, s.bm_dense, q, records));
     return LRX_OK;
 }
 

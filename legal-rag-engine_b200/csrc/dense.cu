@@ -11,14 +11,15 @@
 //                       and keeps a per-CTA top-`width` candidate list in shared
 //                       memory (threshold test in registers; block-wide bitonic
 //                       prune only when the buffer fills).  Scores never touch HBM.
-//   merge_keys_kernel   one CTA per query merges the per-CTA lists.
-//   dense_rescore_kernel re-scores the `width` survivors EXACTLY in float64 (exact
+//   dense_merge_rescore_kernel  one CTA per query merges the per-CTA lists (merge.cuh) and
+//                       re-scores the `width` survivors EXACTLY in float64 (exact
 //                       and order independent, see oracle/flat_ip.py), orders them by
 //                       (score desc, id asc), emits the best K and the guard flag.
 //
 // Algorithmic HBM bytes per launch of dense_scan_kernel: n_local * 768.
 #include "common.cuh"
 #include "handle.h"
+#include "merge.cuh"
 
 namespace lrx {
 
@@ -317,10 +318,6 @@ dense_scan_kernel(const unsigned char* __restrict__ x, int64_t n_rows,
 #undef SCAN_TRACE
 }
 
-// merge.cu
-cudaError_t launch_merge_u64(cudaStream_t st, const uint64_t* part, int n_lists, int list_stride,
-                             int width, int nq, uint64_t* out);
-
 // ---------------------------------------------------------------------------
 // Exact float64 inner product of one fp16 row with one fp16 query, by a warp.
 __device__ __forceinline__ double warp_exact_dot(const unsigned char* __restrict__ x, int64_t row,
@@ -346,27 +343,35 @@ __device__ __forceinline__ double warp_exact_dot(const unsigned char* __restrict
     return acc;
 }
 
-constexpr int kRescoreThreads = 256;
-
-__global__ void __launch_bounds__(kRescoreThreads)
-dense_rescore_kernel(const unsigned char* __restrict__ x, int64_t n_rows, int64_t id_base,
-                     const __half* __restrict__ q, const uint64_t* __restrict__ merged, int width,
-                     int K, double eps, double* __restrict__ out_exact, float* __restrict__ out_D,
-                     int64_t* __restrict__ out_I, int32_t* __restrict__ out_flag) {
+// Merge of the per-CTA lists of one query + exact re-score of the survivors, one CTA per query:
+//   merge_lists_block  -> the best `width` fp32-scored keys, in shared memory
+//   re-score           each warp takes 4 survivors per pass, all 12 row loads in flight before
+//                      the first reduction; exact float64 dot products (order independent)
+//   order              rank by counting on (exact score desc, id asc); emit the best K + guard flag
+__global__ void __launch_bounds__(kMergeThreads, 1)
+dense_merge_rescore_kernel(const uint64_t* __restrict__ part, int n_lists, int list_stride,
+                           const unsigned char* __restrict__ x, int64_t n_rows, int64_t id_base,
+                           const __half* __restrict__ q, int width, int K, double eps,
+                           double* __restrict__ out_exact, float* __restrict__ out_D,
+                           int64_t* __restrict__ out_I, int32_t* __restrict__ out_flag) {
+    extern __shared__ __align__(128) unsigned char merge_raw[];
+    uint64_t* buf = reinterpret_cast<uint64_t*>(merge_raw);          // [kMergeCap]
+    __shared__ uint64_t merged[kMaxWidth];
     __shared__ u128 keys[kMaxWidth];
+    __shared__ u128 sorted[kMaxWidth];
+    __shared__ int s_count, s_overflow;
+    __shared__ uint64_t s_bound;
     const int qi = blockIdx.x;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const int wp2 = next_pow2(width);
-    constexpr int kWarps = kRescoreThreads / 32;
-    // each warp: 4 candidates per pass, their 12 row loads issued before any reduction
-    for (int j0 = warp * 4; j0 < wp2; j0 += kWarps * 4) {
+    merge_lists_block<uint64_t>(part, n_lists, list_stride, qi, width, buf, merged, &s_count,
+                                &s_overflow, &s_bound);
+
+    constexpr int kWarps = kMergeThreads / 32;
+    for (int j0 = warp * 4; j0 < width; j0 += kWarps * 4) {
         uint64_t kk[4];
         uint2 rv[4][3];
 #pragma unroll
-        for (int c = 0; c < 4; ++c) {
-            const int j = j0 + c;
-            kk[c] = (j < width) ? merged[(size_t)qi * width + j] : 0ull;
-        }
+        for (int c = 0; c < 4; ++c) kk[c] = (j0 + c < width) ? merged[j0 + c] : 0ull;
 #pragma unroll
         for (int c = 0; c < 4; ++c) {
             const uint2* rowp = reinterpret_cast<const uint2*>(
@@ -395,15 +400,19 @@ dense_rescore_kernel(const unsigned char* __restrict__ x, int64_t n_rows, int64_
             }
 #pragma unroll
             for (int lb = 16; lb > 0; lb >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, lb);
-            if (lane == 0 && j0 + c < wp2)
+            if (lane == 0 && j0 + c < width)
                 keys[j0 + c] = kk[c] ? make_key128(acc, key64_row(kk[c])) : (u128)0;
         }
     }
+    for (int j = tid; j < width; j += kMergeThreads) sorted[j] = 0;
     __syncthreads();
-    if (warp == 0) warp_bitonic_sort_desc<u128>(keys, wp2, lane);
+    for (int j = tid; j < width; j += kMergeThreads) {
+        const u128 key = keys[j];
+        if (key != 0) sorted[merge_rank_of<u128>(keys, width, key)] = key;
+    }
     __syncthreads();
-    for (int j = tid; j < K; j += kRescoreThreads) {
-        const u128 key = (j < wp2) ? keys[j] : (u128)0;
+    for (int j = tid; j < K; j += kMergeThreads) {
+        const u128 key = (j < width) ? sorted[j] : (u128)0;
         const size_t o = (size_t)qi * K + j;
         if (key != 0) {
             const double e = key128_score(key);
@@ -421,9 +430,9 @@ dense_rescore_kernel(const unsigned char* __restrict__ x, int64_t n_rows, int64_
         if (n_rows > width) {
             // rows outside the candidate list have fp32 score <= s_last, hence exact
             // score <= s_last + eps; they must lose strictly to the K-th exact score.
-            const uint64_t last = merged[(size_t)qi * width + width - 1];
+            const uint64_t last = merged[width - 1];
             const int kk = (K < width) ? K : width;
-            const u128 kth = keys[kk - 1];
+            const u128 kth = sorted[kk - 1];
             if (last == 0ull || kth == 0 || K > width) {
                 flag = 1;
             } else {
@@ -493,15 +502,18 @@ cudaError_t launch_dense_topk(lrx_handle* h, const void* qv, int B, int K, int w
                               double* exact, float* D, int64_t* I, int32_t* flags) {
     const int grid = dense_scan_grid(h);
     cudaError_t e;
-    // per-CTA lists for up to 4 queries per pass, merged lists for all B
+    // per-CTA lists for up to 4 queries per pass
     e = ensure_ws(&h->ws_dense_part, &h->ws_dense_part_bytes,
                   (size_t)grid * 4 * width * sizeof(uint64_t) + 64);
     if (e != cudaSuccess) return e;
-    e = ensure_ws(&h->ws_dense_merged, &h->ws_dense_merged_bytes,
-                  (size_t)B * width * sizeof(uint64_t));
-    if (e != cudaSuccess) return e;
+    static bool attr = false;
+    if (!attr) {
+        e = cudaFuncSetAttribute(dense_merge_rescore_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                 (int)(kMergeCap * sizeof(uint64_t)));
+        if (e != cudaSuccess) return e;
+        attr = true;
+    }
     uint64_t* part = (uint64_t*)h->ws_dense_part;
-    uint64_t* merged = (uint64_t*)h->ws_dense_merged;
     const __half* q = (const __half*)qv;
     for (int b0 = 0; b0 < B; b0 += 4) {
         const int nq = (B - b0 < 4) ? (B - b0) : 4;
@@ -510,15 +522,16 @@ cudaError_t launch_dense_topk(lrx_handle* h, const void* qv, int B, int K, int w
         else if (NQ == 2) e = launch_scan<2>(h, q + (size_t)b0 * kDim, nq, width, part, grid);
         else e = launch_scan<1>(h, q + (size_t)b0 * kDim, nq, width, part, grid);
         if (e != cudaSuccess) return e;
-        e = launch_merge_u64(h->stream, part, grid, NQ, width, nq, merged + (size_t)b0 * width);
+        // list l of query qi of this pass: part[(l * NQ + qi) * width]
+        dense_merge_rescore_kernel<<<nq, kMergeThreads, kMergeCap * sizeof(uint64_t), h->stream>>>(
+            part, grid, NQ, (const unsigned char*)h->x, h->n_local, h->id_base,
+            q + (size_t)b0 * kDim, width, K, kDenseEps, exact + (size_t)b0 * K, D + (size_t)b0 * K,
+            I + (size_t)b0 * K, flags + b0);
         h->launches++;
+        e = cudaGetLastError();
         if (e != cudaSuccess) return e;
     }
-    dense_rescore_kernel<<<B, kRescoreThreads, 0, h->stream>>>(
-        (const unsigned char*)h->x, h->n_local, h->id_base, q, merged, width, K, kDenseEps, exact,
-        D, I, flags);
-    h->launches++;
-    return cudaGetLastError();
+    return cudaSuccess;
 }
 
 cudaError_t launch_dense_at(lrx_handle* h, const void* q, int B, const int64_t* ids, int n,

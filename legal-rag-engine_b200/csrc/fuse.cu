@@ -19,32 +19,63 @@ constexpr int kFuseThreads = 128;
 constexpr int kFuseMaxIn = 2048;   // world * K records per list
 constexpr int kFuseMaxK = LRX_MAX_DEPTH;
 
+// One WARP per (query, list position): packs the dense record and the BM25 record of that
+// position; for rrf the BM25 hit's exact dense score (shown as "semantic") is computed here, one
+// float64 dot product by the warp (x == NULL: taken from bm_dense instead).
 __global__ void pack_records_kernel(int B, int K, int mode, const double* __restrict__ dense_exact,
                                     const int64_t* __restrict__ dense_ids,
                                     const double* __restrict__ dense_bm25,
                                     const double* __restrict__ bm_scores,
                                     const int64_t* __restrict__ bm_ids,
                                     const double* __restrict__ bm_dense,
+                                    const unsigned char* __restrict__ x, int64_t n_rows,
+                                    int64_t id_base, const __half* __restrict__ q,
                                     lrx_record* __restrict__ records) {
-    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    const int i = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    const int lane = threadIdx.x & 31;
     if (i >= B * K) return;
     const int b = i / K, j = i - b * K;
-    lrx_record r0;
-    r0.id = dense_ids[i];
-    r0.dense = dense_exact[i];
-    r0.bm25 = (r0.id >= 0) ? dense_bm25[i] : 0.0;
-    records[((size_t)b * 2 + 0) * K + j] = r0;
     lrx_record r1;
+    r1.id = -1;
+    r1.dense = -INFINITY;
+    r1.bm25 = 0.0;
     if (mode == LRX_FUSE_RRF && bm_ids[i] >= 0) {
         r1.id = bm_ids[i];
-        r1.dense = bm_dense[i];
         r1.bm25 = bm_scores[i];
-    } else {
-        r1.id = -1;
-        r1.dense = -INFINITY;
-        r1.bm25 = 0.0;
+        if (x != nullptr) {
+            const int64_t row = r1.id - id_base;
+            if (row >= 0 && row < n_rows) {
+                const uint2* rowp = reinterpret_cast<const uint2*>(x + row * (int64_t)(LRX_DIM * 2));
+                const uint2* qp = reinterpret_cast<const uint2*>(q + (size_t)b * LRX_DIM);
+                double acc = 0.0;
+#pragma unroll
+                for (int s = 0; s < 3; ++s) {
+                    const uint2 v = rowp[s * 32 + lane], w = qp[s * 32 + lane];
+                    const float2 a = __half22float2(*reinterpret_cast<const __half2*>(&v.x));
+                    const float2 c = __half22float2(*reinterpret_cast<const __half2*>(&v.y));
+                    const float2 e = __half22float2(*reinterpret_cast<const __half2*>(&w.x));
+                    const float2 f = __half22float2(*reinterpret_cast<const __half2*>(&w.y));
+                    acc = fma((double)a.x, (double)e.x, acc);
+                    acc = fma((double)a.y, (double)e.y, acc);
+                    acc = fma((double)c.x, (double)f.x, acc);
+                    acc = fma((double)c.y, (double)f.y, acc);
+                }
+#pragma unroll
+                for (int lb = 16; lb > 0; lb >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, lb);
+                r1.dense = acc;
+            }
+        } else {
+            r1.dense = bm_dense[i];
+        }
     }
-    records[((size_t)b * 2 + 1) * K + j] = r1;
+    if (lane == 0) {
+        lrx_record r0;
+        r0.id = dense_ids[i];
+        r0.dense = dense_exact[i];
+        r0.bm25 = (r0.id >= 0) ? dense_bm25[i] : 0.0;
+        records[((size_t)b * 2 + 0) * K + j] = r0;
+        records[((size_t)b * 2 + 1) * K + j] = r1;
+    }
 }
 
 // key = order image (64) | ~id (32) | source slot (32): sorts by (value desc, id asc)
@@ -226,10 +257,12 @@ fuse_kernel(const lrx_record* __restrict__ rec_all, const double* __restrict__ m
 cudaError_t launch_pack_records(lrx_handle* h, int B, int K, int mode, const double* dense_exact,
                                 const int64_t* dense_ids, const double* dense_bm25,
                                 const double* bm_scores, const int64_t* bm_ids,
-                                const double* bm_dense, lrx_record* records) {
+                                const double* bm_dense, const void* q, lrx_record* records) {
+    // q != NULL: the exact dense scores of the BM25 hits are computed in the kernel (bm_dense unused)
     const int n = B * K;
-    pack_records_kernel<<<(n + 255) / 256, 256, 0, h->stream>>>(
-        B, K, mode, dense_exact, dense_ids, dense_bm25, bm_scores, bm_ids, bm_dense, records);
+    pack_records_kernel<<<(n + 7) / 8, 256, 0, h->stream>>>(
+        B, K, mode, dense_exact, dense_ids, dense_bm25, bm_scores, bm_ids, bm_dense,
+        q ? (const unsigned char*)h->x : nullptr, h->n_local, h->id_base, (const __half*)q, records);
     h->launches++;
     return cudaGetLastError();
 }

@@ -98,7 +98,7 @@ cudaError_t launch_bm25_divcheck(lrx_handle* h, double avgdl, double k1, double 
 cudaError_t launch_pack_records(lrx_handle* h, int B, int K, int mode, const double* dense_exact,
                                 const int64_t* dense_ids, const double* dense_bm25,
                                 const double* bm_scores, const int64_t* bm_ids,
-                                const double* bm_dense, lrx_record* records);
+                                const double* bm_dense, const void* q, lrx_record* records);
 cudaError_t launch_fuse(lrx_handle* h, const lrx_record* records_all, const double* max_all,
                         const int32_t* flags_all, int64_t shard_stride, int world, int B, int K,
                         int k, int mode, const double* weights, int64_t* ids, double* score,
