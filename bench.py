@@ -350,8 +350,15 @@ def run_ours(args):
     clocks.start()
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     ev0.record()
+    # host time to ENQUEUE a step, over the first steps only (later ones may wait on a full launch queue)
+    n_host = min(args.steps, 24)
+    t_host = time.perf_counter()
     for i in range(args.steps):
+        if i == n_host:
+            t_host = time.perf_counter() - t_host
         step(i)
+    if n_host == args.steps:
+        t_host = time.perf_counter() - t_host
     ev1.record()
     barrier()
     clk = clocks.stop()
@@ -433,6 +440,7 @@ def run_ours(args):
                     "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                     "ms_per_step": e2e_ms / e2e_steps},
             "gpu_launches": int(launches),
+            "host_enqueue_ms_per_step": t_host * 1e3 / n_host,
             "clocks": clk,
             "roofline": {"bound": "hbm", "kernel": "dense_scan_kernel<4>", "achieved": scan_gbs,
                          "peak": peak, "unit": "GB/s", "frac": scan_gbs / peak, "peak_source": peak_src,
