@@ -26,7 +26,10 @@ namespace lrx {
 constexpr int kScanThreads = 512;
 constexpr int kTileRows = 64;                      // 4 rows per warp per tile
 constexpr int kTileBytes = kTileRows * kRowBytes;  // 49152
-constexpr int kStages = 4;
+#ifndef LRX_SCAN_STAGES
+#define LRX_SCAN_STAGES 4                          // 2, 3 and 4 measure the same (tools/scan_sweep.sh)
+#endif
+constexpr int kStages = LRX_SCAN_STAGES;
 constexpr int kCap = 1024;                         // candidate buffer entries per query
 constexpr int kSoftCap = 256;                      // prune once a buffer holds more than this minus a
                                                    // tile: sorting 256 keys costs ~3 us, 1024 keys ~40 us,
@@ -36,7 +39,9 @@ constexpr int kMaxWidth = 512;                     // max per-CTA list length
 struct ScanSmem {
     // ring first (16-byte aligned bulk-copy destinations)
     unsigned char ring[kStages][kTileBytes];
+    float part[2][kTileRows][4];   // [k half][row][query] partial scores of one tile
     uint64_t full[kStages];
+    int tile_of[kStages];          // tile held (or being loaded) by every stage
     int count[4];
     uint32_t tau[4];
     uint64_t keys[1];   // [NQ][kCap], sized at launch
@@ -175,15 +180,13 @@ dense_scan_kernel(const unsigned char* __restrict__ x, int64_t n_rows,
     const int lane = tid & 31;
     const int warp = tid >> 5;
 
-    constexpr int NV = 4 * NQ;                                   // (row, query) values per warp pass
-    constexpr int LOGV = (NQ == 4) ? 4 : (NQ == 2) ? 3 : 2;     // halving steps
-    constexpr int kRepl = 1 << (5 - LOGV);                       // lanes sharing one result
-
     // width <= 128: prune at 256 entries; wider lists keep the full buffer
     const int soft_cap = (2 * width <= kSoftCap) ? kSoftCap : kCap;
-    const int64_t n_tiles = (n_rows + kTileRows - 1) / kTileRows;
-    const int64_t my_tiles =
-        (n_tiles > (int64_t)blockIdx.x) ? (n_tiles - blockIdx.x + gridDim.x - 1) / gridDim.x : 0;
+    // Tiles are static, blockIdx + i * grid: at any moment the grid reads one contiguous ~7 MB
+    // window of the matrix.  (Measured, tools/scan_sweep.sh: claiming tiles from a grid-wide counter
+    // costs 25 % -- one contended atomic per 48 KB -- and re-filling a stage BEFORE the tile's
+    // per-row tests instead of after the closing barrier costs 30 %.)
+    const int n_tiles = (int)((n_rows + kTileRows - 1) / kTileRows);
 
     if (tid == 0) {
         for (int s = 0; s < kStages; ++s) mbar_init(&sm.full[s], 1);
@@ -195,93 +198,92 @@ dense_scan_kernel(const unsigned char* __restrict__ x, int64_t n_rows,
     }
     __syncthreads();
 
-    auto issue = [&](int64_t it, int s) {
-        const int64_t tile = (int64_t)blockIdx.x + it * gridDim.x;
-        const int64_t row0 = tile * kTileRows;
+    auto issue = [&](int tile, int s) {                      // thread 0 only
+        sm.tile_of[s] = tile;
+        if (tile >= n_tiles) return;
+        const int64_t row0 = (int64_t)tile * kTileRows;
         const int rows = (int)min((int64_t)kTileRows, n_rows - row0);
         const uint32_t bytes = (uint32_t)rows * kRowBytes;
         mbar_arrive_expect_tx(&sm.full[s], bytes);
         bulk_g2s(sm.ring[s], x + row0 * kRowBytes, bytes, &sm.full[s]);
     };
+    int next_tile = (int)blockIdx.x + kStages * (int)gridDim.x;   // thread 0: the next tile to load
     if (tid == 0) {
-        for (int s = 0; s < kStages && s < my_tiles; ++s) issue(s, s);
+        for (int s = 0; s < kStages; ++s) issue((int)blockIdx.x + s * (int)gridDim.x, s);
     }
+    __syncthreads();                                         // tile_of[] visible
 
-    // This lane's 12 query elements per query: halves j*128 + lane*4 + {0..3}, j = 0..2
-    float qf[NQ][12];
+    // ---- scoring on the tensor cores (mma.sync m16n8k16, fp16 x fp16 -> fp32): a tile is four
+    //      16-row blocks x two 192-column halves, one (block, half) per warp of warps 0-7 (the other
+    //      eight only take part in the per-row tests and the prunes; the shared-memory budget has
+    //      no room for more partial sums, and the math is far from the critical path).  The 8 "n"
+    //      columns are the <= 4 queries plus zero padding.  Lane (g = lane / 4, t = lane % 4) reads
+    //      16 contiguous bytes of rows g and g + 8 per 32-column chunk -- two MMAs' worth -- and
+    //      holds the query's halves at the SAME columns, so A and B agree on a (permuted) k order.
+    const int g = lane >> 2, t = lane & 3;
+    const int mblk = warp & 3, kh = (warp >> 2) & 1;
+    const bool mma_warp = warp < 8;
+    uint32_t qb[6][4];                                           // query g, chunks 6*kh .. 6*kh + 5
 #pragma unroll
-    for (int qi = 0; qi < NQ; ++qi) {
-#pragma unroll
-        for (int j = 0; j < 3; ++j) {
-#pragma unroll
-            for (int e = 0; e < 4; ++e) {
-                const int col = j * 128 + lane * 4 + e;
-                qf[qi][j * 4 + e] = (qi < n_q) ? __half2float(q[qi * kDim + col]) : 0.f;
-            }
-        }
+    for (int j = 0; j < 6; ++j) {
+        const uint4 v = (g < n_q && mma_warp)
+            ? *reinterpret_cast<const uint4*>(q + (size_t)g * kDim + (6 * kh + j) * 32 + 8 * t)
+            : make_uint4(0u, 0u, 0u, 0u);
+        qb[j][0] = v.x; qb[j][1] = v.y; qb[j][2] = v.z; qb[j][3] = v.w;
     }
+    const uint32_t a_off = (uint32_t)((mblk * 16 + g) * kRowBytes + (6 * kh) * 64 + 16 * t);
 
     SCAN_TRACE(1);
-    for (int64_t it = 0; it < my_tiles; ++it) {
-        if (it < 20 || (it & 15) == 0) SCAN_TRACE(8 + (it < 20 ? (int)it : 20 + (int)(it >> 4)));
-        const int s = (int)(it % kStages);
+    for (int it = 0;; ++it) {
+        if (it < 20 || (it & 15) == 0) SCAN_TRACE(8 + (it < 20 ? it : min(99, 20 + (it >> 4))));
+        const int s = it % kStages;
         const uint32_t parity = (uint32_t)((it / kStages) & 1);
-        const int64_t tile = (int64_t)blockIdx.x + it * gridDim.x;
-        const int64_t row0 = tile * kTileRows;
+        const int tile = sm.tile_of[s];
+        if (tile >= n_tiles) break;                          // a CTA's tiles come in increasing order
+        const int64_t row0 = (int64_t)tile * kTileRows;
         const int rows = (int)min((int64_t)kTileRows, n_rows - row0);
 
         mbar_wait(&sm.full[s], parity);
 
-        // ---- score 4 rows x NQ queries per warp
-        float acc[NV];
+        if (mma_warp) {
+            float c0[4] = {0.f, 0.f, 0.f, 0.f}, c1[4] = {0.f, 0.f, 0.f, 0.f};   // two accumulation chains
+            const unsigned char* base = sm.ring[s] + a_off;
+            uint4 xa[6], xb[6];
 #pragma unroll
-        for (int i = 0; i < NV; ++i) acc[i] = 0.f;
-        const int r0 = warp * 4;
+            for (int j = 0; j < 6; ++j) {
+                xa[j] = *reinterpret_cast<const uint4*>(base + j * 64);                  // row g
+                xb[j] = *reinterpret_cast<const uint4*>(base + 8 * kRowBytes + j * 64);  // row g + 8
+            }
 #pragma unroll
-        for (int r = 0; r < 4; ++r) {
-            const uint2* rowp = reinterpret_cast<const uint2*>(sm.ring[s] + (r0 + r) * kRowBytes);
-#pragma unroll
-            for (int j = 0; j < 3; ++j) {
-                const uint2 v = rowp[j * 32 + lane];
-                const float2 a = __half22float2(*reinterpret_cast<const __half2*>(&v.x));
-                const float2 b = __half22float2(*reinterpret_cast<const __half2*>(&v.y));
-#pragma unroll
-                for (int qi = 0; qi < NQ; ++qi) {
-                    float t = acc[r * NQ + qi];
-                    t = fmaf(a.x, qf[qi][j * 4 + 0], t);
-                    t = fmaf(a.y, qf[qi][j * 4 + 1], t);
-                    t = fmaf(b.x, qf[qi][j * 4 + 2], t);
-                    t = fmaf(b.y, qf[qi][j * 4 + 3], t);
-                    acc[r * NQ + qi] = t;
-                }
+            for (int j = 0; j < 6; ++j) {
+                asm volatile("mma.sync.aligned.m16n8k16.row.col.f32.f16.f16.f32 "
+                             "{%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+                             : "+f"(c0[0]), "+f"(c0[1]), "+f"(c0[2]), "+f"(c0[3])
+                             : "r"(xa[j].x), "r"(xb[j].x), "r"(xa[j].y), "r"(xb[j].y),
+                               "r"(qb[j][0]), "r"(qb[j][1]));
+                asm volatile("mma.sync.aligned.m16n8k16.row.col.f32.f16.f16.f32 "
+                             "{%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+                             : "+f"(c1[0]), "+f"(c1[1]), "+f"(c1[2]), "+f"(c1[3])
+                             : "r"(xa[j].z), "r"(xb[j].z), "r"(xa[j].w), "r"(xb[j].w),
+                               "r"(qb[j][2]), "r"(qb[j][3]));
+            }
+            // lanes t < 2 hold queries 2t, 2t + 1 of rows g and g + 8; the other columns are padding
+            if (t < 2) {
+                *reinterpret_cast<float2*>(&sm.part[kh][mblk * 16 + g][2 * t]) =
+                    make_float2(c0[0] + c1[0], c0[1] + c1[1]);
+                *reinterpret_cast<float2*>(&sm.part[kh][mblk * 16 + g + 8][2 * t]) =
+                    make_float2(c0[2] + c1[2], c0[3] + c1[3]);
             }
         }
-        // ---- reduce-scatter across the warp: one shuffle per output value.
-        //      Same tree for every (row, query) -> identical rows give identical bits.
-#pragma unroll
-        for (int st = 0; st < LOGV; ++st) {
-            const int lb = 16 >> st;
-            const int half = NV >> (st + 1);
-            const bool up = (lane & lb) != 0;
-#pragma unroll
-            for (int i = 0; i < half; ++i) {
-                const float send = up ? acc[i] : acc[i + half];
-                const float keep = up ? acc[i + half] : acc[i];
-                acc[i] = keep + __shfl_xor_sync(0xffffffffu, send, lb);
-            }
-        }
-#pragma unroll
-        for (int lb = (16 >> LOGV); lb > 0; lb >>= 1)
-            acc[0] += __shfl_xor_sync(0xffffffffu, acc[0], lb);
+        __syncthreads();                       // partial scores visible
 
-        // ---- threshold test in registers; rare append to the shared buffer
-        {
-            const int idx = lane >> (5 - LOGV);
-            const int r = idx / NQ;
-            const int qi = idx - r * NQ;
-            const int row_in_tile = r0 + r;
-            if ((lane & (kRepl - 1)) == 0 && row_in_tile < rows && qi < n_q) {
-                const uint32_t o = f32_ord(acc[0]);
+        // ---- one thread per (row, query): sum of the two halves, threshold test, rare append to
+        //      the shared buffer
+        if (tid < kTileRows * 4) {
+            const int row_in_tile = tid >> 2, qi = tid & 3;
+            const float sc = sm.part[0][row_in_tile][qi] + sm.part[1][row_in_tile][qi];
+            if (row_in_tile < rows && qi < n_q) {
+                const uint32_t o = f32_ord(sc);
                 if (o >= sm.tau[qi]) {
                     const int pos = atomicAdd(&sm.count[qi], 1);
                     keys[qi * kCap + pos] =
@@ -289,18 +291,21 @@ dense_scan_kernel(const unsigned char* __restrict__ x, int64_t n_rows,
                 }
             }
         }
-        // ---- block barrier: frees the stage, decides pruning uniformly
+        // ---- block barrier: partial sums consumed, pruning decided uniformly
         bool need = false;
 #pragma unroll
         for (int qi = 0; qi < NQ; ++qi) need |= (sm.count[qi] > soft_cap - kTileRows);
         const int any = __syncthreads_or(need ? 1 : 0);
-        if (tid == 0 && it + kStages < my_tiles) issue(it + kStages, s);
+        if (tid == 0) {                        // re-fill the stage with the CTA's next tile
+            issue(next_tile, s);
+            next_tile += (int)gridDim.x;
+        }
         if (any) scan_prune<NQ>(keys, sm.count, sm.tau, width, tid, tau_g);
         else if (tid < NQ) {
             // pick up thresholds published by other CTAs (read by the next tile's tests: the
             // barrier of the next iteration orders it; a stale value is only conservative)
-            const uint32_t t = *(volatile unsigned int*)(tau_g + tid);
-            if (t > sm.tau[tid]) sm.tau[tid] = t;
+            const uint32_t tg = *(volatile unsigned int*)(tau_g + tid);
+            if (tg > sm.tau[tid]) sm.tau[tid] = tg;
         }
     }
 

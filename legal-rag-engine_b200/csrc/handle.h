@@ -58,10 +58,11 @@ struct lrx_handle {
 
 namespace lrx {
 
-// Fast-pass score error bound used by the exactness guard:
-// |fp32 scan score - exact| <= 17 roundings * 2^-24 * sum|x_i q_i| <= 1.02e-6
-// for L2-normalised rows; doubled for margin.
-constexpr double kDenseEps = 2.1e-6;
+// Fast-pass score error bound used by the exactness guard: the scan scores with
+// fp16 x fp16 products (exact) accumulated in fp32 by the tensor cores -- 24 accumulation steps
+// per quarter row plus 4 fp32 adds, each off by at most one unit in the last place of a partial
+// sum <= 1 for L2-normalised rows: <= 28 * 2^-23 = 3.4e-6; tripled for margin.
+constexpr double kDenseEps = 1.0e-5;
 
 constexpr int kDim = LRX_DIM;
 constexpr int kRowBytes = LRX_DIM * 2;
