@@ -435,6 +435,7 @@ def run_ours(args):
             "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
             "dtype": "f16 matrix, f32 scan + exact f64 re-score; f64 BM25", "data": "synthetic",
             "config": dict(workload_config(args), parallelism=f"row-shard x{world}",
+                           exchange=(searcher.exchange if world > 1 else "none"),
                            rows_per_gpu=n_local, nnz_per_gpu=nnz_local, build_s=round(t_build, 1)),
             "e2e": {"value": e2e_steps / (e2e_ms * 1e-3), "unit": "queries/s",
                     "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
@@ -467,6 +468,8 @@ def run_ours(args):
             line["cpu_baseline"] = {"value": 1.0 / sec, "unit": "queries/s", "cores": threads,
                                     "kind": "port", "sample": desc}
         print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.barrier()                 # nobody unmaps its exchange region while a peer may store
     dev.close()
     if world > 1:
         dist.destroy_process_group()

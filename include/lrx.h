@@ -37,6 +37,8 @@ extern "C" {
 #define LRX_MAX_BATCH 64            /* sub-queries per lrx_search_* call */
 #define LRX_MAX_DEPTH 256           /* max candidate depth K (= 2k) per list */
 #define LRX_MAX_QUERY_TERMS 64      /* BM25 term slots per sub-query */
+#define LRX_MAX_WORLD 16            /* shards (GPUs of one box) in a peer exchange */
+#define LRX_IPC_HANDLE_BYTES 64     /* sizeof(cudaIpcMemHandle_t) */
 
 enum {
     LRX_OK = 0,
@@ -202,6 +204,26 @@ int lrx_search_finish_packed(lrx_handle* h, const void* dev_packed_all, int32_t 
                              int32_t k, int32_t mode, const double* dev_weights, int64_t* dev_ids,
                              double* dev_score, double* dev_sem, double* dev_kw,
                              int32_t* dev_status);
+
+/* ---- sharded search with the exchange fused into the kernels (world > 1, one box).
+ * Replaces "lrx_search_local_packed -> NCCL all-gather -> lrx_search_finish_packed": every rank
+ * owns an exchange region (two parities x world slots of one packed block, plus sequence flags);
+ * after K2/K3 the rank's block is stored straight into the slot `rank` of EVERY peer's region
+ * over NVLink (peer memory opened through CUDA IPC) followed by a release store of the call's
+ * sequence number, and the fusion kernel acquires the world flags before it merges.  No
+ * collective library call, no host synchronisation; calls must be made in the same order by all
+ * ranks (SPMD), each on its own stream.
+ *   lrx_exchange_export  allocates this rank's region for batches up to (B_max, k_max) and
+ *                        returns its IPC handle (LRX_IPC_HANDLE_BYTES bytes);
+ *   lrx_exchange_import  takes all ranks' handles in rank order (exchanged by the host, e.g. one
+ *                        torch.distributed all-gather at start-up) and opens the peers' regions;
+ *   lrx_search_sharded   K2 + K3 on this shard, exchange, K4: the replicated fused result. */
+int lrx_exchange_export(lrx_handle* h, int32_t B_max, int32_t k_max, void* host_handle_out);
+int lrx_exchange_import(lrx_handle* h, const void* host_handles_all);
+int lrx_search_sharded(lrx_handle* h, const void* dev_q_fp16, const int32_t* dev_q_terms,
+                       const int32_t* dev_q_ptr, const double* dev_weights, int32_t B, int32_t k,
+                       int32_t mode, int32_t width, int64_t* dev_ids, double* dev_score,
+                       double* dev_sem, double* dev_kw, int32_t* dev_status);
 
 /* Host-buffer form of the whole search on ONE shard (world == 1): copies the
  * inputs in, runs K2..K4, copies the results out and synchronises.  This is the

@@ -17,6 +17,7 @@ LRX_DIM = 384
 LRX_MAX_BATCH = 64
 LRX_MAX_DEPTH = 256
 LRX_MAX_QUERY_TERMS = 64
+LRX_IPC_HANDLE_BYTES = 64
 LRX_FUSE_LINEAR, LRX_FUSE_RRF = 0, 1
 LRX_E_AMBIGUOUS = -5
 
@@ -89,6 +90,10 @@ _SIGNATURES = {
     "lrx_search_local_packed": (C.c_int, [_vp, _vp, _vp, _vp, _i32, _i32, _i32, _i32, _vp]),
     "lrx_search_finish_packed": (C.c_int, [_vp, _vp, _i32, _i32, _i32, _i32, _vp, _vp, _vp, _vp,
                                            _vp, _vp]),
+    "lrx_exchange_export": (C.c_int, [_vp, _i32, _i32, _vp]),
+    "lrx_exchange_import": (C.c_int, [_vp, _vp]),
+    "lrx_search_sharded": (C.c_int, [_vp, _vp, _vp, _vp, _vp, _i32, _i32, _i32, _i32, _vp, _vp, _vp, _vp,
+                                     _vp]),
     "lrx_search_batch_host": (C.c_int, [_vp, _vp, _vp, _vp, _vp, _i32, _i32, _i32, _vp, _vp, _vp,
                                         _vp]),
     "lrx_search_text_host": (C.c_int, [_vp, _vp, _vp, _i32, _vp, _vp, _vp, _i32, _i32, _i32, _vp, _vp,

@@ -123,6 +123,10 @@ int lrx_close(lrx_handle* h) {
     for (void* p : ws)
         if (p != nullptr) cudaFree(p);
     encoder_free(h);
+    for (int w = 0; w < LRX_MAX_WORLD; ++w)
+        if (h->xchg_peer[w] != nullptr && w != h->rank) cudaIpcCloseMemHandle(h->xchg_peer[w]);
+    if (h->xchg != nullptr) cudaFree(h->xchg);
+    if (h->xchg_peer_dev != nullptr) cudaFree(h->xchg_peer_dev);
     if (h->ws_host != nullptr) cudaFreeHost(h->ws_host);
     if (h->aux) cudaStreamDestroy(h->aux);
     if (h->ev_fork) cudaEventDestroy(h->ev_fork);
@@ -545,6 +549,91 @@ int lrx_search_finish_packed(lrx_handle* h, const void* dev_packed_all, int32_t 
     return search_finish_locked(h, (const lrx_record*)p, (const double*)(p + o_max),
                                 (const int32_t*)(p + o_flags), (int64_t)total, world, B, k, mode,
                                 dev_weights, dev_ids, dev_score, dev_sem, dev_kw, dev_status);
+}
+
+// ---- peer exchange: region = data [2 parities][world][slot] | flags u64 [2][world]
+static_assert(sizeof(cudaIpcMemHandle_t) == LRX_IPC_HANDLE_BYTES, "IPC handle size");
+
+int lrx_exchange_export(lrx_handle* h, int32_t B_max, int32_t k_max, void* host_handle_out) {
+    if (h == nullptr) return fail(nullptr, LRX_E_ARG, "lrx_exchange_export: null handle");
+    std::lock_guard<std::mutex> g(h->mu);
+    if (host_handle_out == nullptr || B_max < 1 || B_max > LRX_MAX_BATCH || k_max < 1 ||
+        2 * k_max > LRX_MAX_DEPTH)
+        return fail(h, LRX_E_ARG, "lrx_exchange_export: bad argument");
+    if (h->world < 2 || h->world > LRX_MAX_WORLD)
+        return fail(h, LRX_E_STATE, "lrx_exchange_export: world must be in [2,%d]", LRX_MAX_WORLD);
+    if (h->xchg != nullptr) return fail(h, LRX_E_STATE, "lrx_exchange_export: already exported");
+    LRX_CUDA(h, cudaSetDevice(h->device));
+    size_t o_max, o_flags, total;
+    packed_layout(B_max, k_max, &o_max, &o_flags, &total);
+    h->xchg_slot = align_up(total, 256);
+    h->xchg_bytes = 2 * (size_t)h->world * h->xchg_slot + 2 * (size_t)h->world * sizeof(unsigned long long);
+    LRX_CUDA(h, cudaMalloc(&h->xchg, h->xchg_bytes));
+    LRX_CUDA(h, cudaMemset(h->xchg, 0, h->xchg_bytes));
+    LRX_CUDA(h, cudaDeviceSynchronize());
+    cudaIpcMemHandle_t ipc;
+    LRX_CUDA(h, cudaIpcGetMemHandle(&ipc, h->xchg));
+    memcpy(host_handle_out, &ipc, sizeof(ipc));
+    return LRX_OK;
+}
+
+int lrx_exchange_import(lrx_handle* h, const void* host_handles_all) {
+    if (h == nullptr) return fail(nullptr, LRX_E_ARG, "lrx_exchange_import: null handle");
+    std::lock_guard<std::mutex> g(h->mu);
+    if (host_handles_all == nullptr) return fail(h, LRX_E_ARG, "lrx_exchange_import: null pointer");
+    if (h->xchg == nullptr) return fail(h, LRX_E_STATE, "lrx_exchange_import: export first");
+    if (h->xchg_ready) return fail(h, LRX_E_STATE, "lrx_exchange_import: already imported");
+    LRX_CUDA(h, cudaSetDevice(h->device));
+    for (int w = 0; w < h->world; ++w) {
+        if (w == h->rank) { h->xchg_peer[w] = h->xchg; continue; }
+        cudaIpcMemHandle_t ipc;
+        memcpy(&ipc, (const char*)host_handles_all + (size_t)w * sizeof(ipc), sizeof(ipc));
+        LRX_CUDA(h, cudaIpcOpenMemHandle(&h->xchg_peer[w], ipc, cudaIpcMemLazyEnablePeerAccess));
+    }
+    LRX_CUDA(h, cudaMalloc((void**)&h->xchg_peer_dev, LRX_MAX_WORLD * sizeof(void*)));
+    LRX_CUDA(h, cudaMemcpy(h->xchg_peer_dev, h->xchg_peer, LRX_MAX_WORLD * sizeof(void*),
+                           cudaMemcpyHostToDevice));
+    h->xchg_ready = true;
+    return LRX_OK;
+}
+
+int lrx_search_sharded(lrx_handle* h, const void* dev_q_fp16, const int32_t* dev_q_terms,
+                       const int32_t* dev_q_ptr, const double* dev_weights, int32_t B, int32_t k,
+                       int32_t mode, int32_t width, int64_t* dev_ids, double* dev_score,
+                       double* dev_sem, double* dev_kw, int32_t* dev_status) {
+    if (h == nullptr) return fail(nullptr, LRX_E_ARG, "lrx_search_sharded: null handle");
+    std::lock_guard<std::mutex> g(h->mu);
+    if (!h->xchg_ready) return fail(h, LRX_E_STATE, "lrx_search_sharded: exchange not set up");
+    if (dev_q_fp16 == nullptr || dev_q_ptr == nullptr || dev_ids == nullptr || dev_score == nullptr ||
+        dev_sem == nullptr || dev_kw == nullptr || dev_status == nullptr ||
+        (mode == LRX_FUSE_LINEAR && dev_weights == nullptr))
+        return fail(h, LRX_E_ARG, "lrx_search_sharded: null pointer");
+    if (B < 1 || k < 1) return fail(h, LRX_E_ARG, "lrx_search_sharded: bad B/k");
+    size_t o_max, o_flags, total;
+    packed_layout(B, k, &o_max, &o_flags, &total);
+    if (total > h->xchg_slot)
+        return fail(h, LRX_E_ARG, "lrx_search_sharded: batch larger than the exported exchange slots");
+    LRX_CUDA(h, cudaSetDevice(h->device));
+    const unsigned long long seq = ++h->xchg_seq;
+    const int par = (int)(seq & 1ull);
+    const size_t data_bytes = 2 * (size_t)h->world * h->xchg_slot;
+    const size_t slot_off = ((size_t)par * h->world + h->rank) * h->xchg_slot;
+    const size_t flag_off = data_bytes + ((size_t)par * h->world + h->rank) * sizeof(unsigned long long);
+    char* mine = (char*)h->xchg + slot_off;
+    int rc = search_local_locked(h, dev_q_fp16, dev_q_terms, dev_q_ptr, B, k, mode, width,
+                                 (lrx_record*)mine, (double*)(mine + o_max), (int32_t*)(mine + o_flags));
+    if (rc != LRX_OK) return rc;
+    LRX_CUDA(h, launch_exchange(h, mine, total, slot_off, flag_off, seq));
+    const char* all = (const char*)h->xchg + (size_t)par * h->world * h->xchg_slot;
+    const unsigned long long* flags =
+        (const unsigned long long*)((const char*)h->xchg + data_bytes) + (size_t)par * h->world;
+    const int K = 2 * k;
+    if (h->world * K > 2048) return fail(h, LRX_E_ARG, "lrx_search_sharded: world*2k must be <= 2048");
+    LRX_CUDA(h, launch_fuse(h, (const lrx_record*)all, (const double*)(all + o_max),
+                            (const int32_t*)(all + o_flags), (int64_t)h->xchg_slot, h->world, B, K, k,
+                            mode, dev_weights, dev_ids, dev_score, dev_sem, dev_kw, dev_status, flags,
+                            seq, h->rank));
+    return LRX_OK;
 }
 
 // Shared body of the two host-buffer entry points: the query vectors either come from the

@@ -103,7 +103,9 @@ fuse_kernel(const lrx_record* __restrict__ rec_all, const double* __restrict__ m
             int world, int B, int K, int k, int mode,
             const double* __restrict__ weights, int64_t* __restrict__ out_ids,
             double* __restrict__ out_score, double* __restrict__ out_sem,
-            double* __restrict__ out_kw, int32_t* __restrict__ out_status) {
+            double* __restrict__ out_kw, int32_t* __restrict__ out_status,
+            const unsigned long long* wait_flags /* [world] or NULL */, unsigned long long wait_seq,
+            int self) {
     extern __shared__ __align__(16) unsigned char fuse_dyn[];
     u128* keys = reinterpret_cast<u128*>(fuse_dyn);   // [kFuseMaxIn]
     __shared__ lrx_record dsel[kFuseMaxK];      // global dense top-K
@@ -115,6 +117,23 @@ fuse_kernel(const lrx_record* __restrict__ rec_all, const double* __restrict__ m
     const int tid = threadIdx.x;
     const int n_in = world * K;
     if (tid == 0) { n_dense = 0; n_sparse = 0; n_fused = 0; }
+    // peer exchange: the blocks of the other shards were stored into this GPU's memory by THEIR
+    // kernels; acquire every shard's sequence flag before touching its block (bounded spin: a
+    // lost peer surfaces as status -1, not as a hung GPU)
+    __shared__ int wait_failed;
+    if (tid == 0) wait_failed = 0;
+    __syncthreads();
+    if (wait_flags != nullptr && tid < world && tid != self) {
+        const long long t0 = clock64();
+        unsigned long long v;
+        for (;;) {
+            asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(wait_flags + tid) : "memory");
+            if (v >= wait_seq) break;
+            if (clock64() - t0 > 4000000000ll) { wait_failed = 1; break; }
+            __nanosleep(100);
+        }
+    }
+    __syncthreads();
 
     // max_bm25 = max(scores) if max(scores) > 0 else 1.0   (retrieval_engine.py:74)
     double maxbm = 0.0;
@@ -123,28 +142,34 @@ fuse_kernel(const lrx_record* __restrict__ rec_all, const double* __restrict__ m
         const double* mw = shard_stride
             ? reinterpret_cast<const double*>(reinterpret_cast<const char*>(max_all) + w * shard_stride)
             : max_all + (size_t)w * B;
-        maxbm = fmax(maxbm, mw[b]);
+        maxbm = fmax(maxbm, __ldcg(mw + b));
         if (flags_all != nullptr) {
             const int32_t* fw = shard_stride
                 ? reinterpret_cast<const int32_t*>(reinterpret_cast<const char*>(flags_all) + w * shard_stride)
                 : flags_all + (size_t)w * B;
-            status |= fw[b];
+            status |= __ldcg(fw + b);
         }
     }
     if (!(maxbm > 0.0)) maxbm = 1.0;
 
-    auto rec_at = [&](int list, int src) -> const lrx_record& {
+    // by value, through L2 (ld.cg): the records may have been written by another GPU
+    auto rec_at = [&](int list, int src) -> lrx_record {
         const int w = src / K, j = src - w * K;
         const lrx_record* rw = shard_stride
             ? reinterpret_cast<const lrx_record*>(reinterpret_cast<const char*>(rec_all) + w * shard_stride)
             : rec_all + (size_t)w * B * 2 * K;
-        return rw[((size_t)b * 2 + list) * K + j];
+        const lrx_record* r = rw + ((size_t)b * 2 + list) * K + j;
+        lrx_record out;
+        out.id = __ldcg(&r->id);
+        out.dense = __ldcg(&r->dense);
+        out.bm25 = __ldcg(&r->bm25);
+        return out;
     };
     // merged top-K of the shards' sorted lists `list` (0 dense, 1 BM25) into sel[]; count in *n_sel
     auto merge_lists = [&](int list, lrx_record* sel, int* n_sel) {
         __syncthreads();                                      // keys[] free
         for (int i = tid; i < n_in; i += kFuseThreads) {
-            const lrx_record& r = rec_at(list, i);
+            const lrx_record r = rec_at(list, i);
             keys[i] = (r.id >= 0) ? rec_key(list ? r.bm25 : r.dense, r.id, (uint32_t)i) : (u128)0;
         }
         __syncthreads();
@@ -251,7 +276,35 @@ fuse_kernel(const lrx_record* __restrict__ rec_all, const double* __restrict__ m
             }
         }
     }
-    if (tid == 0) out_status[b] = status;
+    if (tid == 0) out_status[b] = wait_failed ? -1 : status;
+}
+
+// Peer exchange, sending side: CTA j stores this rank's packed block into slot `rank` of peer
+// (rank + 1 + j) % world over NVLink, then publishes the call's sequence number there with a
+// release store at system scope (fence cumulativity carries the whole CTA's stores).
+__global__ void exchange_kernel(const uint4* __restrict__ mine, int n16, void* const* __restrict__ peers,
+                                int rank, int world, size_t slot_off, size_t flag_off,
+                                unsigned long long seq) {
+    const int p = (rank + 1 + (int)blockIdx.x) % world;
+    char* base = reinterpret_cast<char*>(peers[p]);
+    uint4* dst = reinterpret_cast<uint4*>(base + slot_off);
+    for (int i = threadIdx.x; i < n16; i += blockDim.x) dst[i] = mine[i];
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        __threadfence_system();
+        unsigned long long* flag = reinterpret_cast<unsigned long long*>(base + flag_off);
+        asm volatile("st.release.sys.global.u64 [%0], %1;" :: "l"(flag), "l"(seq) : "memory");
+    }
+}
+
+cudaError_t launch_exchange(lrx_handle* h, const void* mine, size_t bytes, size_t slot_off,
+                            size_t flag_off, unsigned long long seq) {
+    if (h->world < 2) return cudaSuccess;
+    exchange_kernel<<<h->world - 1, 256, 0, h->stream>>>((const uint4*)mine, (int)(bytes / 16),
+                                                         h->xchg_peer_dev, h->rank, h->world, slot_off,
+                                                         flag_off, seq);
+    h->launches++;
+    return cudaGetLastError();
 }
 
 cudaError_t launch_pack_records(lrx_handle* h, int B, int K, int mode, const double* dense_exact,
@@ -270,7 +323,8 @@ cudaError_t launch_pack_records(lrx_handle* h, int B, int K, int mode, const dou
 cudaError_t launch_fuse(lrx_handle* h, const lrx_record* records_all, const double* max_all,
                         const int32_t* flags_all, int64_t shard_stride, int world, int B, int K,
                         int k, int mode, const double* weights, int64_t* ids, double* score,
-                        double* sem, double* kw, int32_t* status) {
+                        double* sem, double* kw, int32_t* status, const unsigned long long* wait_flags,
+                        unsigned long long wait_seq, int self) {
     static bool attr = false;
     if (!attr) {
         cudaError_t e = cudaFuncSetAttribute(fuse_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
@@ -281,7 +335,7 @@ cudaError_t launch_fuse(lrx_handle* h, const lrx_record* records_all, const doub
     if (world * K > kFuseMaxIn || K > kFuseMaxK) return cudaErrorInvalidValue;
     fuse_kernel<<<B, kFuseThreads, kFuseMaxIn * sizeof(u128), h->stream>>>(
         records_all, max_all, flags_all, shard_stride, world, B, K, k, mode, weights, ids, score,
-        sem, kw, status);
+        sem, kw, status, wait_flags, wait_seq, self);
     h->launches++;
     return cudaGetLastError();
 }

@@ -51,6 +51,14 @@ struct lrx_handle {
     void* ws_host = nullptr;         size_t ws_host_bytes = 0;          // pinned staging
     void* ws_io = nullptr;           size_t ws_io_bytes = 0;            // device staging
 
+    // peer exchange (lrx_exchange_*): this rank's region, the peers' (IPC-mapped), a device copy of
+    // the pointer table, the per-call sequence number
+    void* xchg = nullptr;            size_t xchg_slot = 0, xchg_bytes = 0;
+    void* xchg_peer[LRX_MAX_WORLD] = {nullptr};
+    void** xchg_peer_dev = nullptr;
+    bool xchg_ready = false;
+    unsigned long long xchg_seq = 0;
+
     // K1 encoder state (packed weights, activation workspaces, tensor maps): encoder.cu
     void* encoder = nullptr;
     void* debug_trace = nullptr;     // device int64[128]: GEMM timeline of CTA 0 (lrx_debug_set_trace)
@@ -103,7 +111,11 @@ cudaError_t launch_pack_records(lrx_handle* h, int B, int K, int mode, const dou
 cudaError_t launch_fuse(lrx_handle* h, const lrx_record* records_all, const double* max_all,
                         const int32_t* flags_all, int64_t shard_stride, int world, int B, int K,
                         int k, int mode, const double* weights, int64_t* ids, double* score,
-                        double* sem, double* kw, int32_t* status);
+                        double* sem, double* kw, int32_t* status,
+                        const unsigned long long* wait_flags = nullptr,
+                        unsigned long long wait_seq = 0, int self = -1);
+cudaError_t launch_exchange(lrx_handle* h, const void* mine, size_t bytes, size_t slot_off,
+                            size_t flag_off, unsigned long long seq);
 
 // encoder.cu
 cudaError_t encoder_set_weights(lrx_handle* h, const lrx_bert_weights* w);

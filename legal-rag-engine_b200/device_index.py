@@ -184,6 +184,35 @@ class DeviceIndex:
                                                    _ptr(kw), _ptr(status)))
         return outs
 
+    # ------------------------------------ peer-memory exchange (world > 1, one box)
+    def exchange_setup(self, B_max: int, k_max: int, group=None):
+        """Allocate this rank's exchange region, swap IPC handles with the other ranks (one
+        all-gather of 64 bytes at start-up) and open theirs: afterwards `search_sharded` needs no
+        collective call per query batch."""
+        import torch.distributed as dist
+        from ._lib import LRX_IPC_HANDLE_BYTES
+        mine = (C.c_ubyte * LRX_IPC_HANDLE_BYTES)()
+        self._ck(self.lib.lrx_exchange_export(self.h, B_max, k_max, C.cast(mine, C.c_void_p)))
+        world = dist.get_world_size(group)
+        t = torch.tensor(list(mine), dtype=torch.uint8, device=self.device)
+        every = torch.empty(world * LRX_IPC_HANDLE_BYTES, dtype=torch.uint8, device=self.device)
+        dist.all_gather_into_tensor(every, t, group=group)
+        host = every.cpu().numpy().tobytes()
+        buf = (C.c_ubyte * len(host)).from_buffer_copy(host)
+        self._ck(self.lib.lrx_exchange_import(self.h, C.cast(buf, C.c_void_p)))
+        dist.barrier(group=group)                 # every region is mapped before the first store
+
+    def search_sharded(self, q, q_terms, q_ptr, k: int, mode: int, weights, outs, width: int = 0):
+        """K2 + K3 on this shard, block stored into every peer's region, K4: replicated result."""
+        B = int(q.shape[0])
+        ids, score, sem, kw, status = outs
+        if q_terms.numel() == 0:
+            q_terms = torch.zeros(1, dtype=torch.int32, device=self.device)
+        self._ck(self.lib.lrx_search_sharded(self.h, _ptr(q), _ptr(q_terms), _ptr(q_ptr), _ptr(weights),
+                                             B, k, mode, width, _ptr(ids), _ptr(score), _ptr(sem),
+                                             _ptr(kw), _ptr(status)))
+        return outs
+
     def alloc_outputs(self, B: int, k: int):
         return (torch.empty((B, k), dtype=torch.int64, device=self.device),
                 torch.empty((B, k), dtype=torch.float64, device=self.device),

@@ -5,14 +5,21 @@ GPU g owns the contiguous global id range ``shard_range(N, g, G)`` of BOTH the f
 matrix and the BM25 postings (doc ids local, ``id_base`` added on the way out).  idf / avgdl
 are whole-corpus statistics (``global_bm25_stats``: two all-reduces at build time), so a
 shard's BM25 scores equal the unsharded ones bit for bit.  Per query batch each rank runs
-K2 + K3 on its shard (``lrx_search_local_packed``), the packed blocks
-``[B][2][2k] records | [B] max | [B] flags`` are exchanged with ONE ``all_gather_into_tensor``
-(NCCL over NVLink; ~1 KB per sub-query per rank -- latency-bound, hence one call per batch),
-and every rank runs the same deterministic merge + fusion (``lrx_search_finish_packed``).
+K2 + K3 on its shard, the packed blocks ``[B][2][2k] records | [B] max | [B] flags`` (~1 KB per
+sub-query per rank -- latency-bound) are exchanged, and every rank runs the same deterministic
+merge + fusion.  Two exchanges:
+
+* ``exchange="peer"`` (default on CUDA): ``lrx_search_sharded`` -- the block is stored straight
+  into every peer's memory over NVLink by a kernel of the chain and the fusion kernel acquires the
+  peers' sequence flags; no collective call per batch (the IPC handles are swapped once).
+* ``exchange="nccl"``: ``lrx_search_local_packed`` -> ONE ``all_gather_into_tensor`` ->
+  ``lrx_search_finish_packed`` (also what the gloo CPU test of the host logic mirrors).
 """
 from __future__ import annotations
 
 from typing import Optional, Tuple
+
+import os
 
 import numpy as np
 import torch
@@ -57,12 +64,18 @@ def unpack(block: np.ndarray, B: int, k: int):
 class ShardedSearcher:
     """K2+K3 local -> all-gather -> K4, for device-resident query batches."""
 
-    def __init__(self, dev, group=None):
+    def __init__(self, dev, group=None, exchange: Optional[str] = None, B_max: int = 64,
+                 k_max: int = 128):
         self.dev = dev
         self.group = group
         self.world = dist.get_world_size(group) if dist.is_initialized() else 1
         self.rank = dist.get_rank(group) if dist.is_initialized() else 0
         self._bufs = {}
+        self.exchange = exchange or os.environ.get("LRX_EXCHANGE", "peer")
+        if self.exchange not in ("peer", "nccl"):
+            raise ValueError("exchange must be 'peer' or 'nccl'")
+        if self.world > 1 and self.exchange == "peer":
+            dev.exchange_setup(B_max, k_max, group)
 
     def buffers(self, B: int, k: int):
         key = (B, k)
@@ -80,6 +93,8 @@ class ShardedSearcher:
         rank).  Asynchronous on torch's current stream."""
         B = int(q_fp16.shape[0])
         mine, every, outs = self.buffers(B, k)
+        if self.world > 1 and self.exchange == "peer":
+            return self.dev.search_sharded(q_fp16, q_terms, q_ptr, k, mode, weights, outs)
         self.dev.search_local_packed(q_fp16, q_terms, q_ptr, k, mode, mine)
         if self.world > 1:
             dist.all_gather_into_tensor(every, mine, group=self.group)

@@ -2,6 +2,7 @@
 the unsharded oracle.  Skipped on single-GPU boxes (run with `gpurun --gpus 2`)."""
 import os
 import socket
+import time
 
 import numpy as np
 import pytest
@@ -22,7 +23,7 @@ def _inputs():
     return x, idx, q, terms, ptr
 
 
-def _worker(rank, world, port, mode, ret):
+def _worker(rank, world, port, mode, exchange, ret):
     import torch.distributed as dist
     from legal_rag_engine_b200 import sharding
     from legal_rag_engine_b200.device_index import DeviceIndex, FUSION
@@ -37,18 +38,29 @@ def _worker(rank, world, port, mode, ret):
         dev = DeviceIndex(rank, rank, world)
         dev.set_corpus(torch.from_numpy(x[lo:hi]).cuda(), lo)
         dev.set_postings(sh.term_ptr, sh.postings, sh.doc_len, sh.idf, sh.avgdl)
-        s = sharding.ShardedSearcher(dev)
+        s = sharding.ShardedSearcher(dev, exchange=exchange)
         c = lambda a: torch.from_numpy(np.ascontiguousarray(a)).cuda()
-        outs = s.search(c(q), c(terms), c(ptr), K_TOP, FUSION[mode], c(np.array(WEIGHTS)))
+        # several batches back to back: the exchange slots and flags are reused every second call;
+        # a different (reversed) batch in between must not leak into the last one
+        dq, dt, dp, dw = c(q), c(terms), c(ptr), c(np.array(WEIGHTS))
+        dq2 = c(q[::-1])
+        for i in range(5):
+            s.search(dq2 if i % 2 else dq, dt, dp, K_TOP, FUSION[mode], dw)
+        torch.cuda.synchronize()
+        if rank == 1:
+            time.sleep(0.05)                                  # ranks drift apart: flags must hold
+        outs = s.search(dq, dt, dp, K_TOP, FUSION[mode], dw)
         torch.cuda.synchronize()
         ret[rank] = [t.cpu().numpy() for t in outs]
+        dist.barrier()                                        # nobody unmaps while a peer may store
         dev.close()
     finally:
         dist.destroy_process_group()
 
 
+@pytest.mark.parametrize("exchange", ["peer", "nccl"])
 @pytest.mark.parametrize("mode", ["linear", "rrf"])
-def test_two_gpu_sharded_search_equals_oracle(mode):
+def test_two_gpu_sharded_search_equals_oracle(mode, exchange):
     if torch.cuda.device_count() < 2:
         pytest.skip("needs 2 GPUs")
     import torch.multiprocessing as mp
@@ -64,7 +76,7 @@ def test_two_gpu_sharded_search_equals_oracle(mode):
         port = so.getsockname()[1]
     with mp.Manager() as mgr:
         ret = mgr.dict()
-        mp.spawn(_worker, args=(2, port, mode, ret), nprocs=2, join=True)
+        mp.spawn(_worker, args=(2, port, mode, exchange, ret), nprocs=2, join=True)
         r0, r1 = ret[0], ret[1]
     for a, b in zip(r0, r1):
         np.testing.assert_array_equal(a, b)                   # replicated result
