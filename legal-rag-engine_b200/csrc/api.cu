@@ -25,14 +25,14 @@ cudaError_t ensure_ws(void** p, size_t* have, size_t need) {
     return e;
 }
 
-void prof_begin(lrx_handle* h, int which) {
+void prof_begin(lrx_handle* h, int which, cudaStream_t st) {
     if (!h->prof) return;
     cudaEvent_t e;
     if (cudaEventCreate(&e) != cudaSuccess) return;
-    cudaEventRecord(e, h->stream);
+    cudaEventRecord(e, st ? st : h->stream);
     h->prof_ev[which].push_back(e);
 }
-void prof_end(lrx_handle* h, int which) { prof_begin(h, which); }
+void prof_end(lrx_handle* h, int which, cudaStream_t st) { prof_begin(h, which, st); }
 
 static std::string g_err;   // failures before a handle exists
 static std::mutex g_err_mu;
@@ -442,16 +442,22 @@ static int search_local_locked(lrx_handle* h, const void* q, const int32_t* q_te
     s.dense_I = (int64_t*)p;    p += n * sizeof(int64_t);
     s.bm_ids = (int64_t*)p;     p += n * sizeof(int64_t);
     s.dense_D = (float*)p;
-    // fork: tile bounds of every query token (needs only the query) on the side stream
+    // Two chains side by side.  Main stream: dense scan -> merge + exact re-score.  Side stream:
+    // BM25 range bounds -> BM25 scan -> merge + max.  Neither needs the other's result (the BM25
+    // scores AT the dense candidates are looked up afterwards by bm25_at_kernel), and the two scans
+    // are built to share an SM -- the dense scan is bound by HBM and leaves the issue slots idle,
+    // the BM25 scan is bound by issue/FP64 latency and leaves HBM idle; one CTA of each fits the
+    // registers and the shared memory of an SM.  The dense scan is launched first so that its 148
+    // CTAs are placed before the BM25 CTAs fill the rest.
+    const int Kb = (mode == LRX_FUSE_RRF) ? K : 0;
     LRX_CUDA(h, cudaEventRecord(h->ev_fork, h->stream));
     LRX_CUDA(h, cudaStreamWaitEvent(h->aux, h->ev_fork, 0));
-    LRX_CUDA(h, launch_bm25_bounds(h, q_terms, q_ptr, B, h->aux));
-    LRX_CUDA(h, cudaEventRecord(h->ev_join, h->aux));
     LRX_CUDA(h, launch_dense_topk(h, q, B, K, width, s.dense_exact, s.dense_D, s.dense_I, flags));
+    LRX_CUDA(h, launch_bm25_bounds(h, q_terms, q_ptr, B, h->aux));
+    LRX_CUDA(h, launch_bm25_scan(h, q_terms, q_ptr, B, maxbm, Kb, s.bm_scores, s.bm_ids, h->aux));
+    LRX_CUDA(h, cudaEventRecord(h->ev_join, h->aux));
     LRX_CUDA(h, cudaStreamWaitEvent(h->stream, h->ev_join, 0));   // join
-    const int Kb = (mode == LRX_FUSE_RRF) ? K : 0;
-    LRX_CUDA(h, launch_bm25_scan(h, q_terms, q_ptr, B, s.dense_I, K, s.dense_bm, maxbm, Kb,
-                                 s.bm_scores, s.bm_ids));
+    LRX_CUDA(h, launch_bm25_at(h, q_terms, q_ptr, B, s.dense_I, K, s.dense_bm, h->stream));
     LRX_CUDA(h, launch_pack_records(h, B, K, mode, s.dense_exact, s.dense_I, s.dense_bm, s.bm_scores,
                                     s.bm_ids, s.bm_dense, q, records));
     return LRX_OK;

@@ -23,11 +23,12 @@
 
 namespace lrx {
 
-constexpr int kScanThreads = 512;
+constexpr int kScanThreads = 256;                  // 8 warps: the SM is shared with a BM25 scan CTA
 constexpr int kTileRows = 64;                      // 4 rows per warp per tile
 constexpr int kTileBytes = kTileRows * kRowBytes;  // 49152
 #ifndef LRX_SCAN_STAGES
-#define LRX_SCAN_STAGES 4                          // 2, 3 and 4 measure the same (tools/scan_sweep.sh)
+#define LRX_SCAN_STAGES 2                          // 2, 3 and 4 measure the same (tools/scan_sweep.sh);
+                                                   // 2 leaves shared memory for a co-resident BM25 CTA
 #endif
 constexpr int kStages = LRX_SCAN_STAGES;
 constexpr int kCap = 1024;                         // candidate buffer entries per query
@@ -98,39 +99,42 @@ __device__ __forceinline__ void scan_prune(uint64_t* keys, int* count, uint32_t*
 #pragma unroll
     for (int q = 0; q < NQ; ++q) nmax = max(nmax, count[q]);
     if (width == 64 && nmax <= 256) {
-        // fast path (the default list width, pruned at the soft cap): four warps per query sort
-        // 64 keys each in registers; the best 64 of two descending runs A, B are the bitonic
-        // sequence max(A[i], B[63 - i]), sorted by one bitonic merge -- two rounds, 4 -> 2 -> 1.
+        // fast path (the default list width, pruned at the soft cap): two warps per query, each
+        // sorts two 64-key quarters in registers; the best 64 of two descending runs A, B are the
+        // bitonic sequence max(A[i], B[63 - i]), sorted by one bitonic merge -- once inside the
+        // warp (B reversed by a shuffle), once across the two warps through shared memory.
         const int lane = tid & 31, warp = tid >> 5;
-        const int q = warp & 3, part = warp >> 2;            // 16 warps: (query, quarter)
+        const int q = warp & 3, half = warp >> 2;            // 8 warps: (query, half)
         uint64_t* kq = keys + q * kCap;
         const bool active = q < NQ;
         const int n = active ? count[q] : 0;
         uint64_t v0 = 0ull, v1 = 0ull;
         if (active) {
-            const int i0 = part * 64 + 2 * lane;
+            const int i0 = half * 128 + 2 * lane;
             v0 = (i0 < n) ? kq[i0] : 0ull;
             v1 = (i0 + 1 < n) ? kq[i0 + 1] : 0ull;
+            uint64_t w0 = (i0 + 64 < n) ? kq[i0 + 64] : 0ull;
+            uint64_t w1 = (i0 + 65 < n) ? kq[i0 + 65] : 0ull;
             warp64_sort_desc(v0, v1, lane);
+            warp64_sort_desc(w0, w1, lane);
+            // B[63 - 2l] and B[62 - 2l] live in lane 31 - l as its second and first key
+            const uint64_t r0 = __shfl_sync(0xffffffffu, w1, 31 - lane);
+            const uint64_t r1 = __shfl_sync(0xffffffffu, w0, 31 - lane);
+            v0 = max(v0, r0);
+            v1 = max(v1, r1);
+            warp64_merge_desc(v0, v1, lane);
         }
         __syncthreads();                                     // all reads of keys done
-#pragma unroll
-        for (int round = 0; round < 2; ++round) {
-            const int stride = 1 << round;                   // partner quarter = part ^ stride
-            if (active && (part & ((2 << round) - 1)) == stride) {   // the giving quarter
-                kq[part * 64 + 2 * lane] = v0;
-                kq[part * 64 + 2 * lane + 1] = v1;
-            }
-            __syncthreads();
-            if (active && (part & ((2 << round) - 1)) == 0) {         // the keeping quarter
-                const uint64_t* other = kq + (part + stride) * 64;
-                v0 = max(v0, other[63 - 2 * lane]);
-                v1 = max(v1, other[62 - 2 * lane]);
-                warp64_merge_desc(v0, v1, lane);
-            }
-            __syncthreads();
+        if (active && half == 1) {
+            kq[64 + 2 * lane] = v0;
+            kq[64 + 2 * lane + 1] = v1;
         }
-        if (active && part == 0) {
+        __syncthreads();
+        if (active && half == 0) {
+            const uint64_t* other = kq + 64;
+            v0 = max(v0, other[63 - 2 * lane]);
+            v1 = max(v1, other[62 - 2 * lane]);
+            warp64_merge_desc(v0, v1, lane);
             kq[2 * lane] = v0;
             kq[2 * lane + 1] = v1;
         }
@@ -164,7 +168,7 @@ __device__ __forceinline__ void scan_prune(uint64_t* keys, int* count, uint32_t*
 }
 
 template <int NQ>
-__global__ void __launch_bounds__(kScanThreads, 1)
+__global__ void __launch_bounds__(kScanThreads, 2)          // <= 128 registers: see kScanThreads
 dense_scan_kernel(const unsigned char* __restrict__ x, int64_t n_rows,
                   const __half* __restrict__ q, int n_q, int width,
                   uint64_t* __restrict__ part /* [grid][NQ][width] */,
@@ -214,15 +218,13 @@ dense_scan_kernel(const unsigned char* __restrict__ x, int64_t n_rows,
     __syncthreads();                                         // tile_of[] visible
 
     // ---- scoring on the tensor cores (mma.sync m16n8k16, fp16 x fp16 -> fp32): a tile is four
-    //      16-row blocks x two 192-column halves, one (block, half) per warp of warps 0-7 (the other
-    //      eight only take part in the per-row tests and the prunes; the shared-memory budget has
-    //      no room for more partial sums, and the math is far from the critical path).  The 8 "n"
+    //      16-row blocks x two 192-column halves, one (block, half) per warp.  The 8 "n"
     //      columns are the <= 4 queries plus zero padding.  Lane (g = lane / 4, t = lane % 4) reads
     //      16 contiguous bytes of rows g and g + 8 per 32-column chunk -- two MMAs' worth -- and
     //      holds the query's halves at the SAME columns, so A and B agree on a (permuted) k order.
     const int g = lane >> 2, t = lane & 3;
     const int mblk = warp & 3, kh = (warp >> 2) & 1;
-    const bool mma_warp = warp < 8;
+    constexpr bool mma_warp = true;
     uint32_t qb[6][4];                                           // query g, chunks 6*kh .. 6*kh + 5
 #pragma unroll
     for (int j = 0; j < 6; ++j) {
@@ -482,6 +484,11 @@ static cudaError_t launch_scan(lrx_handle* h, const __half* q, int n_q, int widt
     if (!attr) {
         cudaError_t e = cudaFuncSetAttribute(dense_scan_kernel<NQ>,
                                              cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return e;
+        // the SM's L1 / shared-memory split is fixed while a CTA is resident: ask for all of it as
+        // shared memory so that a BM25 scan CTA (90 KB) can join this kernel's CTA (133 KB)
+        e = cudaFuncSetAttribute(dense_scan_kernel<NQ>, cudaFuncAttributePreferredSharedMemoryCarveout,
+                                 cudaSharedmemCarveoutMaxShared);
         if (e != cudaSuccess) return e;
         attr = true;
     }

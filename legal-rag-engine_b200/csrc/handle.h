@@ -95,8 +95,10 @@ cudaError_t launch_bm25(lrx_handle* h, const int32_t* q_terms, const int32_t* q_
 cudaError_t launch_bm25_bounds(lrx_handle* h, const int32_t* q_terms, const int32_t* q_ptr, int B,
                                cudaStream_t st);
 cudaError_t launch_bm25_scan(lrx_handle* h, const int32_t* q_terms, const int32_t* q_ptr, int B,
-                             const int64_t* cand_ids, int n_cand, double* cand_scores,
-                             double* out_max, int K, double* top_scores, int64_t* top_ids);
+                             double* out_max, int K, double* top_scores, int64_t* top_ids,
+                             cudaStream_t st);
+cudaError_t launch_bm25_at(lrx_handle* h, const int32_t* q_terms, const int32_t* q_ptr, int B,
+                           const int64_t* ids, int n, double* out, cudaStream_t st);
 cudaError_t launch_bm25_pack(lrx_handle* h, const uint32_t* doc_tf, int64_t nnz, const uint32_t* doc_len,
                              void* out, int* host_overflow);
 cudaError_t launch_bm25_lut(lrx_handle* h, double avgdl, double k1, double b, int max_len);
@@ -130,8 +132,8 @@ cudaError_t gemm_f16_adhoc(lrx_handle* h, const void* a, const void* w, int M, i
                            const float* beta, float eps, void* out);
 
 // profiling hooks (no-ops unless lrx_profile_enable(h, 1))
-void prof_begin(lrx_handle* h, int which);
-void prof_end(lrx_handle* h, int which);
+void prof_begin(lrx_handle* h, int which, cudaStream_t st = nullptr);   // nullptr: h->stream
+void prof_end(lrx_handle* h, int which, cudaStream_t st = nullptr);
 
 // shared helper: grow a device workspace
 cudaError_t ensure_ws(void** p, size_t* have, size_t need);
