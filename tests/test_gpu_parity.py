@@ -224,6 +224,25 @@ def test_search_batch_host_matches_oracle(dev, n, fusion):
         _assert_results(got, want, k)
 
 
+@pytest.mark.parametrize("fusion", ["linear", "rrf"])
+def test_search_top100_config_c5_depth(dev, fusion):
+    """Config C5's depth (top-100: dense top-200, width 256, BM25 list of 200) on one shard."""
+    n = 120000
+    x = synth.host_vectors(n, seed=91, dup_frac=0.005)
+    idx = synth.host_bm25(n, seed=92, vocab=4000)
+    csr = _csr_of(idx)
+    dev.set_corpus(_cuda(x), 0)
+    _set_postings(dev, idx)
+    B = 3
+    q = synth.host_queries(B, seed=93)
+    terms, ptr = synth.host_query_terms(B, 8, seed=94, vocab=4000)
+    lists = [terms[ptr[b]:ptr[b + 1]].tolist() for b in range(B)]
+    weights = [0.5, 0.6, 0.5]
+    want = _oracle_search(x, csr, q, lists, 100, weights, fusion)
+    got = dev.search_batch_host(q, lists, 100, weights, fusion)
+    _assert_results(got, want, 100)
+
+
 def test_real_corpus_hybrid_search(dev, legal_texts, reference_queries):
     """Config C1 minus the encoder: real BM25 side, seeded stand-in vectors."""
     idx = BM25Index.from_texts(legal_texts)
