@@ -479,7 +479,8 @@ int dense_scan_grid(const lrx_handle* h) {
 template <int NQ>
 static cudaError_t launch_scan(lrx_handle* h, const __half* q, int n_q, int width, uint64_t* part,
                                int grid) {
-    static bool attr = false;
+    static bool attr_dev[64] = {false};   // function attributes are per device
+    bool& attr = attr_dev[h->device & 63];
     const size_t smem = scan_smem_bytes(NQ);
     if (!attr) {
         cudaError_t e = cudaFuncSetAttribute(dense_scan_kernel<NQ>,
@@ -518,7 +519,8 @@ cudaError_t launch_dense_topk(lrx_handle* h, const void* qv, int B, int K, int w
     e = ensure_ws(&h->ws_dense_part, &h->ws_dense_part_bytes,
                   (size_t)grid * 4 * width * sizeof(uint64_t) + 64);
     if (e != cudaSuccess) return e;
-    static bool attr = false;
+    static bool attr_dev[64] = {false};   // function attributes are per device
+    bool& attr = attr_dev[h->device & 63];
     if (!attr) {
         e = cudaFuncSetAttribute(dense_merge_rescore_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                  (int)(kMergeCap * sizeof(uint64_t)));

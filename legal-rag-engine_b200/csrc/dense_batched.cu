@@ -322,7 +322,8 @@ int dense_batched_max_stride(int64_t n_rows, int K) {
 
 cudaError_t launch_dense_topk_batched(lrx_handle* h, const void* q, int B, int K, int stride,
                                       double* exact, float* D, int64_t* I, int32_t* flags) {
-    static bool attr = false;
+    static bool attr_dev[64] = {false};   // function attributes are per device
+    bool& attr = attr_dev[h->device & 63];
     cudaError_t e;
     if (!attr) {
         const void* ks[] = {(const void*)dense_tc_kernel<1, 1>, (const void*)dense_tc_kernel<2, 1>,

@@ -523,7 +523,8 @@ cudaError_t encoder_forward(lrx_handle* h, const int32_t* ids, const int32_t* le
     if (seq_per_chunk < 1) seq_per_chunk = 1;
     if (seq_per_chunk > B) seq_per_chunk = B;
     ENC_CK(encoder_reserve(e, (int64_t)seq_per_chunk * S));
-    static bool attr = false;
+    static bool attr_dev[64] = {false};   // function attributes are per device
+    bool& attr = attr_dev[h->device & 63];
     if (!attr) {
         ENC_CK(cudaFuncSetAttribute(attention_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                     96 * 1024));

@@ -325,7 +325,8 @@ cudaError_t launch_fuse(lrx_handle* h, const lrx_record* records_all, const doub
                         int k, int mode, const double* weights, int64_t* ids, double* score,
                         double* sem, double* kw, int32_t* status, const unsigned long long* wait_flags,
                         unsigned long long wait_seq, int self) {
-    static bool attr = false;
+    static bool attr_dev[64] = {false};   // function attributes are per device
+    bool& attr = attr_dev[h->device & 63];
     if (!attr) {
         cudaError_t e = cudaFuncSetAttribute(fuse_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                              (int)(kFuseMaxIn * sizeof(u128)));

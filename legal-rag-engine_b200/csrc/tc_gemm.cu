@@ -581,7 +581,8 @@ template <int BN, int EPI, bool ARES, int CS>
 static cudaError_t launch_cfg(lrx_handle* h, const CUtensorMap& ta, const CUtensorMap& tb,
                               const CUtensorMap& tout, const CUtensorMap& tres, int M,
                               int N, int K, const GemmEpi& ep) {
-    static bool attr = false;
+    static bool attr_dev[64] = {false};   // function attributes are per device
+    bool& attr = attr_dev[h->device & 63];
     auto kern = tc_gemm_kernel<BN, EPI, ARES, CS>;
     constexpr size_t smem = GemmCfg<BN, ARES, CS>::kSmem;
     if (!attr) {
