@@ -189,7 +189,10 @@ dense_scan_kernel(const unsigned char* __restrict__ x, int64_t n_rows,
     // Tiles are static, blockIdx + i * grid: at any moment the grid reads one contiguous ~7 MB
     // window of the matrix.  (Measured, tools/scan_sweep.sh: claiming tiles from a grid-wide counter
     // costs 25 % -- one contended atomic per 48 KB -- and re-filling a stage BEFORE the tile's
-    // per-row tests instead of after the closing barrier costs 30 %.)
+    // per-row tests instead of after the closing barrier costs 30 %; 32-row tiles cost 50 %; a
+    // variant without the k split -- 8 rows per warp over the whole k, half of each MMA redundant,
+    // one barrier per tile, no partial sums -- measures the same but needs 122 registers, which
+    // leaves no margin for the BM25 CTA on the same SM.)
     const int n_tiles = (int)((n_rows + kTileRows - 1) / kTileRows);
 
     if (tid == 0) {
