@@ -418,13 +418,9 @@ struct LocalScratch {
     double* bm_dense;
 };
 
-// tok_ids != NULL: the query vectors `q` do not exist yet -- K1 encodes them from the token ids on
-// the main stream while the BM25 chain (which needs only the term ids) already runs beside it.
 static int search_local_locked(lrx_handle* h, const void* q, const int32_t* q_terms,
                                const int32_t* q_ptr, int B, int k, int mode, int width,
-                               lrx_record* records, double* maxbm, int32_t* flags,
-                               const int32_t* tok_ids = nullptr, const int32_t* tok_lens = nullptr,
-                               int S = 0) {
+                               lrx_record* records, double* maxbm, int32_t* flags) {
     const int K = 2 * k;   // index.search(query_vector, k * 2)  (retrieval_engine.py:64)
     int rc = check_dense(h, "lrx_search_local", B, K);
     if (rc != LRX_OK) return rc;
@@ -456,22 +452,9 @@ static int search_local_locked(lrx_handle* h, const void* q, const int32_t* q_te
     const int Kb = (mode == LRX_FUSE_RRF) ? K : 0;
     LRX_CUDA(h, cudaEventRecord(h->ev_fork, h->stream));
     LRX_CUDA(h, cudaStreamWaitEvent(h->aux, h->ev_fork, 0));
-    if (tok_ids != nullptr) {
-        // BM25 chain first (a few SMs left free for the encoder's GEMM CTAs), then K1 -> K2 on the
-        // main stream: the BM25 scan runs under the encoder, the dense scan after both
-        h->bm_spare_sms = 12;
-        cudaError_t eb = launch_bm25_bounds(h, q_terms, q_ptr, B, h->aux);
-        if (eb == cudaSuccess)
-            eb = launch_bm25_scan(h, q_terms, q_ptr, B, maxbm, Kb, s.bm_scores, s.bm_ids, h->aux);
-        h->bm_spare_sms = 0;
-        LRX_CUDA(h, eb);
-        LRX_CUDA(h, encoder_forward(h, tok_ids, tok_lens, B, S, nullptr, const_cast<void*>(q)));
-        LRX_CUDA(h, launch_dense_topk(h, q, B, K, width, s.dense_exact, s.dense_D, s.dense_I, flags));
-    } else {
-        LRX_CUDA(h, launch_dense_topk(h, q, B, K, width, s.dense_exact, s.dense_D, s.dense_I, flags));
-        LRX_CUDA(h, launch_bm25_bounds(h, q_terms, q_ptr, B, h->aux));
-        LRX_CUDA(h, launch_bm25_scan(h, q_terms, q_ptr, B, maxbm, Kb, s.bm_scores, s.bm_ids, h->aux));
-    }
+    LRX_CUDA(h, launch_dense_topk(h, q, B, K, width, s.dense_exact, s.dense_D, s.dense_I, flags));
+    LRX_CUDA(h, launch_bm25_bounds(h, q_terms, q_ptr, B, h->aux));
+    LRX_CUDA(h, launch_bm25_scan(h, q_terms, q_ptr, B, maxbm, Kb, s.bm_scores, s.bm_ids, h->aux));
     LRX_CUDA(h, cudaEventRecord(h->ev_join, h->aux));
     LRX_CUDA(h, cudaStreamWaitEvent(h->stream, h->ev_join, 0));   // join
     LRX_CUDA(h, launch_bm25_at(h, q_terms, q_ptr, B, s.dense_I, K, s.dense_bm, h->stream));
@@ -719,18 +702,20 @@ static int search_host_locked(lrx_handle* h, const char* fn, const void* host_q_
         memcpy(hp + o_len, host_lens, (size_t)B * sizeof(int32_t));
     }
     LRX_CUDA(h, cudaMemcpyAsync(dp, hp, in_bytes, cudaMemcpyHostToDevice, h->stream));
-    // K1 (token ids -> fp16 unit query vectors, straight into the K2 operand slot) is launched
-    // inside search_local_locked, beside the BM25 chain; a widened rerun reuses the vectors
-    bool encode_now = encode;
+    // K1: token ids -> fp16 unit query vectors, straight into the K2 operand slot.  (Measured: the
+    // BM25 chain cannot usefully run UNDER the encoder -- its persistent CTAs take every SM and the
+    // encoder's GEMM CTAs, which need a whole SM's shared memory, wait for them -- so K1 runs
+    // first and the two scans share the SMs afterwards.)
+    if (encode)
+        LRX_CUDA(h, encoder_forward(h, (const int32_t*)(dp + o_tok), (const int32_t*)(dp + o_len), B, S,
+                                    nullptr, dp + o_q));
+
     int width = dense_default_width(K);
     for (;;) {
         int rc = search_local_locked(h, dp + o_q, (const int32_t*)(dp + o_terms),
                                      (const int32_t*)(dp + o_ptr), B, k, mode, width,
                                      (lrx_record*)(dp + o_rec), (double*)(dp + o_max),
-                                     (int32_t*)(dp + o_flags),
-                                     encode_now ? (const int32_t*)(dp + o_tok) : nullptr,
-                                     (const int32_t*)(dp + o_len), S);
-        encode_now = false;
+                                     (int32_t*)(dp + o_flags));
         if (rc != LRX_OK) return rc;
         rc = search_finish_locked(h, (const lrx_record*)(dp + o_rec), (const double*)(dp + o_max),
                                   (const int32_t*)(dp + o_flags), 0, 1, B, k, mode,

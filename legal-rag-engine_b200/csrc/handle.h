@@ -41,7 +41,6 @@ struct lrx_handle {
     void* bm_lut = nullptr;          size_t bm_lut_bytes = 0;
     int bm_lut_ld = 0;
     double bm_avgdl = 0.0, bm_k1 = 1.5, bm_b = 0.75;
-    int bm_spare_sms = 0;            // SMs the BM25 scan leaves free (set around one launch)
 
     // workspaces (handle-owned, grown on demand)
     void* ws_dense_part = nullptr;   size_t ws_dense_part_bytes = 0;    // per-CTA key lists
