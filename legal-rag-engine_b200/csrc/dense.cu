@@ -140,8 +140,11 @@ __device__ __forceinline__ void scan_prune(uint64_t* keys, int* count, uint32_t*
         }
         __syncthreads();
     } else {
-        // general path: sort only as many slots as are in use (power of two >= the fullest
-        // buffer, >= width), pad the unused ones with the empty key, all NQ buffers at once
+        // general path (wider lists): sort only as many slots as are in use (power of two >= the
+        // fullest buffer, >= width; unused ones padded with the empty key), all NQ buffers at once.
+        // Bitonic sort with the 64-key stages in registers: chunks of 64 are sorted by one warp
+        // each (alternating direction), and of every later merge only the steps at distance >= 64
+        // go through shared memory -- 10 block-wide steps for 1024 keys instead of 55.
         const int n2 = min(kCap, next_pow2(nmax));
 #pragma unroll
         for (int q = 0; q < NQ; ++q) {
@@ -150,7 +153,44 @@ __device__ __forceinline__ void scan_prune(uint64_t* keys, int* count, uint32_t*
                 if (i >= n) keys[q * kCap + i] = 0ull;
         }
         __syncthreads();
-        block_bitonic_sort_desc<uint64_t>(keys, n2, NQ, kCap, tid, kScanThreads);
+        if (n2 < 128) {
+            block_bitonic_sort_desc<uint64_t>(keys, n2, NQ, kCap, tid, kScanThreads);
+        } else {
+            const int lane = tid & 31, warp = tid >> 5;
+            const int chunks = n2 >> 6, total = chunks * NQ;
+            // one pass over the 64-key chunks: sort (first = true) or bitonic-merge them, written
+            // back descending when the chunk lies in a descending block of size k, else ascending
+            auto chunk_pass = [&](int k, bool first) {
+                for (int c = warp; c < total; c += kScanThreads / 32) {
+                    const int q = c / chunks, ch = c - q * chunks;
+                    uint64_t* kc = keys + q * kCap + ch * 64;
+                    uint64_t v0 = kc[2 * lane], v1 = kc[2 * lane + 1];
+                    if (first) warp64_sort_desc(v0, v1, lane); else warp64_merge_desc(v0, v1, lane);
+                    const bool desc = ((ch * 64) & k) == 0;
+                    __syncwarp();
+                    kc[desc ? 2 * lane : 63 - 2 * lane] = v0;
+                    kc[desc ? 2 * lane + 1 : 62 - 2 * lane] = v1;
+                }
+                __syncthreads();
+            };
+            chunk_pass(64, true);
+            const int half = n2 >> 1, lh = 31 - __clz(half);
+            for (int k = 128; k <= n2; k <<= 1) {
+                for (int j = k >> 1; j >= 64; j >>= 1) {
+                    for (int t = tid; t < half * NQ; t += kScanThreads) {
+                        const int q = t >> lh, u = t & (half - 1);
+                        const int i = ((u & ~(j - 1)) << 1) | (u & (j - 1));
+                        const int p = i | j;
+                        uint64_t* kk = keys + q * kCap;
+                        const uint64_t a = kk[i], b = kk[p];
+                        const bool desc = ((i & k) == 0);
+                        if (desc ? (a < b) : (a > b)) { kk[i] = b; kk[p] = a; }
+                    }
+                    __syncthreads();
+                }
+                chunk_pass(k, false);
+            }
+        }
     }
     if (tid < NQ) {
         const int c = min(count[tid], width);
