@@ -61,6 +61,13 @@ __device__ __forceinline__ void bulk_g2s(void* dst, const void* src, uint32_t by
         : "memory");
 }
 
+// Programmatic dependent launch: a kernel launched with launch_pdl() (handle.h) may start while
+// its predecessor in the stream still runs; pdl_wait() blocks until the predecessor grid has
+// completed and its memory is visible (a no-op under a normal launch), pdl_trigger() lets the
+// successor's CTAs be scheduled from now on (a no-op without such a successor).
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+
 // ------------------------------------------------------- order-preserving keys
 // Unsigned images of IEEE values whose integer order equals the float order.
 __device__ __forceinline__ uint32_t f32_ord(float f) {

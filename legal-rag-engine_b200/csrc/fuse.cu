@@ -31,6 +31,8 @@ __global__ void pack_records_kernel(int B, int K, int mode, const double* __rest
                                     const unsigned char* __restrict__ x, int64_t n_rows,
                                     int64_t id_base, const __half* __restrict__ q,
                                     lrx_record* __restrict__ records) {
+    pdl_trigger();                       // the exchange / fusion kernel may be scheduled
+    pdl_wait();                          // bm25_at_kernel's scores are visible
     const int i = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
     const int lane = threadIdx.x & 31;
     if (i >= B * K) return;
@@ -106,6 +108,7 @@ fuse_kernel(const lrx_record* __restrict__ rec_all, const double* __restrict__ m
             double* __restrict__ out_kw, int32_t* __restrict__ out_status,
             const unsigned long long* wait_flags /* [world] or NULL */, unsigned long long wait_seq,
             int self) {
+    pdl_wait();                                  // the packing / exchange kernel has finished
     extern __shared__ __align__(16) unsigned char fuse_dyn[];
     u128* keys = reinterpret_cast<u128*>(fuse_dyn);   // [kFuseMaxIn]
     __shared__ lrx_record dsel[kFuseMaxK];      // global dense top-K
@@ -285,6 +288,8 @@ fuse_kernel(const lrx_record* __restrict__ rec_all, const double* __restrict__ m
 __global__ void exchange_kernel(const uint4* __restrict__ mine, int n16, void* const* __restrict__ peers,
                                 int rank, int world, size_t slot_off, size_t flag_off,
                                 unsigned long long seq) {
+    pdl_trigger();                       // the fusion kernel may be scheduled (it waits for us)
+    pdl_wait();                          // pack_records_kernel's block is visible
     const int p = (rank + 1 + (int)blockIdx.x) % world;
     char* base = reinterpret_cast<char*>(peers[p]);
     uint4* dst = reinterpret_cast<uint4*>(base + slot_off);
@@ -300,11 +305,11 @@ __global__ void exchange_kernel(const uint4* __restrict__ mine, int n16, void* c
 cudaError_t launch_exchange(lrx_handle* h, const void* mine, size_t bytes, size_t slot_off,
                             size_t flag_off, unsigned long long seq) {
     if (h->world < 2) return cudaSuccess;
-    exchange_kernel<<<h->world - 1, 256, 0, h->stream>>>((const uint4*)mine, (int)(bytes / 16),
-                                                         h->xchg_peer_dev, h->rank, h->world, slot_off,
-                                                         flag_off, seq);
+    cudaError_t e = launch_pdl(exchange_kernel, dim3(h->world - 1), dim3(256), 0, h->stream,
+                               (const uint4*)mine, (int)(bytes / 16), (void* const*)h->xchg_peer_dev, h->rank,
+                               h->world, slot_off, flag_off, seq);
     h->launches++;
-    return cudaGetLastError();
+    return e;
 }
 
 cudaError_t launch_pack_records(lrx_handle* h, int B, int K, int mode, const double* dense_exact,
@@ -313,11 +318,12 @@ cudaError_t launch_pack_records(lrx_handle* h, int B, int K, int mode, const dou
                                 const double* bm_dense, const void* q, lrx_record* records) {
     // q != NULL: the exact dense scores of the BM25 hits are computed in the kernel (bm_dense unused)
     const int n = B * K;
-    pack_records_kernel<<<(n + 7) / 8, 256, 0, h->stream>>>(
-        B, K, mode, dense_exact, dense_ids, dense_bm25, bm_scores, bm_ids, bm_dense,
-        q ? (const unsigned char*)h->x : nullptr, h->n_local, h->id_base, (const __half*)q, records);
+    cudaError_t e = launch_pdl(pack_records_kernel, dim3((n + 7) / 8), dim3(256), 0, h->stream,
+                               B, K, mode, dense_exact, dense_ids, dense_bm25, bm_scores, bm_ids, bm_dense,
+                               q ? (const unsigned char*)h->x : (const unsigned char*)nullptr, h->n_local,
+                               h->id_base, (const __half*)q, records);
     h->launches++;
-    return cudaGetLastError();
+    return e;
 }
 
 cudaError_t launch_fuse(lrx_handle* h, const lrx_record* records_all, const double* max_all,
@@ -334,11 +340,11 @@ cudaError_t launch_fuse(lrx_handle* h, const lrx_record* records_all, const doub
         attr = true;
     }
     if (world * K > kFuseMaxIn || K > kFuseMaxK) return cudaErrorInvalidValue;
-    fuse_kernel<<<B, kFuseThreads, kFuseMaxIn * sizeof(u128), h->stream>>>(
-        records_all, max_all, flags_all, shard_stride, world, B, K, k, mode, weights, ids, score,
-        sem, kw, status, wait_flags, wait_seq, self);
+    cudaError_t e = launch_pdl(fuse_kernel, dim3(B), dim3(kFuseThreads), kFuseMaxIn * sizeof(u128), h->stream,
+                               records_all, max_all, flags_all, shard_stride, world, B, K, k, mode, weights,
+                               ids, score, sem, kw, status, wait_flags, wait_seq, self);
     h->launches++;
-    return cudaGetLastError();
+    return e;
 }
 
 }  // namespace lrx

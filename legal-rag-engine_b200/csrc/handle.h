@@ -131,6 +131,25 @@ cudaError_t gemm_f16_adhoc(lrx_handle* h, const void* a, const void* w, int M, i
                            const float* bias, const void* residual, const float* gamma,
                            const float* beta, float eps, void* out);
 
+// Launch with the programmatic-stream-serialization attribute: the kernel's CTAs may be scheduled
+// while the previous kernel of the stream still runs; it must call pdl_wait() before it reads
+// anything that kernel wrote (common.cuh).
+template <typename... KArgs, typename... Args>
+inline cudaError_t launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem,
+                              cudaStream_t st, Args... args) {
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = grid;
+    cfg.blockDim = block;
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = st;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    at[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = at;
+    cfg.numAttrs = 1;
+    return cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);
+}
+
 // profiling hooks (no-ops unless lrx_profile_enable(h, 1))
 void prof_begin(lrx_handle* h, int which, cudaStream_t st = nullptr);   // nullptr: h->stream
 void prof_end(lrx_handle* h, int which, cudaStream_t st = nullptr);
