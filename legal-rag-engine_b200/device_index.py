@@ -88,10 +88,27 @@ class DeviceIndex:
         self._ck(self.lib.lrx_bm25_build_postings(self.h, _ptr(po), nnz, _ptr(dl), _ptr(p8)))
         del po
         self._post = (tp, p8, idf_t)
+        self._post_args = (nnz, float(avgdl), float(k1), float(b), max_len)
         self.doc_len = dl
         self.n_terms = int(tp.numel() - 1)
         self._ck(self.lib.lrx_set_postings(self.h, _ptr(tp), _ptr(p8), _ptr(idf_t), self.n_terms, nnz,
                                            float(avgdl), float(k1), float(b), max_len))
+
+    def clone_view(self) -> "DeviceIndex":
+        """A second handle (own stream binding, workspaces, exchange region) over the SAME resident
+        matrix and postings -- no copies: lets two query batches be in flight on two streams, one
+        batch's merges and fusion running under the other's scans."""
+        other = DeviceIndex(self.device.index, self.rank, self.world)
+        if self.x is not None:
+            other.set_corpus(self.x, self.id_base)
+        if self._post is not None:
+            tp, p8, idf_t = self._post
+            nnz, avgdl, k1, b, max_len = self._post_args
+            other._post, other._post_args = self._post, self._post_args
+            other.doc_len, other.n_terms = self.doc_len, self.n_terms
+            other._ck(self.lib.lrx_set_postings(other.h, _ptr(tp), _ptr(p8), _ptr(idf_t), self.n_terms,
+                                                nnz, avgdl, k1, b, max_len))
+        return other
 
     # ---------------------------------------------------------------- stages
     def dense_topk(self, q: torch.Tensor, K: int, width: int = 0):
