@@ -243,6 +243,51 @@ def test_search_top100_config_c5_depth(dev, fusion):
     _assert_results(got, want, 100)
 
 
+def test_clone_view_two_batches_in_flight(dev):
+    """A second handle over the same resident index (DeviceIndex.clone_view), each on its own stream:
+    batches interleaved on the two streams give the oracle's results."""
+    n = 50000
+    x = synth.host_vectors(n, seed=17, dup_frac=0.01)
+    idx = synth.host_bm25(n, seed=18, vocab=3000)
+    csr = _csr_of(idx)
+    dev.set_corpus(_cuda(x), 0)
+    _set_postings(dev, idx)
+    other = dev.clone_view()
+    try:
+        from legal_rag_engine_b200.device_index import FUSION
+        from legal_rag_engine_b200.sharding import ShardedSearcher
+        streams = [torch.cuda.Stream(), torch.cuda.Stream()]
+        devs = [dev, other]
+        for d, st in zip(devs, streams):
+            with torch.cuda.stream(st):
+                d.use_current_stream()
+        searchers = [ShardedSearcher(d) for d in devs]
+        B, k, weights = 4, 10, [0.5, 0.6, 0.5, 0.6]
+        batches = []
+        for i in range(6):
+            q = synth.host_queries(B, seed=100 + i)
+            terms, ptr = synth.host_query_terms(B, 8, seed=200 + i, vocab=3000)
+            lists = [terms[ptr[b]:ptr[b + 1]].tolist() for b in range(B)]
+            batches.append((q, terms, ptr, lists))
+        torch.cuda.synchronize()
+        w = _cuda(np.array(weights))
+        got = []
+        for i, (q, terms, ptr, lists) in enumerate(batches):
+            j = i % 2
+            with torch.cuda.stream(streams[j]):
+                outs = searchers[j].search(_cuda(q), _cuda(terms), _cuda(ptr), k, FUSION["rrf"], w)
+                got.append([t.clone() for t in outs])            # clone on the same stream
+        torch.cuda.synchronize()
+        for (q, terms, ptr, lists), outs in zip(batches, got):
+            want = _oracle_search(x, csr, q, lists, k, weights, "rrf")
+            ids, score, sem, kw, status = [t.cpu().numpy() for t in outs]
+            assert status.sum() == 0
+            _assert_results((ids, score, sem, kw), want, k)
+    finally:
+        dev.use_current_stream()
+        other.close()
+
+
 def test_real_corpus_hybrid_search(dev, legal_texts, reference_queries):
     """Config C1 minus the encoder: real BM25 side, seeded stand-in vectors."""
     idx = BM25Index.from_texts(legal_texts)
