@@ -202,22 +202,38 @@ class DeviceIndex:
         return outs
 
     # ------------------------------------ peer-memory exchange (world > 1, one box)
-    def exchange_setup(self, B_max: int, k_max: int, group=None):
+    def exchange_setup(self, B_max: int, k_max: int, group=None) -> bool:
         """Allocate this rank's exchange region, swap IPC handles with the other ranks (one
         all-gather of 64 bytes at start-up) and open theirs: afterwards `search_sharded` needs no
-        collective call per query batch."""
+        collective call per query batch.  Returns False -- on EVERY rank, the outcome is agreed by
+        an all-reduce -- when some rank could not export or map a region (e.g. no peer access
+        between the GPUs); the caller then keeps the NCCL exchange."""
         import torch.distributed as dist
-        from ._lib import LRX_IPC_HANDLE_BYTES
+        from ._lib import LRX_IPC_HANDLE_BYTES, LrxError
+        ok = 1
         mine = (C.c_ubyte * LRX_IPC_HANDLE_BYTES)()
-        self._ck(self.lib.lrx_exchange_export(self.h, B_max, k_max, C.cast(mine, C.c_void_p)))
+        try:
+            self._ck(self.lib.lrx_exchange_export(self.h, B_max, k_max, C.cast(mine, C.c_void_p)))
+        except LrxError:
+            ok = 0
         world = dist.get_world_size(group)
         t = torch.tensor(list(mine), dtype=torch.uint8, device=self.device)
         every = torch.empty(world * LRX_IPC_HANDLE_BYTES, dtype=torch.uint8, device=self.device)
         dist.all_gather_into_tensor(every, t, group=group)
-        host = every.cpu().numpy().tobytes()
-        buf = (C.c_ubyte * len(host)).from_buffer_copy(host)
-        self._ck(self.lib.lrx_exchange_import(self.h, C.cast(buf, C.c_void_p)))
-        dist.barrier(group=group)                 # every region is mapped before the first store
+        flag = torch.tensor([ok], dtype=torch.int32, device=self.device)
+        dist.all_reduce(flag, op=dist.ReduceOp.MIN, group=group)      # did everybody export?
+        if int(flag.item()) == 1:
+            host = every.cpu().numpy().tobytes()
+            buf = (C.c_ubyte * len(host)).from_buffer_copy(host)
+            try:
+                self._ck(self.lib.lrx_exchange_import(self.h, C.cast(buf, C.c_void_p)))
+            except LrxError:
+                ok = 0
+        else:
+            ok = 0
+        flag = torch.tensor([ok], dtype=torch.int32, device=self.device)
+        dist.all_reduce(flag, op=dist.ReduceOp.MIN, group=group)      # ... and map every region?
+        return int(flag.item()) == 1       # the all-reduce also orders "mapped" before the first store
 
     def search_sharded(self, q, q_terms, q_ptr, k: int, mode: int, weights, outs, width: int = 0):
         """K2 + K3 on this shard, block stored into every peer's region, K4: replicated result."""

@@ -75,7 +75,11 @@ class ShardedSearcher:
         if self.exchange not in ("peer", "nccl"):
             raise ValueError("exchange must be 'peer' or 'nccl'")
         if self.world > 1 and self.exchange == "peer":
-            dev.exchange_setup(B_max, k_max, group)
+            if not dev.exchange_setup(B_max, k_max, group):
+                import warnings
+                warnings.warn("peer-memory exchange unavailable on this box (no CUDA IPC / peer access "
+                              "between the GPUs): using the NCCL all-gather exchange")
+                self.exchange = "nccl"
 
     def buffers(self, B: int, k: int):
         key = (B, k)
