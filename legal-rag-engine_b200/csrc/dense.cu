@@ -252,7 +252,11 @@ dense_scan_kernel(const unsigned char* __restrict__ x, int64_t n_rows,
         const int rows = (int)min((int64_t)kTileRows, n_rows - row0);
         const uint32_t bytes = (uint32_t)rows * kRowBytes;
         mbar_arrive_expect_tx(&sm.full[s], bytes);
+#ifdef LRX_SCAN_NO_HINT
         bulk_g2s(sm.ring[s], x + row0 * kRowBytes, bytes, &sm.full[s]);
+#else
+        bulk_g2s_hint(sm.ring[s], x + row0 * kRowBytes, bytes, &sm.full[s], l2_policy_evict_first());
+#endif
     };
     int next_tile = (int)blockIdx.x + kStages * (int)gridDim.x;   // thread 0: the next tile to load
     if (tid == 0) {
