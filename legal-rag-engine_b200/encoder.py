@@ -116,7 +116,8 @@ class SentenceEncoder:
         processed longest-first so batches are dense, results returned in input order."""
         texts = list(texts)
         out = np.empty((len(texts), 384), dtype=np.float32)
-        enc = [self.tokenizer.encode(t, self.MAX_SEQ) for t in texts]
+        enc = (self.tokenizer.encode_batch(texts, self.MAX_SEQ) if hasattr(self.tokenizer, "encode_batch")
+               else [self.tokenizer.encode(t, self.MAX_SEQ) for t in texts])
         order = sorted(range(len(texts)), key=lambda i: -len(enc[i]))
         for s in range(0, len(order), batch_size):
             idx = order[s:s + batch_size]

@@ -96,6 +96,33 @@ class WordPieceTokenizer:
         ids = [i for tok in basic_tokenize(text) for i in self.wordpiece(tok)]
         return [self.cls] + ids[:max_len - 2] + [self.sep]
 
+    def encode_batch(self, texts, max_len: int = 256) -> List[List[int]]:
+        """Index-build path: many texts at once.  When the `tokenizers` package
+        is importable its multi-threaded BertWordPieceTokenizer does the work over the same
+        vocabulary (tests/test_oracle_encoder.py pins this class to it on the reference's corpus);
+        otherwise the pure-Python loop."""
+        fast = self._fast(max_len)
+        if fast is None:
+            return [self.encode(t, max_len) for t in texts]
+        return [e.ids for e in fast.encode_batch(list(texts))]
+
+    def _fast(self, max_len: int):
+        cache = self.__dict__.setdefault("_fast_cache", {})
+        if max_len in cache:
+            return cache[max_len]
+        tok = None
+        try:
+            from tokenizers import BertWordPieceTokenizer
+            # the ids must be the line numbers of a vocab.txt: only possible for a dense vocabulary
+            if sorted(self.vocab.values()) == list(range(len(self.vocab))) and \
+                    all(s in self.vocab for s in ("[UNK]", "[CLS]", "[SEP]", "[PAD]", "[MASK]")):
+                tok = BertWordPieceTokenizer(dict(self.vocab), lowercase=True)
+                tok.enable_truncation(max_len)
+        except Exception:
+            tok = None
+        cache[max_len] = tok
+        return tok
+
 
 class HashTokenizer:
     """Stand-in when no vocab.txt is available: md5(token) -> id in [1000, vocab)."""
@@ -109,6 +136,9 @@ class HashTokenizer:
                                                      "little") % span
                if self.vocab_size > 1000 else 1 for t in text.lower().split()]
         return [CLS % self.vocab_size] + ids[:max_len - 2] + [SEP % self.vocab_size]
+
+    def encode_batch(self, texts, max_len: int = 256) -> List[List[int]]:
+        return [self.encode(t, max_len) for t in texts]
 
 
 def load_tokenizer(model_dir: Optional[str], vocab_size: int = 30522):

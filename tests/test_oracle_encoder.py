@@ -53,3 +53,27 @@ def test_tokenizers():
     assert ids[0] == 101 and ids[-1] == 102 and len(ids) == 7
     assert all(1000 <= i < 30522 for i in ids[1:-1])
     assert ids == h.encode("zero fir   registration procedure bnss")
+
+
+def test_wordpiece_pinned_to_hf_tokenizers_on_reference_corpus(legal_texts, reference_queries):
+    """The reference tokenises with the BertTokenizer of all-MiniLM-L6-v2 (HF `tokenizers`
+    underneath).  Without its vocab.txt the pin is on the ALGORITHM: over a WordPiece vocabulary
+    built from the reference's own corpus, WordPieceTokenizer must give the ids of
+    tokenizers.BertWordPieceTokenizer(lowercase=True) for every chunk and query."""
+    tokenizers = pytest.importorskip("tokenizers")
+    from collections import Counter
+    cnt = Counter(t for x in legal_texts for t in basic_tokenize(x))
+    vocab = ["[PAD]"] + [f"[unused{i}]" for i in range(99)] + ["[UNK]", "[CLS]", "[SEP]", "[MASK]"]
+    chars = sorted({ch for w in cnt for ch in w})
+    vocab += chars + ["##" + c for c in chars]
+    vocab += [w for w, _ in cnt.most_common(4000) if len(w) > 1]
+    vocab += ["##" + w[2:] for w, _ in cnt.most_common(600) if len(w) > 4]      # some real suffix pieces
+    v = {w: i for i, w in enumerate(dict.fromkeys(vocab))}
+    tok = WordPieceTokenizer(v)
+    hf = tokenizers.BertWordPieceTokenizer(dict(v), lowercase=True)
+    hf.enable_truncation(256)
+    texts = list(legal_texts) + list(reference_queries) + ["Caf\u00e9 na\u00efve \u2014 \u00a7 173(1) \u201cZero FIR\u201d \u4e2d\u6587"]
+    want = [e.ids for e in hf.encode_batch(texts)]
+    got = [tok.encode(t, 256) for t in texts]
+    assert got == want
+    assert tok.encode_batch(texts, 256) == want               # the batch path is the library itself
