@@ -88,7 +88,7 @@ int lrx_set_corpus(lrx_handle* h, const void* dev_x_fp16, int64_t n_local, int64
  * lengths), 16-byte aligned and readable up to nnz rounded up to an even count (the scan
  * moves 16-byte units).  The query-independent BM25Okapi factor
  *   impact(tf, len) = tf*(k1+1) / (tf + k1*(1 - b + b*len/avgdl))          (float64)
- * is looked up in a handle-owned table built here from the GLOBAL avgdl with rank_bm25's
+ * is recomputed by the scan from (tf, len) and the GLOBAL avgdl given here, with rank_bm25's
  * float64 operation order.  dev_idf: GLOBAL idf per term (rank_bm25 semantics: epsilon
  * floor applied).  max_doc_len <= 65535.  Replaces pickle.load(bm25.pkl). */
 int lrx_set_postings(lrx_handle* h, const uint64_t* dev_term_ptr, const void* dev_postings,

@@ -118,8 +118,7 @@ int lrx_close(lrx_handle* h) {
     if (h == nullptr) return LRX_OK;
     cudaSetDevice(h->device);
     cudaDeviceSynchronize();
-    void* ws[] = {h->ws_dense_part, h->ws_dense_merged, h->ws_bm_part, h->ws_bm_max, h->ws_misc,
-                  h->ws_io, h->bm_lut};
+    void* ws[] = {h->ws_dense_part, h->ws_bm_part, h->ws_bm_max, h->ws_misc, h->ws_io};
     for (void* p : ws)
         if (p != nullptr) cudaFree(p);
     encoder_free(h);

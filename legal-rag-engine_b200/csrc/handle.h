@@ -37,14 +37,13 @@ struct lrx_handle {
     const void* postings = nullptr;
     const double* idf = nullptr;
     int64_t n_terms = 0, nnz = 0;
-    // BM25 impact table [8][bm_lut_ld] (handle-owned) and the constants behind it
-    void* bm_lut = nullptr;          size_t bm_lut_bytes = 0;
+    // BM25 constants; bm_lut_ld = longest document + 1 (selects the scan variant whose shared
+    // c[len] table needs no fallback)
     int bm_lut_ld = 0;
     double bm_avgdl = 0.0, bm_k1 = 1.5, bm_b = 0.75;
 
     // workspaces (handle-owned, grown on demand)
     void* ws_dense_part = nullptr;   size_t ws_dense_part_bytes = 0;    // per-CTA key lists
-    void* ws_dense_merged = nullptr; size_t ws_dense_merged_bytes = 0;  // [B][width] keys
     void* ws_bm_part = nullptr;      size_t ws_bm_part_bytes = 0;       // per-chunk key lists
     void* ws_bm_max = nullptr;       size_t ws_bm_max_bytes = 0;        // per-CTA max
     void* ws_misc = nullptr;         size_t ws_misc_bytes = 0;          // search_local scratch
