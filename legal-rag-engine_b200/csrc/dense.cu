@@ -3,14 +3,16 @@
 // Replaces faiss IndexFlatIP.search (reference: src/retrieval/retrieval_engine.py:64)
 // for small query batches (the B <= 4 sub-queries of one fan-out).
 //
-// Three kernels:
-//   dense_scan_kernel   HBM-bound: streams the [n,384] fp16 matrix once through a
-//                       4-stage shared-memory ring filled by 1-D bulk async copies
-//                       (TMA engine, mbarrier byte counting), scores NQ queries per
-//                       row with fp32 FFMA (fp16 x fp16 products are exact in fp32),
-//                       and keeps a per-CTA top-`width` candidate list in shared
-//                       memory (threshold test in registers; block-wide bitonic
-//                       prune only when the buffer fills).  Scores never touch HBM.
+// Kernels:
+//   dense_scan_kernel   HBM-bound: streams the [n,384] fp16 matrix once through a 2-stage
+//                       shared-memory ring filled by 1-D bulk async copies (TMA engine,
+//                       mbarrier byte counting, L2 evict-first), scores up to 4 queries per row
+//                       on the tensor cores (mma.sync m16n8k16, fp16 x fp16 -> fp32: products
+//                       exact, accumulation within the guard band kDenseEps) and keeps a per-CTA
+//                       top-`width` candidate list in shared memory (threshold test per (row,
+//                       query), register sorting networks when a buffer fills, thresholds shared
+//                       grid-wide).  Scores never touch HBM.  256 threads, 133 KB: one BM25 scan
+//                       CTA fits beside it on the SM (api.cu runs the two scans side by side).
 //   dense_merge_rescore_kernel  one CTA per query merges the per-CTA lists (merge.cuh) and
 //                       re-scores the `width` survivors EXACTLY in float64 (exact
 //                       and order independent, see oracle/flat_ip.py), orders them by
