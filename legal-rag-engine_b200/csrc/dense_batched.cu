@@ -234,19 +234,61 @@ dense_tc_kernel(const __grid_constant__ CUtensorMap tma_q, const __grid_constant
 }
 
 // T[q] = (K-th largest tile maximum) - slack; -FLT_MAX when fewer than K tiles were sampled.
-// One CTA per query, bitonic sort in shared memory (n_samp <= 16384).
+// One CTA per query.  Only the K-th largest of up to 16 384 values is needed, so this is a radix
+// SELECT over the order images (four 8-bit passes: shared-memory histogram of the keys that match
+// the prefix found so far, then warp 0 walks the 256 bins from the top), not a sort.
 __global__ void __launch_bounds__(256)
 tilemax_kth_kernel(const float* __restrict__ tilemax, int n_samp, int K, float slack,
                    float* __restrict__ thr, int* __restrict__ cnt) {
     extern __shared__ uint32_t tm_keys[];
-    const int q = blockIdx.x, tid = threadIdx.x;
-    const int p2 = next_pow2(max(n_samp, 2));
-    for (int i = tid; i < p2; i += 256)
-        tm_keys[i] = (i < n_samp) ? f32_ord(tilemax[(size_t)q * n_samp + i]) : 0u;
+    __shared__ uint32_t hist[256];
+    __shared__ uint32_t s_prefix, s_rank;
+    const int q = blockIdx.x, tid = threadIdx.x, lane = tid & 31;
+    for (int i = tid; i < n_samp; i += 256) tm_keys[i] = f32_ord(tilemax[(size_t)q * n_samp + i]);
+    if (tid == 0) { s_prefix = 0u; s_rank = (uint32_t)K; }   // rank counted from the largest, 1-based
     __syncthreads();
-    block_bitonic_sort_desc<uint32_t>(tm_keys, p2, 1, p2, tid, 256);
+    if (K <= n_samp) {
+        for (int pass = 3; pass >= 0; --pass) {
+            hist[tid] = 0u;
+            __syncthreads();
+            const uint32_t prefix = s_prefix;
+            const int hs = 8 * (pass + 1);                   // bits above this byte
+            for (int i = tid; i < n_samp; i += 256) {
+                const uint32_t key = tm_keys[i];
+                if (pass == 3 || (key >> hs) == (prefix >> hs)) atomicAdd(&hist[(key >> (8 * pass)) & 255u], 1u);
+            }
+            __syncthreads();
+            if (tid < 32) {
+                // lane l owns bins 255 - 8l .. 248 - 8l (descending); exclusive prefix over lanes
+                uint32_t local = 0;
+#pragma unroll
+                for (int j = 0; j < 8; ++j) local += hist[255 - (8 * lane + j)];
+                uint32_t incl = local;
+#pragma unroll
+                for (int d = 1; d < 32; d <<= 1) {
+                    const uint32_t v = __shfl_up_sync(0xffffffffu, incl, d);
+                    if (lane >= d) incl += v;
+                }
+                const uint32_t before = incl - local, rank = s_rank;
+                if (before < rank && rank <= incl) {         // the K-th key falls into this lane's bins
+                    uint32_t cum = before;
+                    for (int j = 0; j < 8; ++j) {
+                        const uint32_t bin = 255u - (uint32_t)(8 * lane + j);
+                        const uint32_t c = hist[bin];
+                        if (rank <= cum + c) {
+                            s_prefix = prefix | (bin << (8 * pass));
+                            s_rank = rank - cum;
+                            break;
+                        }
+                        cum += c;
+                    }
+                }
+            }
+            __syncthreads();
+        }
+    }
     if (tid == 0) {
-        thr[q] = (K <= n_samp) ? ord_f32(tm_keys[K - 1]) - slack : -FLT_MAX;
+        thr[q] = (K <= n_samp) ? ord_f32(s_prefix) - slack : -FLT_MAX;
         cnt[q] = 0;
     }
 }
