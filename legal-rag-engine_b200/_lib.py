@@ -9,8 +9,11 @@ import ctypes as C
 import re
 from pathlib import Path
 
+import os
+
 HERE = Path(__file__).resolve().parent
-LIB_PATH = HERE / "csrc" / "liblrx.so"
+# LRX_LIB: another build of the same library (kernel A/B runs); default = the in-tree build
+LIB_PATH = Path(os.environ["LRX_LIB"]) if os.environ.get("LRX_LIB") else HERE / "csrc" / "liblrx.so"
 HEADER = HERE.parent / "include" / "lrx.h"
 
 LRX_DIM = 384
