@@ -293,7 +293,9 @@ tilemax_kth_kernel(const float* __restrict__ tilemax, int n_samp, int K, float s
     }
 }
 
-// Exact float64 re-score of a query's (unsorted) candidate list, best K out.
+// Exact float64 re-score of a query's (unsorted) candidate list, best K out.  Each warp takes four
+// candidates per pass, all twelve row loads in flight before the first reduction; the order is a
+// rank by counting on the unique (exact score, id) keys -- a few hundred candidates, no sort.
 constexpr int kRlThreads = 256;
 __global__ void __launch_bounds__(kRlThreads)
 dense_rescore_list_kernel(const unsigned char* __restrict__ x, int64_t id_base,
@@ -302,6 +304,7 @@ dense_rescore_list_kernel(const unsigned char* __restrict__ x, int64_t id_base,
                           float* __restrict__ out_D, int64_t* __restrict__ out_I,
                           int32_t* __restrict__ out_flag) {
     __shared__ u128 keys[kDbCap];
+    __shared__ u128 best[LRX_MAX_DEPTH];
     const int qi = blockIdx.x;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int total = cnt[qi];
@@ -310,17 +313,28 @@ dense_rescore_list_kernel(const unsigned char* __restrict__ x, int64_t id_base,
     uint2 qv[3];
 #pragma unroll
     for (int s = 0; s < 3; ++s) qv[s] = qp[s * 32 + lane];
-    for (int j = warp; j < kDbCap; j += kRlThreads / 32) {
-        u128 key = 0;
-        if (j < n) {
-            const uint32_t row = key64_row(cand[(size_t)qi * kDbCap + j]);
-            const uint2* rowp = reinterpret_cast<const uint2*>(x + (int64_t)row * kRowBytes);
+    for (int j = tid; j < K && j < LRX_MAX_DEPTH; j += kRlThreads) best[j] = 0;
+    constexpr int kWarps = kRlThreads / 32;
+    for (int j0 = warp * 4; j0 < n; j0 += kWarps * 4) {
+        uint32_t row[4];
+        uint2 rv[4][3];
+#pragma unroll
+        for (int c = 0; c < 4; ++c)
+            row[c] = (j0 + c < n) ? key64_row(cand[(size_t)qi * kDbCap + j0 + c]) : 0u;
+#pragma unroll
+        for (int c = 0; c < 4; ++c) {
+            const uint2* rowp = reinterpret_cast<const uint2*>(x + (int64_t)row[c] * kRowBytes);
+#pragma unroll
+            for (int s = 0; s < 3; ++s)
+                rv[c][s] = (j0 + c < n) ? rowp[s * 32 + lane] : make_uint2(0u, 0u);
+        }
+#pragma unroll
+        for (int c = 0; c < 4; ++c) {
             double acc = 0.0;
 #pragma unroll
             for (int s = 0; s < 3; ++s) {
-                const uint2 v = rowp[s * 32 + lane];
-                const float2 a = __half22float2(*reinterpret_cast<const __half2*>(&v.x));
-                const float2 b = __half22float2(*reinterpret_cast<const __half2*>(&v.y));
+                const float2 a = __half22float2(*reinterpret_cast<const __half2*>(&rv[c][s].x));
+                const float2 b = __half22float2(*reinterpret_cast<const __half2*>(&rv[c][s].y));
                 const float2 e = __half22float2(*reinterpret_cast<const __half2*>(&qv[s].x));
                 const float2 f = __half22float2(*reinterpret_cast<const __half2*>(&qv[s].y));
                 acc = fma((double)a.x, (double)e.x, acc);
@@ -330,14 +344,19 @@ dense_rescore_list_kernel(const unsigned char* __restrict__ x, int64_t id_base,
             }
 #pragma unroll
             for (int lb = 16; lb > 0; lb >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, lb);
-            key = make_key128(acc, row);
+            if (lane == 0 && j0 + c < n) keys[j0 + c] = make_key128(acc, row[c]);
         }
-        if (lane == 0) keys[j] = key;
     }
     __syncthreads();
-    block_bitonic_sort_desc<u128>(keys, kDbCap, 1, kDbCap, tid, kRlThreads);
+    for (int j = tid; j < n; j += kRlThreads) {
+        const u128 key = keys[j];
+        int rank = 0;
+        for (int i = 0; i < n && rank < K; ++i) rank += (keys[i] > key) ? 1 : 0;
+        if (rank < K) best[rank] = key;
+    }
+    __syncthreads();
     for (int j = tid; j < K; j += kRlThreads) {
-        const u128 key = (j < kDbCap) ? keys[j] : (u128)0;
+        const u128 key = (j < LRX_MAX_DEPTH) ? best[j] : (u128)0;
         const size_t o = (size_t)qi * K + j;
         if (key != 0) {
             const double e = key128_score(key);
