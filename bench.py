@@ -8,14 +8,18 @@ query = 4 fan-out sub-queries, RRF fusion), strong-scaled over 1/2/4/8 B200.
     torchrun ... bench.py --gpus N ...                       # N > 1, one rank per GPU
 
 One JSON line on stdout (rank 0).  A "step" is one user query: K2 (dense scan + top-k)
--> K3 (BM25) -> all-gather of candidate records (N > 1) -> K4 (fusion).  `value` is
-measured with the queries already resident in HBM; `e2e` goes through the host-buffer
-C-ABI call with the H2D / D2H copies inside the timed region.
+|| K3 (BM25) -> candidate exchange between the shards (N > 1, inside the kernels) -> K4
+(fusion), one captured launch chain.  `value` is measured with the queries already resident
+in HBM; `e2e` goes through the host-buffer C-ABI calls (lrx_search_host_begin / _end) with the
+H2D / D2H copies of every step inside the timed region.  Both keep `in_flight` query batches in
+flight (one handle + stream each), the same number at every N.  Before the timed region a
+sample of the pool queries is checked against an on-device float64 brute force (`parity`).
 """
 from __future__ import annotations
 
 import argparse
 import json
+import math
 import os
 import sys
 import threading
@@ -32,6 +36,7 @@ N_SUB = 4                      # fan-out sub-queries per user query (orchestrato
 N_TERMS = 8                    # BM25 tokens per sub-query
 WEIGHTS = [0.5, 0.6, 0.5, 0.6]  # orchestrator.py:56
 POOL = 16                      # distinct user queries cycled through the timed steps
+RRF_K0 = 60.0
 
 
 def parse():
@@ -42,15 +47,18 @@ def parse():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--rows", type=int, default=10_000_000)
     ap.add_argument("--fusion", default="rrf", choices=["rrf", "linear"])
-    ap.add_argument("--in-flight", type=int, default=0,
-                    help="query batches in flight (one handle + stream each) in the throughput loop; "
-                         "0 = auto: 1 on one GPU (2 measures the same there: 740 vs 740 queries/s, and "
-                         "keeps the per-kernel timings of the roofline clean), 2 on several (small "
-                         "shards: one batch's merges / exchange / fusion run under the next one's scans)")
+    ap.add_argument("--in-flight", type=int, default=2,
+                    help="query batches in flight (one handle + stream each), the same at every N: one "
+                         "batch's merges / exchange / fusion run under the next one's scans")
     ap.add_argument("--k", type=int, default=10,
                     help="result depth (10 = the headline metric; 100 with --rows 100000000 --gpus 8 = config C5)")
+    ap.add_argument("--min-time", type=float, default=0.25,
+                    help="the timed region repeats the K-step block until it lasts this long (seconds); "
+                         "`steps` stays K, `timed_steps` says how many were timed")
+    ap.add_argument("--parity-queries", type=int, default=8,
+                    help="pool queries checked against the on-device float64 brute force (0 = skip)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--no-stages", action="store_true", help="skip the K1 / K2b stage measurements")
+    ap.add_argument("--no-stages", action="store_true", help="skip the K1 / K2a / K2b stage measurements")
     ap.add_argument("--cpu-sample-rows", type=int, default=1_000_000)
     return ap.parse_args()
 
@@ -93,7 +101,7 @@ class ClockSampler:
                         self.reasons.add(name)
             except Exception:
                 pass
-            self._stop.wait(0.05)
+            self._stop.wait(0.02)
 
     def start(self):
         if self._nvml is not None:
@@ -119,78 +127,260 @@ def make_query_pool(seed=999):
     return q, terms, ptr
 
 
+# ------------------------------------------------------- fusion, restated for the parity check
+def fuse_expected(dense, sparse, maxbm, k, w, mode):
+    """retrieval_engine.py:71-96 (linear) / the build definition of RRF on the
+    brute-force lists.  dense / sparse: [(id, dense_f64, bm25_f64)] best first."""
+    mx = maxbm if maxbm > 0 else 1.0
+    if mode == "linear":
+        rows = []
+        for i, de, bm in dense:
+            sem = float(np.float32(de))
+            kw = bm / mx
+            rows.append((i, sem * (1 - w) + kw * w, sem, kw))
+        rows.sort(key=lambda r: r[1], reverse=True)          # stable
+        return rows[:k]
+    acc, info = {}, {}
+    for r, (i, de, bm) in enumerate(dense, start=1):
+        acc[i] = 0.0 + 1.0 / (RRF_K0 + r)
+        info[i] = (de, bm)
+    for r, (i, de, bm) in enumerate(sparse, start=1):
+        acc[i] = acc.get(i, 0.0) + 1.0 / (RRF_K0 + r)
+        info[i] = (de, bm)
+    items = sorted(acc.items(), key=lambda kv: (-kv[1], kv[0]))[:k]
+    return [(i, s, float(np.float32(info[i][0])), info[i][1] / mx) for i, s in items]
+
+
+def parity_check(dev, lo, n_local, avgdl, qh, th, pool_ids, k, mode, searcher, ptr_dev, w_dev, world, rank):
+    """Untimed result check at the benchmark's own size: for the pool queries `pool_ids`, every
+    rank computes on its shard, with torch float64 on the device buffers the kernels read,
+      * exact inner products of all rows (fp16 x fp16 products and their sums are exact in float64
+        in any order) -> local top-2k by (score desc, id asc),
+      * BM25Okapi scores of all local documents, token by token in rank_bm25's operation order
+        -> local max and local top-2k positive scores;
+    the lists are all-gathered, merged, fused by `fuse_expected` and compared BIT FOR BIT with what
+    the engine returns (ids, fused score, semantic, keyword).  Returns (queries checked, mismatches)."""
+    import torch
+    import torch.distributed as dist
+    device = dev.device
+    K = 2 * k
+    PAD = 8
+    tp, p8, idf_t = dev._post
+    x = dev.x
+    nq = len(pool_ids) * N_SUB
+    Q = torch.from_numpy(np.concatenate([qh[p] for p in pool_ids], 0)).to(device)      # [nq,384] fp16
+    Qd = Q.double()
+    # ---- dense: exact scores chunk by chunk, running top-(K+PAD)
+    best_s = torch.full((nq, 0), 0.0, dtype=torch.float64, device=device)
+    best_i = torch.zeros((nq, 0), dtype=torch.int64, device=device)
+    chunk = 1 << 20
+    for r0 in range(0, n_local, chunk):
+        r1 = min(n_local, r0 + chunk)
+        s = Qd @ x[r0:r1].double().T                                   # [nq, rows]
+        kk = min(K + PAD, r1 - r0)
+        v, i = torch.topk(s, kk, dim=1)
+        best_s = torch.cat([best_s, v], 1)
+        best_i = torch.cat([best_i, i + (lo + r0)], 1)
+        if best_s.shape[1] > 4 * (K + PAD):
+            v, j = torch.topk(best_s, K + PAD, dim=1)
+            best_s, best_i = v, torch.gather(best_i, 1, j)
+        del s
+    kk = min(K + PAD, best_s.shape[1])
+    v, j = torch.topk(best_s, kk, dim=1)
+    d_s = torch.full((nq, K + PAD), -float("inf"), dtype=torch.float64, device=device)
+    d_i = torch.full((nq, K + PAD), -1, dtype=torch.int64, device=device)
+    d_s[:, :kk], d_i[:, :kk] = v, torch.gather(best_i, 1, j)
+    # ---- BM25: all local documents
+    k1, b = 1.5, 0.75
+    b_s = torch.zeros((nq, K + PAD), dtype=torch.float64, device=device)
+    b_i = torch.full((nq, K + PAD), -1, dtype=torch.int64, device=device)
+    b_max = torch.zeros(nq, dtype=torch.float64, device=device)
+    bm_full = []
+    for n, p in enumerate(pool_ids):
+        for sq in range(N_SUB):
+            score = torch.zeros(n_local, dtype=torch.float64, device=device)
+            for t in th[p][sq * N_TERMS:(sq + 1) * N_TERMS]:
+                t = int(t)
+                if t < 0:
+                    continue
+                w = float(idf_t[t].item())
+                if w == 0.0:
+                    continue
+                s0, s1 = int(tp[t].item()), int(tp[t + 1].item())
+                if s1 == s0:
+                    continue
+                doc = p8[s0:s1, 0].long()
+                w1 = p8[s0:s1, 1].long()
+                tf = (w1 & 0xffff).double()
+                dl = ((w1 >> 16) & 0xffff).double()
+                den = tf + k1 * (1 - b + b * dl / avgdl)
+                score[doc] += w * (tf * (k1 + 1) / den)                  # doc ids unique within a term
+            qi = n * N_SUB + sq
+            bm_full.append(score)
+            pos = torch.where(score > 0, score, torch.zeros_like(score))
+            b_max[qi] = pos.max() if n_local else 0.0
+            kk = min(K + PAD, n_local)
+            v, i = torch.topk(pos, kk)
+            b_s[qi, :kk] = v
+            b_i[qi, :kk] = torch.where(v > 0, i + lo, torch.full_like(i, -1))
+    # ---- gather the shards' lists
+    def gather(t):
+        if world == 1:
+            return t.unsqueeze(0)
+        out = torch.empty((world,) + tuple(t.shape), dtype=t.dtype, device=device)
+        dist.all_gather_into_tensor(out, t.contiguous())
+        return out
+    gd_s, gd_i, gb_s, gb_i = (gather(t).cpu().numpy() for t in (d_s, d_i, b_s, b_i))
+    if world > 1:
+        dist.all_reduce(b_max, op=dist.ReduceOp.MAX)
+    maxbm = b_max.cpu().numpy()
+
+    def merged(sc, ids, qi, positive):
+        s = sc[:, qi, :].reshape(-1)
+        i = ids[:, qi, :].reshape(-1)
+        keep = (i >= 0) & ((s > 0) if positive else np.isfinite(s))
+        s, i = s[keep], i[keep]
+        order = np.lexsort((i, -s))[:K]
+        return s[order], i[order]
+    dense_lists = [merged(gd_s, gd_i, qi, False) for qi in range(nq)]
+    sparse_lists = [merged(gb_s, gb_i, qi, True) for qi in range(nq)]
+    # ---- the other score of every listed document (owned by exactly one shard)
+    need_b = torch.zeros((nq, K), dtype=torch.float64, device=device)     # bm25 at dense hits
+    need_d = torch.zeros((nq, K), dtype=torch.float64, device=device)     # dense at bm25 hits
+    for qi in range(nq):
+        di = torch.from_numpy(dense_lists[qi][1]).to(device)
+        own = (di >= lo) & (di < lo + n_local)
+        if own.any():
+            need_b[qi, :len(di)][own] = bm_full[qi][di[own] - lo]
+        si = torch.from_numpy(sparse_lists[qi][1]).to(device)
+        own = (si >= lo) & (si < lo + n_local)
+        if own.any():
+            need_d[qi, :len(si)][own] = x[si[own] - lo].double() @ Qd[qi]
+    if world > 1:
+        dist.all_reduce(need_b)
+        dist.all_reduce(need_d)
+    need_b, need_d = need_b.cpu().numpy(), need_d.cpu().numpy()
+    # ---- the engine's answers for the same queries
+    bad = 0
+    detail = []
+    for n, p in enumerate(pool_ids):
+        q_dev = torch.from_numpy(qh[p]).to(device)
+        t_dev = torch.from_numpy(th[p]).to(device)
+        outs = searcher.search_checked(q_dev, t_dev, ptr_dev, k, {"linear": 0, "rrf": 1}[mode], w_dev)
+        ids, score, sem, kw, _ = [o.cpu().numpy() for o in outs]
+        ok = True
+        for sq in range(N_SUB):
+            qi = n * N_SUB + sq
+            ds, di = dense_lists[qi]
+            ss, si = sparse_lists[qi]
+            dense = [(int(i), float(s), float(need_b[qi, j])) for j, (s, i) in enumerate(zip(ds, di))]
+            sparse = [(int(i), float(need_d[qi, j]), float(s)) for j, (s, i) in enumerate(zip(ss, si))]
+            want = fuse_expected(dense, sparse, float(maxbm[qi]), k, WEIGHTS[sq], mode)
+            got = [(int(ids[sq, j]), float(score[sq, j]), float(sem[sq, j]), float(kw[sq, j]))
+                   for j in range(k) if ids[sq, j] >= 0]
+            if got != want:
+                ok = False
+                if len(detail) < 3:
+                    detail.append({"pool": int(p), "sub": sq, "got": got[:3], "want": want[:3]})
+        bad += 0 if ok else 1
+    return len(pool_ids), bad, detail
+
+
 # ------------------------------------------------------------ CPU baseline
-def cpu_reference_step(sample_rows: int, rows_total: int, threads: int, steps: int = 1):
-    """The reference's CPU path for one user query, on a bounded sample, extrapolated
-    linearly in the number of chunks (both stages are O(N) scans):
+class CpuReference:
+    """The reference's CPU path for one user query on bounded samples (both stages are O(N) scans,
+    scaled linearly in the number of chunks afterwards):
       dense : FAISS-style fp32 sequential scan + heap, one core per sub-query
-              (oracle/c/flat_ip_scan.c), on `sample_rows` rows;
+              (oracle/c/flat_ip_scan.c, the published nq < 20 algorithm), on `sample_rows` rows;
       BM25  : rank_bm25's dict-per-document list-comprehension, literally
-              (oracle.bm25.BM25OkapiLiteral), on a 20 000-document sample;
-      fusion: retrieval_engine.py:71-96 loop + stable sort.
-    Returns (seconds per user query at rows_total, description)."""
-    from legal_rag_engine_b200 import synth
-    from oracle import cbaseline, fusion
-    from oracle import bm25 as obm25
-    rng = np.random.default_rng(5)
-    xs = rng.standard_normal((sample_rows, 384), dtype=np.float32)
-    xs /= np.linalg.norm(xs, axis=1, keepdims=True)
-    q, terms, ptr = make_query_pool()
-    bm_docs = 20_000
-    idx = synth.host_bm25(bm_docs, seed=777)
-    # token lists for the literal (string-keyed dict) form
-    term_of = np.repeat(np.arange(idx.n_terms), np.diff(idx.term_ptr.astype(np.int64)))
-    order = np.argsort(idx.postings[:, 0], kind="stable")
-    docs = [[] for _ in range(bm_docs)]
-    for t, d, f in zip(term_of[order], idx.postings[order, 0], idx.postings[order, 1]):
-        docs[d].extend([str(t)] * int(f))
-    lit = obm25.BM25OkapiLiteral(docs)
-    t_dense = t_bm = t_fuse = 0.0
-    for s in range(steps):
-        qs = q[s % POOL].astype(np.float32)
+              (oracle.bm25.BM25OkapiLiteral), on a `bm_docs`-document sample;
+      fusion: the two max() sweeps (:74) + RRF over the two top-2k lists."""
+
+    def __init__(self, sample_rows: int, threads: int, bm_docs: int = 20_000):
+        from legal_rag_engine_b200 import synth
+        from oracle import bm25 as obm25
+        self.sample_rows, self.bm_docs, self.threads = sample_rows, bm_docs, threads
+        rng = np.random.default_rng(5)
+        xs = rng.standard_normal((sample_rows, 384), dtype=np.float32)
+        xs /= np.linalg.norm(xs, axis=1, keepdims=True)
+        self.xs = xs
+        self.q, self.terms, _ = make_query_pool()
+        idx = synth.host_bm25(bm_docs, seed=777)
+        term_of = np.repeat(np.arange(idx.n_terms), np.diff(idx.term_ptr.astype(np.int64)))
+        order = np.argsort(idx.postings[:, 0], kind="stable")
+        docs = [[] for _ in range(bm_docs)]
+        for t, d, f in zip(term_of[order], idx.postings[order, 0], idx.postings[order, 1]):
+            docs[d].extend([str(t)] * int(f))
+        self.lit = obm25.BM25OkapiLiteral(docs)
+
+    def step(self, s: int):
+        """-> (dense seconds, bm25 + max + fusion seconds) of one user query on the samples."""
+        from oracle import cbaseline, fusion
+        from oracle import bm25 as obm25
+        qs = self.q[s % POOL].astype(np.float32)
         t0 = time.perf_counter()
-        D, I = cbaseline.flat_ip_search_f32(xs, qs, 2 * K_TOP, threads)
+        D, I = cbaseline.flat_ip_search_f32(self.xs, qs, 2 * K_TOP, self.threads)
         t1 = time.perf_counter()
-        scores = []
         for b in range(N_SUB):
-            toks = [str(t) for t in terms[s % POOL][b * N_TERMS:(b + 1) * N_TERMS]]
-            scores.append(lit.get_scores(toks))
-        t2 = time.perf_counter()
-        for b in range(N_SUB):
-            bm = scores[b]
+            toks = [str(t) for t in self.terms[s % POOL][b * N_TERMS:(b + 1) * N_TERMS]]
+            bm = self.lit.get_scores(toks)
             mx = max(bm) if max(bm) > 0 else 1.0       # the two Python max() sweeps (:74)
-            Ib = np.minimum(I[b], bm_docs - 1)
-            fusion.linear_fuse(D[b], Ib, bm, mx, K_TOP, WEIGHTS[b])
-        t3 = time.perf_counter()
-        t_dense += t1 - t0; t_bm += t2 - t1; t_fuse += t3 - t2
-    sec = (t_dense * rows_total / sample_rows + (t_bm + t_fuse) * rows_total / bm_docs) / steps
-    desc = (f"dense: fp32 seq scan+heap on {sample_rows} rows x {N_SUB} sub-queries "
-            f"({min(threads, N_SUB)} threads, one per sub-query as FAISS nq<20); BM25: literal "
-            f"rank_bm25 dict loop on {bm_docs} docs x {N_SUB}x{N_TERMS} tokens (1 thread, pure "
-            f"Python as the reference); both scaled linearly to {rows_total} rows; "
-            f"split s/query@full: dense {t_dense * rows_total / sample_rows / steps:.2f}, "
-            f"bm25+max+fuse {(t_bm + t_fuse) * rows_total / bm_docs / steps:.2f}")
-    return sec, desc
+            Ib = np.minimum(I[b], self.bm_docs - 1)
+            dense = [(int(i), float(d), float(bm[i])) for d, i in zip(D[b], Ib)]
+            bs, bi = obm25.topk_positive(bm, 2 * K_TOP)
+            sparse = [(int(i), 0.0, float(sc)) for sc, i in zip(bs, bi)]
+            fusion.rrf_fuse(dense, sparse, mx, K_TOP)
+        t2 = time.perf_counter()
+        return t1 - t0, t2 - t1
+
+    def run(self, steps: int, warmup: int, rows_total: int):
+        for s in range(warmup):
+            self.step(s)
+        td = tb = 0.0
+        for s in range(steps):
+            a, b = self.step(warmup + s)
+            td += a
+            tb += b
+        td /= steps
+        tb /= steps
+        full = td * rows_total / self.sample_rows + tb * rows_total / self.bm_docs
+        return {"measured_ms_per_step_on_samples": (td + tb) * 1e3,
+                "measured_dense_ms": td * 1e3, "measured_bm25_fusion_ms": tb * 1e3,
+                "dense_sample_rows": self.sample_rows, "bm25_sample_docs": self.bm_docs,
+                "dense_scale": rows_total / self.sample_rows, "bm25_scale": rows_total / self.bm_docs,
+                "extrapolated_ms_per_step": full * 1e3,
+                "extrapolated_split_s": {"dense": td * rows_total / self.sample_rows,
+                                         "bm25_max_fusion": tb * rows_total / self.bm_docs}}
+
+    def describe(self):
+        return (f"dense: fp32 seq scan+heap on {self.sample_rows} rows x {N_SUB} sub-queries "
+                f"({min(self.threads, N_SUB)} threads, one per sub-query as FAISS nq<20); BM25: literal "
+                f"rank_bm25 dict loop on {self.bm_docs} docs x {N_SUB}x{N_TERMS} tokens (1 thread, pure "
+                f"Python as the reference) + max() + RRF; both scaled linearly to the full corpus")
 
 
 def run_reference(args):
+    """Reference arm: the oracle port of the reference's CPU path, `--warmup` + `--steps` steps on
+    bounded samples.  `value` is an ESTIMATE at the full configuration (linear in the rows), marked
+    so; the measured per-step time on the samples is printed beside it."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
     threads = os.cpu_count() or 1
-    # warmup + steps on bounded samples
-    cpu_reference_step(100_000, args.rows, threads, steps=1)
-    steps = max(1, min(args.steps, 3))
-    sec, desc = cpu_reference_step(args.cpu_sample_rows, args.rows, threads, steps=steps)
-    qps = 1.0 / sec
+    steps, warmup = max(1, args.steps), max(0, args.warmup)
+    ref = CpuReference(args.cpu_sample_rows, threads)
+    m = ref.run(steps, warmup, args.rows)
+    qps = 1e3 / m["extrapolated_ms_per_step"]
     line = {
         "impl": "reference", "metric": metric_name(args),
         "value": qps, "unit": "queries/s", "n_gpus": args.gpus, "steps": steps,
-        "warmup": 1, "ms_per_step": sec * 1e3, "higher_is_better": True, "scaling": "strong",
-        "vs_baseline": None, "dtype": "f32/f64", "data": "synthetic",
+        "warmup": warmup, "ms_per_step": m["extrapolated_ms_per_step"], "higher_is_better": True,
+        "scaling": "strong", "vs_baseline": None, "dtype": "f32/f64", "data": "synthetic",
+        "estimated": True,
+        "estimate": m,
         "config": workload_config(args),
         "cpu_baseline": {"value": qps, "unit": "queries/s", "cores": threads, "kind": "port",
-                         "sample": desc},
+                         "sample": ref.describe()},
         "e2e": {"value": qps, "unit": "queries/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }
     print(json.dumps(line), flush=True)
@@ -211,109 +401,206 @@ def workload_config(args):
             "l2": "inputs larger than L2 (>= 0.96 GB matrix shard per GPU streamed every step)"}
 
 
-# --------------------------------------------------- stage measurements (K1, K2b)
-def measure_stages(dev, n_local, peaks, th=None, ptr_h=None, fusion="rrf"):
-    """Tensor-core stages beside the headline (rank 0, N = 1): the encoder at config C2
-    (B = 1024, S = 128, seeded random weights) and batched dense scoring at B = 1024 over the
-    resident shard (config C3's batch).  Roofline = tensor pipe, against the measured bf16 peak."""
+# ------------------------------------------------ CPU legs of BASELINE.md section 4 (N = 1, rank 0)
+def cpu_legs(dev, n_local, avgdl, th, threads):
+    """Measured on the box's host cores, bounded to a few seconds each:
+      bm25_csr_full : the "fair CPU" BM25 -- CSR gather in C (oracle/c, float64, rank_bm25's operation
+                      order) over the FULL corpus: the posting lists of the query's terms are copied
+                      from the GPU index as they are, the score vector has one float64 per document;
+      dense_blas    : torch.mm fp32 + topk, B = 1024 over 1 M rows (FAISS's BLAS regime, nq >= 20);
+      encoder_hf    : transformers.BertModel fp32 on CPU, B = 32, S = 128 (random-init MiniLM-L6)."""
+    import ctypes as C
+    import torch
+    from oracle import cbaseline
+    out = {"cores": threads}
+    # ---- fair-CPU BM25 at full size
+    try:
+        tp, p8, idf_t = dev._post
+        terms = sorted({int(t) for t in th[0] if t >= 0})
+        tph = tp.cpu().numpy()
+        remap = {t: i for i, t in enumerate(terms)}
+        ptr = np.zeros(len(terms) + 1, dtype=np.int64)
+        docs, tfs = [], []
+        for i, t in enumerate(terms):
+            seg = p8[int(tph[t]):int(tph[t + 1])].cpu().numpy()
+            docs.append(seg[:, 0].astype(np.int64))
+            tfs.append((seg[:, 1] & 0xffff).astype(np.int64))
+            ptr[i + 1] = ptr[i] + len(seg)
+        post_doc, post_tf = np.concatenate(docs), np.concatenate(tfs)
+        idf = idf_t.cpu().numpy()[terms].copy()
+        dl = dev.doc_len.cpu().numpy().astype(np.float64)
+        doc_norm = 1.5 * (1 - 0.75 + 0.75 * dl / avgdl)
+        lib = cbaseline.load()
+        t0 = time.perf_counter()
+        n_post = 0
+        for b in range(N_SUB):
+            qt = np.array([remap[int(t)] for t in th[0][b * N_TERMS:(b + 1) * N_TERMS] if t >= 0], dtype=np.int32)
+            score = np.zeros(n_local, dtype=np.float64)
+            lib.oracle_bm25_scores(ptr.ctypes.data, post_doc.ctypes.data, post_tf.ctypes.data, idf.ctypes.data,
+                                   doc_norm.ctypes.data, C.c_double(1.5), qt.ctypes.data, len(qt),
+                                   score.ctypes.data)
+            mx = score.max()
+            n_post += int(sum(ptr[i + 1] - ptr[i] for i in qt))
+        dt = time.perf_counter() - t0
+        out["bm25_csr_full"] = {"docs": n_local, "postings_scored": n_post, "s_per_user_query": dt,
+                                "threads": 1, "note": "C CSR gather + max over the full corpus, 4 sub-queries"}
+        del post_doc, post_tf, docs, tfs
+    except Exception as e:
+        out["bm25_csr_full"] = {"error": repr(e)}
+    # ---- dense, BLAS regime
+    try:
+        rows, Bq = 1_000_000, 1024
+        rng = np.random.default_rng(7)
+        xs = torch.from_numpy(rng.standard_normal((rows, 384), dtype=np.float32))
+        qs = torch.from_numpy(rng.standard_normal((Bq, 384), dtype=np.float32))
+        torch.set_num_threads(threads)
+        torch.topk(qs @ xs.T, 20, dim=1)
+        t0 = time.perf_counter()
+        torch.topk(qs @ xs.T, 20, dim=1)
+        dt = time.perf_counter() - t0
+        out["dense_blas"] = {"rows": rows, "batch": Bq, "s_per_call": dt, "queries_per_s": Bq / dt,
+                             "threads": threads}
+        del xs, qs
+    except Exception as e:
+        out["dense_blas"] = {"error": repr(e)}
+    # ---- encoder
+    try:
+        from transformers import BertConfig, BertModel
+        cfg = BertConfig(vocab_size=30522, hidden_size=384, num_hidden_layers=6, num_attention_heads=12,
+                         intermediate_size=1536, max_position_embeddings=512)
+        model = BertModel(cfg, add_pooling_layer=False).eval()
+        ids = torch.randint(1000, 30522, (32, 128))
+        with torch.no_grad():
+            model(input_ids=ids)
+            t0 = time.perf_counter()
+            model(input_ids=ids)
+            dt = time.perf_counter() - t0
+        out["encoder_hf"] = {"batch": 32, "seq_len": 128, "s_per_call": dt, "seq_per_s": 32 / dt,
+                             "threads": threads}
+    except Exception as e:
+        out["encoder_hf"] = {"error": repr(e)}
+    return out
+
+
+# --------------------------------------------------- stage measurements (K1, K2a, K2b)
+def measure_stages(dev, n_local, peaks, hbm_peak, th=None, ptr_h=None, fusion="rrf"):
+    """Stages beside the headline (rank 0, N = 1).  Tensor-bound ones against the measured bf16 peak,
+    HBM-bound ones against the measured copy bandwidth:
+      encoder_sweep  config C2: K1 at B in {1..4096} x S in {128, 256} (seeded random weights);
+      c3_*           config C3: dense top-10 over 1 M rows at batch 1, 4 (K2a, HBM) and 1024 (K2b);
+      dense_batched  K2b at B = 1024 over the whole resident shard;
+      search_text_host  the whole search with the encoder in the call."""
     import torch
     from legal_rag_engine_b200 import synth
+    from legal_rag_engine_b200.device_index import DeviceIndex
     from legal_rag_engine_b200.encoder import SentenceEncoder
     peak_tf = float(peaks.get("bf16_tflops", 1590.0))
     out = {"peak_tflops": peak_tf,
            "peak_source": "measured (MEASURED_PEAKS.json bf16_tflops)" if "bf16_tflops" in peaks else "fallback 1590"}
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
 
-    enc = SentenceEncoder(dev, state_dict=synth.bert_state_dict(42, 0.02))
-    for S in (128, 256):
-        B = 1024
-        ids, lens = synth.token_batch(B, S, seed=1, full=True)
-        d_ids, d_lens = torch.from_numpy(ids).to(dev.device), torch.from_numpy(lens).to(dev.device)
-        for _ in range(3):
-            enc.encode_ids_device(d_ids, d_lens)
+    def timed(fn, n_it, warm=2):
+        for _ in range(warm):
+            fn()
         torch.cuda.synchronize()
         ev0.record()
-        for _ in range(5):
-            enc.encode_ids_device(d_ids, d_lens)
+        for _ in range(n_it):
+            fn()
         ev1.record()
         torch.cuda.synchronize()
-        ms = ev0.elapsed_time(ev1) / 5
-        flop = B * S * (6 * (2 * 384 * 1152 + 2 * 384 * 384 + 2 * 2 * 384 * 1536) + 6 * 4 * S * 384)
-        out[f"encoder_S{S}"] = {"batch": B, "seq_per_s": B / ms * 1e3, "ms": ms, "tflops": flop / ms / 1e9,
-                                "frac": flop / ms / 1e9 / peak_tf, "bound": "tensor",
-                                "flop_per_seq": flop / B}
+        return ev0.elapsed_time(ev1) / n_it
+
+    enc = SentenceEncoder(dev, state_dict=synth.bert_state_dict(42, 0.02))
+    sweep = []
+    for S in (128, 256):
+        for B in (1, 4, 16, 64, 256, 1024, 4096):
+            ids, lens = synth.token_batch(B, S, seed=1, full=True)
+            d_ids, d_lens = torch.from_numpy(ids).to(dev.device), torch.from_numpy(lens).to(dev.device)
+            ms = timed(lambda: enc.encode_ids_device(d_ids, d_lens), 5 if B >= 1024 else 20)
+            flop = B * S * (6 * (2 * 384 * 1152 + 2 * 384 * 384 + 2 * 2 * 384 * 1536) + 6 * 4 * S * 384)
+            rec = {"batch": B, "seq_len": S, "ms": ms, "seq_per_s": B / ms * 1e3, "tflops": flop / ms / 1e9,
+                   "frac": flop / ms / 1e9 / peak_tf, "bound": "tensor"}
+            sweep.append(rec)
+            if B == 1024:
+                out[f"encoder_S{S}"] = dict(rec, flop_per_seq=flop / B)
+    out["encoder_sweep"] = sweep
 
     # ---- the whole of RetrievalEngine.search for one fan-out, encoder included: WordPiece ids and
     #      BM25 term ids in host memory -> K1 -> K2 || K3 -> K4 -> fused results in host memory
-    #      (lrx_search_text_host, the call engine.search_batch makes)
     if th is not None:
-        import ctypes as C
-        from legal_rag_engine_b200.device_index import FUSION
         S = 32
         ids, lens = synth.token_batch(N_SUB, S, seed=5, full=True)
-        ids = np.ascontiguousarray(ids, dtype=np.int32); lens = np.ascontiguousarray(lens, dtype=np.int32)
-        w = np.ascontiguousarray(WEIGHTS, dtype=np.float64)
-        o_ids = np.empty((N_SUB, K_TOP), dtype=np.int64)
-        o_s, o_m, o_k = (np.empty((N_SUB, K_TOP), dtype=np.float64) for _ in range(3))
-        vp = lambda a: a.ctypes.data_as(C.c_void_p)
+        lists = [[th[p][b * N_TERMS:(b + 1) * N_TERMS].tolist() for b in range(N_SUB)] for p in range(POOL)]
+        state = {"i": 0}
 
-        def text_step(i):
-            t = np.ascontiguousarray(th[i % POOL], dtype=np.int32)
-            dev._ck(dev.lib.lrx_search_text_host(dev.h, vp(ids), vp(lens), S, vp(t), vp(ptr_h), vp(w), N_SUB,
-                                                 K_TOP, FUSION[fusion], vp(o_ids), vp(o_s), vp(o_m), vp(o_k)))
-        for i in range(3):
-            text_step(i)
-        n_it = 30
-        ev0.record()
-        for i in range(n_it):
-            text_step(i)
-        ev1.record()
-        torch.cuda.synchronize()
-        ms = ev0.elapsed_time(ev1) / n_it
+        def text_step():
+            state["i"] += 1
+            dev.search_text_host(ids, lens, lists[state["i"] % POOL], K_TOP, WEIGHTS, fusion)
+        ms = timed(text_step, 30, warm=4)
         out["search_text_host"] = {"queries_per_s": 1e3 / ms, "ms": ms, "sub_queries": N_SUB, "seq_len": S,
                                    "note": "encoder (K1) + dense + BM25 + fusion in one call, host buffers "
                                            "in and out; random-init MiniLM-L6 weights"}
+        d_ids, d_lens = torch.from_numpy(ids).to(dev.device), torch.from_numpy(lens).to(dev.device)
+        ms = timed(lambda: enc.encode_ids_device(d_ids, d_lens), 30)
+        out["encoder_query_batch"] = {"batch": N_SUB, "seq_len": S, "ms": ms}
 
-    B, K = 1024, 2 * K_TOP
-    q = torch.from_numpy(synth.host_queries(B, seed=4321)).to(dev.device)
-    for _ in range(2):
-        res = dev.dense_topk_batched(q, K)
-    torch.cuda.synchronize()
-    overflow = int(res[3].sum().item())
-    dev.profile(True)
-    dev.profile_read(0)
-    ev0.record()
-    for _ in range(3):
-        dev.dense_topk_batched(q, K)
-    ev1.record()
-    torch.cuda.synchronize()
-    ms = ev0.elapsed_time(ev1) / 3
-    kms, kn = dev.profile_read(0)
-    dev.profile(False)
-    tiles = (n_local + 255) // 256
-    stride = max(1, min(8, tiles * 8 // (16 * K)))          # mirrors launch_dense_topk_batched
-    if (tiles + stride - 1) // stride * 8 > 16384:
-        stride = (tiles * 8 + 16383) // 16384
-    flop = 2.0 * B * 384 * n_local * (1 + 1.0 / stride)
-    out["dense_batched"] = {"batch": B, "rows": n_local, "K": K, "queries_per_s": B / ms * 1e3, "ms": ms,
-                            "gemm_ms": kms / 3, "tflops": flop / (kms / 3) / 1e9,
-                            "frac": flop / (kms / 3) / 1e9 / peak_tf, "bound": "tensor",
-                            "candidate_overflow_queries": overflow}
+    def k2b(d, rows, label):
+        B, K = 1024, 2 * K_TOP
+        q = torch.from_numpy(synth.host_queries(B, seed=4321)).to(d.device)
+        for _ in range(2):
+            res = d.dense_topk_batched(q, K)
+        torch.cuda.synchronize()
+        overflow = int(res[3].sum().item())
+        d.profile(True)
+        d.profile_read(0)
+        ms = timed(lambda: d.dense_topk_batched(q, K), 3, warm=0)
+        kms, kn = d.profile_read(0)
+        d.profile(False)
+        flop = 2.0 * B * 384 * rows                                   # algorithmic: one pass of Q . X^T
+        return {"batch": B, "rows": rows, "K": K, "queries_per_s": B / ms * 1e3, "ms": ms,
+                "gemm_ms": kms / 3, "tflops_call": flop / ms / 1e9, "frac_call": flop / ms / 1e9 / peak_tf,
+                "tflops_gemm_kernels": flop / (kms / 3) / 1e9, "frac": flop / (kms / 3) / 1e9 / peak_tf,
+                "bound": "tensor", "flops": "algorithmic 2*B*384*rows (the sampled first pass is NOT counted)",
+                "candidate_overflow_queries": overflow, "config": label}
+
+    out["dense_batched"] = k2b(dev, n_local, "resident shard")
+
+    # ---- config C3: 1 M rows
+    rows = min(1_000_000, n_local)
+    d3 = DeviceIndex(dev.device.index)
+    try:
+        d3.set_corpus(dev.x[:rows], 0)
+        for B in (1, 4):
+            q = torch.from_numpy(synth.host_queries(B, seed=77)).to(dev.device)
+            d3.dense_topk(q, 2 * K_TOP)
+            d3.profile(True)
+            d3.profile_read(0)
+            ms = timed(lambda: d3.dense_topk(q, 2 * K_TOP), 20, warm=0)
+            kms, kn = d3.profile_read(0)
+            d3.profile(False)
+            gbs = rows * 768 / (kms / kn * 1e-3) / 1e9
+            out[f"c3_dense_b{B}"] = {"rows": rows, "batch": B, "call_ms": ms, "queries_per_s": B / ms * 1e3,
+                                     "scan_ms": kms / kn, "achieved_GBps": gbs, "frac": gbs / hbm_peak,
+                                     "frac_of_8TBs_nominal": gbs / 8000.0, "bound": "hbm"}
+        out["c3_dense_b1024"] = k2b(d3, rows, "C3: 1 M rows")
+    finally:
+        d3.close()
     return out
 
 
 def scan_traffic_from_profile(n_local):
     """dram bytes of dense_scan_kernel from the committed ncu --set full capture (profiles/),
     scaled per row: the kernel reads each row exactly once, so bytes/row is size independent."""
-    try:
-        prof = json.loads((ROOT / "profiles" / "r1_scan_kernels_v3_full.json").read_text())
-        for l in prof["launches"]:
-            if "dense_scan_kernel" in l["kernel"] and "traffic_bytes_per_launch" in l:
-                rows = 10_000_000                       # the capture ran the 10 M-row shard
-                return l["traffic_bytes_per_launch"] / rows * n_local
-    except Exception:
-        pass
-    return None
+    for name in ("r2_scan_kernels_full.json", "r1_scan_kernels_v3_full.json"):
+        try:
+            prof = json.loads((ROOT / "profiles" / name).read_text())
+            for l in prof["launches"]:
+                if "dense_scan_kernel" in l["kernel"] and "traffic_bytes_per_launch" in l:
+                    rows = prof.get("rows", 10_000_000)
+                    return l["traffic_bytes_per_launch"] / rows * n_local, name
+        except Exception:
+            continue
+    return None, None
 
 
 # ------------------------------------------------------------------- ours
@@ -368,10 +655,10 @@ def run_ours(args):
     ptr_dev = torch.from_numpy(ptr_h).to(device)
     w_dev = torch.tensor(WEIGHTS, dtype=torch.float64, device=device)
     from legal_rag_engine_b200.sharding import ShardedSearcher
-    # Throughput loop: `in_flight` query batches at a time, each on its own handle (same resident
-    # matrix and postings, own workspaces / exchange region) and stream, so that one batch's
-    # merges, exchange and fusion run under the next batch's scans.
-    n_fly = args.in_flight if args.in_flight > 0 else (1 if world == 1 else 2)
+    # `in_flight` query batches at a time, each on its own handle (same resident matrix and
+    # postings, own workspaces / exchange region) and stream, so that one batch's merges,
+    # exchange and fusion run under the next batch's scans.
+    n_fly = max(1, args.in_flight)
     devs = [dev] + [dev.clone_view() for _ in range(n_fly - 1)]
     streams = [torch.cuda.Stream(device) for _ in range(n_fly)]
     for d, st in zip(devs, streams):
@@ -380,7 +667,6 @@ def run_ours(args):
     searchers = [ShardedSearcher(d) for d in devs]     # K2+K3 local -> exchange -> K4
     searcher = searchers[0]
     all_outs = [sr.buffers(N_SUB, K_TOP)[2] for sr in searchers]
-    outs = all_outs[0]
 
     def step(i):
         p, j = i % POOL, i % n_fly
@@ -392,97 +678,127 @@ def run_ours(args):
             dist.barrier()
         torch.cuda.synchronize()
 
-    for i in range(max(args.warmup, 3)):
+    # the kernel-event nodes are part of the captured chains: profile on before the first call.  Every
+    # (handle, query buffer) pair needs a direct call and a capturing call before it replays.
+    for d in devs:
+        d.profile(True)
+    warm = max(args.warmup, 3, 2 * POOL * n_fly // math.gcd(POOL, n_fly) + n_fly)
+    for i in range(warm):
         step(i)
     barrier()
     for o in all_outs:
-        assert int(o[4].sum().item()) == 0, "exactness guard tripped on the benchmark queries"
+        assert int(o[4].sum().item()) == 0, "status words set on the benchmark queries"
+
+    # ---- parity at the benchmark's own size (untimed)
+    parity = None
+    if args.parity_queries > 0:
+        with torch.cuda.stream(streams[0]):
+            pool_ids = list(range(0, POOL, max(1, POOL // args.parity_queries)))[:args.parity_queries]
+            t0 = time.time()
+            n_checked, n_bad, detail = parity_check(dev, lo, n_local, avgdl, qh, th, pool_ids, K_TOP,
+                                                    args.fusion, searcher, ptr_dev, w_dev, world, rank)
+            parity = {"queries": n_checked, "sub_queries": n_checked * N_SUB, "mismatches": n_bad,
+                      "against": "on-device float64 brute force of every shard (exact inner products of all "
+                                 "rows; BM25Okapi of all documents in rank_bm25's operation order), lists "
+                                 "all-gathered, merged (score desc, id asc), fused; ids, fused score, "
+                                 "semantic and keyword compared bit for bit",
+                      "seconds": round(time.time() - t0, 1)}
+            if n_bad:
+                parity["detail"] = detail
+        barrier()
+        if n_bad:
+            if rank == 0:
+                print(json.dumps({"error": "parity check failed", "parity": parity}), flush=True)
+            raise SystemExit(3)
 
     # ---- timed region: device-resident queries
     clocks = ClockSampler(local)
     launches0 = sum(d.launches for d in devs)
     for d in devs:
-        d.profile(True)
         d.profile_read(0); d.profile_read(1)
-    barrier()
-    clocks.start()
     ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    ev0.record()
-    for st in streams:
-        st.wait_event(ev0)
-    # host time to ENQUEUE a step, over the first steps only (later ones may wait on a full launch queue)
-    n_host = min(args.steps, 24)
-    t_host = time.perf_counter()
-    for i in range(args.steps):
-        if i == n_host:
-            t_host = time.perf_counter() - t_host
-        step(i)
-    if n_host == args.steps:
-        t_host = time.perf_counter() - t_host
-    for st in streams:
-        torch.cuda.current_stream().wait_stream(st)
-    ev1.record()
-    barrier()
+
+    def timed_block(n_steps, i0):
+        barrier()
+        ev0.record()
+        for st in streams:
+            st.wait_event(ev0)
+        t_h = time.perf_counter()
+        for i in range(n_steps):
+            step(i0 + i)
+        t_h = time.perf_counter() - t_h
+        for st in streams:
+            torch.cuda.current_stream().wait_stream(st)
+        ev1.record()
+        barrier()
+        t = torch.tensor([ev0.elapsed_time(ev1)], dtype=torch.float64, device=device)
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item()), t_h
+
+    clocks.start()
+    ms, t_host = timed_block(args.steps, warm)                  # exactly K steps
+    timed_steps, blocks = args.steps, 1
+    if ms * 1e-3 < args.min_time:
+        # K steps are too short a region to measure (pipeline fill / drain, rank skew): time R more
+        # blocks of K steps as ONE region and report that; every rank computes the same R
+        blocks = int(math.ceil(args.min_time / max(ms * 1e-3, 1e-6)))
+        blocks = max(2, min(blocks, 2000))
+        ms, t_host = timed_block(args.steps * blocks, warm + args.steps)
+        timed_steps = args.steps * blocks
     clk = clocks.stop()
-    ms = ev0.elapsed_time(ev1)
     scan_ms = scan_n = bm_ms = bm_n = 0
     for d in devs:
         a, b_ = d.profile_read(0); scan_ms += a; scan_n += b_
         a, b_ = d.profile_read(1); bm_ms += a; bm_n += b_
         d.profile(False)
     launches = sum(d.launches for d in devs) - launches0
-    dev.use_current_stream()           # handle 0 back on torch's default stream for what follows
-    tms = torch.tensor([ms], dtype=torch.float64, device=device)
-    if world > 1:
-        dist.all_reduce(tms, op=dist.ReduceOp.MAX)
-    ms = float(tms.item())
+    for o in all_outs:
+        assert int(o[4].sum().item()) == 0, "status words set in the timed region"
 
-    # ---- end to end: host buffers through the public call, copies inside the timed region
-    pin_q = torch.from_numpy(qh).pin_memory()
-    pin_t = torch.from_numpy(th).pin_memory()
-    pin_out = [torch.empty(o.shape, dtype=o.dtype).pin_memory() for o in outs[:4]]
+    # ---- end to end: host buffers through the C ABI (lrx_search_host_begin / _end), the H2D copy of
+    #      every step's inputs and the D2H copy of its results inside the timed region, the same
+    #      number of batches in flight
     h2d = N_SUB * 384 * 2 + N_SUB * N_TERMS * 4 + (N_SUB + 1) * 4 + N_SUB * 8
     d2h = N_SUB * K_TOP * (8 * 4) + N_SUB * 4
+    lists = [[th[p][b * N_TERMS:(b + 1) * N_TERMS].tolist() for b in range(N_SUB)] for p in range(POOL)]
 
-    if world == 1:
-        lists = [[th[p][b * N_TERMS:(b + 1) * N_TERMS].tolist() for b in range(N_SUB)] for p in range(POOL)]
+    def e2e_run(n):
+        res = None
+        for i in range(n):
+            d = devs[i % n_fly]
+            if i >= n_fly:
+                res = d.search_host_end()
+            d.search_host_begin(qh[i % POOL], lists[i % POOL], K_TOP, WEIGHTS, args.fusion)
+        for i in range(max(0, n - n_fly), n):
+            res = devs[i % n_fly].search_host_end()
+        return res
 
-        def e2e_step(i):
-            p = i % POOL
-            return dev.search_batch_host(qh[p], lists[p], K_TOP, WEIGHTS, args.fusion)
-    else:
-        qd = torch.empty_like(q_dev[0]); td = torch.empty_like(t_dev[0])
-
-        def e2e_step(i):
-            p = i % POOL
-            qd.copy_(pin_q[p], non_blocking=True)
-            td.copy_(pin_t[p], non_blocking=True)
-            searcher.search(qd, td, ptr_dev, K_TOP, mode, w_dev)
-            for o, po in zip(outs[:4], pin_out):
-                po.copy_(o, non_blocking=True)
-            torch.cuda.current_stream().synchronize()
-
-    for i in range(3):
-        e2e_step(i)
+    e2e_run(max(6, 3 * n_fly))
     barrier()
-    e2e_steps = max(10, args.steps // 2)
+    e2e_steps = max(args.steps, int(timed_steps // 4), 10)
     ev0.record()
-    for i in range(e2e_steps):
-        e2e_step(i)
+    last = e2e_run(e2e_steps)
     ev1.record()
     barrier()
     e2e_ms = torch.tensor([ev0.elapsed_time(ev1)], dtype=torch.float64, device=device)
     if world > 1:
         dist.all_reduce(e2e_ms, op=dist.ReduceOp.MAX)
     e2e_ms = float(e2e_ms.item())
+    assert last is not None and (last[0][:, 0] >= 0).all()
 
     # ---- the dominant kernel ALONE (no BM25 scan beside it): the same launches through
     #      lrx_dense_topk, events inside the library -- what the kernel does with the HBM to itself
-    dev.profile(True); dev.profile_read(0)
+    dev.use_current_stream()           # handle 0 back on torch's default stream for what follows
+    dev.profile(True); dev.profile_read(0); dev.profile_read(1)
     for i in range(20):
         dev.dense_topk(q_dev[i % POOL], 2 * K_TOP)
     torch.cuda.synchronize()
     alone_ms, alone_n = dev.profile_read(0)
+    for i in range(20):
+        dev.bm25(t_dev[i % POOL], ptr_dev, None, 2 * K_TOP if args.fusion == "rrf" else 0)
+    torch.cuda.synchronize()
+    bm_alone_ms, bm_alone_n = dev.profile_read(1)
     dev.profile(False)
 
     # ---- roofline of the dominant kernel (dense_scan_kernel), algorithmic bytes / event time
@@ -499,35 +815,43 @@ def run_ours(args):
     # averaged over the pool
     bm_bytes = float(np.mean([df_local[th[p]].sum() * 8 for p in range(POOL)]))
     bm_gbs = bm_bytes / (bm_ms / max(bm_n, 1) * 1e-3) / 1e9 if bm_ms > 0 else 0.0
+    bm_alone_gbs = bm_bytes / (bm_alone_ms / max(bm_alone_n, 1) * 1e-3) / 1e9 if bm_alone_ms > 0 else 0.0
+    traffic, traffic_src = scan_traffic_from_profile(n_local)
 
     if rank == 0:
-        qps = args.steps / (ms * 1e-3)
+        qps = timed_steps / (ms * 1e-3)
+        step_ms = ms / timed_steps
         line = {
             "metric": metric_name(args),
             "value": qps, "unit": "queries/s", "n_gpus": world, "steps": args.steps,
-            "warmup": max(args.warmup, 3), "ms_per_step": ms / args.steps,
+            "warmup": warm, "ms_per_step": step_ms,
+            "timed_steps": timed_steps, "timed_blocks": blocks, "timed_region_ms": ms,
             "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
             "dtype": "f16 matrix, f32 scan + exact f64 re-score; f64 BM25", "data": "synthetic",
             "config": dict(workload_config(args), parallelism=f"row-shard x{world}",
                            exchange=(searcher.exchange if world > 1 else "none"),
-                           in_flight=n_fly,
+                           in_flight=n_fly, launch="one captured CUDA graph per batch",
                            rows_per_gpu=n_local, nnz_per_gpu=nnz_local, build_s=round(t_build, 1)),
+            "parity": parity,
             "e2e": {"value": e2e_steps / (e2e_ms * 1e-3), "unit": "queries/s",
                     "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
-                    "ms_per_step": e2e_ms / e2e_steps},
+                    "ms_per_step": e2e_ms / e2e_steps, "steps": e2e_steps, "in_flight": n_fly,
+                    "call": "lrx_search_host_begin / lrx_search_host_end (host buffers in and out)"},
             "gpu_launches": int(launches),
-            "host_enqueue_ms_per_step": t_host * 1e3 / n_host,
+            "host_enqueue_ms_per_step": t_host * 1e3 / timed_steps,
             "clocks": clk,
             "roofline": {"bound": "hbm", "kernel": "dense_scan_kernel<4>", "achieved": scan_gbs,
                          "peak": peak, "unit": "GB/s", "frac": scan_gbs / peak, "peak_source": peak_src,
                          "peak_note": "the measured peak is a COPY (reads + writes); a read-only stream can "
                                       "exceed it, so frac may pass 1 -- see frac_of_8TBs_nominal",
-                         "frac_of_8TBs_nominal": scan_gbs / 8000.0, "traffic": scan_traffic_from_profile(n_local),
-                         "traffic_source": "ncu --set full dram__bytes_read+write per launch at 10 M rows "
-                                           "(profiles/r1_scan_kernels_v3_full.json), scaled by rows",
+                         "frac_of_8TBs_nominal": scan_gbs / 8000.0, "traffic": traffic,
+                         "traffic_source": f"ncu --set full dram__bytes_read+write per launch "
+                                           f"(profiles/{traffic_src}), scaled by rows",
                          "bytes_per_launch": scan_bytes, "ms_per_launch": scan_ms / max(scan_n, 1),
                          "launches_timed": int(scan_n),
-                         "share_of_step": (scan_ms / max(scan_n, 1)) * (scan_n / args.steps) / (ms / args.steps),
+                         "timing": "CUDA event nodes around the kernel inside the captured chains, read for the "
+                                   "last replay of every chain of the timed region",
+                         "share_of_step": (scan_ms / max(scan_n, 1)) / step_ms,
                          "alone": {"note": "dense_scan_kernel with the GPU to itself (20 launches of "
                                            "lrx_dense_topk after the timed region, same events)",
                                    "ms_per_launch": alone_ms / max(alone_n, 1),
@@ -536,28 +860,36 @@ def run_ours(args):
                                    "frac": n_local * 768 / (alone_ms / max(alone_n, 1) * 1e-3) / 1e9 / peak
                                    if alone_ms > 0 else 0.0},
                          "concurrent": {"note": "bm25_scan_kernel runs on the same SMs at the same time "
-                                                "(side stream) and shares the HBM bandwidth; alone the "
-                                                "dense scan takes 1.11 ms at 10 M rows (6.9 TB/s)",
-                                        "bytes_per_launch": bm_bytes,
-                                        "combined_achieved": (scan_bytes + bm_bytes) / (scan_ms / max(scan_n, 1) * 1e-3) / 1e9
-                                        if scan_ms > 0 else 0.0,
-                                        "combined_frac": (scan_bytes + bm_bytes) / (scan_ms / max(scan_n, 1) * 1e-3) / 1e9 / peak
-                                        if scan_ms > 0 else 0.0}},
-            "bm25_kernel": {"kernel": "bm25_scan_kernel", "bound": "hbm (issue/latency-bound as measured); "
-                            "timed while sharing the SMs with dense_scan_kernel (alone: 0.33 ms at 10 M rows)",
-                            "achieved": bm_gbs, "unit": "GB/s", "frac": bm_gbs / peak,
-                            "bytes_per_launch": bm_bytes, "ms_per_launch": bm_ms / max(bm_n, 1)},
+                                                "(side stream) and, with two batches in flight, so do the "
+                                                "other batch's kernels: they share the HBM bandwidth",
+                                        "bytes_per_step": scan_bytes + bm_bytes,
+                                        "step_achieved": (scan_bytes + bm_bytes) / (step_ms * 1e-3) / 1e9,
+                                        "step_frac": (scan_bytes + bm_bytes) / (step_ms * 1e-3) / 1e9 / peak}},
+            "bm25_kernel": {"kernel": "bm25_scan_kernel", "bound": "hbm",
+                            "in_step": {"achieved": bm_gbs, "frac": bm_gbs / peak,
+                                        "ms_per_launch": bm_ms / max(bm_n, 1),
+                                        "note": "sharing the SMs and the HBM with dense_scan_kernel"},
+                            "alone": {"achieved": bm_alone_gbs, "frac": bm_alone_gbs / peak,
+                                      "ms_per_launch": bm_alone_ms / max(bm_alone_n, 1)},
+                            "unit": "GB/s", "bytes_per_launch": bm_bytes},
         }
         if world == 1 and not args.no_stages:
             try:
-                line["stages"] = measure_stages(dev, n_local, peaks, th, ptr_h, args.fusion)
+                line["stages"] = measure_stages(dev, n_local, peaks, peak, th, ptr_h, args.fusion)
             except Exception as e:                      # a stage problem must not void the headline
                 line["stages"] = {"error": repr(e)}
         if world == 1 and not args.no_cpu_baseline:
             threads = os.cpu_count() or 1
-            sec, desc = cpu_reference_step(args.cpu_sample_rows, args.rows, threads, steps=1)
-            line["cpu_baseline"] = {"value": 1.0 / sec, "unit": "queries/s", "cores": threads,
-                                    "kind": "port", "sample": desc}
+            ref = CpuReference(args.cpu_sample_rows, threads)
+            m = ref.run(2, 1, args.rows)
+            line["cpu_baseline"] = {"value": 1e3 / m["extrapolated_ms_per_step"], "unit": "queries/s",
+                                    "cores": threads, "kind": "port", "estimated": True,
+                                    "sample": ref.describe(), "estimate": m}
+            del ref
+            try:
+                line["cpu_legs"] = cpu_legs(dev, n_local, avgdl, th, threads)
+            except Exception as e:
+                line["cpu_legs"] = {"error": repr(e)}
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.barrier()                 # nobody unmaps its exchange region while a peer may store

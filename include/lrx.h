@@ -36,7 +36,9 @@ extern "C" {
 #define LRX_DIM 384                 /* all-MiniLM-L6-v2 embedding width */
 #define LRX_MAX_BATCH 64            /* sub-queries per lrx_search_* call */
 #define LRX_MAX_DEPTH 256           /* max candidate depth K (= 2k) per list */
-#define LRX_MAX_QUERY_TERMS 64      /* BM25 term slots per sub-query */
+#define LRX_MAX_QUERY_TERMS 64      /* default token capacity per sub-query of the device-pointer entry
+                                     * points (raise it with lrx_set_query_capacity); the host-buffer
+                                     * entry points size the capacity from the batch: no limit */
 #define LRX_MAX_WORLD 16            /* shards (GPUs of one box) in a peer exchange */
 #define LRX_IPC_HANDLE_BYTES 64     /* sizeof(cudaIpcMemHandle_t) */
 
@@ -47,7 +49,8 @@ enum {
     LRX_E_CUDA = -3,       /* CUDA runtime error (message has the detail) */
     LRX_E_STATE = -4,      /* corpus / postings / weights not set */
     LRX_E_AMBIGUOUS = -5,  /* exactness guard could not be met */
-    LRX_E_NOMEM = -6
+    LRX_E_NOMEM = -6,
+    LRX_E_PEER = -7        /* a peer shard did not publish its block in time */
 };
 
 enum { LRX_FUSE_LINEAR = 0, LRX_FUSE_RRF = 1 };
@@ -164,6 +167,15 @@ int lrx_dense_topk_batched(lrx_handle* h, const void* dev_q_fp16, int32_t B, int
 int lrx_dense_at(lrx_handle* h, const void* dev_q_fp16, int32_t B, const int64_t* dev_ids,
                  int32_t n, double* dev_out);
 
+/* Token capacity of a query batch for the DEVICE-pointer entry points (lrx_bm25, lrx_search_local*,
+ * lrx_search_sharded): the library cannot see dev_q_ptr[B] from the host, so the rows of its
+ * per-token tables are sized from this figure; 0 (default) = B * LRX_MAX_QUERY_TERMS.  Every token
+ * is scored, in order, as the reference does (retrieval_engine.py:67-68 has no limit).  A batch with
+ * MORE tokens than the capacity is never scored short silently: lrx_bm25 returns NaN maxima and the
+ * search entry points set bit 2 of the status words.  The host-buffer entry points size the
+ * capacity from host_q_ptr themselves. */
+int lrx_set_query_capacity(lrx_handle* h, int32_t max_total_terms);
+
 /* K3: replaces BM25Okapi.get_scores + max()  (retrieval_engine.py:68,74).
  * dev_q_terms: concatenated term ids (-1 = out of vocabulary), dev_q_ptr [B+1].
  * Emits (i) exact scores at dev_cand_ids [B,n_cand] (may be NULL / n_cand 0; ids outside
@@ -207,12 +219,16 @@ int lrx_search_finish_packed(lrx_handle* h, const void* dev_packed_all, int32_t 
 
 /* ---- sharded search with the exchange fused into the kernels (world > 1, one box).
  * Replaces "lrx_search_local_packed -> NCCL all-gather -> lrx_search_finish_packed": every rank
- * owns an exchange region (two parities x world slots of one packed block, plus sequence flags);
- * after K2/K3 the rank's block is stored straight into the slot `rank` of EVERY peer's region
- * over NVLink (peer memory opened through CUDA IPC) followed by a release store of the call's
- * sequence number, and the fusion kernel acquires the world flags before it merges.  No
- * collective library call, no host synchronisation; calls must be made in the same order by all
- * ranks (SPMD), each on its own stream.
+ * owns an exchange region (two parities x world slots of one packed block, sequence flags and the
+ * call counter); the packing kernel stores the rank's records straight into the slot `rank` of EVERY
+ * peer's region over NVLink (peer memory opened through CUDA IPC), its last CTA publishes the
+ * call's sequence number with a release store, and the fusion kernel acquires the world flags
+ * before it merges.  The sequence number lives on the device, so the whole chain is one captured
+ * CUDA graph replayed per batch: no collective library call, no host synchronisation, one launch.
+ * Calls must be made in the same order by all ranks (SPMD), each on its own stream.  dev_status[b]:
+ * 0 ok, bit 0 = exactness guard (rerun with a larger width), bit 1 = token capacity exceeded,
+ * -1 = a peer's block did not arrive within the exchange timeout.  world == 1 is accepted (no
+ * exchange): the same call then serves every shard count.
  *   lrx_exchange_export  allocates this rank's region for batches up to (B_max, k_max) and
  *                        returns its IPC handle (LRX_IPC_HANDLE_BYTES bytes);
  *   lrx_exchange_import  takes all ranks' handles in rank order (exchanged by the host, e.g. one
@@ -225,16 +241,42 @@ int lrx_search_sharded(lrx_handle* h, const void* dev_q_fp16, const int32_t* dev
                        int32_t mode, int32_t width, int64_t* dev_ids, double* dev_score,
                        double* dev_sem, double* dev_kw, int32_t* dev_status);
 
-/* Host-buffer form of the whole search on ONE shard (world == 1): copies the
- * inputs in, runs K2..K4, copies the results out and synchronises.  This is the
- * call `RetrievalEngine.search` / `search_batch` makes (retrieval_engine.py:59). */
+/* Bounded spin of the fusion kernel on a peer's sequence flag (default 2000 ms); expiry is reported
+ * as status -1 / LRX_E_PEER, never as a hung GPU. */
+int lrx_set_exchange_timeout(lrx_handle* h, int32_t milliseconds);
+
+/* Host-buffer form of the whole search: copies the inputs in, runs K2..K4 (exchange included when
+ * the handle is a shard, world > 1: every rank makes the same call), copies the results out and
+ * synchronises; widens the dense candidate lists and reruns when the exactness guard trips (the
+ * status is replicated, so all ranks rerun together).  This is the call `RetrievalEngine.search` /
+ * `search_batch` makes (retrieval_engine.py:59).  Any number of tokens per query. */
 int lrx_search_batch_host(lrx_handle* h, const void* host_q_fp16, const int32_t* host_q_terms,
                           const int32_t* host_q_ptr, const double* host_weights, int32_t B,
                           int32_t k, int32_t mode, int64_t* host_ids, double* host_score,
                           double* host_sem, double* host_kw);
 
+/* The same under the name the sharded callers use (world >= 1). */
+int lrx_search_sharded_host(lrx_handle* h, const void* host_q_fp16, const int32_t* host_q_terms,
+                            const int32_t* host_q_ptr, const double* host_weights, int32_t B,
+                            int32_t k, int32_t mode, int64_t* host_ids, double* host_score,
+                            double* host_sem, double* host_kw);
+
+/* Split form for pipelining: _begin stages the inputs in pinned memory and enqueues H2D + the chain
+ * + D2H on the handle's stream and returns at once; _end synchronises, checks the status words
+ * (rerunning wider if needed) and copies the results out.  One search in flight per handle; several
+ * handles over the same index (same corpus / postings pointers, each with its own stream and
+ * exchange region) keep several batches in flight on one GPU. */
+int lrx_search_host_begin(lrx_handle* h, const void* host_q_fp16, const int32_t* host_q_terms,
+                          const int32_t* host_q_ptr, const double* host_weights, int32_t B, int32_t k,
+                          int32_t mode);
+int lrx_search_text_host_begin(lrx_handle* h, const int32_t* host_tok_ids, const int32_t* host_tok_lens,
+                               int32_t S, const int32_t* host_q_terms, const int32_t* host_q_ptr,
+                               const double* host_weights, int32_t B, int32_t k, int32_t mode);
+int lrx_search_host_end(lrx_handle* h, int64_t* host_ids, double* host_score, double* host_sem,
+                        double* host_kw);
+
 /* The whole of RetrievalEngine.search for a batch of query STRINGS already tokenised on the host
- * (world == 1): H2D of WordPiece ids [B,S] + lens [B] and of the BM25 term ids, K1 (encoder) ->
+ * (world >= 1; a shard encodes the strings redundantly): H2D of WordPiece ids [B,S] + lens [B] and of the BM25 term ids, K1 (encoder) ->
  * K2 -> K3 -> K4, D2H of the fused results, synchronised.  Replaces retrieval_engine.py:59-96
  * end to end; `search_batch` with B = 4 is the orchestrator fan-out (orchestrator.py:38-62). */
 int lrx_search_text_host(lrx_handle* h, const int32_t* host_tok_ids, const int32_t* host_tok_lens,

@@ -23,6 +23,7 @@ LRX_MAX_QUERY_TERMS = 64
 LRX_IPC_HANDLE_BYTES = 64
 LRX_FUSE_LINEAR, LRX_FUSE_RRF = 0, 1
 LRX_E_AMBIGUOUS = -5
+LRX_E_PEER = -7
 
 
 class LrxError(RuntimeError):
@@ -97,6 +98,13 @@ _SIGNATURES = {
     "lrx_exchange_import": (C.c_int, [_vp, _vp]),
     "lrx_search_sharded": (C.c_int, [_vp, _vp, _vp, _vp, _vp, _i32, _i32, _i32, _i32, _vp, _vp, _vp, _vp,
                                      _vp]),
+    "lrx_set_query_capacity": (C.c_int, [_vp, _i32]),
+    "lrx_set_exchange_timeout": (C.c_int, [_vp, _i32]),
+    "lrx_search_sharded_host": (C.c_int, [_vp, _vp, _vp, _vp, _vp, _i32, _i32, _i32, _vp, _vp, _vp,
+                                          _vp]),
+    "lrx_search_host_begin": (C.c_int, [_vp, _vp, _vp, _vp, _vp, _i32, _i32, _i32]),
+    "lrx_search_text_host_begin": (C.c_int, [_vp, _vp, _vp, _i32, _vp, _vp, _vp, _i32, _i32, _i32]),
+    "lrx_search_host_end": (C.c_int, [_vp, _vp, _vp, _vp, _vp]),
     "lrx_search_batch_host": (C.c_int, [_vp, _vp, _vp, _vp, _vp, _i32, _i32, _i32, _vp, _vp, _vp,
                                         _vp]),
     "lrx_search_text_host": (C.c_int, [_vp, _vp, _vp, _i32, _vp, _vp, _vp, _i32, _i32, _i32, _vp, _vp,

@@ -3,6 +3,7 @@
 // through one K2 -> K3 -> K4 chain).  No CPU fallback anywhere.
 #include <cstdarg>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <new>
 
@@ -11,8 +12,12 @@
 
 namespace lrx {
 
-cudaError_t ensure_ws(void** p, size_t* have, size_t need) {
+cudaError_t ensure_ws(lrx_handle* h, void** p, size_t* have, size_t need) {
     if (*have >= need && *p != nullptr) return cudaSuccess;
+    // a captured launch chain holds the old pointers: never move a workspace while capturing, and
+    // retire every instantiated plan when one moves
+    if (h->capturing) return cudaErrorStreamCaptureUnsupported;
+    h->ws_epoch++;
     if (*p != nullptr) {
         cudaError_t e = cudaFree(*p);   // synchronises: safe against in-flight users
         *p = nullptr;
@@ -29,10 +34,22 @@ void prof_begin(lrx_handle* h, int which, cudaStream_t st) {
     if (!h->prof) return;
     cudaEvent_t e;
     if (cudaEventCreate(&e) != cudaSuccess) return;
-    cudaEventRecord(e, st ? st : h->stream);
-    h->prof_ev[which].push_back(e);
+    if (h->capturing && h->cap_plan != nullptr) {
+        // inside a captured chain: an external event-record node, re-recorded by every replay of
+        // the plan (lrx_profile_read takes each plan's last replay)
+        cudaEventRecordWithFlags(e, st ? st : h->stream, cudaEventRecordExternal);
+        h->cap_plan->prof_ev[which].push_back(e);
+    } else {
+        cudaEventRecord(e, st ? st : h->stream);
+        h->prof_ev[which].push_back(e);
+    }
 }
 void prof_end(lrx_handle* h, int which, cudaStream_t st) { prof_begin(h, which, st); }
+
+std::recursive_mutex& attr_mutex() {
+    static std::recursive_mutex m;
+    return m;
+}
 
 static std::string g_err;   // failures before a handle exists
 static std::mutex g_err_mu;
@@ -62,13 +79,23 @@ static int fail(lrx_handle* h, int code, const char* fmt, ...) {
 
 static size_t align_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
 
+static void drop_plans(lrx_handle* h) {
+    for (lrx_plan* pl : h->plans) {
+        if (pl->exec != nullptr) cudaGraphExecDestroy(pl->exec);
+        for (int w = 0; w < 2; ++w)
+            for (cudaEvent_t e : pl->prof_ev[w]) cudaEventDestroy(e);
+        delete pl;
+    }
+    h->plans.clear();
+}
+
 }  // namespace lrx
 
 using namespace lrx;
 
 extern "C" {
 
-const char* lrx_version(void) { return "lrx 0.1 sm_100a"; }
+const char* lrx_version(void) { return "lrx 0.2 sm_100a"; }
 
 const char* lrx_last_error(const lrx_handle* h) {
     if (h != nullptr) return h->err.c_str();
@@ -105,11 +132,16 @@ int lrx_open(const lrx_config* cfg, lrx_handle** out) {
     h->rank = cfg->rank;
     h->world = cfg->world > 0 ? cfg->world : 1;
     if (cudaStreamCreateWithFlags(&h->aux, cudaStreamNonBlocking) != cudaSuccess ||
+        cudaStreamCreateWithFlags(&h->cap, cudaStreamNonBlocking) != cudaSuccess ||
         cudaEventCreateWithFlags(&h->ev_fork, cudaEventDisableTiming) != cudaSuccess ||
-        cudaEventCreateWithFlags(&h->ev_join, cudaEventDisableTiming) != cudaSuccess) {
+        cudaEventCreateWithFlags(&h->ev_join, cudaEventDisableTiming) != cudaSuccess ||
+        cudaMalloc((void**)&h->pack_done, 256) != cudaSuccess ||
+        cudaMemset(h->pack_done, 0, 256) != cudaSuccess) {
         delete h;
         return fail(nullptr, LRX_E_CUDA, "lrx_open: cannot create side stream / events");
     }
+    const char* ng = getenv("LRX_NO_GRAPH");
+    h->graphs = !(ng != nullptr && ng[0] != '\0' && ng[0] != '0');
     *out = h;
     return LRX_OK;
 }
@@ -118,12 +150,18 @@ int lrx_close(lrx_handle* h) {
     if (h == nullptr) return LRX_OK;
     cudaSetDevice(h->device);
     cudaDeviceSynchronize();
+    drop_plans(h);
+    for (int w = 0; w < 2; ++w)
+        for (cudaEvent_t e : h->prof_ev[w]) cudaEventDestroy(e);
+    if (h->cap) cudaStreamDestroy(h->cap);
+    if (h->pack_done) cudaFree(h->pack_done);
     void* ws[] = {h->ws_dense_part, h->ws_bm_part, h->ws_bm_max, h->ws_misc, h->ws_io};
     for (void* p : ws)
         if (p != nullptr) cudaFree(p);
     encoder_free(h);
     for (int w = 0; w < LRX_MAX_WORLD; ++w)
         if (h->xchg_peer[w] != nullptr && w != h->rank) cudaIpcCloseMemHandle(h->xchg_peer[w]);
+    if (h->bm_ctab != nullptr) cudaFree(h->bm_ctab);
     if (h->xchg != nullptr) cudaFree(h->xchg);
     if (h->xchg_peer_dev != nullptr) cudaFree(h->xchg_peer_dev);
     if (h->ws_host != nullptr) cudaFreeHost(h->ws_host);
@@ -180,15 +218,23 @@ int lrx_profile_read(lrx_handle* h, int32_t which, double* total_ms, int64_t* n_
     std::vector<cudaEvent_t>& ev = h->prof_ev[which];
     double ms = 0.0;
     int64_t n = 0;
-    for (size_t i = 0; i + 1 < ev.size(); i += 2) {
-        float t = 0.f;
-        if (cudaEventElapsedTime(&t, ev[i], ev[i + 1]) == cudaSuccess) {
-            ms += t;
-            ++n;
+    auto add = [&](const std::vector<cudaEvent_t>& v) {
+        for (size_t i = 0; i + 1 < v.size(); i += 2) {
+            float t = 0.f;
+            if (cudaEventElapsedTime(&t, v[i], v[i + 1]) == cudaSuccess) {
+                ms += t;
+                ++n;
+            }
         }
-    }
+    };
+    add(ev);
     for (cudaEvent_t e : ev) cudaEventDestroy(e);
     ev.clear();
+    // captured chains: the event nodes hold the times of each plan's LAST replay
+    for (lrx_plan* pl : h->plans)
+        if (pl->replayed) add(pl->prof_ev[which]);
+    if (which == 1)
+        for (lrx_plan* pl : h->plans) pl->replayed = false;
     *total_ms = ms;
     *n_launches = n;
     return LRX_OK;
@@ -208,6 +254,7 @@ int lrx_set_corpus(lrx_handle* h, const void* dev_x_fp16, int64_t n_local, int64
     h->x = dev_x_fp16;
     h->n_local = n_local;
     h->id_base = id_base;
+    h->ws_epoch++;                        // captured chains hold the old matrix
     return LRX_OK;
 }
 
@@ -232,6 +279,7 @@ int lrx_set_postings(lrx_handle* h, const uint64_t* dev_term_ptr, const void* de
     h->idf = dev_idf;
     h->n_terms = n_terms;
     h->nnz = nnz;
+    h->ws_epoch++;                        // captured chains hold the old postings
     return LRX_OK;
 }
 
@@ -401,64 +449,226 @@ int lrx_bm25(lrx_handle* h, const int32_t* dev_q_terms, const int32_t* dev_q_ptr
         (K > 0 && (dev_top_scores == nullptr || dev_top_ids == nullptr)))
         return fail(h, LRX_E_ARG, "lrx_bm25: null pointer");
     LRX_CUDA(h, cudaSetDevice(h->device));
+    h->bm_rows = h->bm_rows_cfg;
     LRX_CUDA(h, launch_bm25(h, dev_q_terms, dev_q_ptr, B, dev_cand_ids, n_cand, dev_cand_scores,
                             dev_max, K, dev_top_scores, dev_top_ids));
     return LRX_OK;
 }
 
-// scratch carved out of ws_misc for one lrx_search_local call
+}  // extern "C"
+
+// ---------------------------------------------------------------------------------------------
+// K5: the launch chain of one query batch.
+//
+// Two chains side by side.  Main stream: dense scan -> merge + exact re-score.  Side stream: BM25
+// range bounds -> BM25 scan -> merge + max.  Neither needs the other's result (the BM25 scores AT
+// the dense candidates are looked up afterwards, inside the packing kernel), and the two scans
+// are built to share an SM -- the dense scan is bound by HBM and leaves the issue slots idle, the
+// BM25 scan is bound by issue/FP64 latency and leaves HBM idle; one CTA of each fits the registers
+// and the shared memory of an SM.  The dense scan is launched first so that its 148 CTAs are
+// placed before the BM25 CTAs fill the rest.  After the join: pack (+ peer exchange) -> fusion.
+//
+// The whole chain is captured once per (shape, pointers) into a CUDA graph and replayed with a
+// single cudaGraphLaunch (run_planned): 8 launches + 4 event operations from the host per batch
+// become one, which is what the small shards of an 8-GPU box need (0.18 ms of GPU work per batch).
+
+// ---- packed block: [B][2][2k] records | [B] double | [B] int32, 16-byte padded
+static void packed_layout(int B, int k, size_t* o_max, size_t* o_flags, size_t* total) {
+    const size_t rec = (size_t)B * 2 * (2 * k) * sizeof(lrx_record);
+    *o_max = rec;
+    *o_flags = rec + (size_t)B * sizeof(double);
+    *total = align_up(*o_flags + (size_t)B * sizeof(int32_t), 16);
+}
+
+// scratch carved out of ws_misc for one local chain
 struct LocalScratch {
     double* dense_exact;
     float* dense_D;
     int64_t* dense_I;
-    double* dense_bm;
     double* bm_scores;
     int64_t* bm_ids;
-    double* bm_dense;
+    double* maxbm;
+    int32_t* flags;
+    unsigned char* block;       // packed block of this shard (world == 1 / unpacked outputs)
 };
 
-static int search_local_locked(lrx_handle* h, const void* q, const int32_t* q_terms,
-                               const int32_t* q_ptr, int B, int k, int mode, int width,
-                               lrx_record* records, double* maxbm, int32_t* flags) {
-    const int K = 2 * k;   // index.search(query_vector, k * 2)  (retrieval_engine.py:64)
-    int rc = check_dense(h, "lrx_search_local", B, K);
-    if (rc != LRX_OK) return rc;
-    if (h->term_ptr == nullptr) return fail(h, LRX_E_STATE, "lrx_search_local: postings not set");
-    if (mode != LRX_FUSE_LINEAR && mode != LRX_FUSE_RRF)
-        return fail(h, LRX_E_ARG, "lrx_search_local: unknown fusion mode %d", mode);
-    if (width <= 0) width = dense_default_width(K);
-    if (width < K || width > 512 || (width & (width - 1)) != 0)
-        return fail(h, LRX_E_ARG, "lrx_search_local: width must be a power of two in [2k,512]");
+static int carve_scratch(lrx_handle* h, int B, int k, LocalScratch* s) {
+    const int K = 2 * k;
     const size_t n = (size_t)B * K;
-    const size_t need = n * (5 * sizeof(double) + 2 * sizeof(int64_t)) + 1024;
-    LRX_CUDA(h, ensure_ws(&h->ws_misc, &h->ws_misc_bytes, need));
-    LocalScratch s;
+    size_t o_max, o_flags, total;
+    packed_layout(B, k, &o_max, &o_flags, &total);
+    const size_t need = n * (2 * sizeof(double) + 2 * sizeof(int64_t) + sizeof(float)) +
+                        (size_t)B * (sizeof(double) + sizeof(int32_t)) + total + 2048;
+    LRX_CUDA(h, ensure_ws(h, &h->ws_misc, &h->ws_misc_bytes, need));
     char* p = (char*)h->ws_misc;
-    s.dense_exact = (double*)p; p += n * sizeof(double);
-    s.dense_bm = (double*)p;    p += n * sizeof(double);
-    s.bm_scores = (double*)p;   p += n * sizeof(double);
-    s.bm_dense = (double*)p;    p += n * sizeof(double);
-    s.dense_I = (int64_t*)p;    p += n * sizeof(int64_t);
-    s.bm_ids = (int64_t*)p;     p += n * sizeof(int64_t);
-    s.dense_D = (float*)p;
-    // Two chains side by side.  Main stream: dense scan -> merge + exact re-score.  Side stream:
-    // BM25 range bounds -> BM25 scan -> merge + max.  Neither needs the other's result (the BM25
-    // scores AT the dense candidates are looked up afterwards by bm25_at_kernel), and the two scans
-    // are built to share an SM -- the dense scan is bound by HBM and leaves the issue slots idle,
-    // the BM25 scan is bound by issue/FP64 latency and leaves HBM idle; one CTA of each fits the
-    // registers and the shared memory of an SM.  The dense scan is launched first so that its 148
-    // CTAs are placed before the BM25 CTAs fill the rest.
+    s->dense_exact = (double*)p; p += n * sizeof(double);
+    s->bm_scores = (double*)p;   p += n * sizeof(double);
+    s->dense_I = (int64_t*)p;    p += n * sizeof(int64_t);
+    s->bm_ids = (int64_t*)p;     p += n * sizeof(int64_t);
+    s->maxbm = (double*)p;       p += align_up((size_t)B * sizeof(double), 16);
+    s->block = (unsigned char*)p; p += align_up(total, 256);
+    s->dense_D = (float*)p;      p += align_up(n * sizeof(float), 16);
+    s->flags = (int32_t*)p;
+    return LRX_OK;
+}
+
+static int check_search_args(lrx_handle* h, const char* fn, int B, int k, int mode, int* width) {
+    const int K = 2 * k;   // index.search(query_vector, k * 2)  (retrieval_engine.py:64)
+    if (k < 1) return fail(h, LRX_E_ARG, "%s: k must be >= 1", fn);
+    int rc = check_dense(h, fn, B, K);
+    if (rc != LRX_OK) return rc;
+    if (h->term_ptr == nullptr) return fail(h, LRX_E_STATE, "%s: postings not set", fn);
+    if (mode != LRX_FUSE_LINEAR && mode != LRX_FUSE_RRF)
+        return fail(h, LRX_E_ARG, "%s: unknown fusion mode %d", fn, mode);
+    if (*width <= 0) *width = dense_default_width(K);
+    if (*width < K || *width > 512 || (*width & (*width - 1)) != 0)
+        return fail(h, LRX_E_ARG, "%s: width must be a power of two in [2k,512]", fn);
+    if (h->world * K > 2048) return fail(h, LRX_E_ARG, "%s: world*2k must be <= 2048", fn);
+    return LRX_OK;
+}
+
+// K2 + K3 on this shard and the packed block to `block` (or, to_peers, into every shard's
+// exchange region).  Arguments are checked by the callers.
+static int enqueue_local(lrx_handle* h, const void* q, const int32_t* q_terms, const int32_t* q_ptr,
+                         int B, int k, int mode, int width, const LocalScratch& s, void* block,
+                         bool to_peers) {
+    const int K = 2 * k;
+    size_t o_max, o_flags, total;
+    packed_layout(B, k, &o_max, &o_flags, &total);
     const int Kb = (mode == LRX_FUSE_RRF) ? K : 0;
     LRX_CUDA(h, cudaEventRecord(h->ev_fork, h->stream));
     LRX_CUDA(h, cudaStreamWaitEvent(h->aux, h->ev_fork, 0));
-    LRX_CUDA(h, launch_dense_topk(h, q, B, K, width, s.dense_exact, s.dense_D, s.dense_I, flags));
+    LRX_CUDA(h, launch_dense_topk(h, q, B, K, width, s.dense_exact, s.dense_D, s.dense_I, s.flags));
     LRX_CUDA(h, launch_bm25_bounds(h, q_terms, q_ptr, B, h->aux));
-    LRX_CUDA(h, launch_bm25_scan(h, q_terms, q_ptr, B, maxbm, Kb, s.bm_scores, s.bm_ids, h->aux));
+    LRX_CUDA(h, launch_bm25_scan(h, q_terms, q_ptr, B, s.maxbm, Kb, s.bm_scores, s.bm_ids, h->aux));
     LRX_CUDA(h, cudaEventRecord(h->ev_join, h->aux));
     LRX_CUDA(h, cudaStreamWaitEvent(h->stream, h->ev_join, 0));   // join
-    LRX_CUDA(h, launch_bm25_at(h, q_terms, q_ptr, B, s.dense_I, K, s.dense_bm, h->stream));
-    LRX_CUDA(h, launch_pack_records(h, B, K, mode, s.dense_exact, s.dense_I, s.dense_bm, s.bm_scores,
-                                    s.bm_ids, s.bm_dense, q, records));
+    LRX_CUDA(h, launch_pack_exchange(h, q_terms, q_ptr, B, K, mode, s.dense_exact, s.dense_I, s.bm_scores,
+                                     s.bm_ids, s.maxbm, s.flags, q, block, to_peers, o_max, o_flags));
+    return LRX_OK;
+}
+
+// K4 on [world] packed blocks `all` (stride bytes apart), or on this rank's exchange region.
+static int enqueue_fuse_packed(lrx_handle* h, const void* all, size_t stride, int world, bool from_peers,
+                               int B, int k, int mode, const double* weights, int64_t* ids,
+                               double* score, double* sem, double* kw, int32_t* status) {
+    size_t o_max, o_flags, total;
+    packed_layout(B, k, &o_max, &o_flags, &total);
+    const char* p = (const char*)all;
+    LRX_CUDA(h, launch_fuse(h, (const lrx_record*)p, (const double*)(p + o_max),
+                            (const int32_t*)(p + o_flags), (int64_t)stride, world, B, 2 * k, k, mode,
+                            weights, ids, score, sem, kw, status, from_peers));
+    return LRX_OK;
+}
+
+// ---- captured chains
+static bool key_in(const std::vector<std::vector<uint64_t>>& set, const std::vector<uint64_t>& key) {
+    for (const auto& k : set)
+        if (k == key) return true;
+    return false;
+}
+
+// Runs `enqueue` (a callable that launches a chain on h->stream / h->aux) either directly or as a
+// replay of its captured graph.  First call with a key: direct (it also grows the workspaces and
+// sets the function attributes, neither of which may happen while capturing).  Second call:
+// capture + instantiate + replay.  Later calls: one cudaGraphLaunch.  A chain that cannot be
+// captured stays on the direct path.
+template <typename F>
+static int run_planned(lrx_handle* h, std::vector<uint64_t> key, F&& enqueue) {
+    if (!h->graphs) return enqueue();
+    key.push_back(h->prof ? 1u : 0u);
+    for (size_t i = 0; i < h->plans.size(); ++i) {
+        lrx_plan* pl = h->plans[i];
+        if (pl->key != key) continue;
+        if (pl->epoch == h->ws_epoch) {
+            LRX_CUDA(h, cudaGraphLaunch(pl->exec, h->stream));
+            h->launches += pl->kernels;
+            pl->stamp = ++h->plan_clock;
+            pl->replayed = true;
+            return LRX_OK;
+        }
+        cudaGraphExecDestroy(pl->exec);                      // stale: a workspace or the index moved
+        for (int w = 0; w < 2; ++w)
+            for (cudaEvent_t e : pl->prof_ev[w]) cudaEventDestroy(e);
+        delete pl;
+        h->plans.erase(h->plans.begin() + (long)i);
+        break;
+    }
+    if (key_in(h->eager_keys, key)) return enqueue();
+    if (!key_in(h->seen_keys, key)) {
+        if (h->seen_keys.size() >= 256) h->seen_keys.clear();
+        h->seen_keys.push_back(key);
+        return enqueue();
+    }
+    // ---- capture on the handle's own stream (the user's may be the legacy default stream)
+    lrx_plan* pl = new (std::nothrow) lrx_plan();
+    if (pl == nullptr) return enqueue();
+    cudaStream_t user = h->stream;
+    const int64_t l0 = h->launches;
+    cudaGraph_t graph = nullptr;
+    cudaError_t ce = cudaStreamBeginCapture(h->cap, cudaStreamCaptureModeRelaxed);
+    int rc = LRX_E_CUDA;
+    if (ce == cudaSuccess) {
+        h->capturing = true; h->cap_plan = pl; h->stream = h->cap;
+        rc = enqueue();
+        h->stream = user; h->capturing = false; h->cap_plan = nullptr;
+        ce = cudaStreamEndCapture(h->cap, &graph);
+    }
+    pl->kernels = h->launches - l0;
+    h->launches = l0;
+    if (rc == LRX_OK && ce == cudaSuccess && graph != nullptr)
+        ce = cudaGraphInstantiate(&pl->exec, graph, 0);
+    if (graph != nullptr) cudaGraphDestroy(graph);
+    if (rc != LRX_OK || ce != cudaSuccess || pl->exec == nullptr) {
+        cudaGetLastError();                                  // clear the capture error
+        for (int w = 0; w < 2; ++w)
+            for (cudaEvent_t e : pl->prof_ev[w]) cudaEventDestroy(e);
+        if (pl->exec != nullptr) cudaGraphExecDestroy(pl->exec);
+        delete pl;
+        if (h->eager_keys.size() >= 256) h->eager_keys.clear();
+        h->eager_keys.push_back(key);
+        return enqueue();
+    }
+    pl->key = key;
+    pl->epoch = h->ws_epoch;
+    if (h->plans.size() >= 96) {                             // evict the least recently used plan
+        size_t lru = 0;
+        for (size_t i = 1; i < h->plans.size(); ++i)
+            if (h->plans[i]->stamp < h->plans[lru]->stamp) lru = i;
+        lrx_plan* old = h->plans[lru];
+        cudaGraphExecDestroy(old->exec);
+        for (int w = 0; w < 2; ++w)
+            for (cudaEvent_t e : old->prof_ev[w]) cudaEventDestroy(e);
+        delete old;
+        h->plans.erase(h->plans.begin() + (long)lru);
+    }
+    h->plans.push_back(pl);
+    LRX_CUDA(h, cudaGraphLaunch(pl->exec, h->stream));
+    h->launches += pl->kernels;
+    pl->stamp = ++h->plan_clock;
+    pl->replayed = true;
+    return LRX_OK;
+}
+
+static uint64_t pk(const void* p) { return (uint64_t)(uintptr_t)p; }
+
+extern "C" {
+
+int lrx_set_query_capacity(lrx_handle* h, int32_t max_total_terms) {
+    if (h == nullptr) return fail(nullptr, LRX_E_ARG, "lrx_set_query_capacity: null handle");
+    std::lock_guard<std::mutex> g(h->mu);
+    if (max_total_terms < 0 || max_total_terms > (1 << 20))
+        return fail(h, LRX_E_ARG, "lrx_set_query_capacity: capacity must be in [0, 2^20]");
+    h->bm_rows_cfg = max_total_terms;
+    return LRX_OK;
+}
+
+int lrx_set_exchange_timeout(lrx_handle* h, int32_t milliseconds) {
+    if (h == nullptr) return fail(nullptr, LRX_E_ARG, "lrx_set_exchange_timeout: null handle");
+    std::lock_guard<std::mutex> g(h->mu);
+    if (milliseconds < 1) return fail(h, LRX_E_ARG, "lrx_set_exchange_timeout: must be >= 1 ms");
+    h->xchg_timeout_ms = milliseconds;
+    h->ws_epoch++;                        // the bound is a kernel argument of the captured chains
     return LRX_OK;
 }
 
@@ -470,23 +680,22 @@ int lrx_search_local(lrx_handle* h, const void* dev_q_fp16, const int32_t* dev_q
     if (dev_q_fp16 == nullptr || dev_q_ptr == nullptr || dev_records == nullptr ||
         dev_maxbm25 == nullptr || dev_flags == nullptr)
         return fail(h, LRX_E_ARG, "lrx_search_local: null pointer");
+    int rc = check_search_args(h, "lrx_search_local", B, k, mode, &width);
+    if (rc != LRX_OK) return rc;
     LRX_CUDA(h, cudaSetDevice(h->device));
-    return search_local_locked(h, dev_q_fp16, dev_q_terms, dev_q_ptr, B, k, mode, width, dev_records,
-                               dev_maxbm25, dev_flags);
-}
-
-static int search_finish_locked(lrx_handle* h, const lrx_record* rec_all, const double* max_all,
-                                const int32_t* flags_all, int64_t shard_stride, int world, int B,
-                                int k, int mode,
-                                const double* weights, int64_t* ids, double* score, double* sem,
-                                double* kw, int32_t* status) {
-    const int K = 2 * k;
-    if (world < 1 || world * K > 2048)
-        return fail(h, LRX_E_ARG, "lrx_search_finish: world*2k must be in [1,2048]");
-    if (B < 1 || B > LRX_MAX_BATCH || k < 1 || K > LRX_MAX_DEPTH)
-        return fail(h, LRX_E_ARG, "lrx_search_finish: bad B/k");
-    LRX_CUDA(h, launch_fuse(h, rec_all, max_all, flags_all, shard_stride, world, B, K, k, mode,
-                            weights, ids, score, sem, kw, status));
+    h->bm_rows = h->bm_rows_cfg;
+    LocalScratch s;
+    rc = carve_scratch(h, B, k, &s);
+    if (rc != LRX_OK) return rc;
+    rc = enqueue_local(h, dev_q_fp16, dev_q_terms, dev_q_ptr, B, k, mode, width, s, s.block, false);
+    if (rc != LRX_OK) return rc;
+    size_t o_max, o_flags, total;
+    packed_layout(B, k, &o_max, &o_flags, &total);
+    LRX_CUDA(h, cudaMemcpyAsync(dev_records, s.block, o_max, cudaMemcpyDeviceToDevice, h->stream));
+    LRX_CUDA(h, cudaMemcpyAsync(dev_maxbm25, s.block + o_max, (size_t)B * sizeof(double),
+                                cudaMemcpyDeviceToDevice, h->stream));
+    LRX_CUDA(h, cudaMemcpyAsync(dev_flags, s.block + o_flags, (size_t)B * sizeof(int32_t),
+                                cudaMemcpyDeviceToDevice, h->stream));
     return LRX_OK;
 }
 
@@ -500,17 +709,15 @@ int lrx_search_finish(lrx_handle* h, const lrx_record* dev_records_all, const do
         dev_score == nullptr || dev_sem == nullptr || dev_kw == nullptr || dev_status == nullptr ||
         (mode == LRX_FUSE_LINEAR && dev_weights == nullptr))
         return fail(h, LRX_E_ARG, "lrx_search_finish: null pointer");
+    const int K = 2 * k;
+    if (world < 1 || world * K > 2048)
+        return fail(h, LRX_E_ARG, "lrx_search_finish: world*2k must be in [1,2048]");
+    if (B < 1 || B > LRX_MAX_BATCH || k < 1 || K > LRX_MAX_DEPTH)
+        return fail(h, LRX_E_ARG, "lrx_search_finish: bad B/k");
     LRX_CUDA(h, cudaSetDevice(h->device));
-    return search_finish_locked(h, dev_records_all, dev_max_all, dev_flags_all, 0, world, B, k, mode,
-                                dev_weights, dev_ids, dev_score, dev_sem, dev_kw, dev_status);
-}
-
-// ---- packed form: one contiguous block per shard = one all-gather per batch
-static void packed_layout(int B, int k, size_t* o_max, size_t* o_flags, size_t* total) {
-    const size_t rec = (size_t)B * 2 * (2 * k) * sizeof(lrx_record);
-    *o_max = rec;
-    *o_flags = rec + (size_t)B * sizeof(double);
-    *total = align_up(*o_flags + (size_t)B * sizeof(int32_t), 16);
+    LRX_CUDA(h, launch_fuse(h, dev_records_all, dev_max_all, dev_flags_all, 0, world, B, K, k, mode,
+                            dev_weights, dev_ids, dev_score, dev_sem, dev_kw, dev_status, false));
+    return LRX_OK;
 }
 
 int64_t lrx_packed_bytes(int32_t B, int32_t k) {
@@ -527,13 +734,17 @@ int lrx_search_local_packed(lrx_handle* h, const void* dev_q_fp16, const int32_t
     std::lock_guard<std::mutex> g(h->mu);
     if (dev_q_fp16 == nullptr || dev_q_ptr == nullptr || dev_packed == nullptr)
         return fail(h, LRX_E_ARG, "lrx_search_local_packed: null pointer");
-    if (B < 1 || k < 1) return fail(h, LRX_E_ARG, "lrx_search_local_packed: bad B/k");
-    size_t o_max, o_flags, total;
-    packed_layout(B, k, &o_max, &o_flags, &total);
+    int rc = check_search_args(h, "lrx_search_local_packed", B, k, mode, &width);
+    if (rc != LRX_OK) return rc;
     LRX_CUDA(h, cudaSetDevice(h->device));
-    char* p = (char*)dev_packed;
-    return search_local_locked(h, dev_q_fp16, dev_q_terms, dev_q_ptr, B, k, mode, width,
-                               (lrx_record*)p, (double*)(p + o_max), (int32_t*)(p + o_flags));
+    h->bm_rows = h->bm_rows_cfg;
+    LocalScratch s;
+    rc = carve_scratch(h, B, k, &s);
+    if (rc != LRX_OK) return rc;
+    return run_planned(h, {1u, pk(dev_q_fp16), pk(dev_q_terms), pk(dev_q_ptr), pk(dev_packed), (uint64_t)B,
+                           (uint64_t)k, (uint64_t)mode, (uint64_t)width, (uint64_t)h->bm_rows},
+                       [&]() -> int { return enqueue_local(h, dev_q_fp16, dev_q_terms, dev_q_ptr, B, k, mode,
+                                                    width, s, dev_packed, false); });
 }
 
 int lrx_search_finish_packed(lrx_handle* h, const void* dev_packed_all, int32_t world, int32_t B,
@@ -546,17 +757,18 @@ int lrx_search_finish_packed(lrx_handle* h, const void* dev_packed_all, int32_t 
         dev_sem == nullptr || dev_kw == nullptr || dev_status == nullptr ||
         (mode == LRX_FUSE_LINEAR && dev_weights == nullptr))
         return fail(h, LRX_E_ARG, "lrx_search_finish_packed: null pointer");
-    if (B < 1 || k < 1) return fail(h, LRX_E_ARG, "lrx_search_finish_packed: bad B/k");
+    if (B < 1 || B > LRX_MAX_BATCH || k < 1 || 2 * k > LRX_MAX_DEPTH)
+        return fail(h, LRX_E_ARG, "lrx_search_finish_packed: bad B/k");
+    if (world < 1 || world * 2 * k > 2048)
+        return fail(h, LRX_E_ARG, "lrx_search_finish_packed: world*2k must be in [1,2048]");
     size_t o_max, o_flags, total;
     packed_layout(B, k, &o_max, &o_flags, &total);
     LRX_CUDA(h, cudaSetDevice(h->device));
-    const char* p = (const char*)dev_packed_all;
-    return search_finish_locked(h, (const lrx_record*)p, (const double*)(p + o_max),
-                                (const int32_t*)(p + o_flags), (int64_t)total, world, B, k, mode,
-                                dev_weights, dev_ids, dev_score, dev_sem, dev_kw, dev_status);
+    return enqueue_fuse_packed(h, dev_packed_all, total, world, false, B, k, mode, dev_weights, dev_ids,
+                               dev_score, dev_sem, dev_kw, dev_status);
 }
 
-// ---- peer exchange: region = data [2 parities][world][slot] | flags u64 [2][world]
+// ---- peer exchange: region = data [2 parities][world][slot] | flags u64 [2][world] | ctr u64
 static_assert(sizeof(cudaIpcMemHandle_t) == LRX_IPC_HANDLE_BYTES, "IPC handle size");
 
 int lrx_exchange_export(lrx_handle* h, int32_t B_max, int32_t k_max, void* host_handle_out) {
@@ -572,7 +784,8 @@ int lrx_exchange_export(lrx_handle* h, int32_t B_max, int32_t k_max, void* host_
     size_t o_max, o_flags, total;
     packed_layout(B_max, k_max, &o_max, &o_flags, &total);
     h->xchg_slot = align_up(total, 256);
-    h->xchg_bytes = 2 * (size_t)h->world * h->xchg_slot + 2 * (size_t)h->world * sizeof(unsigned long long);
+    h->xchg_bytes = 2 * (size_t)h->world * h->xchg_slot +
+                    (2 * (size_t)h->world + 2) * sizeof(unsigned long long);
     LRX_CUDA(h, cudaMalloc(&h->xchg, h->xchg_bytes));
     LRX_CUDA(h, cudaMemset(h->xchg, 0, h->xchg_bytes));
     LRX_CUDA(h, cudaDeviceSynchronize());
@@ -602,144 +815,249 @@ int lrx_exchange_import(lrx_handle* h, const void* host_handles_all) {
     return LRX_OK;
 }
 
+// K2 + K3 on this shard -> packed block (world == 1: handle workspace; world > 1: every shard's
+// exchange region) -> K4.  Every argument is checked BEFORE anything is enqueued: the call's
+// sequence number lives on the device and only advances when the packing kernel runs, so a call
+// that is refused here leaves this rank in step with its peers.
+static int search_device_locked(lrx_handle* h, const char* fn, const void* q, const int32_t* q_terms,
+                                const int32_t* q_ptr, const double* weights, int B, int k, int mode,
+                                int width, int64_t* ids, double* score, double* sem, double* kw,
+                                int32_t* status) {
+    int rc = check_search_args(h, fn, B, k, mode, &width);
+    if (rc != LRX_OK) return rc;
+    const bool peers = h->world > 1;
+    if (peers && !h->xchg_ready) return fail(h, LRX_E_STATE, "%s: exchange not set up", fn);
+    size_t o_max, o_flags, total;
+    packed_layout(B, k, &o_max, &o_flags, &total);
+    if (peers && total > h->xchg_slot)
+        return fail(h, LRX_E_ARG, "%s: batch larger than the exported exchange slots", fn);
+    LocalScratch s;
+    rc = carve_scratch(h, B, k, &s);
+    if (rc != LRX_OK) return rc;
+    return run_planned(
+        h, {2u, pk(q), pk(q_terms), pk(q_ptr), pk(weights), pk(ids), pk(score), pk(sem), pk(kw), pk(status),
+            (uint64_t)B, (uint64_t)k, (uint64_t)mode, (uint64_t)width, (uint64_t)h->bm_rows},
+        [&]() -> int {
+            int r = enqueue_local(h, q, q_terms, q_ptr, B, k, mode, width, s, s.block, peers);
+            if (r != LRX_OK) return r;
+            return peers ? enqueue_fuse_packed(h, h->xchg, h->xchg_slot, h->world, true, B, k, mode, weights,
+                                               ids, score, sem, kw, status)
+                         : enqueue_fuse_packed(h, s.block, total, 1, false, B, k, mode, weights, ids, score,
+                                               sem, kw, status);
+        });
+}
+
 int lrx_search_sharded(lrx_handle* h, const void* dev_q_fp16, const int32_t* dev_q_terms,
                        const int32_t* dev_q_ptr, const double* dev_weights, int32_t B, int32_t k,
                        int32_t mode, int32_t width, int64_t* dev_ids, double* dev_score,
                        double* dev_sem, double* dev_kw, int32_t* dev_status) {
     if (h == nullptr) return fail(nullptr, LRX_E_ARG, "lrx_search_sharded: null handle");
     std::lock_guard<std::mutex> g(h->mu);
-    if (!h->xchg_ready) return fail(h, LRX_E_STATE, "lrx_search_sharded: exchange not set up");
     if (dev_q_fp16 == nullptr || dev_q_ptr == nullptr || dev_ids == nullptr || dev_score == nullptr ||
         dev_sem == nullptr || dev_kw == nullptr || dev_status == nullptr ||
         (mode == LRX_FUSE_LINEAR && dev_weights == nullptr))
         return fail(h, LRX_E_ARG, "lrx_search_sharded: null pointer");
-    if (B < 1 || k < 1) return fail(h, LRX_E_ARG, "lrx_search_sharded: bad B/k");
-    size_t o_max, o_flags, total;
-    packed_layout(B, k, &o_max, &o_flags, &total);
-    if (total > h->xchg_slot)
-        return fail(h, LRX_E_ARG, "lrx_search_sharded: batch larger than the exported exchange slots");
     LRX_CUDA(h, cudaSetDevice(h->device));
-    const unsigned long long seq = ++h->xchg_seq;
-    const int par = (int)(seq & 1ull);
-    const size_t data_bytes = 2 * (size_t)h->world * h->xchg_slot;
-    const size_t slot_off = ((size_t)par * h->world + h->rank) * h->xchg_slot;
-    const size_t flag_off = data_bytes + ((size_t)par * h->world + h->rank) * sizeof(unsigned long long);
-    char* mine = (char*)h->xchg + slot_off;
-    int rc = search_local_locked(h, dev_q_fp16, dev_q_terms, dev_q_ptr, B, k, mode, width,
-                                 (lrx_record*)mine, (double*)(mine + o_max), (int32_t*)(mine + o_flags));
-    if (rc != LRX_OK) return rc;
-    LRX_CUDA(h, launch_exchange(h, mine, total, slot_off, flag_off, seq));
-    const char* all = (const char*)h->xchg + (size_t)par * h->world * h->xchg_slot;
-    const unsigned long long* flags =
-        (const unsigned long long*)((const char*)h->xchg + data_bytes) + (size_t)par * h->world;
-    const int K = 2 * k;
-    if (h->world * K > 2048) return fail(h, LRX_E_ARG, "lrx_search_sharded: world*2k must be <= 2048");
-    LRX_CUDA(h, launch_fuse(h, (const lrx_record*)all, (const double*)(all + o_max),
-                            (const int32_t*)(all + o_flags), (int64_t)h->xchg_slot, h->world, B, K, k,
-                            mode, dev_weights, dev_ids, dev_score, dev_sem, dev_kw, dev_status, flags,
-                            seq, h->rank));
-    return LRX_OK;
+    h->bm_rows = h->bm_rows_cfg;
+    return search_device_locked(h, "lrx_search_sharded", dev_q_fp16, dev_q_terms, dev_q_ptr, dev_weights,
+                                B, k, mode, width, dev_ids, dev_score, dev_sem, dev_kw, dev_status);
 }
 
-// Shared body of the two host-buffer entry points: the query vectors either come from the
-// host as fp16 (host_q_fp16) or are produced on the device by the encoder from token ids.
-static int search_host_locked(lrx_handle* h, const char* fn, const void* host_q_fp16,
-                              const int32_t* host_ids, const int32_t* host_lens, int S,
-                              const int32_t* host_q_terms, const int32_t* host_q_ptr,
-                              const double* host_weights, int32_t B, int32_t k, int32_t mode,
-                              int64_t* host_ids_out, double* host_score, double* host_sem,
-                              double* host_kw) {
-    if (B < 1 || B > LRX_MAX_BATCH) return fail(h, LRX_E_ARG, "%s: B must be in [1,%d]", fn, LRX_MAX_BATCH);
-    if (k < 1 || 2 * k > LRX_MAX_DEPTH) return fail(h, LRX_E_ARG, "%s: k must be in [1,%d]", fn, LRX_MAX_DEPTH / 2);
-    if (h->world != 1)
-        return fail(h, LRX_E_STATE, "%s: handle is a shard (world=%d); use lrx_search_local / "
-                                    "all-gather / lrx_search_finish", fn, h->world);
+// ---- host-buffer searches: staging layout (same offsets in pinned host memory and on the device)
+struct HostLayout {
+    size_t o_q, o_w, o_ptr, o_terms, o_tok, o_len, in_bytes;
+    size_t o_ids, o_score, o_sem, o_kw, o_status, out_bytes, total;
+};
+
+static HostLayout host_layout(int B, int k, int rows, bool encode, int S) {
+    HostLayout L;
+    size_t off = 0;
+    L.o_q = off;       off = align_up(off + (size_t)B * kRowBytes, 256);
+    L.o_w = off;       off = align_up(off + (size_t)B * sizeof(double), 256);
+    L.o_ptr = off;     off = align_up(off + (size_t)(B + 1) * sizeof(int32_t), 256);
+    L.o_terms = off;   off = align_up(off + (size_t)rows * sizeof(int32_t), 256);
+    L.o_tok = off;     off = align_up(off + (encode ? (size_t)B * S * sizeof(int32_t) : 0), 256);
+    L.o_len = off;     off = align_up(off + (encode ? (size_t)B * sizeof(int32_t) : 0), 256);
+    L.in_bytes = off;
+    L.o_ids = off;     off = align_up(off + (size_t)B * k * sizeof(int64_t), 256);
+    L.o_score = off;   off = align_up(off + (size_t)B * k * sizeof(double), 256);
+    L.o_sem = off;     off = align_up(off + (size_t)B * k * sizeof(double), 256);
+    L.o_kw = off;      off = align_up(off + (size_t)B * k * sizeof(double), 256);
+    L.o_status = off;  off = align_up(off + (size_t)B * sizeof(int32_t), 256);
+    L.out_bytes = off - L.in_bytes;
+    L.total = off;
+    return L;
+}
+
+// H2D of the staged inputs, (K1,) K2..K4, D2H of the results -- one captured chain per shape.
+static int enqueue_host_chain(lrx_handle* h, const lrx_pending& p) {
+    const HostLayout L = host_layout(p.B, p.k, p.rows, p.encode, p.S);
+    char* hp = (char*)h->ws_host;
+    char* dp = (char*)h->ws_io;
+    h->bm_rows = p.rows;
+    return run_planned(
+        h, {3u, (uint64_t)p.B, (uint64_t)p.k, (uint64_t)p.mode, (uint64_t)p.width, (uint64_t)p.rows,
+            (uint64_t)p.encode, (uint64_t)p.S, pk(hp), pk(dp)},
+        [&]() -> int {
+            LRX_CUDA(h, cudaMemcpyAsync(dp, hp, L.in_bytes, cudaMemcpyHostToDevice, h->stream));
+            // K1: token ids -> fp16 unit query vectors, straight into the K2 operand slot.  (Measured:
+            // the BM25 chain cannot usefully run UNDER the encoder -- its persistent CTAs take every SM
+            // and the encoder's GEMM CTAs, which need a whole SM's shared memory, wait for them -- so
+            // K1 runs first and the two scans share the SMs afterwards.)
+            if (p.encode)
+                LRX_CUDA(h, encoder_forward(h, (const int32_t*)(dp + L.o_tok), (const int32_t*)(dp + L.o_len),
+                                            p.B, p.S, nullptr, dp + L.o_q));
+            LocalScratch s;
+            int rc = carve_scratch(h, p.B, p.k, &s);
+            if (rc != LRX_OK) return rc;
+            size_t o_max, o_flags, total;
+            packed_layout(p.B, p.k, &o_max, &o_flags, &total);
+            const bool peers = h->world > 1;
+            rc = enqueue_local(h, dp + L.o_q, (const int32_t*)(dp + L.o_terms), (const int32_t*)(dp + L.o_ptr),
+                               p.B, p.k, p.mode, p.width, s, s.block, peers);
+            if (rc != LRX_OK) return rc;
+            rc = peers ? enqueue_fuse_packed(h, h->xchg, h->xchg_slot, h->world, true, p.B, p.k, p.mode,
+                                             (const double*)(dp + L.o_w), (int64_t*)(dp + L.o_ids),
+                                             (double*)(dp + L.o_score), (double*)(dp + L.o_sem),
+                                             (double*)(dp + L.o_kw), (int32_t*)(dp + L.o_status))
+                       : enqueue_fuse_packed(h, s.block, total, 1, false, p.B, p.k, p.mode,
+                                             (const double*)(dp + L.o_w), (int64_t*)(dp + L.o_ids),
+                                             (double*)(dp + L.o_score), (double*)(dp + L.o_sem),
+                                             (double*)(dp + L.o_kw), (int32_t*)(dp + L.o_status));
+            if (rc != LRX_OK) return rc;
+            LRX_CUDA(h, cudaMemcpyAsync(hp + L.in_bytes, dp + L.in_bytes, L.out_bytes, cudaMemcpyDeviceToHost,
+                                        h->stream));
+            return LRX_OK;
+        });
+}
+
+// Stage the inputs of a host-buffer search and enqueue its chain; the results are collected by
+// host_end_locked.  host_q_fp16 == NULL: the query vectors come from the encoder (token ids).
+static int host_begin_locked(lrx_handle* h, const char* fn, const void* host_q_fp16,
+                             const int32_t* host_tok, const int32_t* host_lens, int S,
+                             const int32_t* host_q_terms, const int32_t* host_q_ptr,
+                             const double* host_weights, int32_t B, int32_t k, int32_t mode) {
+    if (h->pend.active)
+        return fail(h, LRX_E_STATE, "%s: a host search is already in flight on this handle "
+                                    "(call lrx_search_host_end first)", fn);
+    const bool encode = (host_q_fp16 == nullptr);
+    int width = 0;
+    int rc = check_search_args(h, fn, B, k, mode, &width);
+    if (rc != LRX_OK) return rc;
+    if (h->world > 1 && !h->xchg_ready) return fail(h, LRX_E_STATE, "%s: exchange not set up", fn);
     const int nt = host_q_ptr[B];
-    if (nt < 0 || host_q_ptr[0] != 0) return fail(h, LRX_E_ARG, "%s: bad q_ptr", fn);
+    if (nt < 0 || host_q_ptr[0] != 0 || nt > (1 << 20)) return fail(h, LRX_E_ARG, "%s: bad q_ptr", fn);
     if (nt > 0 && host_q_terms == nullptr) return fail(h, LRX_E_ARG, "%s: null terms", fn);
     for (int b = 0; b < B; ++b)
-        if (host_q_ptr[b + 1] < host_q_ptr[b] || host_q_ptr[b + 1] - host_q_ptr[b] > LRX_MAX_QUERY_TERMS)
-            return fail(h, LRX_E_ARG, "%s: query %d has more than %d terms", fn, b, LRX_MAX_QUERY_TERMS);
-    const bool encode = (host_q_fp16 == nullptr);
+        if (host_q_ptr[b + 1] < host_q_ptr[b]) return fail(h, LRX_E_ARG, "%s: q_ptr must not decrease", fn);
+    if (h->world > 1) {
+        size_t o_max, o_flags, total;
+        packed_layout(B, k, &o_max, &o_flags, &total);
+        if (total > h->xchg_slot)
+            return fail(h, LRX_E_ARG, "%s: batch larger than the exported exchange slots", fn);
+    }
     LRX_CUDA(h, cudaSetDevice(h->device));
-    const int K = 2 * k;
-    // ---- staging layout (same offsets on host and device)
-    size_t off = 0;
-    const size_t o_q = off;       off = align_up(off + (size_t)B * kRowBytes, 256);
-    const size_t o_w = off;       off = align_up(off + (size_t)B * sizeof(double), 256);
-    const size_t o_ptr = off;     off = align_up(off + (size_t)(B + 1) * sizeof(int32_t), 256);
-    const size_t o_terms = off;   off = align_up(off + (size_t)(nt > 0 ? nt : 1) * sizeof(int32_t), 256);
-    const size_t o_tok = off;     off = align_up(off + (encode ? (size_t)B * S * sizeof(int32_t) : 0), 256);
-    const size_t o_len = off;     off = align_up(off + (encode ? (size_t)B * sizeof(int32_t) : 0), 256);
-    const size_t in_bytes = off;
-    const size_t o_ids = off;     off = align_up(off + (size_t)B * k * sizeof(int64_t), 256);
-    const size_t o_score = off;   off = align_up(off + (size_t)B * k * sizeof(double), 256);
-    const size_t o_sem = off;     off = align_up(off + (size_t)B * k * sizeof(double), 256);
-    const size_t o_kw = off;      off = align_up(off + (size_t)B * k * sizeof(double), 256);
-    const size_t o_status = off;  off = align_up(off + (size_t)B * sizeof(int32_t), 256);
-    const size_t out_bytes = off - in_bytes;
-    const size_t o_rec = off;     off = align_up(off + (size_t)B * 2 * K * sizeof(lrx_record), 256);
-    const size_t o_max = off;     off = align_up(off + (size_t)B * sizeof(double), 256);
-    const size_t o_flags = off;   off = align_up(off + (size_t)B * sizeof(int32_t), 256);
-    const size_t total = off;
-    if (h->ws_host_bytes < total) {
+    // token capacity of the batch: every token is scored (retrieval_engine.py:67-68 has no limit);
+    // rounded up so that batches of similar size share a captured chain
+    int rows = 32;
+    while (rows < nt) rows *= 2;
+    lrx_pending p;
+    p.active = true; p.encode = encode; p.B = B; p.k = k; p.mode = mode; p.width = width; p.rows = rows;
+    p.S = encode ? S : 0;
+    const HostLayout L = host_layout(B, k, rows, encode, p.S);
+    if (h->ws_host_bytes < L.total) {
         if (h->ws_host != nullptr) cudaFreeHost(h->ws_host);
         h->ws_host = nullptr;
         h->ws_host_bytes = 0;
-        LRX_CUDA(h, cudaMallocHost(&h->ws_host, total * 2));
-        h->ws_host_bytes = total * 2;
+        h->ws_epoch++;
+        LRX_CUDA(h, cudaMallocHost(&h->ws_host, L.total * 2));
+        h->ws_host_bytes = L.total * 2;
     }
-    LRX_CUDA(h, ensure_ws(&h->ws_io, &h->ws_io_bytes, total));
+    LRX_CUDA(h, ensure_ws(h, &h->ws_io, &h->ws_io_bytes, L.total));
     char* hp = (char*)h->ws_host;
-    char* dp = (char*)h->ws_io;
-    if (!encode) memcpy(hp + o_q, host_q_fp16, (size_t)B * kRowBytes);
-    memcpy(hp + o_w, host_weights, (size_t)B * sizeof(double));
-    memcpy(hp + o_ptr, host_q_ptr, (size_t)(B + 1) * sizeof(int32_t));
-    if (nt > 0) memcpy(hp + o_terms, host_q_terms, (size_t)nt * sizeof(int32_t));
+    if (!encode) memcpy(hp + L.o_q, host_q_fp16, (size_t)B * kRowBytes);
+    memcpy(hp + L.o_w, host_weights, (size_t)B * sizeof(double));
+    memcpy(hp + L.o_ptr, host_q_ptr, (size_t)(B + 1) * sizeof(int32_t));
+    if (nt > 0) memcpy(hp + L.o_terms, host_q_terms, (size_t)nt * sizeof(int32_t));
     if (encode) {
-        memcpy(hp + o_tok, host_ids, (size_t)B * S * sizeof(int32_t));
-        memcpy(hp + o_len, host_lens, (size_t)B * sizeof(int32_t));
+        memcpy(hp + L.o_tok, host_tok, (size_t)B * S * sizeof(int32_t));
+        memcpy(hp + L.o_len, host_lens, (size_t)B * sizeof(int32_t));
     }
-    LRX_CUDA(h, cudaMemcpyAsync(dp, hp, in_bytes, cudaMemcpyHostToDevice, h->stream));
-    // K1: token ids -> fp16 unit query vectors, straight into the K2 operand slot.  (Measured: the
-    // BM25 chain cannot usefully run UNDER the encoder -- its persistent CTAs take every SM and the
-    // encoder's GEMM CTAs, which need a whole SM's shared memory, wait for them -- so K1 runs
-    // first and the two scans share the SMs afterwards.)
-    if (encode)
-        LRX_CUDA(h, encoder_forward(h, (const int32_t*)(dp + o_tok), (const int32_t*)(dp + o_len), B, S,
-                                    nullptr, dp + o_q));
+    rc = enqueue_host_chain(h, p);
+    if (rc != LRX_OK) return rc;
+    h->pend = p;
+    return LRX_OK;
+}
 
-    int width = dense_default_width(K);
+static int host_end_locked(lrx_handle* h, const char* fn, int64_t* host_ids_out, double* host_score,
+                           double* host_sem, double* host_kw) {
+    if (!h->pend.active) return fail(h, LRX_E_STATE, "%s: no host search in flight", fn);
+    lrx_pending p = h->pend;
+    h->pend.active = false;
+    LRX_CUDA(h, cudaSetDevice(h->device));
+    char* hp = (char*)h->ws_host;
     for (;;) {
-        int rc = search_local_locked(h, dp + o_q, (const int32_t*)(dp + o_terms),
-                                     (const int32_t*)(dp + o_ptr), B, k, mode, width,
-                                     (lrx_record*)(dp + o_rec), (double*)(dp + o_max),
-                                     (int32_t*)(dp + o_flags));
-        if (rc != LRX_OK) return rc;
-        rc = search_finish_locked(h, (const lrx_record*)(dp + o_rec), (const double*)(dp + o_max),
-                                  (const int32_t*)(dp + o_flags), 0, 1, B, k, mode,
-                                  (const double*)(dp + o_w), (int64_t*)(dp + o_ids),
-                                  (double*)(dp + o_score), (double*)(dp + o_sem),
-                                  (double*)(dp + o_kw), (int32_t*)(dp + o_status));
-        if (rc != LRX_OK) return rc;
-        LRX_CUDA(h, cudaMemcpyAsync(hp + in_bytes, dp + in_bytes, out_bytes, cudaMemcpyDeviceToHost,
-                                    h->stream));
+        const HostLayout L = host_layout(p.B, p.k, p.rows, p.encode, p.S);
         LRX_CUDA(h, cudaStreamSynchronize(h->stream));
-        bool ambiguous = false;
-        const int32_t* st = (const int32_t*)(hp + o_status);
-        for (int b = 0; b < B; ++b) ambiguous |= (st[b] != 0);
-        if (!ambiguous) break;
-        if (width >= 512)
+        int st = 0;
+        const int32_t* sp = (const int32_t*)(hp + L.o_status);
+        for (int b = 0; b < p.B; ++b) {
+            if (sp[b] < 0) return fail(h, LRX_E_PEER, "%s: a peer shard did not publish its candidates within "
+                                                      "%d ms (lrx_set_exchange_timeout)", fn, h->xchg_timeout_ms);
+            st |= sp[b];
+        }
+        if (st & 2) return fail(h, LRX_E_ARG, "%s: a shard saw more query tokens than its capacity", fn);
+        if (st == 0) {
+            memcpy(host_ids_out, hp + L.o_ids, (size_t)p.B * p.k * sizeof(int64_t));
+            memcpy(host_score, hp + L.o_score, (size_t)p.B * p.k * sizeof(double));
+            memcpy(host_sem, hp + L.o_sem, (size_t)p.B * p.k * sizeof(double));
+            memcpy(host_kw, hp + L.o_kw, (size_t)p.B * p.k * sizeof(double));
+            return LRX_OK;
+        }
+        // the exactness guard of the dense scan tripped on some shard (the status is the OR over all
+        // shards, so every rank takes this branch together): widen the candidate lists and rerun on
+        // the inputs still staged on the device
+        if (p.width >= 512)
             return fail(h, LRX_E_AMBIGUOUS,
                         "dense candidates are not separable at width 512 (more than ~500 rows "
                         "within the fp32 error band of the 2k-th score)");
-        width *= 2;   // rare: widen the candidate list and rerun
+        p.width *= 2;
+        int rc = enqueue_host_chain(h, p);
+        if (rc != LRX_OK) return rc;
     }
-    memcpy(host_ids_out, hp + o_ids, (size_t)B * k * sizeof(int64_t));
-    memcpy(host_score, hp + o_score, (size_t)B * k * sizeof(double));
-    memcpy(host_sem, hp + o_sem, (size_t)B * k * sizeof(double));
-    memcpy(host_kw, hp + o_kw, (size_t)B * k * sizeof(double));
-    return LRX_OK;
+}
+
+int lrx_search_host_begin(lrx_handle* h, const void* host_q_fp16, const int32_t* host_q_terms,
+                          const int32_t* host_q_ptr, const double* host_weights, int32_t B, int32_t k,
+                          int32_t mode) {
+    if (h == nullptr) return fail(nullptr, LRX_E_ARG, "lrx_search_host_begin: null handle");
+    std::lock_guard<std::mutex> g(h->mu);
+    if (host_q_fp16 == nullptr || host_q_ptr == nullptr || host_weights == nullptr)
+        return fail(h, LRX_E_ARG, "lrx_search_host_begin: null pointer");
+    return host_begin_locked(h, "lrx_search_host_begin", host_q_fp16, nullptr, nullptr, 0, host_q_terms,
+                             host_q_ptr, host_weights, B, k, mode);
+}
+
+int lrx_search_text_host_begin(lrx_handle* h, const int32_t* host_tok_ids, const int32_t* host_tok_lens,
+                               int32_t S, const int32_t* host_q_terms, const int32_t* host_q_ptr,
+                               const double* host_weights, int32_t B, int32_t k, int32_t mode) {
+    if (h == nullptr) return fail(nullptr, LRX_E_ARG, "lrx_search_text_host_begin: null handle");
+    std::lock_guard<std::mutex> g(h->mu);
+    if (host_tok_ids == nullptr || host_tok_lens == nullptr || host_q_ptr == nullptr || host_weights == nullptr)
+        return fail(h, LRX_E_ARG, "lrx_search_text_host_begin: null pointer");
+    if (h->encoder == nullptr) return fail(h, LRX_E_STATE, "lrx_search_text_host_begin: encoder weights not set");
+    if (S < 1 || S > 512) return fail(h, LRX_E_ARG, "lrx_search_text_host_begin: S must be in [1,512]");
+    return host_begin_locked(h, "lrx_search_text_host_begin", nullptr, host_tok_ids, host_tok_lens, S,
+                             host_q_terms, host_q_ptr, host_weights, B, k, mode);
+}
+
+int lrx_search_host_end(lrx_handle* h, int64_t* host_ids, double* host_score, double* host_sem,
+                        double* host_kw) {
+    if (h == nullptr) return fail(nullptr, LRX_E_ARG, "lrx_search_host_end: null handle");
+    std::lock_guard<std::mutex> g(h->mu);
+    if (host_ids == nullptr || host_score == nullptr || host_sem == nullptr || host_kw == nullptr)
+        return fail(h, LRX_E_ARG, "lrx_search_host_end: null pointer");
+    return host_end_locked(h, "lrx_search_host_end", host_ids, host_score, host_sem, host_kw);
 }
 
 int lrx_search_batch_host(lrx_handle* h, const void* host_q_fp16, const int32_t* host_q_terms,
@@ -751,9 +1069,18 @@ int lrx_search_batch_host(lrx_handle* h, const void* host_q_fp16, const int32_t*
     if (host_q_fp16 == nullptr || host_q_ptr == nullptr || host_weights == nullptr ||
         host_ids == nullptr || host_score == nullptr || host_sem == nullptr || host_kw == nullptr)
         return fail(h, LRX_E_ARG, "lrx_search_batch_host: null pointer");
-    return search_host_locked(h, "lrx_search_batch_host", host_q_fp16, nullptr, nullptr, 0,
-                              host_q_terms, host_q_ptr, host_weights, B, k, mode, host_ids,
-                              host_score, host_sem, host_kw);
+    int rc = host_begin_locked(h, "lrx_search_batch_host", host_q_fp16, nullptr, nullptr, 0, host_q_terms,
+                               host_q_ptr, host_weights, B, k, mode);
+    if (rc != LRX_OK) return rc;
+    return host_end_locked(h, "lrx_search_batch_host", host_ids, host_score, host_sem, host_kw);
+}
+
+int lrx_search_sharded_host(lrx_handle* h, const void* host_q_fp16, const int32_t* host_q_terms,
+                            const int32_t* host_q_ptr, const double* host_weights, int32_t B,
+                            int32_t k, int32_t mode, int64_t* host_ids, double* host_score,
+                            double* host_sem, double* host_kw) {
+    return lrx_search_batch_host(h, host_q_fp16, host_q_terms, host_q_ptr, host_weights, B, k, mode,
+                                 host_ids, host_score, host_sem, host_kw);
 }
 
 int lrx_search_text_host(lrx_handle* h, const int32_t* host_tok_ids, const int32_t* host_tok_lens,
@@ -768,9 +1095,10 @@ int lrx_search_text_host(lrx_handle* h, const int32_t* host_tok_ids, const int32
         return fail(h, LRX_E_ARG, "lrx_search_text_host: null pointer");
     if (h->encoder == nullptr) return fail(h, LRX_E_STATE, "lrx_search_text_host: encoder weights not set");
     if (S < 1 || S > 512) return fail(h, LRX_E_ARG, "lrx_search_text_host: S must be in [1,512]");
-    return search_host_locked(h, "lrx_search_text_host", nullptr, host_tok_ids, host_tok_lens, S,
-                              host_q_terms, host_q_ptr, host_weights, B, k, mode, host_ids,
-                              host_score, host_sem, host_kw);
+    int rc = host_begin_locked(h, "lrx_search_text_host", nullptr, host_tok_ids, host_tok_lens, S,
+                               host_q_terms, host_q_ptr, host_weights, B, k, mode);
+    if (rc != LRX_OK) return rc;
+    return host_end_locked(h, "lrx_search_text_host", host_ids, host_score, host_sem, host_kw);
 }
 
 }  // extern "C"

@@ -528,6 +528,7 @@ int dense_scan_grid(const lrx_handle* h) {
 template <int NQ>
 static cudaError_t launch_scan(lrx_handle* h, const __half* q, int n_q, int width, uint64_t* part,
                                int grid) {
+    std::lock_guard<std::recursive_mutex> attr_guard(attr_mutex());   // the flags below are process-wide
     static bool attr_dev[64] = {false};   // function attributes are per device
     bool& attr = attr_dev[h->device & 63];
     const size_t smem = scan_smem_bytes(NQ);
@@ -565,9 +566,10 @@ cudaError_t launch_dense_topk(lrx_handle* h, const void* qv, int B, int K, int w
     const int grid = dense_scan_grid(h);
     cudaError_t e;
     // per-CTA lists for up to 4 queries per pass
-    e = ensure_ws(&h->ws_dense_part, &h->ws_dense_part_bytes,
+    e = ensure_ws(h, &h->ws_dense_part, &h->ws_dense_part_bytes,
                   (size_t)grid * 4 * width * sizeof(uint64_t) + 64);
     if (e != cudaSuccess) return e;
+    std::lock_guard<std::recursive_mutex> attr_guard(attr_mutex());   // the flags below are process-wide
     static bool attr_dev[64] = {false};   // function attributes are per device
     bool& attr = attr_dev[h->device & 63];
     if (!attr) {

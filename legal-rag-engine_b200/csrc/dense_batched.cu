@@ -383,6 +383,7 @@ int dense_batched_max_stride(int64_t n_rows, int K) {
 
 cudaError_t launch_dense_topk_batched(lrx_handle* h, const void* q, int B, int K, int stride,
                                       double* exact, float* D, int64_t* I, int32_t* flags) {
+    std::lock_guard<std::recursive_mutex> attr_guard(attr_mutex());   // the flags below are process-wide
     static bool attr_dev[64] = {false};   // function attributes are per device
     bool& attr = attr_dev[h->device & 63];
     cudaError_t e;
@@ -431,7 +432,7 @@ cudaError_t launch_dense_topk_batched(lrx_handle* h, const void* q, int B, int K
     const size_t o_thr = take((size_t)Bp * sizeof(float));
     const size_t o_cnt = take((size_t)Bp * sizeof(int));
     const size_t o_cand = take((size_t)Bp * kDbCap * sizeof(uint64_t));
-    e = ensure_ws(&h->ws_dense_part, &h->ws_dense_part_bytes, off);
+    e = ensure_ws(h, &h->ws_dense_part, &h->ws_dense_part_bytes, off);
     if (e != cudaSuccess) return e;
     char* W = (char*)h->ws_dense_part;
     CUtensorMap tq, tx;

@@ -522,7 +522,13 @@ cudaError_t encoder_forward(lrx_handle* h, const int32_t* ids, const int32_t* le
     int seq_per_chunk = (int)(kChunkTokens / S);
     if (seq_per_chunk < 1) seq_per_chunk = 1;
     if (seq_per_chunk > B) seq_per_chunk = B;
+    if ((int64_t)seq_per_chunk * S > e->cap) {
+        // the activation workspace moves: not inside a capture, and captured chains are retired
+        if (h->capturing) return cudaErrorStreamCaptureUnsupported;
+        h->ws_epoch++;
+    }
     ENC_CK(encoder_reserve(e, (int64_t)seq_per_chunk * S));
+    std::lock_guard<std::recursive_mutex> attr_guard(attr_mutex());   // the flags below are process-wide
     static bool attr_dev[64] = {false};   // function attributes are per device
     bool& attr = attr_dev[h->device & 63];
     if (!attr) {

@@ -12,6 +12,7 @@
 // sorted, so merging is rank arithmetic (binary searches), not sorting.
 #include "common.cuh"
 #include "handle.h"
+#include "bm25_at.cuh"
 
 namespace lrx {
 
@@ -19,33 +20,67 @@ constexpr int kFuseThreads = 128;
 constexpr int kFuseMaxIn = 2048;   // world * K records per list
 constexpr int kFuseMaxK = LRX_MAX_DEPTH;
 
-// One WARP per (query, list position): packs the dense record and the BM25 record of that
-// position; for rrf the BM25 hit's exact dense score (shown as "semantic") is computed here, one
-// float64 dot product by the warp (x == NULL: taken from bm_dense instead).
-__global__ void pack_records_kernel(int B, int K, int mode, const double* __restrict__ dense_exact,
-                                    const int64_t* __restrict__ dense_ids,
-                                    const double* __restrict__ dense_bm25,
-                                    const double* __restrict__ bm_scores,
-                                    const int64_t* __restrict__ bm_ids,
-                                    const double* __restrict__ bm_dense,
-                                    const unsigned char* __restrict__ x, int64_t n_rows,
-                                    int64_t id_base, const __half* __restrict__ q,
-                                    lrx_record* __restrict__ records) {
-    pdl_trigger();                       // the exchange / fusion kernel may be scheduled
-    pdl_wait();                          // bm25_at_kernel's scores are visible
+// Where a shard's packed block `[B][2][K] records | [B] max | [B] flags` goes.
+//   world == 1 / NCCL exchange : `local` (handle workspace or the caller's all-gather buffer).
+//   peer exchange              : slot `rank` of parity `seq & 1` in EVERY shard's exchange region
+//     (region = data [2][world][slot] | flags u64 [2][world] | ctr u64 | done u32), stored over
+//     NVLink, then a release store of the call's sequence number into the flag word.  The
+//     sequence number lives ON THE DEVICE (`ctr` in this rank's own region, advanced by the last
+//     CTA of this kernel), so the launch is the same for every call: a CUDA graph can replay it.
+struct PackDst {
+    unsigned char* local;          // non-peer destination (or NULL)
+    void* const* peers;            // [world] exchange regions (device table), NULL = no peer exchange
+    int rank, world;
+    size_t slot;                   // bytes per slot
+    size_t o_max, o_flags;         // byte offsets of [B] max / [B] flags inside a block
+};
+
+__device__ __forceinline__ void st_rec(lrx_record* p, const lrx_record& r) {
+    p->id = r.id; p->dense = r.dense; p->bm25 = r.bm25;
+}
+
+// One WARP per (query, list position) i = (b, j): record 0 = dense candidate j of query b with its
+// BM25 score (`kw = bm25[idx] / max_bm25`, retrieval_engine.py:82: looked up here by
+// bm25_score_at, the scan's float64 operations in token order); record 1 (rrf) = BM25 hit j with
+// its exact dense score (shown as "semantic": one float64 dot product by the warp).  The records go
+// straight to their destination(s); the last CTA to finish appends the shard's [B] maxima and
+// exactness flags and -- peer exchange -- publishes the sequence number to every shard.
+__global__ void pack_exchange_kernel(int B, int K, int mode, const double* __restrict__ dense_exact,
+                                     const int64_t* __restrict__ dense_ids,
+                                     const double* __restrict__ bm_scores,
+                                     const int64_t* __restrict__ bm_ids,
+                                     const double* __restrict__ maxbm, const int32_t* __restrict__ flags,
+                                     const unsigned char* __restrict__ x, int64_t n_rows,
+                                     const __half* __restrict__ q, const BmAtParams A, const PackDst D,
+                                     unsigned int* __restrict__ done /* zero between launches */) {
+    pdl_trigger();                       // the fusion kernel may be scheduled (it waits for us)
+    pdl_wait();                          // the dense merge's candidates are visible
     const int i = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
     const int lane = threadIdx.x & 31;
-    if (i >= B * K) return;
-    const int b = i / K, j = i - b * K;
-    lrx_record r1;
-    r1.id = -1;
-    r1.dense = -INFINITY;
-    r1.bm25 = 0.0;
-    if (mode == LRX_FUSE_RRF && bm_ids[i] >= 0) {
-        r1.id = bm_ids[i];
-        r1.bm25 = bm_scores[i];
-        if (x != nullptr) {
-            const int64_t row = r1.id - id_base;
+    // this call's sequence number and parity (peer exchange): ctr is advanced by the LAST CTA only
+    // after every CTA has read it (its atomicAdd on `done` comes after the read)
+    unsigned long long seq = 0;
+    unsigned long long* ctr = nullptr;
+    if (D.peers != nullptr) {
+        unsigned char* own = reinterpret_cast<unsigned char*>(D.peers[D.rank]);
+        ctr = reinterpret_cast<unsigned long long*>(own + 2 * (size_t)D.world * D.slot +
+                                                    2 * (size_t)D.world * sizeof(unsigned long long));
+        seq = *reinterpret_cast<volatile unsigned long long*>(ctr) + 1ull;
+    }
+    const size_t slot_off = ((size_t)(seq & 1ull) * D.world + D.rank) * D.slot;
+    if (i < B * K) {
+        const int b = i / K, j = i - b * K;
+        lrx_record r0, r1;
+        r0.id = dense_ids[i];
+        r0.dense = dense_exact[i];
+        r0.bm25 = bm25_score_at(A, b, r0.id, lane);          // 0 for -1 pads
+        r1.id = -1;
+        r1.dense = -INFINITY;
+        r1.bm25 = 0.0;
+        if (mode == LRX_FUSE_RRF && bm_ids[i] >= 0) {
+            r1.id = bm_ids[i];
+            r1.bm25 = bm_scores[i];
+            const int64_t row = r1.id - A.id_base;
             if (row >= 0 && row < n_rows) {
                 const uint2* rowp = reinterpret_cast<const uint2*>(x + row * (int64_t)(LRX_DIM * 2));
                 const uint2* qp = reinterpret_cast<const uint2*>(q + (size_t)b * LRX_DIM);
@@ -66,17 +101,49 @@ __global__ void pack_records_kernel(int B, int K, int mode, const double* __rest
                 for (int lb = 16; lb > 0; lb >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, lb);
                 r1.dense = acc;
             }
+        }
+        const size_t o0 = (((size_t)b * 2 + 0) * K + j) * sizeof(lrx_record);
+        const size_t o1 = (((size_t)b * 2 + 1) * K + j) * sizeof(lrx_record);
+        if (D.peers == nullptr) {
+            if (lane == 0) {
+                st_rec(reinterpret_cast<lrx_record*>(D.local + o0), r0);
+                st_rec(reinterpret_cast<lrx_record*>(D.local + o1), r1);
+            }
         } else {
-            r1.dense = bm_dense[i];
+            for (int w = lane; w < D.world; w += 32) {        // lane w stores to shard w
+                unsigned char* dst = reinterpret_cast<unsigned char*>(D.peers[w]) + slot_off;
+                st_rec(reinterpret_cast<lrx_record*>(dst + o0), r0);
+                st_rec(reinterpret_cast<lrx_record*>(dst + o1), r1);
+            }
         }
     }
-    if (lane == 0) {
-        lrx_record r0;
-        r0.id = dense_ids[i];
-        r0.dense = dense_exact[i];
-        r0.bm25 = (r0.id >= 0) ? dense_bm25[i] : 0.0;
-        records[((size_t)b * 2 + 0) * K + j] = r0;
-        records[((size_t)b * 2 + 1) * K + j] = r1;
+    // ---- last CTA done: maxima + flags, then (peer exchange) the sequence flags
+    __threadfence_system();              // this thread's record stores before the counter
+    __syncthreads();
+    __shared__ int s_last;
+    if (threadIdx.x == 0) s_last = (atomicAdd(done, 1u) == gridDim.x - 1) ? 1 : 0;
+    __syncthreads();
+    if (!s_last) return;
+    __threadfence();                     // the other CTAs' stores (their fences precede their atomics)
+    const int n_dst = (D.peers == nullptr) ? 1 : D.world;
+    for (int t = threadIdx.x; t < n_dst * B; t += blockDim.x) {
+        const int w = t / B, b = t - w * B;
+        unsigned char* dst = (D.peers == nullptr)
+            ? D.local : reinterpret_cast<unsigned char*>(D.peers[w]) + slot_off;
+        reinterpret_cast<double*>(dst + D.o_max)[b] = maxbm[b];
+        reinterpret_cast<int32_t*>(dst + D.o_flags)[b] = flags[b];
+    }
+    __threadfence_system();
+    __syncthreads();
+    if (D.peers != nullptr && threadIdx.x < D.world) {
+        unsigned char* base = reinterpret_cast<unsigned char*>(D.peers[threadIdx.x]);
+        unsigned long long* flag = reinterpret_cast<unsigned long long*>(base + 2 * (size_t)D.world * D.slot) +
+                                   (size_t)(seq & 1ull) * D.world + D.rank;
+        asm volatile("st.release.sys.global.u64 [%0], %1;" :: "l"(flag), "l"(seq) : "memory");
+    }
+    if (threadIdx.x == 0) {
+        if (ctr != nullptr) *ctr = seq;
+        *done = 0u;                      // ready for the next launch (stream order)
     }
 }
 
@@ -106,8 +173,8 @@ fuse_kernel(const lrx_record* __restrict__ rec_all, const double* __restrict__ m
             const double* __restrict__ weights, int64_t* __restrict__ out_ids,
             double* __restrict__ out_score, double* __restrict__ out_sem,
             double* __restrict__ out_kw, int32_t* __restrict__ out_status,
-            const unsigned long long* wait_flags /* [world] or NULL */, unsigned long long wait_seq,
-            int self) {
+            const void* xchg /* this rank's exchange region, or NULL */, size_t xchg_slot,
+            long long timeout_ns, int self) {
     pdl_wait();                                  // the packing / exchange kernel has finished
     extern __shared__ __align__(16) unsigned char fuse_dyn[];
     u128* keys = reinterpret_cast<u128*>(fuse_dyn);   // [kFuseMaxIn]
@@ -121,19 +188,34 @@ fuse_kernel(const lrx_record* __restrict__ rec_all, const double* __restrict__ m
     const int n_in = world * K;
     if (tid == 0) { n_dense = 0; n_sparse = 0; n_fused = 0; }
     // peer exchange: the blocks of the other shards were stored into this GPU's memory by THEIR
-    // kernels; acquire every shard's sequence flag before touching its block (bounded spin: a
-    // lost peer surfaces as status -1, not as a hung GPU)
+    // kernels.  The call's sequence number is the counter this rank's packing kernel has just
+    // advanced; its parity selects the half of the region.  Acquire every shard's sequence flag
+    // before touching its block (bounded spin: a lost peer surfaces as status -1, not as a hung GPU).
     __shared__ int wait_failed;
     if (tid == 0) wait_failed = 0;
     __syncthreads();
-    if (wait_flags != nullptr && tid < world && tid != self) {
-        const long long t0 = clock64();
-        unsigned long long v;
-        for (;;) {
-            asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(wait_flags + tid) : "memory");
-            if (v >= wait_seq) break;
-            if (clock64() - t0 > 4000000000ll) { wait_failed = 1; break; }
-            __nanosleep(100);
+    if (xchg != nullptr) {
+        const unsigned char* base = reinterpret_cast<const unsigned char*>(xchg);
+        const size_t data_bytes = 2 * (size_t)world * xchg_slot;
+        const unsigned long long* fl = reinterpret_cast<const unsigned long long*>(base + data_bytes);
+        const unsigned long long seq = __ldcg(fl + 2 * world);           // ctr
+        const size_t par_off = (size_t)(seq & 1ull) * world * xchg_slot;
+        rec_all = reinterpret_cast<const lrx_record*>(reinterpret_cast<const unsigned char*>(rec_all) + par_off);
+        max_all = reinterpret_cast<const double*>(reinterpret_cast<const unsigned char*>(max_all) + par_off);
+        flags_all = reinterpret_cast<const int32_t*>(reinterpret_cast<const unsigned char*>(flags_all) + par_off);
+        if (tid < world && tid != self) {
+            const unsigned long long* wf = fl + (size_t)(seq & 1ull) * world + tid;
+            long long t0;
+            asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t0));
+            unsigned long long v;
+            for (;;) {
+                asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(wf) : "memory");
+                if (v >= seq) break;
+                long long t1;
+                asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t1));
+                if (t1 - t0 > timeout_ns) { wait_failed = 1; break; }
+                __nanosleep(100);
+            }
         }
     }
     __syncthreads();
@@ -145,7 +227,9 @@ fuse_kernel(const lrx_record* __restrict__ rec_all, const double* __restrict__ m
         const double* mw = shard_stride
             ? reinterpret_cast<const double*>(reinterpret_cast<const char*>(max_all) + w * shard_stride)
             : max_all + (size_t)w * B;
-        maxbm = fmax(maxbm, __ldcg(mw + b));
+        const double mv = __ldcg(mw + b);
+        if (mv != mv) status |= 2;               // NaN: a shard saw more query tokens than its capacity
+        maxbm = fmax(maxbm, mv);
         if (flags_all != nullptr) {
             const int32_t* fw = shard_stride
                 ? reinterpret_cast<const int32_t*>(reinterpret_cast<const char*>(flags_all) + w * shard_stride)
@@ -282,67 +366,49 @@ fuse_kernel(const lrx_record* __restrict__ rec_all, const double* __restrict__ m
     if (tid == 0) out_status[b] = wait_failed ? -1 : status;
 }
 
-// Peer exchange, sending side: CTA j stores this rank's packed block into slot `rank` of peer
-// (rank + 1 + j) % world over NVLink, then publishes the call's sequence number there with a
-// release store at system scope (fence cumulativity carries the whole CTA's stores).
-__global__ void exchange_kernel(const uint4* __restrict__ mine, int n16, void* const* __restrict__ peers,
-                                int rank, int world, size_t slot_off, size_t flag_off,
-                                unsigned long long seq) {
-    pdl_trigger();                       // the fusion kernel may be scheduled (it waits for us)
-    pdl_wait();                          // pack_records_kernel's block is visible
-    const int p = (rank + 1 + (int)blockIdx.x) % world;
-    char* base = reinterpret_cast<char*>(peers[p]);
-    uint4* dst = reinterpret_cast<uint4*>(base + slot_off);
-    for (int i = threadIdx.x; i < n16; i += blockDim.x) dst[i] = mine[i];
-    __syncthreads();
-    if (threadIdx.x == 0) {
-        __threadfence_system();
-        unsigned long long* flag = reinterpret_cast<unsigned long long*>(base + flag_off);
-        asm volatile("st.release.sys.global.u64 [%0], %1;" :: "l"(flag), "l"(seq) : "memory");
-    }
-}
-
-cudaError_t launch_exchange(lrx_handle* h, const void* mine, size_t bytes, size_t slot_off,
-                            size_t flag_off, unsigned long long seq) {
-    if (h->world < 2) return cudaSuccess;
-    cudaError_t e = launch_pdl(exchange_kernel, dim3(h->world - 1), dim3(256), 0, h->stream,
-                               (const uint4*)mine, (int)(bytes / 16), (void* const*)h->xchg_peer_dev, h->rank,
-                               h->world, slot_off, flag_off, seq);
-    h->launches++;
-    return e;
-}
-
-cudaError_t launch_pack_records(lrx_handle* h, int B, int K, int mode, const double* dense_exact,
-                                const int64_t* dense_ids, const double* dense_bm25,
-                                const double* bm_scores, const int64_t* bm_ids,
-                                const double* bm_dense, const void* q, lrx_record* records) {
-    // q != NULL: the exact dense scores of the BM25 hits are computed in the kernel (bm_dense unused)
+cudaError_t launch_pack_exchange(lrx_handle* h, const int32_t* q_terms, const int32_t* q_ptr, int B, int K,
+                                 int mode, const double* dense_exact, const int64_t* dense_ids,
+                                 const double* bm_scores, const int64_t* bm_ids, const double* maxbm,
+                                 const int32_t* flags, const void* q, void* local_block, bool to_peers,
+                                 size_t o_max, size_t o_flags) {
+    BmAtParams A;
+    cudaError_t e = bm25_at_params(h, q_terms, q_ptr, B, &A);
+    if (e != cudaSuccess) return e;
+    PackDst D;
+    D.local = (unsigned char*)local_block;
+    D.peers = to_peers ? (void* const*)h->xchg_peer_dev : nullptr;
+    D.rank = h->rank; D.world = h->world; D.slot = h->xchg_slot;
+    D.o_max = o_max; D.o_flags = o_flags;
     const int n = B * K;
-    cudaError_t e = launch_pdl(pack_records_kernel, dim3((n + 7) / 8), dim3(256), 0, h->stream,
-                               B, K, mode, dense_exact, dense_ids, dense_bm25, bm_scores, bm_ids, bm_dense,
-                               q ? (const unsigned char*)h->x : (const unsigned char*)nullptr, h->n_local,
-                               h->id_base, (const __half*)q, records);
+    // a plain launch: the kernel follows the join of the two chains (its griddepcontrol.wait is a
+    // no-op); the fusion kernel behind it is the programmatic dependent
+    pack_exchange_kernel<<<(n + 7) / 8, 256, 0, h->stream>>>(
+        B, K, mode, dense_exact, dense_ids, bm_scores, bm_ids, maxbm, flags, (const unsigned char*)h->x,
+        h->n_local, (const __half*)q, A, D, h->pack_done);
     h->launches++;
-    return e;
+    return cudaGetLastError();
 }
 
 cudaError_t launch_fuse(lrx_handle* h, const lrx_record* records_all, const double* max_all,
                         const int32_t* flags_all, int64_t shard_stride, int world, int B, int K,
                         int k, int mode, const double* weights, int64_t* ids, double* score,
-                        double* sem, double* kw, int32_t* status, const unsigned long long* wait_flags,
-                        unsigned long long wait_seq, int self) {
-    static bool attr_dev[64] = {false};   // function attributes are per device
-    bool& attr = attr_dev[h->device & 63];
-    if (!attr) {
-        cudaError_t e = cudaFuncSetAttribute(fuse_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                             (int)(kFuseMaxIn * sizeof(u128)));
-        if (e != cudaSuccess) return e;
-        attr = true;
+                        double* sem, double* kw, int32_t* status, bool from_peers) {
+    {
+        std::lock_guard<std::recursive_mutex> attr_guard(attr_mutex());   // the flags below are process-wide
+        static bool attr_dev[64] = {false};   // function attributes are per device
+        bool& attr = attr_dev[h->device & 63];
+        if (!attr) {
+            cudaError_t e = cudaFuncSetAttribute(fuse_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                                 (int)(kFuseMaxIn * sizeof(u128)));
+            if (e != cudaSuccess) return e;
+            attr = true;
+        }
     }
     if (world * K > kFuseMaxIn || K > kFuseMaxK) return cudaErrorInvalidValue;
     cudaError_t e = launch_pdl(fuse_kernel, dim3(B), dim3(kFuseThreads), kFuseMaxIn * sizeof(u128), h->stream,
                                records_all, max_all, flags_all, shard_stride, world, B, K, k, mode, weights,
-                               ids, score, sem, kw, status, wait_flags, wait_seq, self);
+                               ids, score, sem, kw, status, from_peers ? (const void*)h->xchg : (const void*)nullptr,
+                               h->xchg_slot, (long long)h->xchg_timeout_ms * 1000000ll, h->rank);
     h->launches++;
     return e;
 }

@@ -10,6 +10,25 @@
 
 #include "../../include/lrx.h"
 
+// One captured launch chain (CUDA graph) of a search entry point, keyed on everything the
+// launches depend on (shapes, mode, pointers); replayed with one cudaGraphLaunch.
+struct lrx_plan {
+    std::vector<uint64_t> key;
+    cudaGraphExec_t exec = nullptr;
+    uint64_t epoch = 0;                    // handle->ws_epoch at capture: a moved workspace retires it
+    int64_t kernels = 0;                   // kernel launches inside (lrx_launch_count)
+    uint64_t stamp = 0;                    // last use (LRU eviction)
+    bool replayed = false;                 // since the last lrx_profile_read
+    std::vector<cudaEvent_t> prof_ev[2];   // external event nodes around the two streaming kernels
+};
+
+// A host-buffer search between lrx_search_host_begin and lrx_search_host_end.
+struct lrx_pending {
+    bool active = false;
+    bool encode = false;
+    int B = 0, k = 0, mode = 0, width = 0, rows = 0, S = 0;
+};
+
 struct lrx_handle {
     int device = 0;
     int num_sms = 0;
@@ -40,6 +59,8 @@ struct lrx_handle {
     // BM25 constants; bm_lut_ld = longest document + 1 (selects the scan variant whose shared
     // c[len] table needs no fallback)
     int bm_lut_ld = 0;
+    int bm_rows = 0;              // token capacity of a query batch (rows of the bounds table); 0 = B * 64
+    double* bm_ctab = nullptr;    // device float64 [2048]: c[len] = k1*(1 - b + b*len/avgdl), built at lrx_set_postings
     double bm_avgdl = 0.0, bm_k1 = 1.5, bm_b = 0.75;
 
     // workspaces (handle-owned, grown on demand)
@@ -56,7 +77,19 @@ struct lrx_handle {
     void* xchg_peer[LRX_MAX_WORLD] = {nullptr};
     void** xchg_peer_dev = nullptr;
     bool xchg_ready = false;
-    unsigned long long xchg_seq = 0;
+    int xchg_timeout_ms = 2000;          // bounded spin of the fusion kernel on a peer's flag
+    unsigned int* pack_done = nullptr;   // device counter of pack_exchange_kernel (last CTA done)
+
+    // captured launch chains (api.cu: run_planned)
+    bool graphs = true;                  // LRX_NO_GRAPH=1 -> every call enqueues its kernels one by one
+    bool capturing = false;
+    lrx_plan* cap_plan = nullptr;
+    cudaStream_t cap = nullptr;          // capture origin (the user's stream may be the legacy default one)
+    uint64_t ws_epoch = 1, plan_clock = 0;
+    std::vector<lrx_plan*> plans;
+    std::vector<std::vector<uint64_t>> seen_keys, eager_keys;
+    int bm_rows_cfg = 0;                 // lrx_set_query_capacity (device-pointer entry points)
+    lrx_pending pend;
 
     // K1 encoder state (packed weights, activation workspaces, tensor maps): encoder.cu
     void* encoder = nullptr;
@@ -96,6 +129,9 @@ cudaError_t launch_bm25_bounds(lrx_handle* h, const int32_t* q_terms, const int3
 cudaError_t launch_bm25_scan(lrx_handle* h, const int32_t* q_terms, const int32_t* q_ptr, int B,
                              double* out_max, int K, double* top_scores, int64_t* top_ids,
                              cudaStream_t st);
+struct BmAtParams;
+cudaError_t bm25_at_params(lrx_handle* h, const int32_t* q_terms, const int32_t* q_ptr, int B,
+                           BmAtParams* P);
 cudaError_t launch_bm25_at(lrx_handle* h, const int32_t* q_terms, const int32_t* q_ptr, int B,
                            const int64_t* ids, int n, double* out, cudaStream_t st);
 cudaError_t launch_bm25_pack(lrx_handle* h, const uint32_t* doc_tf, int64_t nnz, const uint32_t* doc_len,
@@ -105,18 +141,15 @@ cudaError_t launch_bm25_divcheck(lrx_handle* h, double avgdl, double k1, double 
                                  unsigned long long* host_mismatches);
 
 // fuse.cu
-cudaError_t launch_pack_records(lrx_handle* h, int B, int K, int mode, const double* dense_exact,
-                                const int64_t* dense_ids, const double* dense_bm25,
-                                const double* bm_scores, const int64_t* bm_ids,
-                                const double* bm_dense, const void* q, lrx_record* records);
+cudaError_t launch_pack_exchange(lrx_handle* h, const int32_t* q_terms, const int32_t* q_ptr, int B, int K,
+                                 int mode, const double* dense_exact, const int64_t* dense_ids,
+                                 const double* bm_scores, const int64_t* bm_ids, const double* maxbm,
+                                 const int32_t* flags, const void* q, void* local_block, bool to_peers,
+                                 size_t o_max, size_t o_flags);
 cudaError_t launch_fuse(lrx_handle* h, const lrx_record* records_all, const double* max_all,
                         const int32_t* flags_all, int64_t shard_stride, int world, int B, int K,
                         int k, int mode, const double* weights, int64_t* ids, double* score,
-                        double* sem, double* kw, int32_t* status,
-                        const unsigned long long* wait_flags = nullptr,
-                        unsigned long long wait_seq = 0, int self = -1);
-cudaError_t launch_exchange(lrx_handle* h, const void* mine, size_t bytes, size_t slot_off,
-                            size_t flag_off, unsigned long long seq);
+                        double* sem, double* kw, int32_t* status, bool from_peers);
 
 // encoder.cu
 cudaError_t encoder_set_weights(lrx_handle* h, const lrx_bert_weights* w);
@@ -149,11 +182,15 @@ inline cudaError_t launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, s
     return cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);
 }
 
+// One process-wide lock for the per-device "function attribute already set" tables of the
+// launchers: handles are locked one by one, but two handles on one device (clone_view) share them.
+std::recursive_mutex& attr_mutex();
+
 // profiling hooks (no-ops unless lrx_profile_enable(h, 1))
 void prof_begin(lrx_handle* h, int which, cudaStream_t st = nullptr);   // nullptr: h->stream
 void prof_end(lrx_handle* h, int which, cudaStream_t st = nullptr);
 
 // shared helper: grow a device workspace
-cudaError_t ensure_ws(void** p, size_t* have, size_t need);
+cudaError_t ensure_ws(lrx_handle* h, void** p, size_t* have, size_t need);
 
 }  // namespace lrx

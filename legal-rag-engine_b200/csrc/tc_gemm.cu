@@ -581,6 +581,7 @@ template <int BN, int EPI, bool ARES, int CS>
 static cudaError_t launch_cfg(lrx_handle* h, const CUtensorMap& ta, const CUtensorMap& tb,
                               const CUtensorMap& tout, const CUtensorMap& tres, int M,
                               int N, int K, const GemmEpi& ep) {
+    std::lock_guard<std::recursive_mutex> attr_guard(attr_mutex());   // the flags below are process-wide
     static bool attr_dev[64] = {false};   // function attributes are per device
     bool& attr = attr_dev[h->device & 63];
     auto kern = tc_gemm_kernel<BN, EPI, ARES, CS>;

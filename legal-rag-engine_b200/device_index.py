@@ -33,6 +33,8 @@ class DeviceIndex:
         self.n_local = 0
         self.id_base = 0
         self._post = None
+        self._capacity = 0
+        self._pending = None
         self.use_current_stream()
 
     def close(self):
@@ -110,6 +112,18 @@ class DeviceIndex:
                                                 nnz, avgdl, k1, b, max_len))
         return other
 
+    def _cap(self, q_terms: Optional[torch.Tensor], B: int):
+        """Device-pointer calls: the library sizes its per-token tables from a capacity it cannot
+        read off the device; the tensor's length is an upper bound of the batch's token count."""
+        n = int(q_terms.numel()) if q_terms is not None else 0
+        want = n if n > B * _lib.LRX_MAX_QUERY_TERMS else 0          # 0 = the default B * 64
+        if want != self._capacity:
+            self._ck(self.lib.lrx_set_query_capacity(self.h, want))
+            self._capacity = want
+
+    def set_exchange_timeout(self, milliseconds: int):
+        self._ck(self.lib.lrx_set_exchange_timeout(self.h, int(milliseconds)))
+
     # ---------------------------------------------------------------- stages
     def dense_topk(self, q: torch.Tensor, K: int, width: int = 0):
         assert q.dtype == torch.float16 and q.is_cuda and q.is_contiguous()
@@ -151,6 +165,7 @@ class DeviceIndex:
         ti = torch.empty((B, max(K, 1)), dtype=torch.int64, device=self.device)
         if q_terms.numel() == 0:
             q_terms = torch.zeros(1, dtype=torch.int32, device=self.device)
+        self._cap(q_terms, B)
         self._ck(self.lib.lrx_bm25(self.h, _ptr(q_terms), _ptr(q_ptr), B,
                                    _ptr(cand_ids.contiguous() if n else None), n, _ptr(cs), _ptr(mx),
                                    K, _ptr(ts), _ptr(ti)))
@@ -165,6 +180,7 @@ class DeviceIndex:
         flags = torch.empty(B, dtype=torch.int32, device=self.device)
         if q_terms.numel() == 0:
             q_terms = torch.zeros(1, dtype=torch.int32, device=self.device)
+        self._cap(q_terms, B)
         self._ck(self.lib.lrx_search_local(self.h, _ptr(q), _ptr(q_terms), _ptr(q_ptr), B, k, mode,
                                            width, _ptr(rec), _ptr(mx), _ptr(flags)))
         return rec, mx, flags
@@ -189,6 +205,7 @@ class DeviceIndex:
                             width: int = 0):
         """K2 + K3 on this shard into `out` (uint8 [packed_bytes]) -- the all-gather unit."""
         B = int(q.shape[0])
+        self._cap(q_terms, B)
         self._ck(self.lib.lrx_search_local_packed(self.h, _ptr(q), _ptr(q_terms), _ptr(q_ptr), B, k,
                                                   mode, width, _ptr(out)))
         return out
@@ -236,11 +253,13 @@ class DeviceIndex:
         return int(flag.item()) == 1       # the all-reduce also orders "mapped" before the first store
 
     def search_sharded(self, q, q_terms, q_ptr, k: int, mode: int, weights, outs, width: int = 0):
-        """K2 + K3 on this shard, block stored into every peer's region, K4: replicated result."""
+        """K2 + K3 on this shard, block stored into every peer's region (world > 1), K4: the
+        replicated result.  One captured launch chain per (shape, buffers), replayed per call."""
         B = int(q.shape[0])
         ids, score, sem, kw, status = outs
         if q_terms.numel() == 0:
             q_terms = torch.zeros(1, dtype=torch.int32, device=self.device)
+        self._cap(q_terms, B)
         self._ck(self.lib.lrx_search_sharded(self.h, _ptr(q), _ptr(q_terms), _ptr(q_ptr), _ptr(weights),
                                              B, k, mode, width, _ptr(ids), _ptr(score), _ptr(sem),
                                              _ptr(kw), _ptr(status)))
@@ -254,10 +273,8 @@ class DeviceIndex:
                 torch.empty(B, dtype=torch.int32, device=self.device))
 
     # ----------------------------------------------------- whole search, host
-    def search_batch_host(self, q_fp16: np.ndarray, term_lists: Sequence[Sequence[int]], k: int,
-                          weights: Sequence[float], fusion: str = "linear"):
-        """Host buffers in, host buffers out (H2D + kernels + D2H inside the call).
-        Returns (ids int64 [B,k], score, semantic, keyword float64 [B,k])."""
+    @staticmethod
+    def _host_args(q_fp16, term_lists, weights):
         q_fp16 = np.ascontiguousarray(q_fp16, dtype=np.float16)
         B = q_fp16.shape[0]
         ptr = np.zeros(B + 1, dtype=np.int32)
@@ -266,14 +283,51 @@ class DeviceIndex:
         terms = np.fromiter((int(x) for t in term_lists for x in t), dtype=np.int32, count=int(ptr[-1]))
         if terms.size == 0:
             terms = np.zeros(1, dtype=np.int32)
-        w = np.ascontiguousarray(weights, dtype=np.float64)
+        return q_fp16, B, terms, ptr, np.ascontiguousarray(weights, dtype=np.float64)
+
+    def search_batch_host(self, q_fp16: np.ndarray, term_lists: Sequence[Sequence[int]], k: int,
+                          weights: Sequence[float], fusion: str = "linear"):
+        """Host buffers in, host buffers out (H2D + kernels + D2H inside the call); on a shard
+        (world > 1) every rank makes the same call and gets the replicated result.
+        Returns (ids int64 [B,k], score, semantic, keyword float64 [B,k])."""
+        self.search_host_begin(q_fp16, term_lists, k, weights, fusion)
+        return self.search_host_end()
+
+    def search_host_begin(self, q_fp16: np.ndarray, term_lists: Sequence[Sequence[int]], k: int,
+                          weights: Sequence[float], fusion: str = "linear"):
+        """Stage + enqueue (H2D, chain, D2H) and return at once; `search_host_end` collects.  With
+        two handles over one index (`clone_view`) two batches are in flight."""
+        q_fp16, B, terms, ptr, w = self._host_args(q_fp16, term_lists, weights)
+        vp = lambda a: a.ctypes.data_as(C.c_void_p)
+        self._ck(self.lib.lrx_search_host_begin(self.h, vp(q_fp16), vp(terms), vp(ptr), vp(w), B, k,
+                                                FUSION[fusion]))
+        self._pending = (B, k)
+
+    def search_host_end(self):
+        B, k = self._pending
+        self._pending = None
         ids = np.empty((B, k), dtype=np.int64)
         score = np.empty((B, k), dtype=np.float64)
         sem = np.empty((B, k), dtype=np.float64)
         kw = np.empty((B, k), dtype=np.float64)
         vp = lambda a: a.ctypes.data_as(C.c_void_p)
-        self._ck(self.lib.lrx_search_batch_host(self.h, vp(q_fp16), vp(terms), vp(ptr), vp(w), B, k,
-                                                FUSION[fusion], vp(ids), vp(score), vp(sem), vp(kw)))
+        self._ck(self.lib.lrx_search_host_end(self.h, vp(ids), vp(score), vp(sem), vp(kw)))
+        return ids, score, sem, kw
+
+    def search_text_host(self, tok_ids: np.ndarray, tok_lens: np.ndarray, term_lists, k: int,
+                         weights: Sequence[float], fusion: str = "linear"):
+        """The whole of RetrievalEngine.search for tokenised strings: WordPiece ids [B,S] + lens [B]
+        and BM25 term-id lists in, fused results out (K1 -> K2 || K3 -> K4 in one call)."""
+        tok_ids = np.ascontiguousarray(tok_ids, dtype=np.int32)
+        tok_lens = np.ascontiguousarray(tok_lens, dtype=np.int32)
+        B, S = tok_ids.shape
+        _, _, terms, ptr, w = self._host_args(np.zeros((B, LRX_DIM), np.float16), term_lists, weights)
+        ids = np.empty((B, k), dtype=np.int64)
+        score, sem, kw = (np.empty((B, k), dtype=np.float64) for _ in range(3))
+        vp = lambda a: a.ctypes.data_as(C.c_void_p)
+        self._ck(self.lib.lrx_search_text_host(self.h, vp(tok_ids), vp(tok_lens), S, vp(terms), vp(ptr),
+                                               vp(w), B, k, FUSION[fusion], vp(ids), vp(score), vp(sem),
+                                               vp(kw)))
         return ids, score, sem, kw
 
     # ------------------------------------------------------ K1 stage: GEMM

@@ -90,7 +90,17 @@ class SentenceEncoder:
         if state_dict is None:
             state_dict = load_checkpoint(model_dir)
         upload_weights(dev, state_dict)
-        self.tokenizer = tokenizer or load_tokenizer(model_dir, dev.vocab_size)
+        # a tokenizer is only needed for text input; it is never guessed: either the caller's, or
+        # the checkpoint's vocab.txt (FileNotFoundError when model_dir has none)
+        self.tokenizer = tokenizer if tokenizer is not None else \
+            (load_tokenizer(model_dir, dev.vocab_size) if model_dir is not None else None)
+
+    def require_tokenizer(self):
+        if self.tokenizer is None:
+            raise ValueError("this encoder was built from a state_dict without a tokenizer: pass "
+                             "tokenizer= (e.g. WordPieceTokenizer.from_file(vocab.txt); HashTokenizer "
+                             "only for seeded synthetic weights)")
+        return self.tokenizer
 
     def encode_ids(self, ids: np.ndarray, lens: np.ndarray) -> np.ndarray:
         """Host buffers in/out through lrx_encode_host."""
@@ -115,6 +125,7 @@ class SentenceEncoder:
         """Tokenise (truncate to 256, pad to the longest of the batch) and embed.  Texts are
         processed longest-first so batches are dense, results returned in input order."""
         texts = list(texts)
+        self.require_tokenizer()
         out = np.empty((len(texts), 384), dtype=np.float32)
         enc = (self.tokenizer.encode_batch(texts, self.MAX_SEQ) if hasattr(self.tokenizer, "encode_batch")
                else [self.tokenizer.encode(t, self.MAX_SEQ) for t in texts])

@@ -23,10 +23,11 @@ import numpy as np
 import torch
 
 from . import store as _store
-from ._lib import LRX_MAX_BATCH, LRX_MAX_QUERY_TERMS
+from ._lib import LRX_MAX_BATCH, LRX_MAX_DEPTH
 from .bm25_index import BM25Index, tokenize
 from .device_index import FUSION, DeviceIndex
 from .encoder import SentenceEncoder
+from .sharding import shard_range
 
 logger = logging.getLogger("LegalRAG-RetrievalEngine")
 
@@ -47,30 +48,64 @@ def _resolve_model_dir(model_dir: Optional[str]) -> Optional[str]:
     return None
 
 
+def _dist_state(group=None):
+    """(rank, world) of an initialised torch.distributed job, (0, 1) otherwise."""
+    import torch.distributed as dist
+    if dist.is_available() and dist.is_initialized():
+        return dist.get_rank(group), dist.get_world_size(group)
+    return 0, 1
+
+
 class RetrievalEngine:
-    def __init__(self, store_dir: str = "data/vector_store", *, device: int = 0,
+    """``RetrievalEngine(store_dir)`` / ``search(query, k, hybrid_weight)`` exactly as the reference
+    (retrieval_engine.py:23-96).
+
+    One process: the whole store on one GPU.  Under ``torchrun`` (torch.distributed initialised,
+    one rank per GPU): rank g keeps the contiguous row range ``shard_range(N, g, G)`` of the chunk
+    matrix and of the BM25 postings (idf / avgdl stay the whole-corpus statistics), every rank
+    encodes the <= 4 query strings redundantly and makes the same ``lrx_search_text_host`` call; the
+    candidate exchange runs inside the kernels over NVLink and the fused result is replicated.  The
+    server process is rank 0: it calls ``search`` as always (the strings are broadcast to the other
+    ranks first); the other ranks sit in ``worker_loop()``.
+    """
+
+    def __init__(self, store_dir: str = "data/vector_store", *, device: Optional[int] = None,
                  model_dir: Optional[str] = None, encoder_state_dict: Optional[Dict] = None,
-                 tokenizer=None, fusion: str = "linear"):
+                 tokenizer=None, fusion: str = "linear", group=None, sharded: Optional[bool] = None):
         self.store_dir = Path(store_dir)
         self.fusion = fusion
-        self.dev = DeviceIndex(device)
+        self.group = group
+        # sharded=None: shard iff torch.distributed is initialised with more than one rank
+        self.rank, self.world = _dist_state(group) if sharded in (None, True) else (0, 1)
+        if device is None:
+            device = int(os.environ.get("LOCAL_RANK", "0")) if self.world > 1 else 0
+        self.dev = DeviceIndex(device, self.rank, self.world)
         # 1. model (retrieval_engine.py:27-33)
         if encoder_state_dict is None:
             model_dir = _resolve_model_dir(model_dir)
             if model_dir is None:
                 raise FileNotFoundError(
                     "all-MiniLM-L6-v2 weights not found: set EMBEDDING_MODEL_DIR to a directory "
-                    "holding model.safetensors and vocab.txt (or pass encoder_state_dict=)")
+                    "holding model.safetensors and vocab.txt (or pass encoder_state_dict= and tokenizer=)")
         self.model = SentenceEncoder(self.dev, state_dict=encoder_state_dict, model_dir=model_dir,
                                      tokenizer=tokenizer)
-        # 2-4. index, BM25, metadata (retrieval_engine.py:35-56)
-        self.chunks, xh, self.bm25 = _store.load_store(self.store_dir)
-        self._x = torch.from_numpy(xh).to(self.dev.device)
-        self.dev.set_corpus(self._x, 0)
-        self.dev.set_postings(self.bm25.term_ptr, self.bm25.postings, self.bm25.doc_len, self.bm25.idf,
-                              self.bm25.avgdl, self.bm25.k1, self.bm25.b)
-        logger.info("Store resident on GPU %d: %d chunks, %d postings", device, len(self.chunks),
-                    self.bm25.nnz)
+        self.model.require_tokenizer()
+        # 2-4. index, BM25, metadata (retrieval_engine.py:35-56); a shard keeps its row range
+        self.chunks, xh, bm25 = _store.load_store(self.store_dir, mmap=self.world > 1)
+        self.n_total = len(self.chunks)
+        self.lo, self.hi = shard_range(self.n_total, self.rank, self.world)
+        self.bm25 = bm25                                   # whole-corpus statistics + vocabulary
+        local = bm25 if self.world == 1 else bm25.shard(self.lo, self.hi)
+        self._x = torch.from_numpy(np.ascontiguousarray(xh[self.lo:self.hi])).to(self.dev.device)
+        self.dev.set_corpus(self._x, self.lo)
+        self.dev.set_postings(local.term_ptr, local.postings, local.doc_len, bm25.idf, bm25.avgdl,
+                              bm25.k1, bm25.b)
+        if self.world > 1:
+            if not self.dev.exchange_setup(LRX_MAX_BATCH, LRX_MAX_DEPTH // 2, group):
+                raise RuntimeError("the GPUs of this box cannot map each other's memory (CUDA IPC / peer "
+                                   "access): the sharded engine needs it")
+        logger.info("Store resident on GPU %d (shard %d/%d): rows [%d,%d) of %d chunks, %d postings", device,
+                    self.rank, self.world, self.lo, self.hi, self.n_total, local.nnz)
 
     # ------------------------------------------------------------------ API
     def encode(self, texts: Sequence[str]) -> np.ndarray:
@@ -82,46 +117,65 @@ class RetrievalEngine:
     def search_batch(self, queries: Sequence[str], k: int = 5,
                      hybrid_weights: Optional[Sequence[float]] = None, fusion: Optional[str] = None):
         """All queries through one encoder pass and one K2 -> K3 -> K4 chain.  Returns one
-        result list per query, each exactly what ``search`` returns."""
+        result list per query, each exactly what ``search`` returns.  Sharded: called on rank 0
+        (the other ranks are in ``worker_loop``)."""
         queries = list(queries)
         if hybrid_weights is None:
             hybrid_weights = [0.5] * len(queries)
         mode = fusion or self.fusion
+        FUSION[mode]                                        # KeyError for an unknown fusion
+        k = int(k)
+        if k > LRX_MAX_DEPTH // 2:
+            # the reference honours any k; this library's candidate depth is 2k <= LRX_MAX_DEPTH
+            raise ValueError(f"k={k} exceeds the supported result depth {LRX_MAX_DEPTH // 2}")
+        if self.world > 1:
+            import torch.distributed as dist
+            if self.rank != 0:
+                raise RuntimeError("search() is called on rank 0; the other ranks run worker_loop()")
+            dist.broadcast_object_list([("search", queries, k, list(hybrid_weights), mode)], src=0,
+                                       group=self.group)
+        return self._search_all(queries, k, list(hybrid_weights), mode)
+
+    def worker_loop(self):
+        """Ranks 1..G-1 of a sharded engine: repeat rank 0's calls until it closes."""
+        import torch.distributed as dist
+        assert self.world > 1 and self.rank != 0
+        while True:
+            box = [None]
+            dist.broadcast_object_list(box, src=0, group=self.group)
+            msg = box[0]
+            if msg[0] == "stop":
+                return
+            _, queries, k, weights, mode = msg
+            self._search_all(queries, k, weights, mode)
+
+    def _search_all(self, queries, k, weights, mode):
         out: List[List[dict]] = []
         for s in range(0, len(queries), LRX_MAX_BATCH):
-            out.extend(self._search_block(queries[s:s + LRX_MAX_BATCH],
-                                          list(hybrid_weights[s:s + LRX_MAX_BATCH]), k, mode))
+            out.extend(self._search_block(queries[s:s + LRX_MAX_BATCH], weights[s:s + LRX_MAX_BATCH], k, mode))
         return out
 
     def _search_block(self, queries, weights, k, mode):
         B = len(queries)
-        enc = [self.model.tokenizer.encode(q, self.model.MAX_SEQ) for q in queries]
+        if k < 1 or B == 0:
+            return [[] for _ in queries]
+        tok = self.model.tokenizer
+        enc = [tok.encode(q, self.model.MAX_SEQ) for q in queries]
         S = max(len(e) for e in enc)
         ids = np.zeros((B, S), dtype=np.int32)
         lens = np.empty(B, dtype=np.int32)
         for i, e in enumerate(enc):
             ids[i, :len(e)] = e
             lens[i] = len(e)
-        # BM25 side: query.lower().split() -> term ids, unknown -> -1 (retrieval_engine.py:67)
-        term_lists = [self.bm25.term_ids(tokenize(q))[:LRX_MAX_QUERY_TERMS] for q in queries]
-        ptr = np.zeros(B + 1, dtype=np.int32)
-        for i, t in enumerate(term_lists):
-            ptr[i + 1] = ptr[i] + len(t)
-        terms = np.fromiter((x for t in term_lists for x in t), dtype=np.int32, count=int(ptr[-1]))
-        if terms.size == 0:
-            terms = np.zeros(1, dtype=np.int32)
-        w = np.ascontiguousarray(weights, dtype=np.float64)
-        kk = max(1, min(int(k), 128))
-        o_ids = np.empty((B, kk), dtype=np.int64)
-        o_score, o_sem, o_kw = (np.empty((B, kk), dtype=np.float64) for _ in range(3))
-        vp = lambda a: a.ctypes.data_as(C.c_void_p)
-        self.dev._ck(self.dev.lib.lrx_search_text_host(
-            self.dev.h, vp(ids), vp(lens), S, vp(terms), vp(ptr), vp(w), B, kk, FUSION[mode],
-            vp(o_ids), vp(o_score), vp(o_sem), vp(o_kw)))
+        # BM25 side: query.lower().split() -> term ids (retrieval_engine.py:67).  EVERY token is
+        # scored, in order, repeats included, as rank_bm25 does; out-of-vocabulary tokens are
+        # dropped here because `idf.get(q) or 0` makes them add exactly 0.0.
+        term_lists = [[t for t in self.bm25.term_ids(tokenize(q)) if t >= 0] for q in queries]
+        o_ids, o_score, o_sem, o_kw = self.dev.search_text_host(ids, lens, term_lists, k, weights, mode)
         results = []
         for b in range(B):
             rows = []
-            for j in range(min(kk, int(k))):
+            for j in range(k):
                 idx = int(o_ids[b, j])
                 if idx < 0:
                     continue
@@ -131,6 +185,12 @@ class RetrievalEngine:
         return results
 
     def close(self):
+        if getattr(self, "world", 1) > 1 and self.rank == 0 and self.dev.h:
+            import torch.distributed as dist
+            dist.broadcast_object_list([("stop",)], src=0, group=self.group)
+        if getattr(self, "world", 1) > 1 and self.dev.h:
+            import torch.distributed as dist
+            dist.barrier(group=self.group)                  # nobody unmaps while a peer may store
         self.dev.close()
 
 
@@ -162,11 +222,13 @@ def merge_fanout(result_lists: Sequence[List[dict]]) -> List[dict]:
 
 
 def create_vector_store(chunks_path: str = "legal_chunks.json", save_dir: str = "data/vector_store",
-                        *, device: int = 0, model_dir: Optional[str] = None,
+                        *, device: Optional[int] = None, model_dir: Optional[str] = None,
                         encoder_state_dict: Optional[Dict] = None, tokenizer=None,
-                        batch_size: int = 1024):
+                        batch_size: int = 1024, group=None):
     """Index build (create_vector_store.py:14-83): embed every chunk text on the GPU, build the
-    BM25 statistics/postings, write the store."""
+    BM25 statistics/postings, write the store.  Under ``torchrun`` the encode loop
+    (create_vector_store.py:41-46) is data-parallel: rank g embeds the chunk range
+    ``shard_range(N, g, G)``, the rows are gathered over NCCL and rank 0 writes the store."""
     chunks_path = Path(chunks_path)
     if not chunks_path.exists():
         print(f"Error: {chunks_path} not found. Run ingest_legal_docs.py first.")
@@ -180,14 +242,32 @@ def create_vector_store(chunks_path: str = "legal_chunks.json", save_dir: str = 
         model_dir = _resolve_model_dir(model_dir)
         if model_dir is None:
             raise FileNotFoundError("all-MiniLM-L6-v2 weights not found: set EMBEDDING_MODEL_DIR")
+    rank, world = _dist_state(group)
+    if device is None:
+        device = int(os.environ.get("LOCAL_RANK", "0")) if world > 1 else 0
     dev = DeviceIndex(device)
     try:
         enc = SentenceEncoder(dev, state_dict=encoder_state_dict, model_dir=model_dir, tokenizer=tokenizer)
+        enc.require_tokenizer()
         texts = [c["text"] for c in chunks]
-        x = enc.encode(texts, batch_size=batch_size)          # unit float32 rows
-        bm25 = BM25Index.from_texts(texts)                     # text.lower().split()
-        _store.save_store(save_dir, chunks, x, bm25)
+        lo, hi = shard_range(len(texts), rank, world)
+        x = enc.encode(texts[lo:hi], batch_size=batch_size)   # unit float32 rows of this rank's range
+        if world > 1:
+            import torch.distributed as dist
+            per = -(-len(texts) // world)
+            mine = torch.zeros((per, x.shape[1]), dtype=torch.float32, device=dev.device)
+            mine[:hi - lo] = torch.from_numpy(x).to(dev.device)
+            every = torch.empty((world * per, x.shape[1]), dtype=torch.float32, device=dev.device)
+            dist.all_gather_into_tensor(every, mine, group=group)
+            x = every[:len(texts)].cpu().numpy()
+        if rank == 0:
+            bm25 = BM25Index.from_texts(texts)                 # text.lower().split()
+            _store.save_store(save_dir, chunks, x, bm25)
+        if world > 1:
+            import torch.distributed as dist
+            dist.barrier(group=group)
     finally:
         dev.close()
-    print(f"Vector store created: {save_dir}  ({len(chunks)} chunks, dim {x.shape[1]})")
+    if rank == 0:
+        print(f"Vector store created: {save_dir}  ({len(chunks)} chunks, dim {x.shape[1]})")
     return save_dir

@@ -92,14 +92,39 @@ class ShardedSearcher:
         return self._bufs[key]
 
     def search(self, q_fp16: torch.Tensor, q_terms: torch.Tensor, q_ptr: torch.Tensor, k: int, mode: int,
-               weights: torch.Tensor):
+               weights: torch.Tensor, width: int = 0):
         """-> (ids, score, semantic, keyword, status) device tensors [B,k] (replicated on every
-        rank).  Asynchronous on torch's current stream."""
+        rank).  Asynchronous on torch's current stream; `status` must be looked at by the caller
+        (`search_checked` does) -- 0 ok, 1 = exactness guard (rerun wider), 2 = token capacity,
+        -1 = a peer's block did not arrive in time."""
         B = int(q_fp16.shape[0])
         mine, every, outs = self.buffers(B, k)
-        if self.world > 1 and self.exchange == "peer":
-            return self.dev.search_sharded(q_fp16, q_terms, q_ptr, k, mode, weights, outs)
-        self.dev.search_local_packed(q_fp16, q_terms, q_ptr, k, mode, mine)
-        if self.world > 1:
-            dist.all_gather_into_tensor(every, mine, group=self.group)
+        if self.world == 1 or self.exchange == "peer":
+            return self.dev.search_sharded(q_fp16, q_terms, q_ptr, k, mode, weights, outs, width)
+        self.dev.search_local_packed(q_fp16, q_terms, q_ptr, k, mode, mine, width)
+        dist.all_gather_into_tensor(every, mine, group=self.group)
         return self.dev.search_finish_packed(every, self.world, B, k, mode, weights, outs)
+
+    def search_checked(self, q_fp16, q_terms, q_ptr, k: int, mode: int, weights):
+        """`search` + a synchronising look at the status words: widens the dense candidate lists
+        (x2 up to 512) while the exactness guard trips, raises on a lost peer or on a query longer
+        than the token capacity.  The status is the OR over all shards and the result is
+        replicated, so every rank takes the same branch (SPMD)."""
+        from ._lib import LRX_E_AMBIGUOUS, LRX_E_PEER, LrxError
+        width = 0
+        while True:
+            outs = self.search(q_fp16, q_terms, q_ptr, k, mode, weights, width)
+            st = outs[4].cpu().numpy()
+            if (st < 0).any():
+                raise LrxError(LRX_E_PEER, "a peer shard did not publish its candidates in time")
+            if (st & 2).any():
+                raise LrxError(-1, "a shard saw more query tokens than its capacity")
+            if not st.any():
+                return outs
+            if width == 0:                                   # the library's default for this depth
+                width = 64
+                while width < 2 * k + 32:
+                    width *= 2
+            width *= 2
+            if width > 512:
+                raise LrxError(LRX_E_AMBIGUOUS, "dense candidates are not separable at width 512")

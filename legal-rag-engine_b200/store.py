@@ -112,14 +112,15 @@ def save_store(save_dir, chunks: List[dict], x_f32: np.ndarray, bm25: BM25Index)
         json.dump(chunks, f, indent=2)                    # create_vector_store.py:77-78
 
 
-def load_store(store_dir) -> Tuple[List[dict], np.ndarray, BM25Index]:
+def load_store(store_dir, mmap: bool = False) -> Tuple[List[dict], np.ndarray, BM25Index]:
     """-> (chunks, float16 [N,384] matrix, BM25Index).  Native files win; otherwise the
-    reference's index.faiss / bm25.pkl are read."""
+    reference's index.faiss / bm25.pkl are read.  mmap: map vectors.f16.npy instead of reading
+    it (a shard of a multi-GPU engine slices its own row range out of it)."""
     store_dir = Path(store_dir)
     with open(store_dir / "metadata.json", "r", encoding="utf-8") as f:
         chunks = json.load(f)                             # retrieval_engine.py:53-55
     if (store_dir / "vectors.f16.npy").exists():
-        xh = np.load(store_dir / "vectors.f16.npy")
+        xh = np.load(store_dir / "vectors.f16.npy", mmap_mode="r" if mmap else None)
     else:
         xh = read_faiss_flat(store_dir / "index.faiss").astype(np.float16)
     if (store_dir / "bm25.npz").exists():
@@ -134,4 +135,4 @@ def load_store(store_dir) -> Tuple[List[dict], np.ndarray, BM25Index]:
     if xh.shape != (len(chunks), DIM) or bm25.n_docs != len(chunks):
         raise ValueError(f"store {store_dir} is inconsistent: {xh.shape} vectors, {bm25.n_docs} BM25 "
                          f"documents, {len(chunks)} chunks")
-    return chunks, np.ascontiguousarray(xh), bm25
+    return chunks, (xh if mmap else np.ascontiguousarray(xh)), bm25

@@ -142,9 +142,16 @@ class HashTokenizer:
 
 
 def load_tokenizer(model_dir: Optional[str], vocab_size: int = 30522):
-    if model_dir is not None:
-        for sub in ("", "0_Transformer"):
-            p = Path(model_dir) / sub / "vocab.txt"
-            if p.exists():
-                return WordPieceTokenizer.from_file(p)
-    return HashTokenizer(vocab_size)
+    """The checkpoint's WordPiece vocabulary (``vocab.txt`` beside the weights, or under
+    ``0_Transformer``).  A checkpoint without it is an error: feeding real weights hashed token ids
+    would give garbage embeddings without any sign of it.  ``HashTokenizer`` is only ever used when
+    a caller passes it explicitly (seeded synthetic weights in tests and the bench)."""
+    if model_dir is None:
+        raise FileNotFoundError("no model directory: a tokenizer cannot be loaded (pass tokenizer= explicitly "
+                                "when using a state_dict of your own)")
+    for sub in ("", "0_Transformer"):
+        p = Path(model_dir) / sub / "vocab.txt"
+        if p.exists():
+            return WordPieceTokenizer.from_file(p)
+    raise FileNotFoundError(f"{model_dir} holds no vocab.txt: the all-MiniLM-L6-v2 checkpoint needs its "
+                            f"WordPiece vocabulary (there is no fallback tokenizer)")

@@ -17,9 +17,11 @@ def built(tmp_path_factory, legal_chunks):
     d = tmp_path_factory.mktemp("store")
     src = d / "legal_chunks.json"
     src.write_text(json.dumps(legal_chunks), encoding="utf-8")
+    from legal_rag_engine_b200.tokenizer import HashTokenizer
     sd = synth.bert_state_dict(42, 0.05, ln_jitter=0.1)
-    create_vector_store(str(src), str(d / "vs"), encoder_state_dict=sd)
-    eng = RetrievalEngine(str(d / "vs"), encoder_state_dict=sd)
+    tok = HashTokenizer(30522)          # seeded synthetic weights: the stand-in tokenizer, passed explicitly
+    create_vector_store(str(src), str(d / "vs"), encoder_state_dict=sd, tokenizer=tok)
+    eng = RetrievalEngine(str(d / "vs"), encoder_state_dict=sd, tokenizer=tok)
     yield eng, sd, d / "vs"
     eng.close()
 
@@ -85,3 +87,69 @@ def test_small_k_and_bad_fusion(built):
     assert len(eng.search("zero fir", k=3)) == 3
     with pytest.raises(KeyError):
         eng.search("zero fir", fusion="nope")
+
+
+def test_k_beyond_depth_raises_and_long_query_scores_every_token(built):
+    eng, _, _ = built
+    oracle, csr = _oracle(eng)
+    from oracle.bm25 import tokenize
+    with pytest.raises(ValueError):
+        eng.search("zero fir", k=129)
+    assert len(eng.search("zero fir", k=128)) == 128
+    # a pasted paragraph: 200+ whitespace tokens, every one of them scored (retrieval_engine.py:67-68)
+    long_q = " ".join(eng.chunks[5]["text"].split()[:230])
+    assert len(tokenize(long_q)) > 200
+    got = eng.search(long_q, k=10, hybrid_weight=0.5)
+    qh = eng.encode([long_q]).astype(np.float16)[0]
+    want = oracle.search_vec(qh, csr.term_ids(tokenize(long_q)), 10, 0.5, "linear")
+    assert [(r["score"], r["keyword"]) for r in got] == [(w[1], w[3]) for w in want]
+    assert [r["chunk"] is eng.chunks[w[0]] for r, w in zip(got, want)] == [True] * len(want)
+
+
+def test_state_dict_without_tokenizer_is_refused(built):
+    eng, sd, vs = built
+    from legal_rag_engine_b200.engine import RetrievalEngine
+    with pytest.raises(ValueError):
+        RetrievalEngine(str(vs), encoder_state_dict=sd)
+
+
+def test_orchestrate_flow_on_gpu_equals_oracle_flow(built):
+    """orchestrator.py:28-70 on the GPU engine: fan-out -> search_batch -> merge -> priority boosts ->
+    parent expansion (postprocess.ResultPostProcessor) against the literal restatement over the CPU
+    oracle (oracle/search.py + oracle/postprocess.py).  (The reference's own orchestrator.py runs
+    over the engine's host code in tests/test_orchestrator_dropin.py, where the reference tree is.)"""
+    import copy
+    eng, _, _ = built
+    oracle, csr = _oracle(eng)
+    from legal_rag_engine_b200.engine import fanout_queries
+    from legal_rag_engine_b200.postprocess import ResultPostProcessor
+    from oracle import postprocess as opost
+    from oracle.bm25 import tokenize
+    pp = ResultPostProcessor(eng.chunks)
+    lookup = opost.section_lookup(eng.chunks)
+    cases = [("I was robbed at knife point, what should I do?",
+              dict(category="procedure", sub_intent="report FIR", key_entities=["robbery", "BNSS"],
+                   user_context="victim_distress", confidence=0.9)),
+             ("What is the punishment for murder?",
+              dict(category="punishment", sub_intent=None, key_entities=["BNS"], user_context="informational",
+                   confidence=0.8))]
+    for query, intent in cases:
+        qs, ws = fanout_queries(query, intent["user_context"], intent["key_entities"], intent["category"])
+        got = pp.finish(eng.search_batch(qs, k=5, hybrid_weights=ws), intent, 5)
+        lists = []
+        for q, w in zip(qs, ws):
+            qh = eng.encode([q]).astype(np.float16)[0]
+            rows = oracle.search_vec(qh, csr.term_ids(tokenize(q)), 5, w, "linear")
+            lists.append([{"chunk": copy.deepcopy(eng.chunks[i]), "score": s, "semantic": sem, "keyword": kw}
+                          for i, s, sem, kw in rows])
+        flat, seen = [], set()
+        for rs in lists:                                        # orchestrator.py:54-62
+            for r in rs:
+                cid = r["chunk"].get("canonical_header")
+                if cid and cid not in seen:
+                    flat.append(r)
+                    seen.add(cid)
+        want = opost.expand_results(opost.prioritize_results(flat, dict(intent))[:5], lookup)
+        key = lambda rs: [(r["chunk"]["canonical_header"], r["score"], r["semantic"], r["keyword"],
+                           r.get("parent_context")) for r in rs]
+        assert key(got) == key(want) and 1 <= len(got) <= 5

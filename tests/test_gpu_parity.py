@@ -144,20 +144,44 @@ def test_bm25_synthetic_bit_exact(dev, n, vocab):
     _check_bm25(dev, idx, csr, lists, id_base=77, K=20, seed=n)
 
 
-def test_bm25_long_queries_two_passes(dev):
-    """More than 32 token slots: the scan walks a unit twice (slots 0-31, then 32-63); tokens past
-    LRX_MAX_QUERY_TERMS = 64 are dropped by the library, so the oracle sees 64 too."""
+def test_bm25_long_queries_any_length(dev):
+    """More than 32 token slots: the scan walks a unit once per 32 slots.  EVERY token counts, as in
+    the reference (retrieval_engine.py:67-68 scores all of query.lower().split()): 33, 64, 65 and
+    200 tokens, repeats and out-of-vocabulary ids included."""
     n, vocab = 50000, 2000
     idx = synth.host_bm25(n, seed=5, vocab=vocab)
     csr = _csr_of(idx)
     dev.set_corpus(_cuda(synth.host_vectors(n, seed=2)), 0)
     _set_postings(dev, idx)
-    terms, ptr = synth.host_query_terms(4, 64, seed=11, vocab=vocab)
+    terms, ptr = synth.host_query_terms(4, 200, seed=11, vocab=vocab)
     lists = [terms[ptr[b]:ptr[b + 1]].tolist() for b in range(4)]
     lists[0] = lists[0][:33]
-    lists[1] = lists[1][:32]
-    lists[2] = lists[2][:47] + [-1, lists[2][0], lists[2][40]]
-    _check_bm25(dev, idx, csr, lists, K=20, seed=1)
+    lists[1] = lists[1][:64]
+    lists[2] = lists[2][:62] + [-1, lists[2][0], lists[2][40]]     # 65
+    _check_bm25(dev, idx, csr, lists, K=20, seed=1)                # lists[3]: 200 tokens
+    _check_bm25(dev, idx, csr, [lists[3], lists[3][:100]], K=0, seed=2)
+
+
+def test_bm25_token_capacity_is_never_exceeded_silently(dev):
+    """Device-pointer entry: a batch with more tokens than lrx_set_query_capacity is flagged (NaN
+    maxima), not scored short."""
+    n, vocab = 20000, 1000
+    idx = synth.host_bm25(n, seed=6, vocab=vocab)
+    dev.set_corpus(_cuda(synth.host_vectors(n, seed=2)), 0)
+    _set_postings(dev, idx)
+    terms, ptr = synth.host_query_terms(2, 40, seed=3, vocab=vocab)
+    try:
+        dev._capacity = 48
+        dev._ck(dev.lib.lrx_set_query_capacity(dev.h, 48))           # 80 tokens > 48
+        import ctypes as C
+        mx = torch.empty(2, dtype=torch.float64, device="cuda")
+        t, p = _cuda(terms), _cuda(ptr)
+        dev._ck(dev.lib.lrx_bm25(dev.h, C.c_void_p(t.data_ptr()), C.c_void_p(p.data_ptr()), 2, None, 0, None,
+                                 C.c_void_p(mx.data_ptr()), 0, None, None))
+        assert torch.isnan(mx).all()
+    finally:
+        dev._capacity = 0
+        dev._ck(dev.lib.lrx_set_query_capacity(dev.h, 0))
 
 
 def test_bm25_division_matches_ddiv_rn(dev):
@@ -396,3 +420,105 @@ def test_dense_topk_batched_one_million_rows_b1024(dev):
         assert int(f2.sum().item()) == 0
         np.testing.assert_array_equal(I.cpu().numpy()[b0:b0 + 4], I2.cpu().numpy())
         np.testing.assert_array_equal(E.cpu().numpy()[b0:b0 + 4], E2.cpu().numpy())
+
+
+def test_search_host_200_token_query(dev):
+    """The host-buffer call sizes the token capacity from the batch: a 200-token sub-query beside
+    short ones equals the oracle (the reference has no token limit)."""
+    n = 30000
+    x = synth.host_vectors(n, seed=31)
+    idx = synth.host_bm25(n, seed=32, vocab=1500)
+    csr = _csr_of(idx)
+    dev.set_corpus(_cuda(x), 0)
+    _set_postings(dev, idx)
+    q = synth.host_queries(3, seed=33)
+    terms, ptr = synth.host_query_terms(3, 200, seed=34, vocab=1500)
+    lists = [terms[ptr[b]:ptr[b + 1]].tolist() for b in range(3)]
+    lists[1] = lists[1][:5]
+    lists[2] = lists[2][:70]
+    for fusion in ("linear", "rrf"):
+        want = _oracle_search(x, csr, q, lists, 10, [0.5, 0.6, 0.5], fusion)
+        got = dev.search_batch_host(q, lists, 10, [0.5, 0.6, 0.5], fusion)
+        _assert_results(got, want, 10)
+
+
+def test_captured_chain_replays_equal_first_call(dev):
+    """The launch chain is captured into a CUDA graph on the second call with the same buffers and
+    replayed afterwards: calls 1 (direct), 2 (capture + replay), 3.. (replay) give the oracle's
+    result, with NEW query contents in the same buffers every time."""
+    from legal_rag_engine_b200.device_index import FUSION
+    from legal_rag_engine_b200.sharding import ShardedSearcher
+    n = 40000
+    x = synth.host_vectors(n, seed=41, dup_frac=0.01)
+    idx = synth.host_bm25(n, seed=42, vocab=2500)
+    csr = _csr_of(idx)
+    dev.set_corpus(_cuda(x), 0)
+    _set_postings(dev, idx)
+    s = ShardedSearcher(dev)
+    B, k, weights = 4, 10, [0.5, 0.6, 0.5, 0.6]
+    dq = torch.empty((B, 384), dtype=torch.float16, device="cuda")
+    dt = torch.empty(B * 8, dtype=torch.int32, device="cuda")
+    dp = _cuda((np.arange(B + 1) * 8).astype(np.int32))
+    w = _cuda(np.array(weights))
+    for fusion in ("rrf", "linear"):
+        l0 = dev.launches
+        per_call = []
+        for i in range(5):
+            q = synth.host_queries(B, seed=500 + i)
+            terms, ptr = synth.host_query_terms(B, 8, seed=600 + i, vocab=2500)
+            dq.copy_(_cuda(q)); dt.copy_(_cuda(terms))
+            before = dev.launches
+            outs = s.search_checked(dq, dt, dp, k, FUSION[fusion], w)
+            per_call.append(dev.launches - before)
+            ids, score, sem, kw, status = [t.cpu().numpy() for t in outs]
+            lists = [terms[ptr[b]:ptr[b + 1]].tolist() for b in range(B)]
+            _assert_results((ids, score, sem, kw), _oracle_search(x, csr, q, lists, k, weights, fusion), k)
+        assert len(set(per_call)) == 1 and per_call[0] >= 6, per_call   # replays count their kernels
+    # host-buffer call: same chain with the copies inside, also replayed
+    for i in range(4):
+        q = synth.host_queries(B, seed=700 + i)
+        terms, ptr = synth.host_query_terms(B, 8, seed=800 + i, vocab=2500)
+        lists = [terms[ptr[b]:ptr[b + 1]].tolist() for b in range(B)]
+        got = dev.search_batch_host(q, lists, k, weights, "rrf")
+        _assert_results(got, _oracle_search(x, csr, q, lists, k, weights, "rrf"), k)
+
+
+def test_host_begin_end_two_handles_pipelined(dev):
+    """lrx_search_host_begin / _end on two handles over one index: two batches in flight, results in
+    order, a second begin on a busy handle is refused."""
+    from legal_rag_engine_b200._lib import LrxError
+    n = 30000
+    x = synth.host_vectors(n, seed=51)
+    idx = synth.host_bm25(n, seed=52, vocab=2000)
+    csr = _csr_of(idx)
+    dev.set_corpus(_cuda(x), 0)
+    _set_postings(dev, idx)
+    other = dev.clone_view()
+    try:
+        streams = [torch.cuda.Stream(), torch.cuda.Stream()]
+        devs = [dev, other]
+        for d, st in zip(devs, streams):
+            with torch.cuda.stream(st):
+                d.use_current_stream()
+        B, k, weights = 4, 10, [0.5, 0.6, 0.5, 0.6]
+        batches = []
+        for i in range(7):
+            q = synth.host_queries(B, seed=900 + i)
+            terms, ptr = synth.host_query_terms(B, 8, seed=950 + i, vocab=2000)
+            batches.append((q, [terms[ptr[b]:ptr[b + 1]].tolist() for b in range(B)]))
+        got = [None] * len(batches)
+        for i, (q, lists) in enumerate(batches):
+            d = devs[i % 2]
+            if i >= 2:
+                got[i - 2] = d.search_host_end()
+            d.search_host_begin(q, lists, k, weights, "rrf")
+            if i == 0:
+                with pytest.raises(LrxError):
+                    d.search_host_begin(q, lists, k, weights, "rrf")
+        for i in (len(batches) - 2, len(batches) - 1):
+            got[i] = devs[i % 2].search_host_end()
+        for (q, lists), g in zip(batches, got):
+            _assert_results(g, _oracle_search(x, csr, q, lists, k, weights, "rrf"), k)
+    finally:
+        dev.use_current_stream()
+        other.close()
