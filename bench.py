@@ -57,6 +57,9 @@ def parse():
                          "`steps` stays K, `timed_steps` says how many were timed")
     ap.add_argument("--parity-queries", type=int, default=8,
                     help="pool queries checked against the on-device float64 brute force (0 = skip)")
+    ap.add_argument("--kernel-events", default="on", choices=["on", "off"],
+                    help="CUDA event nodes around the two streaming kernels inside the captured chains of the "
+                         "timed region (the roofline figure); off = A/B runs of the chain without them")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-stages", action="store_true", help="skip the K1 / K2a / K2b stage measurements")
     ap.add_argument("--cpu-sample-rows", type=int, default=1_000_000)
@@ -164,7 +167,7 @@ def parity_check(dev, lo, n_local, avgdl, qh, th, pool_ids, k, mode, searcher, p
     import torch.distributed as dist
     device = dev.device
     K = 2 * k
-    PAD = 8
+    PAD = 32
     tp, p8, idf_t = dev._post
     x = dev.x
     nq = len(pool_ids) * N_SUB
@@ -192,6 +195,8 @@ def parity_check(dev, lo, n_local, avgdl, qh, th, pool_ids, k, mode, searcher, p
     d_s[:, :kk], d_i[:, :kk] = v, torch.gather(best_i, 1, j)
     # ---- BM25: all local documents
     k1, b = 1.5, 0.75
+    avg_t = torch.tensor(avgdl, dtype=torch.float64, device=device)   # a TENSOR divisor: torch turns a
+    #                                  division by a Python scalar into a multiplication by its reciprocal
     b_s = torch.zeros((nq, K + PAD), dtype=torch.float64, device=device)
     b_i = torch.full((nq, K + PAD), -1, dtype=torch.int64, device=device)
     b_max = torch.zeros(nq, dtype=torch.float64, device=device)
@@ -213,7 +218,7 @@ def parity_check(dev, lo, n_local, avgdl, qh, th, pool_ids, k, mode, searcher, p
                 w1 = p8[s0:s1, 1].long()
                 tf = (w1 & 0xffff).double()
                 dl = ((w1 >> 16) & 0xffff).double()
-                den = tf + k1 * (1 - b + b * dl / avgdl)
+                den = tf + k1 * (1 - b + b * dl / avg_t)
                 score[doc] += w * (tf * (k1 + 1) / den)                  # doc ids unique within a term
             qi = n * N_SUB + sq
             bm_full.append(score)
@@ -681,7 +686,7 @@ def run_ours(args):
     # the kernel-event nodes are part of the captured chains: profile on before the first call.  Every
     # (handle, query buffer) pair needs a direct call and a capturing call before it replays.
     for d in devs:
-        d.profile(True)
+        d.profile(args.kernel_events == "on")
     warm = max(args.warmup, 3, 2 * POOL * n_fly // math.gcd(POOL, n_fly) + n_fly)
     for i in range(warm):
         step(i)

@@ -8,6 +8,7 @@ Native layout (``data/vector_store/``)
   metadata.json     the chunk list, ``json.dump(chunks, indent=2)`` exactly as the reference
                     (orchestrator.py:15-16 re-reads this file on its own)
   index.faiss       float32 IndexFlatIP image ("IxFI") so the reference can open our store
+  bm25.pkl          the pickled ``rank_bm25.BM25Okapi`` the reference loads (retrieval_engine.py:45)
 
 Interchange: a store written by the reference (index.faiss + bm25.pkl +
 metadata.json) loads too -- the flat index is parsed directly and the pickled
@@ -26,7 +27,7 @@ from typing import Dict, List, Tuple
 
 import numpy as np
 
-from .bm25_index import BM25Index
+from .bm25_index import BM25Index, okapi_idf
 
 DIM = 384
 
@@ -63,14 +64,72 @@ class _StubBM25:
     doc_freqs, idf, doc_len, k1, b, epsilon, average_idf)."""
 
 
+# Exactly the globals a pickled rank_bm25.BM25Okapi needs (its attributes are ints, floats, lists,
+# dicts and -- depending on the numpy in use when it was written -- numpy scalars / arrays).
+# Anything else (builtins.eval, os.system, numpy.load ...) is refused: a crafted bm25.pkl must not
+# be able to run code.
+_PICKLE_ALLOW = {
+    ("collections", "OrderedDict"), ("collections", "defaultdict"),
+    ("builtins", "dict"), ("builtins", "list"), ("builtins", "tuple"), ("builtins", "set"),
+    ("builtins", "int"), ("builtins", "float"), ("builtins", "str"), ("builtins", "bool"),
+    ("numpy", "ndarray"), ("numpy", "dtype"), ("numpy", "float64"), ("numpy", "int64"),
+    ("numpy.core.multiarray", "_reconstruct"), ("numpy._core.multiarray", "_reconstruct"),
+    ("numpy.core.multiarray", "scalar"), ("numpy._core.multiarray", "scalar"),
+}
+
+
 class _BM25Unpickler(pickle.Unpickler):
     def find_class(self, module, name):
         if module.split(".")[0] == "rank_bm25":
             return _StubBM25
-        if module in ("builtins", "collections", "numpy", "numpy.core.multiarray",
-                      "numpy._core.multiarray", "numpy.core.numeric", "numpy._core.numeric"):
+        if (module, name) in _PICKLE_ALLOW:
             return super().find_class(module, name)
         raise pickle.UnpicklingError(f"refusing to unpickle {module}.{name}")
+
+
+def write_reference_bm25_pickle(path, bm25: BM25Index) -> None:
+    """``bm25.pkl`` as the reference's ``pickle.dump(bm25, f)`` writes it
+    (create_vector_store.py:73-74): an object of class ``rank_bm25.BM25Okapi`` whose ``__dict__``
+    holds rank_bm25 0.2.2's attributes, so that the reference's ``pickle.load``
+    (retrieval_engine.py:45-46) -- with rank_bm25 installed -- gets a working scorer.  rank_bm25 is
+    not importable here, so the class reference is written through a stand-in module of that name
+    that exists only while pickling."""
+    import sys
+    import types
+    terms = [None] * bm25.n_terms
+    for w, i in (bm25.vocab or {}).items():
+        terms[i] = w
+    tp = bm25.term_ptr.astype(np.int64)
+    doc_freqs = [dict() for _ in range(bm25.n_docs)]
+    for t in range(bm25.n_terms):
+        w = terms[t]
+        for d, f in bm25.postings[tp[t]:tp[t + 1]].tolist():
+            doc_freqs[d][w] = int(f)
+    raw_idf = bm25.idf.tolist()
+    mod = types.ModuleType("rank_bm25")
+
+    class BM25Okapi:                     # noqa: N801 -- the pickled class path is rank_bm25.BM25Okapi
+        pass
+    BM25Okapi.__module__ = "rank_bm25"
+    BM25Okapi.__qualname__ = "BM25Okapi"
+    mod.BM25Okapi = BM25Okapi
+    obj = BM25Okapi()
+    obj.__dict__.update(
+        corpus_size=int(bm25.n_docs), avgdl=float(bm25.avgdl), doc_freqs=doc_freqs,
+        idf={terms[t]: float(raw_idf[t]) for t in range(bm25.n_terms)},
+        doc_len=[int(v) for v in bm25.doc_len.tolist()], tokenizer=None,
+        k1=float(bm25.k1), b=float(bm25.b), epsilon=float(bm25.epsilon),
+        average_idf=float(okapi_idf(np.diff(tp), bm25.n_docs, bm25.epsilon)[1]))
+    had = sys.modules.get("rank_bm25")
+    sys.modules["rank_bm25"] = mod
+    try:
+        with open(path, "wb") as f:
+            pickle.dump(obj, f)
+    finally:
+        if had is not None:
+            sys.modules["rank_bm25"] = had
+        else:
+            del sys.modules["rank_bm25"]
 
 
 def bm25_from_reference_pickle(path) -> BM25Index:
@@ -108,6 +167,8 @@ def save_store(save_dir, chunks: List[dict], x_f32: np.ndarray, bm25: BM25Index)
                         doc_len=bm25.doc_len, idf=bm25.idf,
                         scalars=np.array([bm25.avgdl, bm25.k1, bm25.b, bm25.epsilon, bm25.n_docs]),
                         vocab=np.array(json.dumps(terms)))
+    if bm25.vocab is not None:
+        write_reference_bm25_pickle(save_dir / "bm25.pkl", bm25)   # create_vector_store.py:73-74
     with open(save_dir / "metadata.json", "w", encoding="utf-8") as f:
         json.dump(chunks, f, indent=2)                    # create_vector_store.py:77-78
 

@@ -105,7 +105,8 @@ def test_encode_texts_batches_and_order(dev):
     from legal_rag_engine_b200 import synth
     from legal_rag_engine_b200.encoder import SentenceEncoder
     sd = synth.bert_state_dict(51, 0.05)
-    enc = SentenceEncoder(dev, state_dict=sd)
+    from legal_rag_engine_b200.tokenizer import HashTokenizer
+    enc = SentenceEncoder(dev, state_dict=sd, tokenizer=HashTokenizer(30522))
     texts = ["zero fir registration procedure bnss", "what is the punishment for murder?",
              "a", "compensation for victims of acid attack " * 40]
     all_at_once = enc.encode(texts)

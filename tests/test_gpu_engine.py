@@ -97,7 +97,8 @@ def test_k_beyond_depth_raises_and_long_query_scores_every_token(built):
         eng.search("zero fir", k=129)
     assert len(eng.search("zero fir", k=128)) == 128
     # a pasted paragraph: 200+ whitespace tokens, every one of them scored (retrieval_engine.py:67-68)
-    long_q = " ".join(eng.chunks[5]["text"].split()[:230])
+    longest = max(eng.chunks, key=lambda c: len(c["text"].split()))
+    long_q = " ".join(longest["text"].split()[:230])
     assert len(tokenize(long_q)) > 200
     got = eng.search(long_q, k=10, hybrid_weight=0.5)
     qh = eng.encode([long_q]).astype(np.float16)[0]

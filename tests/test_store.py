@@ -73,6 +73,45 @@ def test_reference_store_interchange(tmp_path, monkeypatch):
     np.testing.assert_array_equal(b2.idf, csr.idf)
 
 
+def test_written_store_opens_through_the_reference_files(tmp_path):
+    """save_store also writes what the reference reads (index.faiss + bm25.pkl): with the native
+    files removed the store loads from those two and gives the same index; the pickle names
+    rank_bm25.BM25Okapi and carries rank_bm25 0.2.2's attributes."""
+    texts, chunks, x = _mini()
+    idx = BM25Index.from_texts(texts)
+    store.save_store(tmp_path, chunks, x, idx)
+    raw = (tmp_path / "bm25.pkl").read_bytes()
+    assert b"rank_bm25" in raw and b"BM25Okapi" in raw
+    (tmp_path / "vectors.f16.npy").unlink()
+    (tmp_path / "bm25.npz").unlink()
+    c2, xh, b2 = store.load_store(tmp_path)
+    np.testing.assert_array_equal(xh, x.astype(np.float16))
+    np.testing.assert_array_equal(b2.term_ptr, idx.term_ptr)
+    np.testing.assert_array_equal(b2.postings, idx.postings)
+    np.testing.assert_array_equal(b2.idf, idx.idf)
+    assert b2.vocab == idx.vocab and b2.avgdl == idx.avgdl
+    lit = obm25.BM25OkapiLiteral([t.lower().split() for t in texts])
+    obj = store._BM25Unpickler(__import__("io").BytesIO(raw)).load()
+    assert obj.doc_freqs == lit.doc_freqs and obj.doc_len == lit.doc_len and obj.idf == lit.idf
+    assert obj.average_idf == lit.average_idf and obj.corpus_size == 4
+
+
+def test_crafted_pickle_cannot_run_code(tmp_path):
+    import pytest
+
+    class Evil:
+        def __reduce__(self):
+            return (eval, ("__import__('os').getpid()",))
+    for payload in (Evil(), {"x": Evil()}):
+        (tmp_path / "bm25.pkl").write_bytes(pickle.dumps(payload))
+        with pytest.raises(pickle.UnpicklingError, match="refusing"):
+            store.bm25_from_reference_pickle(tmp_path / "bm25.pkl")
+    import numpy
+    (tmp_path / "bm25.pkl").write_bytes(pickle.dumps(numpy.load))
+    with pytest.raises(pickle.UnpicklingError, match="refusing"):
+        store.bm25_from_reference_pickle(tmp_path / "bm25.pkl")
+
+
 def test_fanout_helpers_match_oracle():
     for ctx, ents, cat in (("victim_distress", ["Robbery"], "procedure"), ("victim_distress", [], "x"),
                            ("informational", ["theft"], "general")):

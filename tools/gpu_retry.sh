@@ -1,11 +1,13 @@
 #!/bin/bash
-# usage: tools/gpu_retry.sh <logfile> <gpurun args...>   -- retries while the pod answers busy/transient (rc 3)
+# usage: tools/gpu_retry.sh <logfile> <gpurun args...>
+# Retries only while the pod has no box / slot free (gpurun exit code 3 with nothing charged, or a
+# "transient" verdict); any real verdict -- ok or fail -- ends the loop.
 log=$1; shift
 for attempt in $(seq 1 40); do
   gpurun "$@" > "$log" 2>&1
   rc=$?
-  if grep -q "status=transient\|status=busy\|no box\|rc=3" "$log" && ! grep -q "status=ok" "$log"; then
-    sleep 90
+  if grep -q "status=transient\|status=busy\|status=refused" "$log"; then
+    sleep 60
     continue
   fi
   exit $rc
