@@ -377,6 +377,20 @@ int lrx_gemm_f16(lrx_handle* h, const void* dev_a, const void* dev_w, int32_t M,
     return LRX_OK;
 }
 
+// K2 by batch size ("K2a/K2b chosen by B"): up to 4 queries share one streaming pass
+// of the matrix (K2a, HBM-bound); from 5 queries on the tensor-core kernel scores the whole batch in
+// ONE pass (K2b) where K2a would need ceil(B/4) -- measured at 10 M rows: B = 8 1.30 ms against
+// 2.23 ms, B = 64 1.32 ms against 18.1 ms (tools/k2_crossover.py); both emit the same exact lists.
+// A widened retry (exactness guard / candidate overflow) makes K2b sample every tile.
+static cudaError_t launch_dense_auto(lrx_handle* h, const void* q, int B, int K, int width, double* exact,
+                                     float* D, int64_t* I, int32_t* flags) {
+    if (B > 4 && h->n_local > 0 && ((uintptr_t)q & 15) == 0) {
+        const int stride = (width > dense_default_width(K)) ? 1 : 0;
+        return launch_dense_topk_batched(h, q, B, K, stride, exact, D, I, flags);
+    }
+    return launch_dense_topk(h, q, B, K, width, exact, D, I, flags);
+}
+
 static int check_dense(lrx_handle* h, const char* fn, int B, int K) {
     if (h->x == nullptr && h->n_local > 0) return fail(h, LRX_E_STATE, "%s: corpus not set", fn);
     if (B < 1 || B > LRX_MAX_BATCH) return fail(h, LRX_E_ARG, "%s: B must be in [1,%d]", fn, LRX_MAX_BATCH);
@@ -397,7 +411,7 @@ int lrx_dense_topk_ex(lrx_handle* h, const void* dev_q_fp16, int32_t B, int32_t 
     if (width < K || width > 512 || (width & (width - 1)) != 0)
         return fail(h, LRX_E_ARG, "lrx_dense_topk: width must be a power of two in [K,512]");
     LRX_CUDA(h, cudaSetDevice(h->device));
-    LRX_CUDA(h, launch_dense_topk(h, dev_q_fp16, B, K, width, dev_exact, dev_D, dev_I, dev_flags));
+    LRX_CUDA(h, launch_dense_auto(h, dev_q_fp16, B, K, width, dev_exact, dev_D, dev_I, dev_flags));
     return LRX_OK;
 }
 
@@ -538,7 +552,7 @@ static int enqueue_local(lrx_handle* h, const void* q, const int32_t* q_terms, c
     const int Kb = (mode == LRX_FUSE_RRF) ? K : 0;
     LRX_CUDA(h, cudaEventRecord(h->ev_fork, h->stream));
     LRX_CUDA(h, cudaStreamWaitEvent(h->aux, h->ev_fork, 0));
-    LRX_CUDA(h, launch_dense_topk(h, q, B, K, width, s.dense_exact, s.dense_D, s.dense_I, s.flags));
+    LRX_CUDA(h, launch_dense_auto(h, q, B, K, width, s.dense_exact, s.dense_D, s.dense_I, s.flags));
     LRX_CUDA(h, launch_bm25_bounds(h, q_terms, q_ptr, B, h->aux));
     LRX_CUDA(h, launch_bm25_scan(h, q_terms, q_ptr, B, s.maxbm, Kb, s.bm_scores, s.bm_ids, h->aux));
     LRX_CUDA(h, cudaEventRecord(h->ev_join, h->aux));

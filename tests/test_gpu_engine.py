@@ -154,3 +154,36 @@ def test_orchestrate_flow_on_gpu_equals_oracle_flow(built):
         key = lambda rs: [(r["chunk"]["canonical_header"], r["score"], r["semantic"], r["keyword"],
                            r.get("parent_context")) for r in rs]
         assert key(got) == key(want) and 1 <= len(got) <= 5
+
+
+def test_micro_batching_front_under_concurrent_clients(built):
+    """serving.MicroBatchingEngine over the real engine: 24 client threads calling search() get
+    exactly what sequential search() returns, and their calls were coalesced into fewer launches."""
+    import threading
+    from legal_rag_engine_b200.serving import MicroBatchingEngine
+    eng, _, _ = built
+    queries = ["What is the procedure for Zero FIR?", "Compensation for victims of acid attack",
+               "Definition of a public servant under BNS", "Procedure after arrest of a suspect in rape case",
+               "How to file FIR for robbery BNSS procedure", "What is the punishment for murder?"]
+    strip = lambda rs: [(r["chunk"]["canonical_header"], r["score"], r["semantic"], r["keyword"]) for r in rs]
+    want = {q: strip(eng.search(q, k=5, hybrid_weight=0.6)) for q in queries}
+    mb = MicroBatchingEngine(eng, max_batch=32, max_wait_ms=5.0)
+    real_close, eng.close = eng.close, (lambda: None)       # the fixture owns the engine
+    try:
+        got = {}
+
+        def client(i):
+            q = queries[i % len(queries)]
+            got[i] = (q, strip(mb.search(q, k=5, hybrid_weight=0.6)))
+        ts = [threading.Thread(target=client, args=(i,)) for i in range(24)]
+        for t in ts:
+            t.start()
+        for t in ts:
+            t.join()
+        assert len(got) == 24
+        for q, res in got.values():
+            assert res == want[q]
+        assert mb.requests == 24 and mb.batches < 24 and mb.largest_batch > 1
+    finally:
+        mb.close()
+        eng.close = real_close

@@ -522,3 +522,25 @@ def test_host_begin_end_two_handles_pipelined(dev):
     finally:
         dev.use_current_stream()
         other.close()
+
+
+@pytest.mark.parametrize("fusion", ["linear", "rrf"])
+@pytest.mark.parametrize("B", [5, 8, 33, 64])
+def test_search_batch_routes_larger_batches_to_tensor_core_scoring(dev, B, fusion):
+    """From 5 sub-queries on, the search chain scores the batch with the tensor-core kernel (K2b) in
+    one pass of the matrix instead of ceil(B/4) streaming passes: same exact results."""
+    n = 90000
+    x = synth.host_vectors(n, seed=61, dup_frac=0.01)
+    idx = synth.host_bm25(n, seed=62, vocab=3000)
+    csr = _csr_of(idx)
+    dev.set_corpus(_cuda(x), 0)
+    _set_postings(dev, idx)
+    q = synth.host_queries(B, seed=63 + B)
+    q[B // 2] = synth.host_planted_queries(x, [n // 3], seed=4)[0]
+    terms, ptr = synth.host_query_terms(B, 8, seed=64 + B, vocab=3000)
+    lists = [terms[ptr[b]:ptr[b + 1]].tolist() for b in range(B)]
+    weights = [0.5 + 0.1 * (b % 2) for b in range(B)]
+    want = _oracle_search(x, csr, q, lists, 10, weights, fusion)
+    for _ in range(3):                                          # direct, captured, replayed
+        got = dev.search_batch_host(q, lists, 10, weights, fusion)
+        _assert_results(got, want, 10)
