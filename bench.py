@@ -47,7 +47,7 @@ def parse():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--rows", type=int, default=10_000_000)
     ap.add_argument("--fusion", default="rrf", choices=["rrf", "linear"])
-    ap.add_argument("--in-flight", type=int, default=2,
+    ap.add_argument("--in-flight", type=int, default=3,
                     help="query batches in flight (one handle + stream each), the same at every N: one "
                          "batch's merges / exchange / fusion run under the next one's scans")
     ap.add_argument("--k", type=int, default=10,

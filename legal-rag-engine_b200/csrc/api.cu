@@ -464,6 +464,7 @@ int lrx_bm25(lrx_handle* h, const int32_t* dev_q_terms, const int32_t* dev_q_ptr
         return fail(h, LRX_E_ARG, "lrx_bm25: null pointer");
     LRX_CUDA(h, cudaSetDevice(h->device));
     h->bm_rows = h->bm_rows_cfg;
+    h->bm_list_k = K;
     LRX_CUDA(h, launch_bm25(h, dev_q_terms, dev_q_ptr, B, dev_cand_ids, n_cand, dev_cand_scores,
                             dev_max, K, dev_top_scores, dev_top_ids));
     return LRX_OK;
@@ -550,6 +551,7 @@ static int enqueue_local(lrx_handle* h, const void* q, const int32_t* q_terms, c
     size_t o_max, o_flags, total;
     packed_layout(B, k, &o_max, &o_flags, &total);
     const int Kb = (mode == LRX_FUSE_RRF) ? K : 0;
+    h->bm_list_k = Kb;
     LRX_CUDA(h, cudaEventRecord(h->ev_fork, h->stream));
     LRX_CUDA(h, cudaStreamWaitEvent(h->aux, h->ev_fork, 0));
     LRX_CUDA(h, launch_dense_auto(h, q, B, K, width, s.dense_exact, s.dense_D, s.dense_I, s.flags));

@@ -586,10 +586,11 @@ cudaError_t launch_dense_topk(lrx_handle* h, const void* qv, int B, int K, int w
     const __half* q = (const __half*)qv;
     for (int b0 = 0; b0 < B; b0 += 4) {
         const int nq = (B - b0 < 4) ? (B - b0) : 4;
-        const int NQ = (nq > 2) ? 4 : nq;
-        if (NQ == 4) e = launch_scan<4>(h, q + (size_t)b0 * kDim, nq, width, part, grid);
-        else if (NQ == 2) e = launch_scan<2>(h, q + (size_t)b0 * kDim, nq, width, part, grid);
-        else e = launch_scan<1>(h, q + (size_t)b0 * kDim, nq, width, part, grid);
+        // always the 4-query instantiation (absent queries are zero columns that never append): the
+        // 1- and 2-query instantiations measured SLOWER (batch 1 over 1 M rows: 0.179 ms against
+        // 0.124 ms for batch 4)
+        constexpr int NQ = 4;
+        e = launch_scan<4>(h, q + (size_t)b0 * kDim, nq, width, part, grid);
         if (e != cudaSuccess) return e;
         // list l of query qi of this pass: part[(l * NQ + qi) * width]
         dense_merge_rescore_kernel<<<nq, kMergeThreads, kMergeCap * sizeof(uint64_t), h->stream>>>(
