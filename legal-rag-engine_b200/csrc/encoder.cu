@@ -13,6 +13,7 @@
 // chunks of whole sequences sized so one chunk's working set stays L2-resident; all
 // statistics (LayerNorm, softmax, pooling, norms) are fp32.
 #include <cmath>
+#include <cstdlib>
 #include <cstring>
 
 #include "handle.h"
@@ -62,6 +63,7 @@ struct Encoder {
     __half *x = nullptr, *x1 = nullptr, *qkv = nullptr, *ctx = nullptr, *ff = nullptr;
     CUtensorMap t_x, t_x1, t_ctx, t_ff;              // A-operand views (128-row boxes, SWIZZLE_128B)
     CUtensorMap io_x, io_x1, io_qkv, io_ff;          // epilogue views (32 x 32 boxes, SWIZZLE_64B)
+    float* ybuf = nullptr;     // [128][384] fp32 pre-LayerNorm sums of encoder_small_kernel
     void* io = nullptr;        // host-form staging (ids, lens, out)
     size_t io_bytes = 0;
     void* io_host = nullptr;
@@ -380,6 +382,451 @@ pool_normalize_kernel(const __half* __restrict__ x, const int32_t* __restrict__ 
     }
 }
 
+// ------------------------------------------------- small batches: one cluster, one launch
+// A query batch (the 1-4 strings of a fan-out, <= 128 tokens in all) through the 31-launch chain
+// above costs 0.37 ms of launch latencies for 0.2 GFLOP of work.  encoder_small_kernel runs the
+// WHOLE forward pass -- embeddings, 6 layers, pooling, both normalisations -- as one launch of a
+// cluster of 8 CTAs:
+//   * the current activations X [128 tokens x 384] live in every CTA's shared memory (replicated);
+//   * every GEMM is split over the cluster by OUTPUT COLUMNS (CTA c computes columns c*N/8 ..), the
+//     weights stream from L2 straight into mma.sync B fragments (16 bytes per lane per 32-wide k
+//     chunk: A and B agree on a permuted k order, as in dense.cu, so no ldmatrix / swizzle; double
+//     buffered in registers), the slices meet in an L2-resident scratch and a cluster barrier
+//     (release / acquire) separates producer and consumer steps: 5 barriers per layer;
+//   * attention runs one (sequence, head) pair per warp over the 64 warps of the cluster, with the
+//     same mma.sync / online-softmax code as attention_kernel on warp-private K / V staging;
+//   * LayerNorm and the residual adds are fp32 on the gathered slices, redundantly in every CTA.
+// At this size the tensor cores are idle either way; what matters is latency: ~45 dependent steps
+// of a few microseconds instead of 31 kernel launches.  Limits: B * S <= 128 tokens, S <= 64.
+constexpr int kSmCtas = 8;
+constexpr int kSmThreads = 256;
+constexpr int kSmRows = 128;
+constexpr int kSmLd = 416;                          // halves per row of X in shared memory: 832 B, so that the
+                                                    // 16-byte fragment loads of 8 rows x 4 lanes hit 32 banks
+constexpr int kSmAttnBytes = 64 * kKPad * 2 * 2;    // per-warp K and V staging (64 keys)
+constexpr size_t kSmSmem = (size_t)kSmRows * kSmLd * 2 + (size_t)(kSmThreads / 32) * kSmAttnBytes;
+
+struct SmallLayer {
+    const __half *wqkv, *wo, *w1, *w2;
+    const float *bqkv, *bo, *b1, *b2, *ln1_g, *ln1_b, *ln2_g, *ln2_b;
+};
+struct SmallParams {
+    const int32_t* ids;
+    const int32_t* lens;
+    int B, S, vocab, max_pos;
+    const float *word, *pos, *type0, *eln_g, *eln_b;
+    SmallLayer L[kLayers];
+    __half *qkv, *ctx, *ff;      // L2-resident scratch: [128][1152], [128][384], [128][1536]
+    float* y;                    // [128][384] pre-LayerNorm sums (fp32)
+    float* out_f32;
+    __half* out_f16;
+};
+
+// acc[mt][nt] += A[m0 + 16 mt .. +16, :] * W[n0 + 8 nt .. +8, :]^T over K (multiple of 64).
+// A: row-major halves, lda apart (shared memory, or global scratch written by other CTAs -> ld.cg);
+// W: [N][K] row-major halves (read-only).  Next chunk's fragments are loaded before this chunk's MMAs.
+template <int NT, bool A_GLOBAL>
+__device__ __forceinline__ void sm_gemm(const __half* A, int lda, const __half* __restrict__ W, int K,
+                                        int m0, int n0, int lane, float (&acc)[2][NT][4]) {
+    const int g = lane >> 2, t = lane & 3;
+#pragma unroll
+    for (int mt = 0; mt < 2; ++mt)
+#pragma unroll
+        for (int nt = 0; nt < NT; ++nt)
+#pragma unroll
+            for (int i = 0; i < 4; ++i) acc[mt][nt][i] = 0.f;
+    const __half* a_base = A + (size_t)(m0 + g) * lda + 8 * t;
+    const __half* w_base = W + (size_t)(n0 + g) * K + 8 * t;
+    uint4 b0[NT], b1[NT], a0[4], a1[4];
+    auto load = [&](uint4 (&bb)[NT], uint4 (&aa)[4], int kc) {
+#pragma unroll
+        for (int nt = 0; nt < NT; ++nt)
+            bb[nt] = __ldg(reinterpret_cast<const uint4*>(w_base + (size_t)nt * 8 * K + kc));
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {                        // i = 2 * mt + (row g / row g + 8)
+            const __half* p = a_base + (size_t)(8 * i) * lda + kc;
+            aa[i] = A_GLOBAL ? __ldcg(reinterpret_cast<const uint4*>(p)) : *reinterpret_cast<const uint4*>(p);
+        }
+    };
+    auto mmas = [&](const uint4 (&bb)[NT], const uint4 (&aa)[4]) {
+#pragma unroll
+        for (int nt = 0; nt < NT; ++nt)
+#pragma unroll
+            for (int mt = 0; mt < 2; ++mt) {
+                const uint32_t lo[4] = {aa[2 * mt].x, aa[2 * mt + 1].x, aa[2 * mt].y, aa[2 * mt + 1].y};
+                const uint32_t hi[4] = {aa[2 * mt].z, aa[2 * mt + 1].z, aa[2 * mt].w, aa[2 * mt + 1].w};
+                mma16816(acc[mt][nt], lo, bb[nt].x, bb[nt].y);
+                mma16816(acc[mt][nt], hi, bb[nt].z, bb[nt].w);
+            }
+    };
+    load(b0, a0, 0);
+    for (int kc = 0; kc < K; kc += 64) {
+        load(b1, a1, kc + 32);
+        mmas(b0, a0);
+        if (kc + 64 < K) load(b0, a0, kc + 64);
+        mmas(b1, a1);
+    }
+}
+
+__device__ __forceinline__ float gelu_erf(float x) { return 0.5f * x * (1.0f + erff(x * 0.70710678118654752f)); }
+
+// LayerNorm of the fp32 rows y[128][384] (written by the whole cluster) into this CTA's X tile.
+__device__ __forceinline__ void sm_layernorm(const float* __restrict__ y, const float* __restrict__ gam,
+                                             const float* __restrict__ bet, __half* xs, int warp, int lane) {
+    for (int r = warp * 16; r < warp * 16 + 16; ++r) {
+        float v[12];
+        float sum = 0.f;
+#pragma unroll
+        for (int j = 0; j < 3; ++j) {
+            const float4 q = __ldcg(reinterpret_cast<const float4*>(y + (size_t)r * kHidden + j * 128 + lane * 4));
+            v[4 * j] = q.x; v[4 * j + 1] = q.y; v[4 * j + 2] = q.z; v[4 * j + 3] = q.w;
+            sum += q.x + q.y + q.z + q.w;
+        }
+#pragma unroll
+        for (int lb = 16; lb > 0; lb >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, lb);
+        const float mean = sum * (1.0f / kHidden);
+        float var = 0.f;
+#pragma unroll
+        for (int i = 0; i < 12; ++i) { const float d = v[i] - mean; var = fmaf(d, d, var); }
+#pragma unroll
+        for (int lb = 16; lb > 0; lb >>= 1) var += __shfl_xor_sync(0xffffffffu, var, lb);
+        const float rstd = 1.0f / sqrtf(var * (1.0f / kHidden) + kLnEps);
+#pragma unroll
+        for (int j = 0; j < 3; ++j) {
+            const int c = j * 128 + lane * 4;
+            const float4 gg = __ldg(reinterpret_cast<const float4*>(gam + c));
+            const float4 bb = __ldg(reinterpret_cast<const float4*>(bet + c));
+            uint2 u;
+            u.x = pack_h2((v[4 * j] - mean) * rstd * gg.x + bb.x, (v[4 * j + 1] - mean) * rstd * gg.y + bb.y);
+            u.y = pack_h2((v[4 * j + 2] - mean) * rstd * gg.z + bb.z, (v[4 * j + 3] - mean) * rstd * gg.w + bb.w);
+            *reinterpret_cast<uint2*>(xs + (size_t)r * kSmLd + c) = u;
+        }
+    }
+}
+
+// attention of ONE (sequence, head) pair by one warp (S <= 64): attention_kernel's arithmetic on
+// warp-private staging.
+__device__ __forceinline__ void sm_attention_pair(const __half* __restrict__ qkv, int seq, int head, int S,
+                                                  int len, __half* sK, __half* sV, __half* __restrict__ ctx,
+                                                  int lane) {
+    const int g = lane >> 2, t = lane & 3;
+    const __half* base = qkv + (size_t)seq * S * kQkv + head * kHeadDim;
+    __syncwarp();                                            // the previous pair's reads are done
+    for (int i = lane; i < 64 * 4; i += 32) {
+        const int s = i >> 2, part = i & 3;
+        const int sr = s < len ? s : 0;
+        const uint32_t nbytes = s < len ? 16u : 0u;
+        const __half* kp = base + (size_t)sr * kQkv + kHidden + part * 8;
+        asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;"
+                     ::"r"(smem_u32(sK + s * kKPad + part * 8)), "l"(kp), "r"(nbytes) : "memory");
+        asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;"
+                     ::"r"(smem_u32(sV + s * kKPad + part * 8)), "l"(kp + kHidden), "r"(nbytes) : "memory");
+    }
+    asm volatile("cp.async.commit_group;" ::: "memory");
+    asm volatile("cp.async.wait_all;" ::: "memory");
+    __syncwarp();
+    const float scale2 = 0.17677669529663687f * 1.4426950408889634f;
+    const int lm = lane >> 3, lr = lane & 7;
+    const int n_qtiles = (S + 15) >> 4;
+    for (int qt = 0; qt < n_qtiles; ++qt) {
+        const int q0 = qt * 16;
+        const int r0 = q0 + g, r1 = q0 + g + 8;
+        __half* o0 = ctx + ((size_t)seq * S + r0) * kHidden + head * kHeadDim;
+        __half* o1 = ctx + ((size_t)seq * S + r1) * kHidden + head * kHeadDim;
+        if (q0 >= len) {                                      // padding tile: zeros
+#pragma unroll
+            for (int nd = 0; nd < 4; ++nd) {
+                if (r0 < S) *reinterpret_cast<uint32_t*>(o0 + nd * 8 + 2 * t) = 0u;
+                if (r1 < S) *reinterpret_cast<uint32_t*>(o1 + nd * 8 + 2 * t) = 0u;
+            }
+            continue;
+        }
+        uint32_t qa[2][4];
+#pragma unroll
+        for (int ks = 0; ks < 2; ++ks) {
+            const __half* q0p = base + (size_t)r0 * kQkv + ks * 16 + 2 * t;
+            const __half* q1p = base + (size_t)r1 * kQkv + ks * 16 + 2 * t;
+            qa[ks][0] = (r0 < len) ? __ldcg(reinterpret_cast<const uint32_t*>(q0p)) : 0u;
+            qa[ks][1] = (r1 < len) ? __ldcg(reinterpret_cast<const uint32_t*>(q1p)) : 0u;
+            qa[ks][2] = (r0 < len) ? __ldcg(reinterpret_cast<const uint32_t*>(q0p + 8)) : 0u;
+            qa[ks][3] = (r1 < len) ? __ldcg(reinterpret_cast<const uint32_t*>(q1p + 8)) : 0u;
+        }
+        float sc[8][4];
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+#pragma unroll
+            for (int i = 0; i < 4; ++i) sc[j][i] = 0.f;
+            uint32_t kf[4];
+            ldsm_x4(kf, sK + (j * 8 + lr) * kKPad + lm * 8);
+            mma16816(sc[j], qa[0], kf[0], kf[1]);
+            mma16816(sc[j], qa[1], kf[2], kf[3]);
+        }
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {                        // mask keys >= len
+            const int key = j * 8 + 2 * t;
+            if (key >= len) { sc[j][0] = -INFINITY; sc[j][2] = -INFINITY; }
+            if (key + 1 >= len) { sc[j][1] = -INFINITY; sc[j][3] = -INFINITY; }
+        }
+        float m0 = -INFINITY, m1 = -INFINITY;
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            m0 = fmaxf(m0, fmaxf(sc[j][0], sc[j][1]));
+            m1 = fmaxf(m1, fmaxf(sc[j][2], sc[j][3]));
+        }
+        m0 = fmaxf(m0, __shfl_xor_sync(0xffffffffu, m0, 1));
+        m0 = fmaxf(m0, __shfl_xor_sync(0xffffffffu, m0, 2));
+        m1 = fmaxf(m1, __shfl_xor_sync(0xffffffffu, m1, 1));
+        m1 = fmaxf(m1, __shfl_xor_sync(0xffffffffu, m1, 2));
+        const float nm0 = -m0 * scale2, nm1 = -m1 * scale2;   // finite: key 0 < len
+        float l0 = 0.f, l1 = 0.f;
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            sc[j][0] = ex2(fmaf(sc[j][0], scale2, nm0));
+            sc[j][1] = ex2(fmaf(sc[j][1], scale2, nm0));
+            sc[j][2] = ex2(fmaf(sc[j][2], scale2, nm1));
+            sc[j][3] = ex2(fmaf(sc[j][3], scale2, nm1));
+            l0 += sc[j][0] + sc[j][1];
+            l1 += sc[j][2] + sc[j][3];
+        }
+        float o[4][4];
+#pragma unroll
+        for (int nd = 0; nd < 4; ++nd)
+#pragma unroll
+            for (int i = 0; i < 4; ++i) o[nd][i] = 0.f;
+#pragma unroll
+        for (int kk = 0; kk < 4; ++kk) {
+            uint32_t pa[4];
+            pa[0] = pack_h2(sc[2 * kk][0], sc[2 * kk][1]);
+            pa[1] = pack_h2(sc[2 * kk][2], sc[2 * kk][3]);
+            pa[2] = pack_h2(sc[2 * kk + 1][0], sc[2 * kk + 1][1]);
+            pa[3] = pack_h2(sc[2 * kk + 1][2], sc[2 * kk + 1][3]);
+#pragma unroll
+            for (int np = 0; np < 2; ++np) {
+                uint32_t vf[4];
+                ldsm_x4_t(vf, sV + (kk * 16 + (lm & 1) * 8 + lr) * kKPad + (2 * np + (lm >> 1)) * 8);
+                mma16816(o[2 * np], pa, vf[0], vf[1]);
+                mma16816(o[2 * np + 1], pa, vf[2], vf[3]);
+            }
+        }
+        l0 += __shfl_xor_sync(0xffffffffu, l0, 1);
+        l0 += __shfl_xor_sync(0xffffffffu, l0, 2);
+        l1 += __shfl_xor_sync(0xffffffffu, l1, 1);
+        l1 += __shfl_xor_sync(0xffffffffu, l1, 2);
+        const float i0 = 1.0f / l0, i1 = 1.0f / l1;
+#pragma unroll
+        for (int nd = 0; nd < 4; ++nd) {
+            if (r0 < S)
+                *reinterpret_cast<uint32_t*>(o0 + nd * 8 + 2 * t) =
+                    (r0 < len) ? pack_h2(o[nd][0] * i0, o[nd][1] * i0) : 0u;
+            if (r1 < S)
+                *reinterpret_cast<uint32_t*>(o1 + nd * 8 + 2 * t) =
+                    (r1 < len) ? pack_h2(o[nd][2] * i1, o[nd][3] * i1) : 0u;
+        }
+    }
+}
+
+__global__ void __launch_bounds__(kSmThreads, 1)
+encoder_small_kernel(const SmallParams P) {
+    extern __shared__ __align__(16) unsigned char sm_raw[];
+    __half* xs = reinterpret_cast<__half*>(sm_raw);                          // [128][kSmLd]
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int g = lane >> 2, t = lane & 3;
+    const int c = (int)cluster_ctarank();
+    const int T = P.B * P.S;
+    __half* sK = reinterpret_cast<__half*>(sm_raw + (size_t)kSmRows * kSmLd * 2 + (size_t)warp * kSmAttnBytes);
+    __half* sV = sK + 64 * kKPad;
+    const int wm = warp & 3, wn = warp >> 2;                 // 4 row blocks of 32 x 2 column halves
+    const int m0 = 32 * wm;
+
+    // ---- embeddings + LayerNorm, every row of X in every CTA (rows >= T: zeros)
+    for (int r = warp * 16; r < warp * 16 + 16; ++r) {
+        if (r >= T) {
+            for (int cc = lane * 4; cc < kHidden; cc += 128)
+                *reinterpret_cast<uint2*>(xs + (size_t)r * kSmLd + cc) = make_uint2(0u, 0u);
+            continue;
+        }
+        int id = P.ids[r];
+        id = (id < 0 || id >= P.vocab) ? 0 : id;
+        int sp = r % P.S;
+        sp = (sp >= P.max_pos) ? P.max_pos - 1 : sp;
+        float v[12];
+        float sum = 0.f;
+#pragma unroll
+        for (int j = 0; j < 3; ++j) {
+            const int cc = j * 128 + lane * 4;
+            const float4 w = __ldg(reinterpret_cast<const float4*>(P.word + (size_t)id * kHidden + cc));
+            const float4 p = __ldg(reinterpret_cast<const float4*>(P.pos + (size_t)sp * kHidden + cc));
+            const float4 ty = __ldg(reinterpret_cast<const float4*>(P.type0 + cc));
+            v[4 * j + 0] = w.x + p.x + ty.x;
+            v[4 * j + 1] = w.y + p.y + ty.y;
+            v[4 * j + 2] = w.z + p.z + ty.z;
+            v[4 * j + 3] = w.w + p.w + ty.w;
+            sum += v[4 * j] + v[4 * j + 1] + v[4 * j + 2] + v[4 * j + 3];
+        }
+#pragma unroll
+        for (int lb = 16; lb > 0; lb >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, lb);
+        const float mean = sum * (1.0f / kHidden);
+        float var = 0.f;
+#pragma unroll
+        for (int i = 0; i < 12; ++i) { const float d = v[i] - mean; var = fmaf(d, d, var); }
+#pragma unroll
+        for (int lb = 16; lb > 0; lb >>= 1) var += __shfl_xor_sync(0xffffffffu, var, lb);
+        const float rstd = 1.0f / sqrtf(var * (1.0f / kHidden) + kLnEps);
+#pragma unroll
+        for (int j = 0; j < 3; ++j) {
+            const int cc = j * 128 + lane * 4;
+            const float4 gg = __ldg(reinterpret_cast<const float4*>(P.eln_g + cc));
+            const float4 bb = __ldg(reinterpret_cast<const float4*>(P.eln_b + cc));
+            uint2 u;
+            u.x = pack_h2((v[4 * j] - mean) * rstd * gg.x + bb.x, (v[4 * j + 1] - mean) * rstd * gg.y + bb.y);
+            u.y = pack_h2((v[4 * j + 2] - mean) * rstd * gg.z + bb.z, (v[4 * j + 3] - mean) * rstd * gg.w + bb.w);
+            *reinterpret_cast<uint2*>(xs + (size_t)r * kSmLd + cc) = u;
+        }
+    }
+    __syncthreads();
+
+    for (int l = 0; l < kLayers; ++l) {
+        const SmallLayer& L = P.L[l];
+        // ---- (1) QKV projection: columns [144 c, 144 c + 144)
+        {
+            float acc[2][9][4];
+            const int n0 = 144 * c + 72 * wn;
+            sm_gemm<9, false>(xs, kSmLd, L.wqkv, kHidden, m0, n0, lane, acc);
+#pragma unroll
+            for (int nt = 0; nt < 9; ++nt) {
+                const int col = n0 + 8 * nt + 2 * t;
+                const float2 bb = __ldg(reinterpret_cast<const float2*>(L.bqkv + col));
+#pragma unroll
+                for (int mt = 0; mt < 2; ++mt) {
+                    const int r0 = m0 + 16 * mt + g;
+                    *reinterpret_cast<uint32_t*>(P.qkv + (size_t)r0 * kQkv + col) =
+                        pack_h2(acc[mt][nt][0] + bb.x, acc[mt][nt][1] + bb.y);
+                    *reinterpret_cast<uint32_t*>(P.qkv + (size_t)(r0 + 8) * kQkv + col) =
+                        pack_h2(acc[mt][nt][2] + bb.x, acc[mt][nt][3] + bb.y);
+                }
+            }
+        }
+        cluster_sync_all();
+        // ---- (2) attention: one (sequence, head) pair per warp of the cluster
+        for (int p = c * (kSmThreads / 32) + warp; p < P.B * kHeads; p += kSmCtas * (kSmThreads / 32)) {
+            const int seq = p / kHeads, head = p - seq * kHeads;
+            int len = P.lens[seq];
+            len = len < 0 ? 0 : (len > P.S ? P.S : len);
+            sm_attention_pair(P.qkv, seq, head, P.S, len, sK, sV, P.ctx, lane);
+        }
+        cluster_sync_all();
+        // ---- (3) output projection + residual -> y (fp32), columns [48 c, 48 c + 48); LayerNorm
+        {
+            float acc[2][3][4];
+            const int n0 = 48 * c + 24 * wn;
+            sm_gemm<3, true>(P.ctx, kHidden, L.wo, kHidden, m0, n0, lane, acc);
+#pragma unroll
+            for (int nt = 0; nt < 3; ++nt) {
+                const int col = n0 + 8 * nt + 2 * t;
+                const float2 bb = __ldg(reinterpret_cast<const float2*>(L.bo + col));
+#pragma unroll
+                for (int mt = 0; mt < 2; ++mt) {
+                    const int r0 = m0 + 16 * mt + g;
+                    const float2 x0 = __half22float2(*reinterpret_cast<const __half2*>(xs + (size_t)r0 * kSmLd + col));
+                    const float2 x1 = __half22float2(*reinterpret_cast<const __half2*>(xs + (size_t)(r0 + 8) * kSmLd + col));
+                    *reinterpret_cast<float2*>(P.y + (size_t)r0 * kHidden + col) =
+                        make_float2(acc[mt][nt][0] + bb.x + x0.x, acc[mt][nt][1] + bb.y + x0.y);
+                    *reinterpret_cast<float2*>(P.y + (size_t)(r0 + 8) * kHidden + col) =
+                        make_float2(acc[mt][nt][2] + bb.x + x1.x, acc[mt][nt][3] + bb.y + x1.y);
+                }
+            }
+        }
+        cluster_sync_all();
+        sm_layernorm(P.y, L.ln1_g, L.ln1_b, xs, warp, lane);
+        __syncthreads();
+        // ---- (4) FFN up + GELU: columns [192 c, 192 c + 192), two passes of 6 column tiles per warp
+#pragma unroll 1
+        for (int pass = 0; pass < 2; ++pass) {
+            float acc[2][6][4];
+            const int n0 = 192 * c + 96 * wn + 48 * pass;
+            sm_gemm<6, false>(xs, kSmLd, L.w1, kHidden, m0, n0, lane, acc);
+#pragma unroll
+            for (int nt = 0; nt < 6; ++nt) {
+                const int col = n0 + 8 * nt + 2 * t;
+                const float2 bb = __ldg(reinterpret_cast<const float2*>(L.b1 + col));
+#pragma unroll
+                for (int mt = 0; mt < 2; ++mt) {
+                    const int r0 = m0 + 16 * mt + g;
+                    *reinterpret_cast<uint32_t*>(P.ff + (size_t)r0 * kFfn + col) =
+                        pack_h2(gelu_erf(acc[mt][nt][0] + bb.x), gelu_erf(acc[mt][nt][1] + bb.y));
+                    *reinterpret_cast<uint32_t*>(P.ff + (size_t)(r0 + 8) * kFfn + col) =
+                        pack_h2(gelu_erf(acc[mt][nt][2] + bb.x), gelu_erf(acc[mt][nt][3] + bb.y));
+                }
+            }
+        }
+        cluster_sync_all();
+        // ---- (5) FFN down + residual -> y, columns [48 c, 48 c + 48); LayerNorm
+        {
+            float acc[2][3][4];
+            const int n0 = 48 * c + 24 * wn;
+            sm_gemm<3, true>(P.ff, kFfn, L.w2, kFfn, m0, n0, lane, acc);
+#pragma unroll
+            for (int nt = 0; nt < 3; ++nt) {
+                const int col = n0 + 8 * nt + 2 * t;
+                const float2 bb = __ldg(reinterpret_cast<const float2*>(L.b2 + col));
+#pragma unroll
+                for (int mt = 0; mt < 2; ++mt) {
+                    const int r0 = m0 + 16 * mt + g;
+                    const float2 x0 = __half22float2(*reinterpret_cast<const __half2*>(xs + (size_t)r0 * kSmLd + col));
+                    const float2 x1 = __half22float2(*reinterpret_cast<const __half2*>(xs + (size_t)(r0 + 8) * kSmLd + col));
+                    *reinterpret_cast<float2*>(P.y + (size_t)r0 * kHidden + col) =
+                        make_float2(acc[mt][nt][0] + bb.x + x0.x, acc[mt][nt][1] + bb.y + x0.y);
+                    *reinterpret_cast<float2*>(P.y + (size_t)(r0 + 8) * kHidden + col) =
+                        make_float2(acc[mt][nt][2] + bb.x + x1.x, acc[mt][nt][3] + bb.y + x1.y);
+                }
+            }
+        }
+        cluster_sync_all();
+        sm_layernorm(P.y, L.ln2_g, L.ln2_b, xs, warp, lane);
+        __syncthreads();
+    }
+
+    // ---- pooling + Normalize + normalize_L2: sequence b on CTA b % 8 (columns tid and tid + 256)
+    __shared__ float red[kSmThreads / 32];
+    auto block_sum = [&](float v) -> float {
+#pragma unroll
+        for (int lb = 16; lb > 0; lb >>= 1) v += __shfl_xor_sync(0xffffffffu, v, lb);
+        __syncthreads();
+        if (lane == 0) red[warp] = v;
+        __syncthreads();
+        float s = 0.f;
+#pragma unroll
+        for (int i = 0; i < kSmThreads / 32; ++i) s += red[i];
+        return s;
+    };
+    for (int b = c; b < P.B; b += kSmCtas) {
+        int len = P.lens[b];
+        len = len < 0 ? 0 : (len > P.S ? P.S : len);
+        const bool two = tid + 256 < kHidden;
+        float a0 = 0.f, a1 = 0.f;
+        for (int sidx = 0; sidx < len; ++sidx) {
+            const __half* row = xs + (size_t)(b * P.S + sidx) * kSmLd;
+            a0 += __half2float(row[tid]);
+            if (two) a1 += __half2float(row[tid + 256]);
+        }
+        const float denom = fmaxf((float)len, 1e-9f);          // torch.clamp(sum_mask, min=1e-9)
+        a0 = a0 / denom; a1 = a1 / denom;
+        const float nrm = fmaxf(sqrtf(block_sum(a0 * a0 + (two ? a1 * a1 : 0.f))), 1e-12f);   // F.normalize
+        a0 = a0 / nrm; a1 = a1 / nrm;
+        const float sq2 = block_sum(a0 * a0 + (two ? a1 * a1 : 0.f));
+        if (sq2 > 0.f) {                                       // faiss.normalize_L2
+            const float inv = 1.0f / sqrtf(sq2);
+            a0 *= inv; a1 *= inv;
+        }
+        const size_t o = (size_t)b * kHidden;
+        if (P.out_f32 != nullptr) { P.out_f32[o + tid] = a0; if (two) P.out_f32[o + tid + 256] = a1; }
+        if (P.out_f16 != nullptr) {
+            P.out_f16[o + tid] = __float2half_rn(a0);
+            if (two) P.out_f16[o + tid + 256] = __float2half_rn(a1);
+        }
+    }
+}
+
 // ------------------------------------------------------------------ host side
 static size_t rup(size_t v, size_t a) { return (v + a - 1) / a * a; }
 
@@ -388,6 +835,7 @@ void encoder_free(lrx_handle* h) {
     if (e == nullptr) return;
     if (e->blob) cudaFree(e->blob);
     if (e->act) cudaFree(e->act);
+    if (e->ybuf) cudaFree(e->ybuf);
     if (e->io) cudaFree(e->io);
     if (e->io_host) cudaFreeHost(e->io_host);
     delete e;
@@ -431,6 +879,7 @@ cudaError_t encoder_set_weights(lrx_handle* h, const lrx_bert_weights* w) {
         for (int i = 8; i < 12; ++i) o_l[l][i] = take(kHidden * 4);
     }
     ENC_CK(cudaMalloc(&e->blob, off));
+    ENC_CK(cudaMalloc((void**)&e->ybuf, (size_t)kSmRows * kHidden * sizeof(float)));
     char* B = (char*)e->blob;
     cudaStream_t st = h->stream;
     auto cpy = [&](size_t o, const float* src, size_t n) {
@@ -516,9 +965,58 @@ static cudaError_t encoder_reserve(Encoder* e, int64_t tokens) {
 }
 
 
+// Query-sized batches (<= 128 tokens, S <= 64): the whole forward pass as ONE launch of a cluster of 8.
+static cudaError_t encoder_forward_small(lrx_handle* h, Encoder* e, const int32_t* ids, const int32_t* lens,
+                                         int B, int S, float* out_f32, void* out_f16) {
+    if (e->cap < kSmRows) {
+        if (h->capturing) return cudaErrorStreamCaptureUnsupported;
+        h->ws_epoch++;
+        ENC_CK(encoder_reserve(e, kSmRows));
+    }
+    {
+        std::lock_guard<std::recursive_mutex> attr_guard(attr_mutex());   // the flags below are process-wide
+        static bool attr_dev[64] = {false};   // function attributes are per device
+        bool& attr = attr_dev[h->device & 63];
+        if (!attr) {
+            ENC_CK(cudaFuncSetAttribute(encoder_small_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                        (int)kSmSmem));
+            attr = true;
+        }
+    }
+    SmallParams P;
+    P.ids = ids; P.lens = lens; P.B = B; P.S = S; P.vocab = e->vocab; P.max_pos = e->max_pos;
+    P.word = e->word; P.pos = e->pos; P.type0 = e->type0; P.eln_g = e->eln_g; P.eln_b = e->eln_b;
+    for (int l = 0; l < kLayers; ++l) {
+        const EncLayer& s = e->L[l];
+        SmallLayer& d = P.L[l];
+        d.wqkv = s.wqkv; d.wo = s.wo; d.w1 = s.w1; d.w2 = s.w2;
+        d.bqkv = s.bqkv; d.bo = s.bo; d.b1 = s.b1; d.b2 = s.b2;
+        d.ln1_g = s.ln1_g; d.ln1_b = s.ln1_b; d.ln2_g = s.ln2_g; d.ln2_b = s.ln2_b;
+    }
+    P.qkv = e->qkv; P.ctx = e->ctx; P.ff = e->ff; P.y = e->ybuf;
+    P.out_f32 = out_f32; P.out_f16 = (__half*)out_f16;
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(kSmCtas);
+    cfg.blockDim = dim3(kSmThreads);
+    cfg.dynamicSmemBytes = kSmSmem;
+    cfg.stream = h->stream;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeClusterDimension;
+    at[0].val.clusterDim.x = kSmCtas;
+    at[0].val.clusterDim.y = 1;
+    at[0].val.clusterDim.z = 1;
+    cfg.attrs = at;
+    cfg.numAttrs = 1;
+    ENC_CK(cudaLaunchKernelEx(&cfg, encoder_small_kernel, P));
+    h->launches++;
+    return cudaSuccess;
+}
+
 cudaError_t encoder_forward(lrx_handle* h, const int32_t* ids, const int32_t* lens, int B, int S,
                             float* out_f32, void* out_f16) {
     Encoder* e = (Encoder*)h->encoder;
+    if ((int64_t)B * S <= kSmRows && S <= 64 && getenv("LRX_NO_SMALL_ENCODER") == nullptr)
+        return encoder_forward_small(h, e, ids, lens, B, S, out_f32, out_f16);
     int seq_per_chunk = (int)(kChunkTokens / S);
     if (seq_per_chunk < 1) seq_per_chunk = 1;
     if (seq_per_chunk > B) seq_per_chunk = B;

@@ -64,7 +64,10 @@ def _cos(a, b):
 
 @pytest.mark.parametrize("wseed,std,jit,B,S,full", [
     (42, 0.02, 0.0, 3, 24, False), (43, 0.06, 0.2, 4, 40, False), (44, 0.05, 0.1, 2, 128, True),
-    (45, 0.05, 0.1, 5, 256, False), (46, 0.04, 0.1, 70, 128, False), (47, 0.05, 0.1, 1, 7, True)])
+    (45, 0.05, 0.1, 5, 256, False), (46, 0.04, 0.1, 70, 128, False), (47, 0.05, 0.1, 1, 7, True),
+    # query-sized batches (<= 128 tokens, S <= 64): the single-launch cluster kernel
+    (48, 0.05, 0.1, 4, 32, False), (49, 0.05, 0.1, 2, 64, True), (50, 0.06, 0.2, 8, 16, False),
+    (51, 0.05, 0.1, 1, 64, False), (52, 0.05, 0.1, 5, 25, False), (53, 0.05, 0.1, 16, 8, True)])
 def test_encoder_matches_fp32_oracle(dev, wseed, std, jit, B, S, full):
     from legal_rag_engine_b200 import synth
     from legal_rag_engine_b200.encoder import SentenceEncoder
@@ -99,6 +102,28 @@ def test_encoder_padding_is_inert(dev):
     wide[:, :48] = ids
     b = enc.encode_ids(wide, lens)
     assert _cos(a.astype(np.float64), b.astype(np.float64)).min() > 0.999999
+
+
+def test_small_batch_kernel_agrees_with_the_gemm_chain(dev, monkeypatch):
+    """The same query batch through the one-launch cluster kernel and (LRX_NO_SMALL_ENCODER) through
+    the tcgen05 GEMM chain: same embeddings to fp16 rounding noise; padding inert on the small path."""
+    from legal_rag_engine_b200 import synth
+    from legal_rag_engine_b200.encoder import SentenceEncoder
+    sd = synth.bert_state_dict(54, 0.05, ln_jitter=0.1)
+    enc = SentenceEncoder(dev, state_dict=sd)
+    ids, lens = synth.token_batch(4, 30, seed=9)
+    small = enc.encode_ids(ids, lens)
+    monkeypatch.setenv("LRX_NO_SMALL_ENCODER", "1")
+    chain = enc.encode_ids(ids, lens)
+    monkeypatch.delenv("LRX_NO_SMALL_ENCODER")
+    assert _cos(small.astype(np.float64), chain.astype(np.float64)).min() > 0.99999
+    ids2 = ids.copy()
+    for i, n in enumerate(lens):
+        ids2[i, n:] = 777
+    np.testing.assert_array_equal(enc.encode_ids(ids2, lens), small)
+    wide = np.zeros((2, 64), dtype=np.int32)
+    wide[:, :30] = ids[:2]
+    assert _cos(enc.encode_ids(wide, lens[:2]).astype(np.float64), small[:2].astype(np.float64)).min() > 0.999999
 
 
 def test_encode_texts_batches_and_order(dev):
