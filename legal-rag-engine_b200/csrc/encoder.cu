@@ -63,7 +63,8 @@ struct Encoder {
     __half *x = nullptr, *x1 = nullptr, *qkv = nullptr, *ctx = nullptr, *ff = nullptr;
     CUtensorMap t_x, t_x1, t_ctx, t_ff;              // A-operand views (128-row boxes, SWIZZLE_128B)
     CUtensorMap io_x, io_x1, io_qkv, io_ff;          // epilogue views (32 x 32 boxes, SWIZZLE_64B)
-    float* ybuf = nullptr;     // [128][384] fp32 pre-LayerNorm sums of encoder_small_kernel
+    void* small_ws = nullptr;  // encoder_small_kernel: per-group scratch (qkv, ctx, ff, pre-LayerNorm sums)
+    size_t small_ws_bytes = 0;
     void* io = nullptr;        // host-form staging (ids, lens, out)
     size_t io_bytes = 0;
     void* io_host = nullptr;
@@ -382,29 +383,52 @@ pool_normalize_kernel(const __half* __restrict__ x, const int32_t* __restrict__ 
     }
 }
 
-// ------------------------------------------------- small batches: one cluster, one launch
-// A query batch (the 1-4 strings of a fan-out, <= 128 tokens in all) through the 31-launch chain
-// above costs 0.37 ms of launch latencies for 0.2 GFLOP of work.  encoder_small_kernel runs the
-// WHOLE forward pass -- embeddings, 6 layers, pooling, both normalisations -- as one launch of a
-// cluster of 8 CTAs:
-//   * the current activations X [128 tokens x 384] live in every CTA's shared memory (replicated);
-//   * every GEMM is split over the cluster by OUTPUT COLUMNS (CTA c computes columns c*N/8 ..), the
-//     weights stream from L2 straight into mma.sync B fragments (16 bytes per lane per 32-wide k
-//     chunk: A and B agree on a permuted k order, as in dense.cu, so no ldmatrix / swizzle; double
-//     buffered in registers), the slices meet in an L2-resident scratch and a cluster barrier
-//     (release / acquire) separates producer and consumer steps: 5 barriers per layer;
-//   * attention runs one (sequence, head) pair per warp over the 64 warps of the cluster, with the
-//     same mma.sync / online-softmax code as attention_kernel on warp-private K / V staging;
-//   * LayerNorm and the residual adds are fp32 on the gathered slices, redundantly in every CTA.
-// At this size the tensor cores are idle either way; what matters is latency: ~45 dependent steps
-// of a few microseconds instead of 31 kernel launches.  Limits: B * S <= 128 tokens, S <= 64.
+// ------------------------------------- query-sized sequences: one cluster per group, one launch
+// A query batch (the 1-4 strings of a fan-out, a few dozen tokens each) through the 31-launch
+// tcgen05 chain above costs 0.37 ms of launch and pipeline start-up latencies for 0.2 GFLOP of work,
+// all of it on the one or two SMs that own the batch's single 128-row tile.  encoder_small_kernel
+// runs the WHOLE forward pass -- embeddings, 6 layers, pooling, both normalisations -- as one
+// launch, and spreads it: sequences are independent, so every GROUP of sequences with at most
+// M = 16 MT tokens (MT = 2: S <= 32, MT = 4: S <= 64) gets its own cluster of 8 CTAs, and inside a
+// cluster every GEMM is cut into UNITS of 8 output columns x 384 k for all M rows:
+//   * a unit's weights are 8 rows x 768 B of W, fetched as 12 independent 16-byte loads per lane
+//     straight into mma.sync B fragments (A and B agree on a permuted k order, as in dense.cu: no
+//     ldmatrix, no swizzle), all issued before the first MMA and one unit ahead -- the first
+//     version kept one 32-k chunk in flight per warp and spent its time waiting for L2;
+//   * the group's activations X [M x 384] live in every CTA's shared memory (replicated); A
+//     operands written by other CTAs (attention output, FFN activations) are staged by cp.async;
+//   * QKV: 144 units, FFN up: 192, attention output: 48 over the cluster's 64 warps; FFN down
+//     (K = 1536) is 48 column tiles x 4 k quarters = 192 units whose partial sums meet in the
+//     LayerNorm IN A FIXED ORDER, so the result does not depend on timing;
+//   * slices meet in an L2-resident scratch, a cluster barrier (release / acquire) separates
+//     producer and consumer steps: 5 per layer; LayerNorm runs redundantly in every CTA (fp32);
+//   * attention: one (sequence, head) pair per warp, mma.sync QK^T / PV with one-shot softmax.
+// Every row's arithmetic is the same whatever the batch, the padded length or the row's place in
+// the tile, so a sequence's embedding does not depend on what it was batched with (the serving
+// front coalesces requests, tests/test_gpu_engine.py::test_micro_batching_front_...).
 constexpr int kSmCtas = 8;
 constexpr int kSmThreads = 256;
-constexpr int kSmRows = 128;
-constexpr int kSmLd = 416;                          // halves per row of X in shared memory: 832 B, so that the
-                                                    // 16-byte fragment loads of 8 rows x 4 lanes hit 32 banks
-constexpr int kSmAttnBytes = 64 * kKPad * 2 * 2;    // per-warp K and V staging (64 keys)
-constexpr size_t kSmSmem = (size_t)kSmRows * kSmLd * 2 + (size_t)(kSmThreads / 32) * kSmAttnBytes;
+constexpr int kSmWarps = kSmThreads / 32;
+constexpr int kSmLd = 416;              // halves per staged row: 832 B = 64 mod 128, so the 16-byte
+                                        // fragment loads of 2 rows x 4 lanes cover all 32 banks
+constexpr int kSmAttnWarps = 5;         // warps per CTA that take attention pairs (their K / V staging
+                                        // shares the A-staging tile)
+constexpr int kSmMaxGroups = 128;       // groups per launch (scratch: 0.45 / 0.9 MB each)
+
+template <int MT>
+struct SmGeom {
+    static constexpr int M = 16 * MT;
+    static constexpr size_t tile_bytes = (size_t)M * kSmLd * 2;
+    static constexpr size_t smem = 2 * tile_bytes;
+    static constexpr size_t o_qkv = 0;
+    static constexpr size_t o_ctx = o_qkv + (size_t)M * kQkv * 2;
+    static constexpr size_t o_ff = o_ctx + (size_t)M * kHidden * 2;
+    static constexpr size_t o_y = o_ff + (size_t)M * kFfn * 2;
+    static constexpr size_t o_ypart = o_y + (size_t)M * kHidden * 4;
+    static constexpr size_t scratch = o_ypart + 4 * (size_t)M * kHidden * 4;
+};
+static_assert(kSmAttnWarps * 2 * 32 * kKPad * 2 <= (int)SmGeom<2>::tile_bytes, "attention staging (MT = 2)");
+static_assert(kSmAttnWarps * 2 * 64 * kKPad * 2 <= (int)SmGeom<4>::tile_bytes, "attention staging (MT = 4)");
 
 struct SmallLayer {
     const __half *wqkv, *wo, *w1, *w2;
@@ -413,106 +437,109 @@ struct SmallLayer {
 struct SmallParams {
     const int32_t* ids;
     const int32_t* lens;
-    int B, S, vocab, max_pos;
+    int B, S, spg, vocab, max_pos;      // spg: sequences per group
     const float *word, *pos, *type0, *eln_g, *eln_b;
     SmallLayer L[kLayers];
-    __half *qkv, *ctx, *ff;      // L2-resident scratch: [128][1152], [128][384], [128][1536]
-    float* y;                    // [128][384] pre-LayerNorm sums (fp32)
+    unsigned char* scratch;             // [groups][SmGeom::scratch]
     float* out_f32;
     __half* out_f16;
 };
 
-// acc[mt][nt] += A[m0 + 16 mt .. +16, :] * W[n0 + 8 nt .. +8, :]^T over K (multiple of 64).
-// A: row-major halves, lda apart (shared memory, or global scratch written by other CTAs -> ld.cg);
-// W: [N][K] row-major halves (read-only).  Next chunk's fragments are loaded before this chunk's MMAs.
-template <int NT, bool A_GLOBAL>
-__device__ __forceinline__ void sm_gemm(const __half* A, int lda, const __half* __restrict__ W, int K,
-                                        int m0, int n0, int lane, float (&acc)[2][NT][4]) {
-    const int g = lane >> 2, t = lane & 3;
-#pragma unroll
-    for (int mt = 0; mt < 2; ++mt)
-#pragma unroll
-        for (int nt = 0; nt < NT; ++nt)
-#pragma unroll
-            for (int i = 0; i < 4; ++i) acc[mt][nt][i] = 0.f;
-    const __half* a_base = A + (size_t)(m0 + g) * lda + 8 * t;
-    const __half* w_base = W + (size_t)(n0 + g) * K + 8 * t;
-    uint4 b0[NT], b1[NT], a0[4], a1[4];
-    auto load = [&](uint4 (&bb)[NT], uint4 (&aa)[4], int kc) {
-#pragma unroll
-        for (int nt = 0; nt < NT; ++nt)
-            bb[nt] = __ldg(reinterpret_cast<const uint4*>(w_base + (size_t)nt * 8 * K + kc));
-#pragma unroll
-        for (int i = 0; i < 4; ++i) {                        // i = 2 * mt + (row g / row g + 8)
-            const __half* p = a_base + (size_t)(8 * i) * lda + kc;
-            aa[i] = A_GLOBAL ? __ldcg(reinterpret_cast<const uint4*>(p)) : *reinterpret_cast<const uint4*>(p);
-        }
-    };
-    auto mmas = [&](const uint4 (&bb)[NT], const uint4 (&aa)[4]) {
-#pragma unroll
-        for (int nt = 0; nt < NT; ++nt)
-#pragma unroll
-            for (int mt = 0; mt < 2; ++mt) {
-                const uint32_t lo[4] = {aa[2 * mt].x, aa[2 * mt + 1].x, aa[2 * mt].y, aa[2 * mt + 1].y};
-                const uint32_t hi[4] = {aa[2 * mt].z, aa[2 * mt + 1].z, aa[2 * mt].w, aa[2 * mt + 1].w};
-                mma16816(acc[mt][nt], lo, bb[nt].x, bb[nt].y);
-                mma16816(acc[mt][nt], hi, bb[nt].z, bb[nt].w);
-            }
-    };
-    load(b0, a0, 0);
-    for (int kc = 0; kc < K; kc += 64) {
-        load(b1, a1, kc + 32);
-        mmas(b0, a0);
-        if (kc + 64 < K) load(b0, a0, kc + 64);
-        mmas(b1, a1);
-    }
-}
-
 __device__ __forceinline__ float gelu_erf(float x) { return 0.5f * x * (1.0f + erff(x * 0.70710678118654752f)); }
+__device__ __forceinline__ uint4 ldcg_u4(const void* p) { return __ldcg(reinterpret_cast<const uint4*>(p)); }
 
-// LayerNorm of the fp32 rows y[128][384] (written by the whole cluster) into this CTA's X tile.
-__device__ __forceinline__ void sm_layernorm(const float* __restrict__ y, const float* __restrict__ gam,
-                                             const float* __restrict__ bet, __half* xs, int warp, int lane) {
-    for (int r = warp * 16; r < warp * 16 + 16; ++r) {
-        float v[12];
-        float sum = 0.f;
+// a unit's B fragments: W rows n0 + g, k = kbase + 32 ch + 8 t .. + 8, ch = 0..11
+__device__ __forceinline__ void sm_unit_load(const __half* __restrict__ w_lane, uint4 (&b)[12]) {
 #pragma unroll
-        for (int j = 0; j < 3; ++j) {
-            const float4 q = __ldcg(reinterpret_cast<const float4*>(y + (size_t)r * kHidden + j * 128 + lane * 4));
-            v[4 * j] = q.x; v[4 * j + 1] = q.y; v[4 * j + 2] = q.z; v[4 * j + 3] = q.w;
-            sum += q.x + q.y + q.z + q.w;
-        }
+    for (int ch = 0; ch < 12; ++ch) b[ch] = __ldg(reinterpret_cast<const uint4*>(w_lane + 32 * ch));
+}
+// acc[mt] = A[16 mt .. + 16, 0:384] * Wunit^T, A in shared memory (rows kSmLd halves apart)
+template <int MT>
+__device__ __forceinline__ void sm_unit_mma(const __half* a_tile, const uint4 (&b)[12], int g, int t,
+                                            float (&acc)[MT][4]) {
 #pragma unroll
-        for (int lb = 16; lb > 0; lb >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, lb);
-        const float mean = sum * (1.0f / kHidden);
-        float var = 0.f;
+    for (int mt = 0; mt < MT; ++mt)
 #pragma unroll
-        for (int i = 0; i < 12; ++i) { const float d = v[i] - mean; var = fmaf(d, d, var); }
+        for (int i = 0; i < 4; ++i) acc[mt][i] = 0.f;
+    const __half* a_lane = a_tile + (size_t)g * kSmLd + 8 * t;
+    // 32 rows at a time over all of k (64-row tiles: two passes over the same B fragments, so that
+    // only two row blocks' A fragments and accumulators are live at once)
 #pragma unroll
-        for (int lb = 16; lb > 0; lb >>= 1) var += __shfl_xor_sync(0xffffffffu, var, lb);
-        const float rstd = 1.0f / sqrtf(var * (1.0f / kHidden) + kLnEps);
+    for (int mh = 0; mh < MT; mh += 2) {
 #pragma unroll
-        for (int j = 0; j < 3; ++j) {
-            const int c = j * 128 + lane * 4;
-            const float4 gg = __ldg(reinterpret_cast<const float4*>(gam + c));
-            const float4 bb = __ldg(reinterpret_cast<const float4*>(bet + c));
-            uint2 u;
-            u.x = pack_h2((v[4 * j] - mean) * rstd * gg.x + bb.x, (v[4 * j + 1] - mean) * rstd * gg.y + bb.y);
-            u.y = pack_h2((v[4 * j + 2] - mean) * rstd * gg.z + bb.z, (v[4 * j + 3] - mean) * rstd * gg.w + bb.w);
-            *reinterpret_cast<uint2*>(xs + (size_t)r * kSmLd + c) = u;
+        for (int ch = 0; ch < 12; ++ch) {
+#pragma unroll
+            for (int mt = mh; mt < mh + 2; ++mt) {
+                const uint4 a0 = *reinterpret_cast<const uint4*>(a_lane + (size_t)(16 * mt) * kSmLd + 32 * ch);
+                const uint4 a1 = *reinterpret_cast<const uint4*>(a_lane + (size_t)(16 * mt + 8) * kSmLd + 32 * ch);
+                const uint32_t lo[4] = {a0.x, a1.x, a0.y, a1.y};
+                const uint32_t hi[4] = {a0.z, a1.z, a0.w, a1.w};
+                mma16816(acc[mt], lo, b[ch].x, b[ch].y);
+                mma16816(acc[mt], hi, b[ch].z, b[ch].w);
+            }
         }
     }
 }
 
-// attention of ONE (sequence, head) pair by one warp (S <= 64): attention_kernel's arithmetic on
-// warp-private staging.
-__device__ __forceinline__ void sm_attention_pair(const __half* __restrict__ qkv, int seq, int head, int S,
-                                                  int len, __half* sK, __half* sV, __half* __restrict__ ctx,
-                                                  int lane) {
+// A warp's units of one GEMM, the next unit's weights in flight under the current unit's MMAs (one
+// copy of the unit's code: the loop is not unrolled, the double buffer is a register copy).
+// w_of(i): this lane's W pointer of unit i; epi(i, acc): the unit's epilogue; b0 holds unit 0's
+// weights on entry (loaded by the caller ahead of the barrier before).
+template <int MT, typename WOf, typename Epi>
+__device__ __forceinline__ void sm_units(int n_units, const __half* a_tile, int g, int t, WOf w_of, Epi epi,
+                                         uint4 (&b0)[12]) {
+    uint4 b1[12];
+    float acc[MT][4];
+#pragma unroll 1
+    for (int i = 0; i < n_units; ++i) {
+        if (i + 1 < n_units) sm_unit_load(w_of(i + 1), b1);
+        sm_unit_mma<MT>(a_tile, b0, g, t, acc);
+        epi(i, acc);
+        if (i + 1 < n_units) {
+#pragma unroll
+            for (int ch = 0; ch < 12; ++ch) b0[ch] = b1[ch];
+        }
+    }
+}
+
+// LayerNorm of row `r`: v[12] = the lane's 12 values (columns j*128 + lane*4 ..), result -> xs row
+__device__ __forceinline__ void sm_ln_row(float (&v)[12], const float* __restrict__ gam,
+                                          const float* __restrict__ bet, __half* xrow, int lane) {
+    float sum = 0.f;
+#pragma unroll
+    for (int i = 0; i < 12; ++i) sum += v[i];
+#pragma unroll
+    for (int lb = 16; lb > 0; lb >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, lb);
+    const float mean = sum * (1.0f / kHidden);
+    float var = 0.f;
+#pragma unroll
+    for (int i = 0; i < 12; ++i) { const float d = v[i] - mean; var = fmaf(d, d, var); }
+#pragma unroll
+    for (int lb = 16; lb > 0; lb >>= 1) var += __shfl_xor_sync(0xffffffffu, var, lb);
+    const float rstd = 1.0f / sqrtf(var * (1.0f / kHidden) + kLnEps);
+#pragma unroll
+    for (int j = 0; j < 3; ++j) {
+        const int c = j * 128 + lane * 4;
+        const float4 gg = __ldg(reinterpret_cast<const float4*>(gam + c));
+        const float4 bb = __ldg(reinterpret_cast<const float4*>(bet + c));
+        uint2 u;
+        u.x = pack_h2((v[4 * j] - mean) * rstd * gg.x + bb.x, (v[4 * j + 1] - mean) * rstd * gg.y + bb.y);
+        u.y = pack_h2((v[4 * j + 2] - mean) * rstd * gg.z + bb.z, (v[4 * j + 3] - mean) * rstd * gg.w + bb.w);
+        *reinterpret_cast<uint2*>(xrow + c) = u;
+    }
+}
+
+// attention of ONE (sequence, head) pair by one warp, S <= 16 MT keys: attention_kernel's arithmetic
+// (one softmax block) on warp-private staging.  qkv / ctx: the group's scratch, row0 = the
+// sequence's first row in it.
+template <int MT>
+__device__ __forceinline__ void sm_attention_pair(const __half* qkv, int row0, int head, int S, int len,
+                                                  __half* sK, __half* sV, __half* ctx, int lane) {
+    constexpr int NKB = 2 * MT;                              // 8-key blocks
     const int g = lane >> 2, t = lane & 3;
-    const __half* base = qkv + (size_t)seq * S * kQkv + head * kHeadDim;
+    const __half* base = qkv + (size_t)row0 * kQkv + head * kHeadDim;
     __syncwarp();                                            // the previous pair's reads are done
-    for (int i = lane; i < 64 * 4; i += 32) {
+    for (int i = lane; i < 16 * MT * 4; i += 32) {
         const int s = i >> 2, part = i & 3;
         const int sr = s < len ? s : 0;
         const uint32_t nbytes = s < len ? 16u : 0u;
@@ -523,16 +550,15 @@ __device__ __forceinline__ void sm_attention_pair(const __half* __restrict__ qkv
                      ::"r"(smem_u32(sV + s * kKPad + part * 8)), "l"(kp + kHidden), "r"(nbytes) : "memory");
     }
     asm volatile("cp.async.commit_group;" ::: "memory");
-    asm volatile("cp.async.wait_all;" ::: "memory");
-    __syncwarp();
     const float scale2 = 0.17677669529663687f * 1.4426950408889634f;
     const int lm = lane >> 3, lr = lane & 7;
     const int n_qtiles = (S + 15) >> 4;
+    bool staged = false;
     for (int qt = 0; qt < n_qtiles; ++qt) {
         const int q0 = qt * 16;
         const int r0 = q0 + g, r1 = q0 + g + 8;
-        __half* o0 = ctx + ((size_t)seq * S + r0) * kHidden + head * kHeadDim;
-        __half* o1 = ctx + ((size_t)seq * S + r1) * kHidden + head * kHeadDim;
+        __half* o0 = ctx + (size_t)(row0 + r0) * kHidden + head * kHeadDim;
+        __half* o1 = ctx + (size_t)(row0 + r1) * kHidden + head * kHeadDim;
         if (q0 >= len) {                                      // padding tile: zeros
 #pragma unroll
             for (int nd = 0; nd < 4; ++nd) {
@@ -551,9 +577,14 @@ __device__ __forceinline__ void sm_attention_pair(const __half* __restrict__ qkv
             qa[ks][2] = (r0 < len) ? __ldcg(reinterpret_cast<const uint32_t*>(q0p + 8)) : 0u;
             qa[ks][3] = (r1 < len) ? __ldcg(reinterpret_cast<const uint32_t*>(q1p + 8)) : 0u;
         }
-        float sc[8][4];
+        if (!staged) {
+            asm volatile("cp.async.wait_all;" ::: "memory");
+            __syncwarp();
+            staged = true;
+        }
+        float sc[NKB][4];
 #pragma unroll
-        for (int j = 0; j < 8; ++j) {
+        for (int j = 0; j < NKB; ++j) {
 #pragma unroll
             for (int i = 0; i < 4; ++i) sc[j][i] = 0.f;
             uint32_t kf[4];
@@ -562,14 +593,14 @@ __device__ __forceinline__ void sm_attention_pair(const __half* __restrict__ qkv
             mma16816(sc[j], qa[1], kf[2], kf[3]);
         }
 #pragma unroll
-        for (int j = 0; j < 8; ++j) {                        // mask keys >= len
+        for (int j = 0; j < NKB; ++j) {                      // mask keys >= len
             const int key = j * 8 + 2 * t;
             if (key >= len) { sc[j][0] = -INFINITY; sc[j][2] = -INFINITY; }
             if (key + 1 >= len) { sc[j][1] = -INFINITY; sc[j][3] = -INFINITY; }
         }
         float m0 = -INFINITY, m1 = -INFINITY;
 #pragma unroll
-        for (int j = 0; j < 8; ++j) {
+        for (int j = 0; j < NKB; ++j) {
             m0 = fmaxf(m0, fmaxf(sc[j][0], sc[j][1]));
             m1 = fmaxf(m1, fmaxf(sc[j][2], sc[j][3]));
         }
@@ -580,7 +611,7 @@ __device__ __forceinline__ void sm_attention_pair(const __half* __restrict__ qkv
         const float nm0 = -m0 * scale2, nm1 = -m1 * scale2;   // finite: key 0 < len
         float l0 = 0.f, l1 = 0.f;
 #pragma unroll
-        for (int j = 0; j < 8; ++j) {
+        for (int j = 0; j < NKB; ++j) {
             sc[j][0] = ex2(fmaf(sc[j][0], scale2, nm0));
             sc[j][1] = ex2(fmaf(sc[j][1], scale2, nm0));
             sc[j][2] = ex2(fmaf(sc[j][2], scale2, nm1));
@@ -594,7 +625,7 @@ __device__ __forceinline__ void sm_attention_pair(const __half* __restrict__ qkv
 #pragma unroll
             for (int i = 0; i < 4; ++i) o[nd][i] = 0.f;
 #pragma unroll
-        for (int kk = 0; kk < 4; ++kk) {
+        for (int kk = 0; kk < MT; ++kk) {
             uint32_t pa[4];
             pa[0] = pack_h2(sc[2 * kk][0], sc[2 * kk][1]);
             pa[1] = pack_h2(sc[2 * kk][2], sc[2 * kk][3]);
@@ -623,34 +654,50 @@ __device__ __forceinline__ void sm_attention_pair(const __half* __restrict__ qkv
                     (r1 < len) ? pack_h2(o[nd][2] * i1, o[nd][3] * i1) : 0u;
         }
     }
+    if (!staged) asm volatile("cp.async.wait_all;" ::: "memory");   // len == 0: nothing was consumed
 }
 
+template <int MT>
 __global__ void __launch_bounds__(kSmThreads, 1)
 encoder_small_kernel(const SmallParams P) {
+    using G = SmGeom<MT>;
+    constexpr int M = G::M;
     extern __shared__ __align__(16) unsigned char sm_raw[];
-    __half* xs = reinterpret_cast<__half*>(sm_raw);                          // [128][kSmLd]
+    __half* xs = reinterpret_cast<__half*>(sm_raw);                       // [M][kSmLd] activations X
+    __half* as = reinterpret_cast<__half*>(sm_raw + G::tile_bytes);       // [M][kSmLd] staged A operand
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int g = lane >> 2, t = lane & 3;
     const int c = (int)cluster_ctarank();
-    const int T = P.B * P.S;
-    __half* sK = reinterpret_cast<__half*>(sm_raw + (size_t)kSmRows * kSmLd * 2 + (size_t)warp * kSmAttnBytes);
-    __half* sV = sK + 64 * kKPad;
-    const int wm = warp & 3, wn = warp >> 2;                 // 4 row blocks of 32 x 2 column halves
-    const int m0 = 32 * wm;
+    const int grp = blockIdx.x / kSmCtas;
+    const int wid = c * kSmWarps + warp;                     // warp of the cluster, 0..63
+    const int seq0 = grp * P.spg;
+    const int nseq = min(P.spg, P.B - seq0);
+    const int T = nseq * P.S;                                // rows in use
+    unsigned char* sc_base = P.scratch + (size_t)grp * G::scratch;
+    __half* s_qkv = reinterpret_cast<__half*>(sc_base + G::o_qkv);
+    __half* s_ctx = reinterpret_cast<__half*>(sc_base + G::o_ctx);
+    __half* s_ff = reinterpret_cast<__half*>(sc_base + G::o_ff);
+    float* s_y = reinterpret_cast<float*>(sc_base + G::o_y);
+    float* s_yp = reinterpret_cast<float*>(sc_base + G::o_ypart);
+    uint4 bw[12];                                            // a unit's weights, loaded ahead
+
+    // the first GEMM's first weights go out before anything else
+    const int n_qkv = (wid < 144 - 128) ? 3 : 2;             // 144 units over 64 warps
+    auto w_qkv = [&](int l, int i) { return P.L[l].wqkv + (size_t)(8 * (wid + 64 * i) + g) * kHidden + 8 * t; };
+    sm_unit_load(w_qkv(0, 0), bw);
 
     // ---- embeddings + LayerNorm, every row of X in every CTA (rows >= T: zeros)
-    for (int r = warp * 16; r < warp * 16 + 16; ++r) {
+    for (int r = warp; r < M; r += kSmWarps) {
+        __half* xrow = xs + (size_t)r * kSmLd;
         if (r >= T) {
-            for (int cc = lane * 4; cc < kHidden; cc += 128)
-                *reinterpret_cast<uint2*>(xs + (size_t)r * kSmLd + cc) = make_uint2(0u, 0u);
+            for (int cc = lane * 4; cc < kHidden; cc += 128) *reinterpret_cast<uint2*>(xrow + cc) = make_uint2(0u, 0u);
             continue;
         }
-        int id = P.ids[r];
+        int id = P.ids[(size_t)seq0 * P.S + r];
         id = (id < 0 || id >= P.vocab) ? 0 : id;
         int sp = r % P.S;
         sp = (sp >= P.max_pos) ? P.max_pos - 1 : sp;
         float v[12];
-        float sum = 0.f;
 #pragma unroll
         for (int j = 0; j < 3; ++j) {
             const int cc = j * 128 + lane * 4;
@@ -661,133 +708,157 @@ encoder_small_kernel(const SmallParams P) {
             v[4 * j + 1] = w.y + p.y + ty.y;
             v[4 * j + 2] = w.z + p.z + ty.z;
             v[4 * j + 3] = w.w + p.w + ty.w;
-            sum += v[4 * j] + v[4 * j + 1] + v[4 * j + 2] + v[4 * j + 3];
         }
-#pragma unroll
-        for (int lb = 16; lb > 0; lb >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, lb);
-        const float mean = sum * (1.0f / kHidden);
-        float var = 0.f;
-#pragma unroll
-        for (int i = 0; i < 12; ++i) { const float d = v[i] - mean; var = fmaf(d, d, var); }
-#pragma unroll
-        for (int lb = 16; lb > 0; lb >>= 1) var += __shfl_xor_sync(0xffffffffu, var, lb);
-        const float rstd = 1.0f / sqrtf(var * (1.0f / kHidden) + kLnEps);
-#pragma unroll
-        for (int j = 0; j < 3; ++j) {
-            const int cc = j * 128 + lane * 4;
-            const float4 gg = __ldg(reinterpret_cast<const float4*>(P.eln_g + cc));
-            const float4 bb = __ldg(reinterpret_cast<const float4*>(P.eln_b + cc));
-            uint2 u;
-            u.x = pack_h2((v[4 * j] - mean) * rstd * gg.x + bb.x, (v[4 * j + 1] - mean) * rstd * gg.y + bb.y);
-            u.y = pack_h2((v[4 * j + 2] - mean) * rstd * gg.z + bb.z, (v[4 * j + 3] - mean) * rstd * gg.w + bb.w);
-            *reinterpret_cast<uint2*>(xs + (size_t)r * kSmLd + cc) = u;
-        }
+        sm_ln_row(v, P.eln_g, P.eln_b, xrow, lane);
     }
     __syncthreads();
 
     for (int l = 0; l < kLayers; ++l) {
         const SmallLayer& L = P.L[l];
-        // ---- (1) QKV projection: columns [144 c, 144 c + 144)
-        {
-            float acc[2][9][4];
-            const int n0 = 144 * c + 72 * wn;
-            sm_gemm<9, false>(xs, kSmLd, L.wqkv, kHidden, m0, n0, lane, acc);
+        // ---- (1) QKV projection -> scratch qkv (fp16)
+        sm_units<MT>(n_qkv, xs, g, t, [&](int i) { return w_qkv(l, i); },
+                     [&](int i, float (&acc)[MT][4]) {
+                         const int col = 8 * (wid + 64 * i) + 2 * t;
+                         const float2 bb = __ldg(reinterpret_cast<const float2*>(L.bqkv + col));
 #pragma unroll
-            for (int nt = 0; nt < 9; ++nt) {
-                const int col = n0 + 8 * nt + 2 * t;
-                const float2 bb = __ldg(reinterpret_cast<const float2*>(L.bqkv + col));
-#pragma unroll
-                for (int mt = 0; mt < 2; ++mt) {
-                    const int r0 = m0 + 16 * mt + g;
-                    *reinterpret_cast<uint32_t*>(P.qkv + (size_t)r0 * kQkv + col) =
-                        pack_h2(acc[mt][nt][0] + bb.x, acc[mt][nt][1] + bb.y);
-                    *reinterpret_cast<uint32_t*>(P.qkv + (size_t)(r0 + 8) * kQkv + col) =
-                        pack_h2(acc[mt][nt][2] + bb.x, acc[mt][nt][3] + bb.y);
-                }
+                         for (int mt = 0; mt < MT; ++mt) {
+                             const int r0 = 16 * mt + g;
+                             *reinterpret_cast<uint32_t*>(s_qkv + (size_t)r0 * kQkv + col) =
+                                 pack_h2(acc[mt][0] + bb.x, acc[mt][1] + bb.y);
+                             *reinterpret_cast<uint32_t*>(s_qkv + (size_t)(r0 + 8) * kQkv + col) =
+                                 pack_h2(acc[mt][2] + bb.x, acc[mt][3] + bb.y);
+                         }
+                     }, bw);
+        // the output projection's weights travel under the attention
+        const bool has_o = wid < 48;
+        if (MT == 2 && has_o) sm_unit_load(L.wo + (size_t)(8 * wid + g) * kHidden + 8 * t, bw);
+        cluster_sync_all();
+        // ---- (2) attention: (sequence, head) pairs over kSmAttnWarps warps per CTA
+        if (warp < kSmAttnWarps) {
+            __half* sK = as + (size_t)warp * (2 * 16 * MT * kKPad);
+            __half* sV = sK + 16 * MT * kKPad;
+            for (int p = c * kSmAttnWarps + warp; p < nseq * kHeads; p += kSmCtas * kSmAttnWarps) {
+                const int sq = p / kHeads, head = p - sq * kHeads;
+                int len = P.lens[seq0 + sq];
+                len = len < 0 ? 0 : (len > P.S ? P.S : len);
+                sm_attention_pair<MT>(s_qkv, sq * P.S, head, P.S, len, sK, sV, s_ctx, lane);
             }
         }
         cluster_sync_all();
-        // ---- (2) attention: one (sequence, head) pair per warp of the cluster
-        for (int p = c * (kSmThreads / 32) + warp; p < P.B * kHeads; p += kSmCtas * (kSmThreads / 32)) {
-            const int seq = p / kHeads, head = p - seq * kHeads;
-            int len = P.lens[seq];
-            len = len < 0 ? 0 : (len > P.S ? P.S : len);
-            sm_attention_pair(P.qkv, seq, head, P.S, len, sK, sV, P.ctx, lane);
+        // ---- (3) output projection + residual -> scratch y (fp32); A = ctx staged from the scratch
+        for (int i = tid; i < M * 48; i += kSmThreads) {
+            const int r = i / 48, part = i - r * 48;
+            asm volatile("cp.async.cg.shared.global [%0], [%1], 16;"
+                         ::"r"(smem_u32(as + (size_t)r * kSmLd + part * 8)), "l"(s_ctx + (size_t)r * kHidden + part * 8)
+                         : "memory");
         }
-        cluster_sync_all();
-        // ---- (3) output projection + residual -> y (fp32), columns [48 c, 48 c + 48); LayerNorm
-        {
-            float acc[2][3][4];
-            const int n0 = 48 * c + 24 * wn;
-            sm_gemm<3, true>(P.ctx, kHidden, L.wo, kHidden, m0, n0, lane, acc);
-#pragma unroll
-            for (int nt = 0; nt < 3; ++nt) {
-                const int col = n0 + 8 * nt + 2 * t;
-                const float2 bb = __ldg(reinterpret_cast<const float2*>(L.bo + col));
-#pragma unroll
-                for (int mt = 0; mt < 2; ++mt) {
-                    const int r0 = m0 + 16 * mt + g;
-                    const float2 x0 = __half22float2(*reinterpret_cast<const __half2*>(xs + (size_t)r0 * kSmLd + col));
-                    const float2 x1 = __half22float2(*reinterpret_cast<const __half2*>(xs + (size_t)(r0 + 8) * kSmLd + col));
-                    *reinterpret_cast<float2*>(P.y + (size_t)r0 * kHidden + col) =
-                        make_float2(acc[mt][nt][0] + bb.x + x0.x, acc[mt][nt][1] + bb.y + x0.y);
-                    *reinterpret_cast<float2*>(P.y + (size_t)(r0 + 8) * kHidden + col) =
-                        make_float2(acc[mt][nt][2] + bb.x + x1.x, acc[mt][nt][3] + bb.y + x1.y);
-                }
-            }
-        }
-        cluster_sync_all();
-        sm_layernorm(P.y, L.ln1_g, L.ln1_b, xs, warp, lane);
+        asm volatile("cp.async.commit_group;" ::: "memory");
+        if (MT != 2 && has_o)                                   // (64-row tiles: registers are short during attention)
+            sm_unit_load(L.wo + (size_t)(8 * wid + g) * kHidden + 8 * t, bw);
+        asm volatile("cp.async.wait_all;" ::: "memory");
         __syncthreads();
-        // ---- (4) FFN up + GELU: columns [192 c, 192 c + 192), two passes of 6 column tiles per warp
-#pragma unroll 1
-        for (int pass = 0; pass < 2; ++pass) {
-            float acc[2][6][4];
-            const int n0 = 192 * c + 96 * wn + 48 * pass;
-            sm_gemm<6, false>(xs, kSmLd, L.w1, kHidden, m0, n0, lane, acc);
+        sm_units<MT>(has_o ? 1 : 0, as, g, t, [&](int) { return L.wo; },
+                     [&](int, float (&acc)[MT][4]) {
+                         const int col = 8 * wid + 2 * t;
+                         const float2 bb = __ldg(reinterpret_cast<const float2*>(L.bo + col));
 #pragma unroll
-            for (int nt = 0; nt < 6; ++nt) {
-                const int col = n0 + 8 * nt + 2 * t;
-                const float2 bb = __ldg(reinterpret_cast<const float2*>(L.b1 + col));
-#pragma unroll
-                for (int mt = 0; mt < 2; ++mt) {
-                    const int r0 = m0 + 16 * mt + g;
-                    *reinterpret_cast<uint32_t*>(P.ff + (size_t)r0 * kFfn + col) =
-                        pack_h2(gelu_erf(acc[mt][nt][0] + bb.x), gelu_erf(acc[mt][nt][1] + bb.y));
-                    *reinterpret_cast<uint32_t*>(P.ff + (size_t)(r0 + 8) * kFfn + col) =
-                        pack_h2(gelu_erf(acc[mt][nt][2] + bb.x), gelu_erf(acc[mt][nt][3] + bb.y));
-                }
-            }
-        }
+                         for (int mt = 0; mt < MT; ++mt) {
+                             const int r0 = 16 * mt + g;
+                             const float2 x0 = __half22float2(*reinterpret_cast<const __half2*>(xs + (size_t)r0 * kSmLd + col));
+                             const float2 x1 = __half22float2(*reinterpret_cast<const __half2*>(xs + (size_t)(r0 + 8) * kSmLd + col));
+                             *reinterpret_cast<float2*>(s_y + (size_t)r0 * kHidden + col) =
+                                 make_float2(acc[mt][0] + bb.x + x0.x, acc[mt][1] + bb.y + x0.y);
+                             *reinterpret_cast<float2*>(s_y + (size_t)(r0 + 8) * kHidden + col) =
+                                 make_float2(acc[mt][2] + bb.x + x1.x, acc[mt][3] + bb.y + x1.y);
+                         }
+                     }, bw);
+        // FFN up: 192 units, three per warp; the first one's weights travel under the barrier + LayerNorm
+        auto w_up = [&](int i) { return L.w1 + (size_t)(8 * (wid + 64 * i) + g) * kHidden + 8 * t; };
+        sm_unit_load(w_up(0), bw);
         cluster_sync_all();
-        // ---- (5) FFN down + residual -> y, columns [48 c, 48 c + 48); LayerNorm
-        {
-            float acc[2][3][4];
-            const int n0 = 48 * c + 24 * wn;
-            sm_gemm<3, true>(P.ff, kFfn, L.w2, kFfn, m0, n0, lane, acc);
+        // ---- (4) LayerNorm 1 (every CTA, all rows) -> X; FFN up + GELU -> scratch ff (fp16)
+        for (int r = warp; r < M; r += kSmWarps) {
+            float v[12];
 #pragma unroll
-            for (int nt = 0; nt < 3; ++nt) {
-                const int col = n0 + 8 * nt + 2 * t;
-                const float2 bb = __ldg(reinterpret_cast<const float2*>(L.b2 + col));
-#pragma unroll
-                for (int mt = 0; mt < 2; ++mt) {
-                    const int r0 = m0 + 16 * mt + g;
-                    const float2 x0 = __half22float2(*reinterpret_cast<const __half2*>(xs + (size_t)r0 * kSmLd + col));
-                    const float2 x1 = __half22float2(*reinterpret_cast<const __half2*>(xs + (size_t)(r0 + 8) * kSmLd + col));
-                    *reinterpret_cast<float2*>(P.y + (size_t)r0 * kHidden + col) =
-                        make_float2(acc[mt][nt][0] + bb.x + x0.x, acc[mt][nt][1] + bb.y + x0.y);
-                    *reinterpret_cast<float2*>(P.y + (size_t)(r0 + 8) * kHidden + col) =
-                        make_float2(acc[mt][nt][2] + bb.x + x1.x, acc[mt][nt][3] + bb.y + x1.y);
-                }
+            for (int j = 0; j < 3; ++j) {
+                const float4 q = __ldcg(reinterpret_cast<const float4*>(s_y + (size_t)r * kHidden + j * 128 + lane * 4));
+                v[4 * j] = q.x; v[4 * j + 1] = q.y; v[4 * j + 2] = q.z; v[4 * j + 3] = q.w;
             }
+            sm_ln_row(v, L.ln1_g, L.ln1_b, xs + (size_t)r * kSmLd, lane);
         }
+        __syncthreads();
+        sm_units<MT>(3, xs, g, t, w_up,
+                     [&](int i, float (&acc)[MT][4]) {
+                         const int col = 8 * (wid + 64 * i) + 2 * t;
+                         const float2 bb = __ldg(reinterpret_cast<const float2*>(L.b1 + col));
+#pragma unroll
+                         for (int mt = 0; mt < MT; ++mt) {
+                             const int r0 = 16 * mt + g;
+                             *reinterpret_cast<uint32_t*>(s_ff + (size_t)r0 * kFfn + col) =
+                                 pack_h2(gelu_erf(acc[mt][0] + bb.x), gelu_erf(acc[mt][1] + bb.y));
+                             *reinterpret_cast<uint32_t*>(s_ff + (size_t)(r0 + 8) * kFfn + col) =
+                                 pack_h2(gelu_erf(acc[mt][2] + bb.x), gelu_erf(acc[mt][3] + bb.y));
+                         }
+                     }, bw);
+        // FFN down: CTA c owns k quarter c & 3 of column tiles (c >> 2) * 24 .. + 24, three per warp
+        const int kq = c & 3;
+        auto w_dn = [&](int i) {
+            return L.w2 + (size_t)(8 * ((c >> 2) * 24 + warp + 8 * i) + g) * kFfn + kq * kHidden + 8 * t;
+        };
+        sm_unit_load(w_dn(0), bw);
         cluster_sync_all();
-        sm_layernorm(P.y, L.ln2_g, L.ln2_b, xs, warp, lane);
+        // ---- (5) FFN down: partial sums over this CTA's k quarter -> scratch ypart[kq] (fp32)
+        for (int i = tid; i < M * 48; i += kSmThreads) {
+            const int r = i / 48, part = i - r * 48;
+            asm volatile("cp.async.cg.shared.global [%0], [%1], 16;"
+                         ::"r"(smem_u32(as + (size_t)r * kSmLd + part * 8)),
+                           "l"(s_ff + (size_t)r * kFfn + kq * kHidden + part * 8)
+                         : "memory");
+        }
+        asm volatile("cp.async.commit_group;" ::: "memory");
+        asm volatile("cp.async.wait_all;" ::: "memory");
+        __syncthreads();
+        sm_units<MT>(3, as, g, t, w_dn,
+                     [&](int i, float (&acc)[MT][4]) {
+                         const int col = 8 * ((c >> 2) * 24 + warp + 8 * i) + 2 * t;
+                         float* yp = s_yp + (size_t)kq * M * kHidden;
+#pragma unroll
+                         for (int mt = 0; mt < MT; ++mt) {
+                             const int r0 = 16 * mt + g;
+                             *reinterpret_cast<float2*>(yp + (size_t)r0 * kHidden + col) = make_float2(acc[mt][0], acc[mt][1]);
+                             *reinterpret_cast<float2*>(yp + (size_t)(r0 + 8) * kHidden + col) = make_float2(acc[mt][2], acc[mt][3]);
+                         }
+                     }, bw);
+        if (l + 1 < kLayers) sm_unit_load(w_qkv(l + 1, 0), bw);
+        cluster_sync_all();
+        // ---- (6) the four k quarters in order + bias + residual, LayerNorm 2 -> X
+        for (int r = warp; r < M; r += kSmWarps) {
+            float v[12];
+            __half* xrow = xs + (size_t)r * kSmLd;
+#pragma unroll
+            for (int j = 0; j < 3; ++j) {
+                const int cc = j * 128 + lane * 4;
+                const size_t o = (size_t)r * kHidden + cc;
+                const float4 p0 = __ldcg(reinterpret_cast<const float4*>(s_yp + o));
+                const float4 p1 = __ldcg(reinterpret_cast<const float4*>(s_yp + (size_t)M * kHidden + o));
+                const float4 p2 = __ldcg(reinterpret_cast<const float4*>(s_yp + 2 * (size_t)M * kHidden + o));
+                const float4 p3 = __ldcg(reinterpret_cast<const float4*>(s_yp + 3 * (size_t)M * kHidden + o));
+                const float4 bb = __ldg(reinterpret_cast<const float4*>(L.b2 + cc));
+                const float2 xa = __half22float2(*reinterpret_cast<const __half2*>(xrow + cc));
+                const float2 xb = __half22float2(*reinterpret_cast<const __half2*>(xrow + cc + 2));
+                v[4 * j + 0] = (((p0.x + p1.x) + p2.x) + p3.x) + bb.x + xa.x;
+                v[4 * j + 1] = (((p0.y + p1.y) + p2.y) + p3.y) + bb.y + xa.y;
+                v[4 * j + 2] = (((p0.z + p1.z) + p2.z) + p3.z) + bb.z + xb.x;
+                v[4 * j + 3] = (((p0.w + p1.w) + p2.w) + p3.w) + bb.w + xb.y;
+            }
+            __syncwarp();                                    // the whole row was read before it is rewritten
+            sm_ln_row(v, L.ln2_g, L.ln2_b, xrow, lane);
+        }
         __syncthreads();
     }
 
-    // ---- pooling + Normalize + normalize_L2: sequence b on CTA b % 8 (columns tid and tid + 256)
-    __shared__ float red[kSmThreads / 32];
+    // ---- pooling + Normalize + normalize_L2: sequence i of the group on CTA i % 8
+    __shared__ float red[kSmWarps];
     auto block_sum = [&](float v) -> float {
 #pragma unroll
         for (int lb = 16; lb > 0; lb >>= 1) v += __shfl_xor_sync(0xffffffffu, v, lb);
@@ -796,16 +867,16 @@ encoder_small_kernel(const SmallParams P) {
         __syncthreads();
         float s = 0.f;
 #pragma unroll
-        for (int i = 0; i < kSmThreads / 32; ++i) s += red[i];
+        for (int i = 0; i < kSmWarps; ++i) s += red[i];
         return s;
     };
-    for (int b = c; b < P.B; b += kSmCtas) {
-        int len = P.lens[b];
+    for (int sq = c; sq < nseq; sq += kSmCtas) {
+        int len = P.lens[seq0 + sq];
         len = len < 0 ? 0 : (len > P.S ? P.S : len);
         const bool two = tid + 256 < kHidden;
         float a0 = 0.f, a1 = 0.f;
         for (int sidx = 0; sidx < len; ++sidx) {
-            const __half* row = xs + (size_t)(b * P.S + sidx) * kSmLd;
+            const __half* row = xs + (size_t)(sq * P.S + sidx) * kSmLd;
             a0 += __half2float(row[tid]);
             if (two) a1 += __half2float(row[tid + 256]);
         }
@@ -818,7 +889,7 @@ encoder_small_kernel(const SmallParams P) {
             const float inv = 1.0f / sqrtf(sq2);
             a0 *= inv; a1 *= inv;
         }
-        const size_t o = (size_t)b * kHidden;
+        const size_t o = (size_t)(seq0 + sq) * kHidden;
         if (P.out_f32 != nullptr) { P.out_f32[o + tid] = a0; if (two) P.out_f32[o + tid + 256] = a1; }
         if (P.out_f16 != nullptr) {
             P.out_f16[o + tid] = __float2half_rn(a0);
@@ -835,7 +906,7 @@ void encoder_free(lrx_handle* h) {
     if (e == nullptr) return;
     if (e->blob) cudaFree(e->blob);
     if (e->act) cudaFree(e->act);
-    if (e->ybuf) cudaFree(e->ybuf);
+    if (e->small_ws) cudaFree(e->small_ws);
     if (e->io) cudaFree(e->io);
     if (e->io_host) cudaFreeHost(e->io_host);
     delete e;
@@ -879,7 +950,6 @@ cudaError_t encoder_set_weights(lrx_handle* h, const lrx_bert_weights* w) {
         for (int i = 8; i < 12; ++i) o_l[l][i] = take(kHidden * 4);
     }
     ENC_CK(cudaMalloc(&e->blob, off));
-    ENC_CK(cudaMalloc((void**)&e->ybuf, (size_t)kSmRows * kHidden * sizeof(float)));
     char* B = (char*)e->blob;
     cudaStream_t st = h->stream;
     auto cpy = [&](size_t o, const float* src, size_t n) {
@@ -965,26 +1035,40 @@ static cudaError_t encoder_reserve(Encoder* e, int64_t tokens) {
 }
 
 
-// Query-sized batches (<= 128 tokens, S <= 64): the whole forward pass as ONE launch of a cluster of 8.
+// Query-sized sequences (S <= 64): the whole forward pass as ONE launch, a cluster of 8 CTAs per
+// group of sequences (at most 32 / 64 tokens); kSmMaxGroups groups per launch.
+template <int MT>
 static cudaError_t encoder_forward_small(lrx_handle* h, Encoder* e, const int32_t* ids, const int32_t* lens,
                                          int B, int S, float* out_f32, void* out_f16) {
-    if (e->cap < kSmRows) {
+    using G = SmGeom<MT>;
+    const int spg = G::M / S;                                  // sequences per group, >= 1
+    const int groups_all = (B + spg - 1) / spg;
+    const int groups_max = groups_all < kSmMaxGroups ? groups_all : kSmMaxGroups;
+    const size_t need = (size_t)groups_max * G::scratch;
+    if (e->small_ws_bytes < need) {
         if (h->capturing) return cudaErrorStreamCaptureUnsupported;
+        ENC_CK(cudaStreamSynchronize(h->stream));
+        if (e->small_ws) cudaFree(e->small_ws);
+        e->small_ws = nullptr; e->small_ws_bytes = 0;
         h->ws_epoch++;
-        ENC_CK(encoder_reserve(e, kSmRows));
+        ENC_CK(cudaMalloc(&e->small_ws, need));
+        // rows of the scratch that no sequence owns are read (row-wise, never mixed with real rows)
+        // but never written: keep them finite
+        ENC_CK(cudaMemsetAsync(e->small_ws, 0, need, h->stream));
+        e->small_ws_bytes = need;
     }
     {
         std::lock_guard<std::recursive_mutex> attr_guard(attr_mutex());   // the flags below are process-wide
         static bool attr_dev[64] = {false};   // function attributes are per device
         bool& attr = attr_dev[h->device & 63];
         if (!attr) {
-            ENC_CK(cudaFuncSetAttribute(encoder_small_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                        (int)kSmSmem));
+            ENC_CK(cudaFuncSetAttribute(encoder_small_kernel<MT>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                        (int)G::smem));
             attr = true;
         }
     }
     SmallParams P;
-    P.ids = ids; P.lens = lens; P.B = B; P.S = S; P.vocab = e->vocab; P.max_pos = e->max_pos;
+    P.S = S; P.spg = spg; P.vocab = e->vocab; P.max_pos = e->max_pos;
     P.word = e->word; P.pos = e->pos; P.type0 = e->type0; P.eln_g = e->eln_g; P.eln_b = e->eln_b;
     for (int l = 0; l < kLayers; ++l) {
         const EncLayer& s = e->L[l];
@@ -993,30 +1077,54 @@ static cudaError_t encoder_forward_small(lrx_handle* h, Encoder* e, const int32_
         d.bqkv = s.bqkv; d.bo = s.bo; d.b1 = s.b1; d.b2 = s.b2;
         d.ln1_g = s.ln1_g; d.ln1_b = s.ln1_b; d.ln2_g = s.ln2_g; d.ln2_b = s.ln2_b;
     }
-    P.qkv = e->qkv; P.ctx = e->ctx; P.ff = e->ff; P.y = e->ybuf;
-    P.out_f32 = out_f32; P.out_f16 = (__half*)out_f16;
-    cudaLaunchConfig_t cfg = {};
-    cfg.gridDim = dim3(kSmCtas);
-    cfg.blockDim = dim3(kSmThreads);
-    cfg.dynamicSmemBytes = kSmSmem;
-    cfg.stream = h->stream;
-    cudaLaunchAttribute at[1];
-    at[0].id = cudaLaunchAttributeClusterDimension;
-    at[0].val.clusterDim.x = kSmCtas;
-    at[0].val.clusterDim.y = 1;
-    at[0].val.clusterDim.z = 1;
-    cfg.attrs = at;
-    cfg.numAttrs = 1;
-    ENC_CK(cudaLaunchKernelEx(&cfg, encoder_small_kernel, P));
-    h->launches++;
+    P.scratch = (unsigned char*)e->small_ws;
+    for (int g0 = 0; g0 < groups_all; g0 += groups_max) {
+        const int ng = (groups_all - g0) < groups_max ? (groups_all - g0) : groups_max;
+        const int b0 = g0 * spg;
+        P.ids = ids + (size_t)b0 * S; P.lens = lens + b0;
+        P.B = (B - b0) < ng * spg ? (B - b0) : ng * spg;
+        P.out_f32 = out_f32 ? out_f32 + (size_t)b0 * kHidden : nullptr;
+        P.out_f16 = out_f16 ? (__half*)out_f16 + (size_t)b0 * kHidden : nullptr;
+        cudaLaunchConfig_t cfg = {};
+        cfg.gridDim = dim3(kSmCtas * ng);
+        cfg.blockDim = dim3(kSmThreads);
+        cfg.dynamicSmemBytes = G::smem;
+        cfg.stream = h->stream;
+        cudaLaunchAttribute at[1];
+        at[0].id = cudaLaunchAttributeClusterDimension;
+        at[0].val.clusterDim.x = kSmCtas;
+        at[0].val.clusterDim.y = 1;
+        at[0].val.clusterDim.z = 1;
+        cfg.attrs = at;
+        cfg.numAttrs = 1;
+        ENC_CK(cudaLaunchKernelEx(&cfg, encoder_small_kernel<MT>, P));
+        h->launches++;
+    }
     return cudaSuccess;
+}
+
+// Which path.  Sequences of at most 64 tokens in batches the cluster kernel covers in one or two
+// waves (a B200 holds 14 clusters of 8 at a time) take it -- its result for a sequence does not
+// depend on the batch, the padded length or the tile variant, so everything a serving front
+// coalesces (<= 32 queries) embeds exactly as it would alone; bulk work (index build) takes the
+// tcgen05 GEMM chain.  0: chain, 2 / 4: cluster kernel with 32- / 64-row groups.
+// LRX_NO_SMALL_ENCODER=1 forces the chain (A/B runs, tests).
+static int small_path(int B, int S) {
+    if (S > 64 || getenv("LRX_NO_SMALL_ENCODER") != nullptr) return 0;
+    if (S <= 32) {
+        const int spg = 32 / S;
+        if ((B + spg - 1) / spg <= 14) return 2;
+    }
+    const int spg4 = 64 / S;
+    return ((B + spg4 - 1) / spg4 <= 32) ? 4 : 0;
 }
 
 cudaError_t encoder_forward(lrx_handle* h, const int32_t* ids, const int32_t* lens, int B, int S,
                             float* out_f32, void* out_f16) {
     Encoder* e = (Encoder*)h->encoder;
-    if ((int64_t)B * S <= kSmRows && S <= 64 && getenv("LRX_NO_SMALL_ENCODER") == nullptr)
-        return encoder_forward_small(h, e, ids, lens, B, S, out_f32, out_f16);
+    const int sp = small_path(B, S);
+    if (sp == 2) return encoder_forward_small<2>(h, e, ids, lens, B, S, out_f32, out_f16);
+    if (sp == 4) return encoder_forward_small<4>(h, e, ids, lens, B, S, out_f32, out_f16);
     int seq_per_chunk = (int)(kChunkTokens / S);
     if (seq_per_chunk < 1) seq_per_chunk = 1;
     if (seq_per_chunk > B) seq_per_chunk = B;

@@ -126,6 +126,26 @@ def test_small_batch_kernel_agrees_with_the_gemm_chain(dev, monkeypatch):
     assert _cos(enc.encode_ids(wide, lens[:2]).astype(np.float64), small[:2].astype(np.float64)).min() > 0.999999
 
 
+def test_query_encoder_is_batch_invariant(dev):
+    """A query's embedding must not depend on what it was batched with, nor on the padded length of
+    the batch (the serving front coalesces concurrent requests): bit-equal alone, inside a batch
+    of 32, and padded to 48 tokens (the kernel's 64-row variant instead of the 32-row one)."""
+    from legal_rag_engine_b200 import synth
+    from legal_rag_engine_b200.encoder import SentenceEncoder
+    sd = synth.bert_state_dict(55, 0.05, ln_jitter=0.1)
+    enc = SentenceEncoder(dev, state_dict=sd)
+    ids, lens = synth.token_batch(32, 30, seed=11)
+    full = enc.encode_ids(ids, lens)                 # 32 sequences: 64-row groups, two per group
+    for i in (0, 5, 31):
+        np.testing.assert_array_equal(enc.encode_ids(ids[i:i + 1], lens[i:i + 1])[0], full[i])
+    np.testing.assert_array_equal(enc.encode_ids(ids[3:11], lens[3:11]), full[3:11])
+    wide = np.zeros((32, 48), dtype=np.int32)
+    wide[:, :30] = ids
+    np.testing.assert_array_equal(enc.encode_ids(wide, lens), full)
+    tight = ids[:, :int(lens.max())]
+    np.testing.assert_array_equal(enc.encode_ids(np.ascontiguousarray(tight), lens), full)
+
+
 def test_encode_texts_batches_and_order(dev):
     from legal_rag_engine_b200 import synth
     from legal_rag_engine_b200.encoder import SentenceEncoder

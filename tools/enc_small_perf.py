@@ -10,7 +10,7 @@ from legal_rag_engine_b200.encoder import SentenceEncoder
 dev = DeviceIndex(0)
 enc = SentenceEncoder(dev, state_dict=synth.bert_state_dict(42, 0.02))
 e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-for B, S in ((1, 16), (4, 16), (4, 32), (2, 64), (1, 128), (8, 16)):
+for B, S in ((1, 16), (4, 16), (4, 32), (2, 64), (8, 16), (16, 32), (32, 32), (64, 32), (32, 64)):
     ids, lens = synth.token_batch(B, S, seed=1, full=True)
     d_ids, d_lens = torch.from_numpy(ids).cuda(), torch.from_numpy(lens).cuda()
     out = {"B": B, "S": S}
