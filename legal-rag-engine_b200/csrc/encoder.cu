@@ -441,6 +441,7 @@ struct SmallParams {
     const float *word, *pos, *type0, *eln_g, *eln_b;
     SmallLayer L[kLayers];
     unsigned char* scratch;             // [groups][SmGeom::scratch]
+    long long* trace;                   // optional timeline of cluster 0 / CTA 0 (lrx_debug_set_trace), else NULL
     float* out_f32;
     __half* out_f16;
 };
@@ -448,57 +449,63 @@ struct SmallParams {
 __device__ __forceinline__ float gelu_erf(float x) { return 0.5f * x * (1.0f + erff(x * 0.70710678118654752f)); }
 __device__ __forceinline__ uint4 ldcg_u4(const void* p) { return __ldcg(reinterpret_cast<const uint4*>(p)); }
 
-// a unit's B fragments: W rows n0 + g, k = kbase + 32 ch + 8 t .. + 8, ch = 0..11
-__device__ __forceinline__ void sm_unit_load(const __half* __restrict__ w_lane, uint4 (&b)[12]) {
+// A warp's tile of one GEMM phase: MW row blocks of 16 (rows mrow0 ..) x nu <= 6 column tiles of 8,
+// K = 384 in 12 chunks of 32, k-pipelined: the B fragments of chunk ch + kSmPd are fetched straight
+// from L2 (one 16-byte load per lane and column tile: W row n0 + g, k = kbase + 32 ch + 8 t .. + 8)
+// while chunk ch is multiplied.  A is read from shared memory once per phase and warp (only the
+// warp's own rows).  The first version gave every warp ALL rows of 8 columns at a time and re-read
+// the whole A tile per 8 columns: 1536 shared-memory wavefront cycles per unit and SM, three times
+// the tensor time.
+constexpr int kSmPd = 4;                // chunks of B in flight
+constexpr int kSmNu = 6;                // column tiles per warp, at most
+struct SmB {
+    uint4 r[kSmPd][kSmNu];
+};
+// w0: this lane's pointer into column tile 0 (row n0 + g, k = kbase + 8 t); tiles are 8 rows of W
+// (8 * ldw halves) apart
+__device__ __forceinline__ void sm_b_fetch(SmB& B, int slot_ch, int ch, const __half* __restrict__ w0,
+                                           int ldw, int nu) {
 #pragma unroll
-    for (int ch = 0; ch < 12; ++ch) b[ch] = __ldg(reinterpret_cast<const uint4*>(w_lane + 32 * ch));
+    for (int j = 0; j < kSmNu; ++j)
+        if (j < nu) B.r[slot_ch][j] = __ldg(reinterpret_cast<const uint4*>(w0 + (size_t)j * 8 * ldw + 32 * ch));
 }
-// acc[mt] = A[16 mt .. + 16, 0:384] * Wunit^T, A in shared memory (rows kSmLd halves apart)
-template <int MT>
-__device__ __forceinline__ void sm_unit_mma(const __half* a_tile, const uint4 (&b)[12], int g, int t,
-                                            float (&acc)[MT][4]) {
+__device__ __forceinline__ void sm_b_prefetch(SmB& B, const __half* __restrict__ w0, int ldw, int nu) {
 #pragma unroll
-    for (int mt = 0; mt < MT; ++mt)
+    for (int ch = 0; ch < kSmPd; ++ch) sm_b_fetch(B, ch, ch, w0, ldw, nu);
+}
+// acc[mw][j] = A[mrow0 + 16 mw .. + 16, 0:384] * W[tile j]^T; B holds chunks 0 .. kSmPd - 1 on entry
+template <int MW>
+__device__ __forceinline__ void sm_tile_mma(const __half* a_tile, int mrow0, SmB& B, const __half* __restrict__ w0,
+                                            int ldw, int nu, int g, int t, float (&acc)[MW][kSmNu][4]) {
 #pragma unroll
-        for (int i = 0; i < 4; ++i) acc[mt][i] = 0.f;
-    const __half* a_lane = a_tile + (size_t)g * kSmLd + 8 * t;
-    // 32 rows at a time over all of k (64-row tiles: two passes over the same B fragments, so that
-    // only two row blocks' A fragments and accumulators are live at once)
+    for (int mw = 0; mw < MW; ++mw)
 #pragma unroll
-    for (int mh = 0; mh < MT; mh += 2) {
+        for (int j = 0; j < kSmNu; ++j)
 #pragma unroll
-        for (int ch = 0; ch < 12; ++ch) {
+            for (int i = 0; i < 4; ++i) acc[mw][j][i] = 0.f;
+    const __half* a_lane = a_tile + (size_t)(mrow0 + g) * kSmLd + 8 * t;
 #pragma unroll
-            for (int mt = mh; mt < mh + 2; ++mt) {
-                const uint4 a0 = *reinterpret_cast<const uint4*>(a_lane + (size_t)(16 * mt) * kSmLd + 32 * ch);
-                const uint4 a1 = *reinterpret_cast<const uint4*>(a_lane + (size_t)(16 * mt + 8) * kSmLd + 32 * ch);
-                const uint32_t lo[4] = {a0.x, a1.x, a0.y, a1.y};
-                const uint32_t hi[4] = {a0.z, a1.z, a0.w, a1.w};
-                mma16816(acc[mt], lo, b[ch].x, b[ch].y);
-                mma16816(acc[mt], hi, b[ch].z, b[ch].w);
+    for (int ch = 0; ch < 12; ++ch) {
+        uint32_t lo[MW][4], hi[MW][4];
+#pragma unroll
+        for (int mw = 0; mw < MW; ++mw) {
+            const uint4 a0 = *reinterpret_cast<const uint4*>(a_lane + (size_t)(16 * mw) * kSmLd + 32 * ch);
+            const uint4 a1 = *reinterpret_cast<const uint4*>(a_lane + (size_t)(16 * mw + 8) * kSmLd + 32 * ch);
+            lo[mw][0] = a0.x; lo[mw][1] = a1.x; lo[mw][2] = a0.y; lo[mw][3] = a1.y;
+            hi[mw][0] = a0.z; hi[mw][1] = a1.z; hi[mw][2] = a0.w; hi[mw][3] = a1.w;
+        }
+#pragma unroll
+        for (int j = 0; j < kSmNu; ++j) {
+            if (j < nu) {
+                const uint4 bb = B.r[ch % kSmPd][j];
+#pragma unroll
+                for (int mw = 0; mw < MW; ++mw) {
+                    mma16816(acc[mw][j], lo[mw], bb.x, bb.y);
+                    mma16816(acc[mw][j], hi[mw], bb.z, bb.w);
+                }
             }
         }
-    }
-}
-
-// A warp's units of one GEMM, the next unit's weights in flight under the current unit's MMAs (one
-// copy of the unit's code: the loop is not unrolled, the double buffer is a register copy).
-// w_of(i): this lane's W pointer of unit i; epi(i, acc): the unit's epilogue; b0 holds unit 0's
-// weights on entry (loaded by the caller ahead of the barrier before).
-template <int MT, typename WOf, typename Epi>
-__device__ __forceinline__ void sm_units(int n_units, const __half* a_tile, int g, int t, WOf w_of, Epi epi,
-                                         uint4 (&b0)[12]) {
-    uint4 b1[12];
-    float acc[MT][4];
-#pragma unroll 1
-    for (int i = 0; i < n_units; ++i) {
-        if (i + 1 < n_units) sm_unit_load(w_of(i + 1), b1);
-        sm_unit_mma<MT>(a_tile, b0, g, t, acc);
-        epi(i, acc);
-        if (i + 1 < n_units) {
-#pragma unroll
-            for (int ch = 0; ch < 12; ++ch) b0[ch] = b1[ch];
-        }
+        if (ch + kSmPd < 12) sm_b_fetch(B, ch % kSmPd, ch + kSmPd, w0, ldw, nu);
     }
 }
 
@@ -669,7 +676,6 @@ encoder_small_kernel(const SmallParams P) {
     const int g = lane >> 2, t = lane & 3;
     const int c = (int)cluster_ctarank();
     const int grp = blockIdx.x / kSmCtas;
-    const int wid = c * kSmWarps + warp;                     // warp of the cluster, 0..63
     const int seq0 = grp * P.spg;
     const int nseq = min(P.spg, P.B - seq0);
     const int T = nseq * P.S;                                // rows in use
@@ -679,12 +685,28 @@ encoder_small_kernel(const SmallParams P) {
     __half* s_ff = reinterpret_cast<__half*>(sc_base + G::o_ff);
     float* s_y = reinterpret_cast<float*>(sc_base + G::o_y);
     float* s_yp = reinterpret_cast<float*>(sc_base + G::o_ypart);
-    uint4 bw[12];                                            // a unit's weights, loaded ahead
-
+    constexpr int MW = MT / 2;                               // 16-row blocks per warp
+    const int mrow0 = (warp & 1) * 16 * MW;                  // the warp's rows
+    const int ng = c * 4 + (warp >> 1);                      // its column group in the cluster, 0..31
+    SmB Bf;                                                  // B fragments in flight
+    float acc[MW][kSmNu][4];
+    int tr_n = 0;
+    auto stamp = [&]() {
+        if (P.trace != nullptr && blockIdx.x == 0 && tid == 0 && tr_n < 128) P.trace[tr_n++] = clock64();
+    };
+    stamp();
+    // column tiles (of 8) per phase: QKV 144 = 16 groups x 5 + 16 x 4; output projection 48 = 16 x 2 +
+    // 16 x 1; FFN up 192 = 32 x 6; FFN down: CTA c owns k quarter c & 3 of tiles (c >> 2) * 24 .. + 24
+    const int qkv_t0 = ng < 16 ? 5 * ng : 80 + 4 * (ng - 16), qkv_nu = ng < 16 ? 5 : 4;
+    const int out_t0 = ng < 16 ? 2 * ng : 32 + (ng - 16), out_nu = ng < 16 ? 2 : 1;
+    const int up_t0 = 6 * ng;
+    const int kq = c & 3;
+    const int dn_t0 = (c >> 2) * 24 + 6 * (warp >> 1);
+    auto w_lane = [&](const __half* w, int tile0, int ldw, int kbase) {
+        return w + (size_t)(8 * tile0 + g) * ldw + kbase + 8 * t;
+    };
     // the first GEMM's first weights go out before anything else
-    const int n_qkv = (wid < 144 - 128) ? 3 : 2;             // 144 units over 64 warps
-    auto w_qkv = [&](int l, int i) { return P.L[l].wqkv + (size_t)(8 * (wid + 64 * i) + g) * kHidden + 8 * t; };
-    sm_unit_load(w_qkv(0, 0), bw);
+    sm_b_prefetch(Bf, w_lane(P.L[0].wqkv, qkv_t0, kHidden, 0), kHidden, qkv_nu);
 
     // ---- embeddings + LayerNorm, every row of X in every CTA (rows >= T: zeros)
     for (int r = warp; r < M; r += kSmWarps) {
@@ -712,27 +734,33 @@ encoder_small_kernel(const SmallParams P) {
         sm_ln_row(v, P.eln_g, P.eln_b, xrow, lane);
     }
     __syncthreads();
+    stamp();
 
     for (int l = 0; l < kLayers; ++l) {
         const SmallLayer& L = P.L[l];
         // ---- (1) QKV projection -> scratch qkv (fp16)
-        sm_units<MT>(n_qkv, xs, g, t, [&](int i) { return w_qkv(l, i); },
-                     [&](int i, float (&acc)[MT][4]) {
-                         const int col = 8 * (wid + 64 * i) + 2 * t;
-                         const float2 bb = __ldg(reinterpret_cast<const float2*>(L.bqkv + col));
+        sm_tile_mma<MW>(xs, mrow0, Bf, w_lane(L.wqkv, qkv_t0, kHidden, 0), kHidden, qkv_nu, g, t, acc);
 #pragma unroll
-                         for (int mt = 0; mt < MT; ++mt) {
-                             const int r0 = 16 * mt + g;
-                             *reinterpret_cast<uint32_t*>(s_qkv + (size_t)r0 * kQkv + col) =
-                                 pack_h2(acc[mt][0] + bb.x, acc[mt][1] + bb.y);
-                             *reinterpret_cast<uint32_t*>(s_qkv + (size_t)(r0 + 8) * kQkv + col) =
-                                 pack_h2(acc[mt][2] + bb.x, acc[mt][3] + bb.y);
-                         }
-                     }, bw);
-        // the output projection's weights travel under the attention
-        const bool has_o = wid < 48;
-        if (MT == 2 && has_o) sm_unit_load(L.wo + (size_t)(8 * wid + g) * kHidden + 8 * t, bw);
+        for (int j = 0; j < kSmNu; ++j) {
+            if (j < qkv_nu) {
+                const int col = 8 * (qkv_t0 + j) + 2 * t;
+                const float2 bb = __ldg(reinterpret_cast<const float2*>(L.bqkv + col));
+#pragma unroll
+                for (int mw = 0; mw < MW; ++mw) {
+                    const int r0 = mrow0 + 16 * mw + g;
+                    *reinterpret_cast<uint32_t*>(s_qkv + (size_t)r0 * kQkv + col) =
+                        pack_h2(acc[mw][j][0] + bb.x, acc[mw][j][1] + bb.y);
+                    *reinterpret_cast<uint32_t*>(s_qkv + (size_t)(r0 + 8) * kQkv + col) =
+                        pack_h2(acc[mw][j][2] + bb.x, acc[mw][j][3] + bb.y);
+                }
+            }
+        }
+        // the output projection's first weights travel under the attention (32-row groups; with 64
+        // rows the attention needs the registers)
+        if (MT == 2) sm_b_prefetch(Bf, w_lane(L.wo, out_t0, kHidden, 0), kHidden, out_nu);
+        stamp();
         cluster_sync_all();
+        stamp();
         // ---- (2) attention: (sequence, head) pairs over kSmAttnWarps warps per CTA
         if (warp < kSmAttnWarps) {
             __half* sK = as + (size_t)warp * (2 * 16 * MT * kKPad);
@@ -744,7 +772,9 @@ encoder_small_kernel(const SmallParams P) {
                 sm_attention_pair<MT>(s_qkv, sq * P.S, head, P.S, len, sK, sV, s_ctx, lane);
             }
         }
+        stamp();
         cluster_sync_all();
+        stamp();
         // ---- (3) output projection + residual -> scratch y (fp32); A = ctx staged from the scratch
         for (int i = tid; i < M * 48; i += kSmThreads) {
             const int r = i / 48, part = i - r * 48;
@@ -753,60 +783,69 @@ encoder_small_kernel(const SmallParams P) {
                          : "memory");
         }
         asm volatile("cp.async.commit_group;" ::: "memory");
-        if (MT != 2 && has_o)                                   // (64-row tiles: registers are short during attention)
-            sm_unit_load(L.wo + (size_t)(8 * wid + g) * kHidden + 8 * t, bw);
+        if (MT != 2) sm_b_prefetch(Bf, w_lane(L.wo, out_t0, kHidden, 0), kHidden, out_nu);
         asm volatile("cp.async.wait_all;" ::: "memory");
         __syncthreads();
-        sm_units<MT>(has_o ? 1 : 0, as, g, t, [&](int) { return L.wo; },
-                     [&](int, float (&acc)[MT][4]) {
-                         const int col = 8 * wid + 2 * t;
-                         const float2 bb = __ldg(reinterpret_cast<const float2*>(L.bo + col));
+        sm_tile_mma<MW>(as, mrow0, Bf, w_lane(L.wo, out_t0, kHidden, 0), kHidden, out_nu, g, t, acc);
 #pragma unroll
-                         for (int mt = 0; mt < MT; ++mt) {
-                             const int r0 = 16 * mt + g;
-                             const float2 x0 = __half22float2(*reinterpret_cast<const __half2*>(xs + (size_t)r0 * kSmLd + col));
-                             const float2 x1 = __half22float2(*reinterpret_cast<const __half2*>(xs + (size_t)(r0 + 8) * kSmLd + col));
-                             *reinterpret_cast<float2*>(s_y + (size_t)r0 * kHidden + col) =
-                                 make_float2(acc[mt][0] + bb.x + x0.x, acc[mt][1] + bb.y + x0.y);
-                             *reinterpret_cast<float2*>(s_y + (size_t)(r0 + 8) * kHidden + col) =
-                                 make_float2(acc[mt][2] + bb.x + x1.x, acc[mt][3] + bb.y + x1.y);
-                         }
-                     }, bw);
-        // FFN up: 192 units, three per warp; the first one's weights travel under the barrier + LayerNorm
-        auto w_up = [&](int i) { return L.w1 + (size_t)(8 * (wid + 64 * i) + g) * kHidden + 8 * t; };
-        sm_unit_load(w_up(0), bw);
-        cluster_sync_all();
-        // ---- (4) LayerNorm 1 (every CTA, all rows) -> X; FFN up + GELU -> scratch ff (fp16)
-        for (int r = warp; r < M; r += kSmWarps) {
-            float v[12];
+        for (int j = 0; j < 2; ++j) {
+            if (j < out_nu) {
+                const int col = 8 * (out_t0 + j) + 2 * t;
+                const float2 bb = __ldg(reinterpret_cast<const float2*>(L.bo + col));
 #pragma unroll
-            for (int j = 0; j < 3; ++j) {
-                const float4 q = __ldcg(reinterpret_cast<const float4*>(s_y + (size_t)r * kHidden + j * 128 + lane * 4));
-                v[4 * j] = q.x; v[4 * j + 1] = q.y; v[4 * j + 2] = q.z; v[4 * j + 3] = q.w;
+                for (int mw = 0; mw < MW; ++mw) {
+                    const int r0 = mrow0 + 16 * mw + g;
+                    const float2 x0 = __half22float2(*reinterpret_cast<const __half2*>(xs + (size_t)r0 * kSmLd + col));
+                    const float2 x1 = __half22float2(*reinterpret_cast<const __half2*>(xs + (size_t)(r0 + 8) * kSmLd + col));
+                    *reinterpret_cast<float2*>(s_y + (size_t)r0 * kHidden + col) =
+                        make_float2(acc[mw][j][0] + bb.x + x0.x, acc[mw][j][1] + bb.y + x0.y);
+                    *reinterpret_cast<float2*>(s_y + (size_t)(r0 + 8) * kHidden + col) =
+                        make_float2(acc[mw][j][2] + bb.x + x1.x, acc[mw][j][3] + bb.y + x1.y);
+                }
             }
-            sm_ln_row(v, L.ln1_g, L.ln1_b, xs + (size_t)r * kSmLd, lane);
+        }
+        // FFN up's first weights travel under the barrier + LayerNorm
+        sm_b_prefetch(Bf, w_lane(L.w1, up_t0, kHidden, 0), kHidden, 6);
+        stamp();
+        cluster_sync_all();
+        stamp();
+        // ---- (4) LayerNorm 1 (every CTA, all rows; the loads of four rows in flight together) -> X;
+        //          FFN up + GELU -> scratch ff (fp16)
+#pragma unroll 1
+        for (int rb = 0; rb < M / kSmWarps; rb += 4) {
+            float v[4][12];
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+                const int r = warp + kSmWarps * (rb + i);
+#pragma unroll
+                for (int j = 0; j < 3; ++j) {
+                    const float4 q = __ldcg(reinterpret_cast<const float4*>(s_y + (size_t)r * kHidden + j * 128 + lane * 4));
+                    v[i][4 * j] = q.x; v[i][4 * j + 1] = q.y; v[i][4 * j + 2] = q.z; v[i][4 * j + 3] = q.w;
+                }
+            }
+#pragma unroll
+            for (int i = 0; i < 4; ++i)
+                sm_ln_row(v[i], L.ln1_g, L.ln1_b, xs + (size_t)(warp + kSmWarps * (rb + i)) * kSmLd, lane);
         }
         __syncthreads();
-        sm_units<MT>(3, xs, g, t, w_up,
-                     [&](int i, float (&acc)[MT][4]) {
-                         const int col = 8 * (wid + 64 * i) + 2 * t;
-                         const float2 bb = __ldg(reinterpret_cast<const float2*>(L.b1 + col));
+        sm_tile_mma<MW>(xs, mrow0, Bf, w_lane(L.w1, up_t0, kHidden, 0), kHidden, 6, g, t, acc);
 #pragma unroll
-                         for (int mt = 0; mt < MT; ++mt) {
-                             const int r0 = 16 * mt + g;
-                             *reinterpret_cast<uint32_t*>(s_ff + (size_t)r0 * kFfn + col) =
-                                 pack_h2(gelu_erf(acc[mt][0] + bb.x), gelu_erf(acc[mt][1] + bb.y));
-                             *reinterpret_cast<uint32_t*>(s_ff + (size_t)(r0 + 8) * kFfn + col) =
-                                 pack_h2(gelu_erf(acc[mt][2] + bb.x), gelu_erf(acc[mt][3] + bb.y));
-                         }
-                     }, bw);
-        // FFN down: CTA c owns k quarter c & 3 of column tiles (c >> 2) * 24 .. + 24, three per warp
-        const int kq = c & 3;
-        auto w_dn = [&](int i) {
-            return L.w2 + (size_t)(8 * ((c >> 2) * 24 + warp + 8 * i) + g) * kFfn + kq * kHidden + 8 * t;
-        };
-        sm_unit_load(w_dn(0), bw);
+        for (int j = 0; j < kSmNu; ++j) {
+            const int col = 8 * (up_t0 + j) + 2 * t;
+            const float2 bb = __ldg(reinterpret_cast<const float2*>(L.b1 + col));
+#pragma unroll
+            for (int mw = 0; mw < MW; ++mw) {
+                const int r0 = mrow0 + 16 * mw + g;
+                *reinterpret_cast<uint32_t*>(s_ff + (size_t)r0 * kFfn + col) =
+                    pack_h2(gelu_erf(acc[mw][j][0] + bb.x), gelu_erf(acc[mw][j][1] + bb.y));
+                *reinterpret_cast<uint32_t*>(s_ff + (size_t)(r0 + 8) * kFfn + col) =
+                    pack_h2(gelu_erf(acc[mw][j][2] + bb.x), gelu_erf(acc[mw][j][3] + bb.y));
+            }
+        }
+        sm_b_prefetch(Bf, w_lane(L.w2, dn_t0, kFfn, kq * kHidden), kFfn, 6);
+        stamp();
         cluster_sync_all();
+        stamp();
         // ---- (5) FFN down: partial sums over this CTA's k quarter -> scratch ypart[kq] (fp32)
         for (int i = tid; i < M * 48; i += kSmThreads) {
             const int r = i / 48, part = i - r * 48;
@@ -818,43 +857,56 @@ encoder_small_kernel(const SmallParams P) {
         asm volatile("cp.async.commit_group;" ::: "memory");
         asm volatile("cp.async.wait_all;" ::: "memory");
         __syncthreads();
-        sm_units<MT>(3, as, g, t, w_dn,
-                     [&](int i, float (&acc)[MT][4]) {
-                         const int col = 8 * ((c >> 2) * 24 + warp + 8 * i) + 2 * t;
-                         float* yp = s_yp + (size_t)kq * M * kHidden;
+        sm_tile_mma<MW>(as, mrow0, Bf, w_lane(L.w2, dn_t0, kFfn, kq * kHidden), kFfn, 6, g, t, acc);
+        {
+            float* yp = s_yp + (size_t)kq * M * kHidden;
 #pragma unroll
-                         for (int mt = 0; mt < MT; ++mt) {
-                             const int r0 = 16 * mt + g;
-                             *reinterpret_cast<float2*>(yp + (size_t)r0 * kHidden + col) = make_float2(acc[mt][0], acc[mt][1]);
-                             *reinterpret_cast<float2*>(yp + (size_t)(r0 + 8) * kHidden + col) = make_float2(acc[mt][2], acc[mt][3]);
-                         }
-                     }, bw);
-        if (l + 1 < kLayers) sm_unit_load(w_qkv(l + 1, 0), bw);
-        cluster_sync_all();
-        // ---- (6) the four k quarters in order + bias + residual, LayerNorm 2 -> X
-        for (int r = warp; r < M; r += kSmWarps) {
-            float v[12];
-            __half* xrow = xs + (size_t)r * kSmLd;
+            for (int j = 0; j < kSmNu; ++j) {
+                const int col = 8 * (dn_t0 + j) + 2 * t;
 #pragma unroll
-            for (int j = 0; j < 3; ++j) {
-                const int cc = j * 128 + lane * 4;
-                const size_t o = (size_t)r * kHidden + cc;
-                const float4 p0 = __ldcg(reinterpret_cast<const float4*>(s_yp + o));
-                const float4 p1 = __ldcg(reinterpret_cast<const float4*>(s_yp + (size_t)M * kHidden + o));
-                const float4 p2 = __ldcg(reinterpret_cast<const float4*>(s_yp + 2 * (size_t)M * kHidden + o));
-                const float4 p3 = __ldcg(reinterpret_cast<const float4*>(s_yp + 3 * (size_t)M * kHidden + o));
-                const float4 bb = __ldg(reinterpret_cast<const float4*>(L.b2 + cc));
-                const float2 xa = __half22float2(*reinterpret_cast<const __half2*>(xrow + cc));
-                const float2 xb = __half22float2(*reinterpret_cast<const __half2*>(xrow + cc + 2));
-                v[4 * j + 0] = (((p0.x + p1.x) + p2.x) + p3.x) + bb.x + xa.x;
-                v[4 * j + 1] = (((p0.y + p1.y) + p2.y) + p3.y) + bb.y + xa.y;
-                v[4 * j + 2] = (((p0.z + p1.z) + p2.z) + p3.z) + bb.z + xb.x;
-                v[4 * j + 3] = (((p0.w + p1.w) + p2.w) + p3.w) + bb.w + xb.y;
+                for (int mw = 0; mw < MW; ++mw) {
+                    const int r0 = mrow0 + 16 * mw + g;
+                    *reinterpret_cast<float2*>(yp + (size_t)r0 * kHidden + col) = make_float2(acc[mw][j][0], acc[mw][j][1]);
+                    *reinterpret_cast<float2*>(yp + (size_t)(r0 + 8) * kHidden + col) = make_float2(acc[mw][j][2], acc[mw][j][3]);
+                }
             }
-            __syncwarp();                                    // the whole row was read before it is rewritten
-            sm_ln_row(v, L.ln2_g, L.ln2_b, xrow, lane);
         }
+        stamp();
+        cluster_sync_all();
+        stamp();
+        // ---- (6) the four k quarters in order + bias + residual, LayerNorm 2 -> X (two rows' loads
+        //          in flight together)
+#pragma unroll 1
+        for (int rb = 0; rb < M / kSmWarps; rb += 2) {
+            float v[2][12];
+#pragma unroll
+            for (int i = 0; i < 2; ++i) {
+                const int r = warp + kSmWarps * (rb + i);
+                const __half* xrow = xs + (size_t)r * kSmLd;
+#pragma unroll
+                for (int j = 0; j < 3; ++j) {
+                    const int cc = j * 128 + lane * 4;
+                    const size_t o = (size_t)r * kHidden + cc;
+                    const float4 p0 = __ldcg(reinterpret_cast<const float4*>(s_yp + o));
+                    const float4 p1 = __ldcg(reinterpret_cast<const float4*>(s_yp + (size_t)M * kHidden + o));
+                    const float4 p2 = __ldcg(reinterpret_cast<const float4*>(s_yp + 2 * (size_t)M * kHidden + o));
+                    const float4 p3 = __ldcg(reinterpret_cast<const float4*>(s_yp + 3 * (size_t)M * kHidden + o));
+                    const float4 bb = __ldg(reinterpret_cast<const float4*>(L.b2 + cc));
+                    const float2 xa = __half22float2(*reinterpret_cast<const __half2*>(xrow + cc));
+                    const float2 xb = __half22float2(*reinterpret_cast<const __half2*>(xrow + cc + 2));
+                    v[i][4 * j + 0] = (((p0.x + p1.x) + p2.x) + p3.x) + bb.x + xa.x;
+                    v[i][4 * j + 1] = (((p0.y + p1.y) + p2.y) + p3.y) + bb.y + xa.y;
+                    v[i][4 * j + 2] = (((p0.z + p1.z) + p2.z) + p3.z) + bb.z + xb.x;
+                    v[i][4 * j + 3] = (((p0.w + p1.w) + p2.w) + p3.w) + bb.w + xb.y;
+                }
+            }
+#pragma unroll
+            for (int i = 0; i < 2; ++i)
+                sm_ln_row(v[i], L.ln2_g, L.ln2_b, xs + (size_t)(warp + kSmWarps * (rb + i)) * kSmLd, lane);
+        }
+        if (l + 1 < kLayers) sm_b_prefetch(Bf, w_lane(P.L[l + 1].wqkv, qkv_t0, kHidden, 0), kHidden, qkv_nu);
         __syncthreads();
+        stamp();
     }
 
     // ---- pooling + Normalize + normalize_L2: sequence i of the group on CTA i % 8
@@ -1078,6 +1130,7 @@ static cudaError_t encoder_forward_small(lrx_handle* h, Encoder* e, const int32_
         d.ln1_g = s.ln1_g; d.ln1_b = s.ln1_b; d.ln2_g = s.ln2_g; d.ln2_b = s.ln2_b;
     }
     P.scratch = (unsigned char*)e->small_ws;
+    P.trace = (long long*)h->debug_trace;
     for (int g0 = 0; g0 < groups_all; g0 += groups_max) {
         const int ng = (groups_all - g0) < groups_max ? (groups_all - g0) : groups_max;
         const int b0 = g0 * spg;
@@ -1103,11 +1156,14 @@ static cudaError_t encoder_forward_small(lrx_handle* h, Encoder* e, const int32_
     return cudaSuccess;
 }
 
-// Which path.  Sequences of at most 64 tokens in batches the cluster kernel covers in one or two
-// waves (a B200 holds 14 clusters of 8 at a time) take it -- its result for a sequence does not
-// depend on the batch, the padded length or the tile variant, so everything a serving front
-// coalesces (<= 32 queries) embeds exactly as it would alone; bulk work (index build) takes the
-// tcgen05 GEMM chain.  0: chain, 2 / 4: cluster kernel with 32- / 64-row groups.
+// Which path.  Sequences of at most 64 tokens in batches of at most 64 groups take the cluster
+// kernel -- its result for a sequence does not depend on the batch, the padded length or the tile
+// variant, so everything a serving front coalesces (serving.py: at most 64 queries per batch)
+// embeds exactly as it would alone; bulk work (index build) takes the tcgen05 GEMM chain.  A B200
+// holds 14 clusters of 8 at a time: up to 14 groups of 32 rows run as one wave (0.16 ms), more
+// sequences are packed into 64-row groups (0.26 ms per wave; from about 30 groups on the chain
+// would be faster -- 0.4 ms for 64 x 32 tokens against 0.74 -- which is the price of the invariance).
+// 0: chain, 2 / 4: cluster kernel with 32- / 64-row groups.
 // LRX_NO_SMALL_ENCODER=1 forces the chain (A/B runs, tests).
 static int small_path(int B, int S) {
     if (S > 64 || getenv("LRX_NO_SMALL_ENCODER") != nullptr) return 0;
@@ -1116,7 +1172,7 @@ static int small_path(int B, int S) {
         if ((B + spg - 1) / spg <= 14) return 2;
     }
     const int spg4 = 64 / S;
-    return ((B + spg4 - 1) / spg4 <= 32) ? 4 : 0;
+    return ((B + spg4 - 1) / spg4 <= 64) ? 4 : 0;
 }
 
 cudaError_t encoder_forward(lrx_handle* h, const int32_t* ids, const int32_t* lens, int B, int S,

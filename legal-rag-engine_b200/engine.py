@@ -150,17 +150,28 @@ class RetrievalEngine:
             self._search_all(queries, k, weights, mode)
 
     def _search_all(self, queries, k, weights, mode):
-        out: List[List[dict]] = []
-        for s in range(0, len(queries), LRX_MAX_BATCH):
-            out.extend(self._search_block(queries[s:s + LRX_MAX_BATCH], weights[s:s + LRX_MAX_BATCH], k, mode))
+        """Blocks of at most LRX_MAX_BATCH queries.  Queries of at most 64 WordPiece tokens and longer
+        ones go in separate blocks: the short ones take the encoder's query path, whose result for a
+        query does not depend on what it is batched with (csrc/encoder.cu, small_path), so a query
+        returns the same scores however a serving front coalesced it."""
+        tok = self.model.tokenizer
+        enc = [tok.encode(q, self.model.MAX_SEQ) for q in queries]
+        out: List[Optional[List[dict]]] = [None] * len(queries)
+        short = [i for i, e in enumerate(enc) if len(e) <= 64]
+        long_ = [i for i, e in enumerate(enc) if len(e) > 64]
+        for part in (short, long_):
+            for s in range(0, len(part), LRX_MAX_BATCH):
+                sel = part[s:s + LRX_MAX_BATCH]
+                res = self._search_block([queries[i] for i in sel], [weights[i] for i in sel], k, mode,
+                                         [enc[i] for i in sel])
+                for i, r in zip(sel, res):
+                    out[i] = r
         return out
 
-    def _search_block(self, queries, weights, k, mode):
+    def _search_block(self, queries, weights, k, mode, enc):
         B = len(queries)
         if k < 1 or B == 0:
             return [[] for _ in queries]
-        tok = self.model.tokenizer
-        enc = [tok.encode(q, self.model.MAX_SEQ) for q in queries]
         S = max(len(e) for e in enc)
         ids = np.zeros((B, S), dtype=np.int32)
         lens = np.empty(B, dtype=np.int32)
