@@ -47,7 +47,8 @@ constexpr int kDbBBytes = kDbN * kDbK * 2;    // 32 KB per stage
 constexpr int kDbEpiWarps = 8;          // two per TMEM lane quarter: column halves of a tile
 constexpr int kDbThreads = (kDbEpiWarps + 2) * 32;
 constexpr size_t kDbSmem = (size_t)kDbKB * kDbABytes + (size_t)kDbStages * kDbBBytes + 1024 + 256;
-constexpr int kDbCap = 1024;          // candidates kept per query
+constexpr int kDbCap = 1024;          // candidates re-scored per query, at most
+constexpr int kDbMaxRegions = 2 * 160; // candidate regions per query (2 per CTA of its query tile)
 // |tensor-core fp32 score - exact| for unit fp16 vectors: 384 exact products accumulated in
 // fp32 (possibly truncating) in 24 instructions -> well below 1e-5
 constexpr float kTcEps = 1e-5f;
@@ -61,8 +62,15 @@ struct DbParams {
     float* tilemax;        // [n_mt*128][n_samp]       (pass 1 out)
     int n_samp;
     const float* thr;      // [n_mt*128]               (pass 2 in)
-    int* cnt;              // [n_mt*128]
-    uint64_t* cand;        // [n_mt*128][kDbCap] keys (f32 image << 32 | ~row)
+    // candidate lists of pass 2: one private region per (query, CTA of the query tile, column half),
+    // filled by the ONE thread that owns it with a counter it keeps in a register -- no atomics.  (A
+    // list per query behind one atomicAdd put a dependent L2 round trip, taken inside a divergent
+    // branch, on every candidate: at 1 M rows 15 % of the (warp, chunk) pairs hit it and the pass ran
+    // at 35 % tensor-pipe activity, 1.20 ms for 0.71 ms of MMAs.)
+    int n_regions;         // 2 * CTAs per query tile
+    int region_cap;        // slots per region
+    int* cnt;              // [n_mt*128][n_regions] candidates found (may exceed region_cap: overflow)
+    uint32_t* cand;        // [n_mt*128][n_regions][region_cap] local row ids
 };
 
 // CS: cluster size.  The CS CTAs of a cluster serve CS different query tiles and walk the SAME chunk
@@ -178,7 +186,13 @@ dense_tc_kernel(const __grid_constant__ CUtensorMap tma_q, const __grid_constant
         const uint32_t trow = tmem_base + ((uint32_t)(quarter * 32) << 16) + half * HB;
         float thr = 0.f;
         if (PASS == 2) thr = q_ok ? P.thr[q] : FLT_MAX;
+#ifdef LRX_DB_NOHIT
+        thr = FLT_MAX;                                       // timing experiment: no candidate ever
+#endif
         uint32_t rb[2][32];
+        const int region = group * 2 + half;
+        int my_cnt = 0;                                      // candidates of (q, region) so far
+        uint32_t* my_cand = P.cand + ((size_t)q * P.n_regions + region) * P.region_cap;
         for (int u = 0; u < my_units; ++u) {
             const int buf = u & 1;
             const uint32_t use = (uint32_t)(u >> 1);
@@ -202,18 +216,31 @@ dense_tc_kernel(const __grid_constant__ CUtensorMap tma_q, const __grid_constant
                         if (c + j < valid) mx = fmaxf(mx, __uint_as_float(r[j]));
                     P.tilemax[(size_t)q * P.n_samp + (size_t)(tile / step) * (kDbN / 32) + half * NCH + ch] = mx;
                 } else {
-                    float best = -FLT_MAX;
+                    // fast path: the chunk's maximum by 3-input max (16 instructions for 32 scores); rows
+                    // past the end of the corpus (last tile only) are masked out in the rare path
+                    float best = __uint_as_float(r[0]);
 #pragma unroll
-                    for (int j = 0; j < 32; ++j) best = fmaxf(best, (c + j < valid) ? __uint_as_float(r[j]) : -FLT_MAX);
-                    if (best >= thr) {                       // rare: some score of the chunk qualifies
+                    for (int j = 1; j + 1 < 32; j += 2)
+                        asm("max.f32 %0, %0, %1, %2;" : "+f"(best) : "f"(__uint_as_float(r[j])), "f"(__uint_as_float(r[j + 1])));
+                    best = fmaxf(best, __uint_as_float(r[31]));
+                    if (best >= thr) {
+                        // rare (a few candidates per tile and warp) and therefore SMALL: a hit mask,
+                        // then one 4-byte row id per set bit.  (The first form, 32 unrolled
+                        // compare-and-store bodies per chunk, was 3 000 instructions of cold code:
+                        // every hit streamed them through the instruction cache, ~1 500 cycles on the
+                        // critical path of an epilogue-bound pipeline -- 1 M rows: 35 % tensor-pipe
+                        // activity with the hits, 77 % of peak without.)
+                        uint32_t mask = 0u;
 #pragma unroll
-                        for (int j = 0; j < 32; ++j) {
-                            const float sc = __uint_as_float(r[j]);
-                            if (sc >= thr && c + j < valid) {
-                                const int slot = atomicAdd(P.cnt + q, 1);
-                                if (slot < kDbCap)
-                                    P.cand[(size_t)q * kDbCap + slot] = make_key64(sc, (uint32_t)(row0 + c + j));
-                            }
+                        for (int j = 0; j < 32; ++j) mask |= (__uint_as_float(r[j]) >= thr) ? (1u << j) : 0u;
+                        const int left = valid - c;
+                        mask &= (left >= 32) ? 0xffffffffu : (left > 0 ? ((1u << left) - 1u) : 0u);
+#pragma unroll 1
+                        while (mask != 0u) {
+                            const int j = __ffs((int)mask) - 1;
+                            mask &= mask - 1u;
+                            if (my_cnt < P.region_cap) my_cand[my_cnt] = (uint32_t)(row0 + c + j);
+                            ++my_cnt;
                         }
                     }
                 }
@@ -223,6 +250,7 @@ dense_tc_kernel(const __grid_constant__ CUtensorMap tma_q, const __grid_constant
             __syncwarp();
             if (lane == 0) mbar_arrive(&t_empty[buf]);
         }
+        if (PASS == 2) P.cnt[(size_t)q * P.n_regions + region] = my_cnt;
     }
     tc_fence_before();
     __syncthreads();
@@ -239,7 +267,7 @@ dense_tc_kernel(const __grid_constant__ CUtensorMap tma_q, const __grid_constant
 // the prefix found so far, then warp 0 walks the 256 bins from the top), not a sort.
 __global__ void __launch_bounds__(256)
 tilemax_kth_kernel(const float* __restrict__ tilemax, int n_samp, int K, float slack,
-                   float* __restrict__ thr, int* __restrict__ cnt) {
+                   float* __restrict__ thr) {
     extern __shared__ uint32_t tm_keys[];
     __shared__ uint32_t hist[256];
     __shared__ uint32_t s_prefix, s_rank;
@@ -287,10 +315,7 @@ tilemax_kth_kernel(const float* __restrict__ tilemax, int n_samp, int K, float s
             __syncthreads();
         }
     }
-    if (tid == 0) {
-        thr[q] = (K <= n_samp) ? ord_f32(s_prefix) - slack : -FLT_MAX;
-        cnt[q] = 0;
-    }
+    if (tid == 0) thr[q] = (K <= n_samp) ? ord_f32(s_prefix) - slack : -FLT_MAX;
 }
 
 // Exact float64 re-score of a query's (unsorted) candidate list, best K out.  Each warp takes four
@@ -299,16 +324,41 @@ tilemax_kth_kernel(const float* __restrict__ tilemax, int n_samp, int K, float s
 constexpr int kRlThreads = 256;
 __global__ void __launch_bounds__(kRlThreads)
 dense_rescore_list_kernel(const unsigned char* __restrict__ x, int64_t id_base,
-                          const __half* __restrict__ q, const uint64_t* __restrict__ cand,
-                          const int* __restrict__ cnt, int K, double* __restrict__ out_exact,
+                          const __half* __restrict__ q, const uint32_t* __restrict__ cand,
+                          const int* __restrict__ cnt, int n_regions, int region_cap, int K,
+                          double* __restrict__ out_exact,
                           float* __restrict__ out_D, int64_t* __restrict__ out_I,
                           int32_t* __restrict__ out_flag) {
     __shared__ u128 keys[kDbCap];
     __shared__ u128 best[LRX_MAX_DEPTH];
+    __shared__ int pre[kDbMaxRegions + 1];                   // candidates before region r
+    __shared__ int s_over;
     const int qi = blockIdx.x;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const int total = cnt[qi];
+    // the query's regions, concatenated: candidate i lives in the region r with pre[r] <= i < pre[r+1]
+    if (tid == 0) {
+        int acc = 0, over = 0;
+        for (int r = 0; r < n_regions; ++r) {
+            const int c = cnt[(size_t)qi * n_regions + r];
+            over |= (c > region_cap) ? 1 : 0;
+            pre[r] = acc;
+            acc += min(c, region_cap);
+        }
+        pre[n_regions] = acc;
+        s_over = over;
+    }
+    __syncthreads();
+    const int total = pre[n_regions];
     const int n = min(total, kDbCap);
+    const uint32_t* qcand = cand + (size_t)qi * n_regions * region_cap;
+    auto cand_at = [&](int i) -> uint32_t {
+        int lo = 0, hi = n_regions;                          // last r with pre[r] <= i
+        while (hi - lo > 1) {
+            const int mid = (lo + hi) >> 1;
+            if (pre[mid] <= i) lo = mid; else hi = mid;
+        }
+        return qcand[(size_t)lo * region_cap + (i - pre[lo])];
+    };
     const uint2* qp = reinterpret_cast<const uint2*>(q + (size_t)qi * kDim);
     uint2 qv[3];
 #pragma unroll
@@ -320,7 +370,7 @@ dense_rescore_list_kernel(const unsigned char* __restrict__ x, int64_t id_base,
         uint2 rv[4][3];
 #pragma unroll
         for (int c = 0; c < 4; ++c)
-            row[c] = (j0 + c < n) ? key64_row(cand[(size_t)qi * kDbCap + j0 + c]) : 0u;
+            row[c] = (j0 + c < n) ? cand_at(j0 + c) : 0u;
 #pragma unroll
         for (int c = 0; c < 4; ++c) {
             const uint2* rowp = reinterpret_cast<const uint2*>(x + (int64_t)row[c] * kRowBytes);
@@ -369,7 +419,7 @@ dense_rescore_list_kernel(const unsigned char* __restrict__ x, int64_t id_base,
             out_I[o] = -1;
         }
     }
-    if (tid == 0) out_flag[qi] = (total > kDbCap) ? 1 : 0;
+    if (tid == 0) out_flag[qi] = (total > kDbCap || s_over) ? 1 : 0;
 }
 
 int dense_batched_max_stride(int64_t n_rows, int K) {
@@ -430,8 +480,12 @@ cudaError_t launch_dense_topk_batched(lrx_handle* h, const void* q, int B, int K
     auto take = [&](size_t bytes) { size_t o = off; off = (off + bytes + 255) / 256 * 256; return o; };
     const size_t o_tm = take((size_t)Bp * n_samp * sizeof(float));
     const size_t o_thr = take((size_t)Bp * sizeof(float));
-    const size_t o_cnt = take((size_t)Bp * sizeof(int));
-    const size_t o_cand = take((size_t)Bp * kDbCap * sizeof(uint64_t));
+    const int n_regions = 2 * (grid / n_mt);
+    if (n_regions > kDbMaxRegions) return cudaErrorInvalidConfiguration;
+    int region_cap = 16;                       // >= 2048 slots per query over its regions: an even
+    while (region_cap * n_regions < 2048) region_cap <<= 1;   // spread fills a few percent of a region
+    const size_t o_cnt = take((size_t)Bp * n_regions * sizeof(int));
+    const size_t o_cand = take((size_t)Bp * n_regions * region_cap * sizeof(uint32_t));
     e = ensure_ws(h, &h->ws_dense_part, &h->ws_dense_part_bytes, off);
     if (e != cudaSuccess) return e;
     char* W = (char*)h->ws_dense_part;
@@ -443,7 +497,8 @@ cudaError_t launch_dense_topk_batched(lrx_handle* h, const void* q, int B, int K
     DbParams P;
     P.B = B; P.n_rows = n; P.n_tiles = n_tiles; P.n_mt = n_mt; P.stride = stride;
     P.tilemax = (float*)(W + o_tm); P.n_samp = n_samp; P.thr = (const float*)(W + o_thr);
-    P.cnt = (int*)(W + o_cnt); P.cand = (uint64_t*)(W + o_cand);
+    P.cnt = (int*)(W + o_cnt); P.cand = (uint32_t*)(W + o_cand);
+    P.n_regions = n_regions; P.region_cap = region_cap;
     auto launch = [&](int pass) -> cudaError_t {
         cudaLaunchConfig_t cfg = {};
         cfg.gridDim = dim3(grid);
@@ -470,7 +525,7 @@ cudaError_t launch_dense_topk_batched(lrx_handle* h, const void* q, int B, int K
     h->launches++;
     if (e != cudaSuccess) return e;
     tilemax_kth_kernel<<<Bp, 256, (size_t)next_pow2(n_samp > 2 ? n_samp : 2) * sizeof(uint32_t), h->stream>>>(
-        P.tilemax, n_samp, K, 2.0f * kTcEps, (float*)(W + o_thr), P.cnt);
+        P.tilemax, n_samp, K, 2.0f * kTcEps, (float*)(W + o_thr));
     h->launches++;
     e = cudaGetLastError();
     if (e != cudaSuccess) return e;
@@ -480,7 +535,8 @@ cudaError_t launch_dense_topk_batched(lrx_handle* h, const void* q, int B, int K
     h->launches++;
     if (e != cudaSuccess) return e;
     dense_rescore_list_kernel<<<B, kRlThreads, 0, h->stream>>>(
-        (const unsigned char*)h->x, h->id_base, (const __half*)q, P.cand, P.cnt, K, exact, D, I, flags);
+        (const unsigned char*)h->x, h->id_base, (const __half*)q, P.cand, P.cnt, n_regions, region_cap, K, exact,
+        D, I, flags);
     h->launches++;
     return cudaGetLastError();
 }
