@@ -67,7 +67,10 @@ struct GemmCfg {
     // epilogue side: bias (whole vector, N <= 1536) / gamma / beta / LayerNorm partial sums, and one 2 KB staging
     // tile (32 rows x 32 halves, SWIZZLE_64B) per epilogue warp for the TMA stores / residual loads
     static constexpr int kParamBytes = 1536 * 4 + 2 * 384 * 4 + 2 * 2 * 128 * 4;
-    static constexpr int kIoBytes = kEpiWarps * 2048 + 2048 /*align*/;
+    // one staging tile per epilogue warp, two for the bias / GELU epilogues (BN <= 256); the
+    // LayerNorm GEMMs (BN = 384) need the space for a third ring stage
+    static constexpr int kIoTile = (BN <= 256) ? 4096 : 2048;
+    static constexpr int kIoBytes = kEpiWarps * kIoTile + 2048 /*align*/;
     static constexpr int kBarBytes = 512;
     static constexpr int kBudget = 224 * 1024 - 1024 - kBarBytes - kParamBytes - kIoBytes;
     static constexpr int kStagesRaw = (kBudget - kResBytes) / kStageBytes;
@@ -78,29 +81,27 @@ struct GemmCfg {
                                     kBarBytes + kParamBytes + kIoBytes;
 };
 
-// GELU(x) = x * Phi(x), Phi(x) = 0.5 erfc(-x / sqrt 2), with erfc from Abramowitz & Stegun 7.1.26
-// (|error| <= 1.5e-7 on erf): h = 0.5 (a1 t + ... + a5 t^5) exp(-x^2 / 2), t = 1 / (1 + p |x| / sqrt 2),
-// Phi = x >= 0 ? 1 - h : h.  Two elements at a time so that the exponential is ONE packed
-// ex2.approx.f16x2 (its ~2^-11 relative error scales h, which is <= 0.5 and shrinks as x^2 grows:
-// far inside the fp16 rounding of the output); 13 FP32 instructions + 1.5 MUFU per element instead
-// of erff's branchy ~40 -- the epilogue has to keep up with the tensor pipe.
+// GELU(x) = x * Phi(x) (exact-erf form), evaluated as 0.5 x (1 + tanh(u(x))) with
+//   u(x) = x (c1 + c3 x^2 + c5 x^4),  x^2 clamped to 64,
+// the coefficients fitted (minimax over |x| <= 8, tools/gelu_fit.py) to the ERF form, not the usual
+// "tanh approximation" constants: |0.5 x (1 + tanh u) - x Phi(x)| <= 2.6e-5 with an exact tanh (the
+// textbook constants: 4.7e-4).  Past |x| = 8 tanh(u) is +-1 in any precision and the result is x or
+// 0.  Two elements at a time so that the hyperbolic tangent is ONE packed tanh.approx.f16x2 (absolute
+// error 2^-11: 2.4e-4 |x| on the result, the size of the fp16 rounding of the output): 9 FP32
+// instructions + half a MUFU per element.  The first form (Abramowitz-Stegun 7.1.26: a reciprocal, a
+// packed exponential and a degree-5 polynomial, 16 FP32 + 1.25 MUFU per element) made the FFN-up
+// epilogue 1.9x as long as the MMAs of its tile -- the kernel ran at 29 % tensor-pipe activity.
 __device__ __forceinline__ float2 gelu2(float x0, float x1) {
-    constexpr float kP = 0.3275911f * 0.70710678118654752440f;
-    constexpr float kE = -0.5f * 1.4426950408889634f;            // exp(-x^2/2) = 2^(kE x^2)
-    float t0, t1;
-    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(t0) : "f"(fmaf(kP, fabsf(x0), 1.0f)));
-    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(t1) : "f"(fmaf(kP, fabsf(x1), 1.0f)));
-    const __half2 arg = __floats2half2_rn(kE * x0 * x0, kE * x1 * x1);
-    uint32_t eh;
-    asm("ex2.approx.f16x2 %0, %1;" : "=r"(eh) : "r"(*reinterpret_cast<const uint32_t*>(&arg)));
-    const float2 e = __half22float2(*reinterpret_cast<const __half2*>(&eh));
-    float p0 = fmaf(0.5f * 1.061405429f, t0, 0.5f * -1.453152027f);
-    float p1 = fmaf(0.5f * 1.061405429f, t1, 0.5f * -1.453152027f);
-    p0 = fmaf(p0, t0, 0.5f * 1.421413741f);   p1 = fmaf(p1, t1, 0.5f * 1.421413741f);
-    p0 = fmaf(p0, t0, 0.5f * -0.284496736f);  p1 = fmaf(p1, t1, 0.5f * -0.284496736f);
-    p0 = fmaf(p0, t0, 0.5f * 0.254829592f);   p1 = fmaf(p1, t1, 0.5f * 0.254829592f);
-    const float h0 = p0 * t0 * e.x, h1 = p1 * t1 * e.y;
-    return make_float2(x0 * (x0 >= 0.f ? 1.0f - h0 : h0), x1 * (x1 >= 0.f ? 1.0f - h1 : h1));
+    constexpr float c1 = 7.97507884e-01f, c3 = 3.70056460e-02f, c5 = -3.51516789e-04f;
+    const float s0 = fminf(x0 * x0, 64.0f), s1 = fminf(x1 * x1, 64.0f);
+    const float u0 = x0 * fmaf(s0, fmaf(s0, c5, c3), c1);
+    const float u1 = x1 * fmaf(s1, fmaf(s1, c5, c3), c1);
+    const __half2 arg = __floats2half2_rn(u0, u1);
+    uint32_t th;
+    asm("tanh.approx.f16x2 %0, %1;" : "=r"(th) : "r"(*reinterpret_cast<const uint32_t*>(&arg)));
+    const float2 t = __half22float2(*reinterpret_cast<const __half2*>(&th));
+    const float h0 = 0.5f * x0, h1 = 0.5f * x1;
+    return make_float2(fmaf(h0, t.x, h0), fmaf(h1, t.y, h1));
 }
 __device__ __forceinline__ void epi_bar() { asm volatile("bar.sync 1, 256;" ::: "memory"); }
 
@@ -338,7 +339,12 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
         }
         const int n_mine = ARES ? ((m_tiles > (int)blockIdx.x) ? (m_tiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x : 0) * n_tiles
                                 : ((total_tiles > (int)blockIdx.x) ? (total_tiles - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x : 0);
-        unsigned char* tile_io = s_io + warp * 2048;      // this warp's staging tile
+        // this warp's staging tiles: two, used in turn by the bias / GELU epilogues, so that a chunk is
+        // written while the TMA store of the chunk before still reads its tile (with one tile every
+        // 32-column chunk waited for the previous store's read: ~1 000 cycles each, serial -- the FFN-up
+        // kernel spent 36 us on 10 us of MMAs)
+        unsigned char* tile_io = s_io + warp * Cfg::kIoTile;
+        uint32_t st_n = 0;
         uint32_t res_n = 0;                               // residual chunks requested so far (phase)
         for (int u = 0; u < n_mine; ++u) {
             int m_blk, n_blk;
@@ -410,9 +416,11 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
                             v[4 * j4 + 2] = x2; v[4 * j4 + 3] = x3;
                         }
                     }
-                    stage_acquire(lane);                              // the previous store has read the tile
-                    stage_put_row(tile_io, lane, v);
-                    stage_store(&tma_out, n0 + cb + c, row_w, tile_io, lane);
+                    stage_acquire1(lane);                             // the store before the previous one has read its tile
+                    unsigned char* tile_w = tile_io + (st_n & 1u) * 2048;
+                    ++st_n;
+                    stage_put_row(tile_w, lane, v);
+                    stage_store(&tma_out, n0 + cb + c, row_w, tile_w, lane);
                     tmem_wait_ld();
                 }
             } else {
