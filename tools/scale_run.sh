@@ -1,10 +1,12 @@
 #!/bin/bash
-# One 8-GPU box: the driver's scaling commands (N = 8, 4, 2) and config C5 (100 M rows, top-100).
-mkdir -p gpurun_out/r2
+# usage: tools/scale_run.sh N [c5]   -- the driver's scaling command at N GPUs (and config C5 at N = 8)
+mkdir -p gpurun_out/r2f
+N=$1
 tr() { python -m torch.distributed.run --nnodes=1 --nproc-per-node $1 --master-addr 127.0.0.1 --master-port $2 bench.py --gpus $1 "${@:3}"; }
-tr 8 29601 --steps 20 --warmup 5 > gpurun_out/r2/scale_n8.json 2> gpurun_out/r2/scale_n8.err
-tr 4 29602 --steps 20 --warmup 5 > gpurun_out/r2/scale_n4.json 2> gpurun_out/r2/scale_n4.err
-tr 2 29603 --steps 20 --warmup 5 > gpurun_out/r2/scale_n2.json 2> gpurun_out/r2/scale_n2.err
-tr 8 29604 --steps 20 --warmup 5 --rows 100000000 --k 100 > gpurun_out/r2/c5_n8.json 2> gpurun_out/r2/c5_n8.err
-tr 8 29605 --steps 20 --warmup 5 --in-flight 3 > gpurun_out/r2/scale_n8_f3.json 2> gpurun_out/r2/scale_n8_f3.err
-nvidia-smi topo -m > gpurun_out/r2/topo.txt 2>&1
+tr $N 29601 --steps 20 --warmup 5 > gpurun_out/r2f/scale_n$N.json 2> gpurun_out/r2f/scale_n$N.err
+if [ "$2" = "c5" ]; then
+  tr $N 29604 --steps 20 --warmup 5 --rows 100000000 --k 100 > gpurun_out/r2f/c5_n$N.json 2> gpurun_out/r2f/c5_n$N.err
+fi
+if [ "$2" = "tests" ]; then
+  timeout 900 python -m pytest tests/test_gpu_multi.py -x -q -m gpu 2>&1 | tail -6 > gpurun_out/r2f/pytest_multi_n$N.log
+fi
