@@ -488,6 +488,47 @@ def cpu_legs(dev, n_local, avgdl, th, threads):
 
 
 # --------------------------------------------------- stage measurements (K1, K2a, K2b)
+def measure_tokenisation():
+    """the host step in front of the path, on the reference's real corpus
+    (tests/golden/legal_chunks.json.gz: 2 620 chunks) with a WordPiece vocabulary built from it
+    (the checkpoint's vocab.txt is not on disk): queries/s of the per-query WordPiece + BM25
+    whitespace tokenisation (retrieval_engine.py:61,67) and chunks/s of the index build's batch
+    encode (create_vector_store.py:45,60)."""
+    import gzip
+    from collections import Counter
+    from legal_rag_engine_b200.bm25_index import tokenize
+    from legal_rag_engine_b200.tokenizer import WordPieceTokenizer, basic_tokenize
+    chunks = json.loads(gzip.open(ROOT / "tests" / "golden" / "legal_chunks.json.gz", "rt", encoding="utf-8").read())
+    texts = [c["text"] for c in chunks]
+    cnt = Counter(w for t in texts for w in basic_tokenize(t))
+    chars = sorted({ch for w in cnt for ch in w})
+    vocab = ["[PAD]"] + [f"[unused{i}]" for i in range(99)] + ["[UNK]", "[CLS]", "[SEP]", "[MASK]"]
+    vocab += chars + ["##" + c for c in chars] + [w for w, _ in cnt.most_common(8000) if len(w) > 1]
+    tok = WordPieceTokenizer({w: i for i, w in enumerate(dict.fromkeys(vocab))})
+    queries = ["What is the procedure for Zero FIR?", "Compensation for victims of acid attack",
+               "Definition of a public servant under BNS", "Procedure after arrest of a suspect in rape case",
+               "How to file FIR for robbery BNSS procedure", "What is the punishment for murder?"] * 200
+    t0 = time.perf_counter()
+    n_tok = sum(len(tok.encode(q, 256)) for q in queries)
+    t_wp = time.perf_counter() - t0
+    t0 = time.perf_counter()
+    n_ws = sum(len(tokenize(q)) for q in queries)
+    t_ws = time.perf_counter() - t0
+    tok.encode_batch(texts[:200], 256)                                # builds the fast tokenizer once
+    t0 = time.perf_counter()
+    enc = tok.encode_batch(texts * 4, 256)[:len(texts)]
+    t_b = (time.perf_counter() - t0) / 4
+    t0 = time.perf_counter()
+    n_ct = sum(len(tokenize(t)) for t in texts)
+    t_c = time.perf_counter() - t0
+    return {"query_wordpiece_per_s": len(queries) / t_wp, "query_whitespace_per_s": len(queries) / t_ws,
+            "query_tokens": n_tok // len(queries), "build_wordpiece_chunks_per_s": len(texts) / t_b,
+            "build_whitespace_chunks_per_s": len(texts) / t_c, "chunks": len(texts),
+            "wordpiece_tokens": int(sum(len(e) for e in enc)), "whitespace_tokens": n_ct,
+            "note": "host side, one process; the batch encode uses the multi-threaded `tokenizers` library when present"}
+
+
+
 def measure_stages(dev, n_local, peaks, hbm_peak, th=None, ptr_h=None, fusion="rrf"):
     """Stages beside the headline (rank 0, N = 1).  Tensor-bound ones against the measured bf16 peak,
     HBM-bound ones against the measured copy bandwidth:
@@ -548,6 +589,10 @@ def measure_stages(dev, n_local, peaks, hbm_peak, th=None, ptr_h=None, fusion="r
         d_ids, d_lens = torch.from_numpy(ids).to(dev.device), torch.from_numpy(lens).to(dev.device)
         ms = timed(lambda: enc.encode_ids_device(d_ids, d_lens), 30)
         out["encoder_query_batch"] = {"batch": N_SUB, "seq_len": S, "ms": ms}
+    try:
+        out["host_tokenisation"] = measure_tokenisation()
+    except Exception as e:                                            # a reported extra, never fatal
+        out["host_tokenisation"] = {"error": repr(e)}
 
     def k2b(d, rows, label):
         B, K = 1024, 2 * K_TOP
