@@ -31,6 +31,9 @@ constexpr float kLnEps = 1e-12f;
 // tokens per chunk: 148 row tiles of 128 = one full wave of the LayerNorm GEMMs (whose tile is
 // the whole 384-wide row); ~7.7 KB of activations per token, consecutive kernels hit in L2
 constexpr int64_t kChunkTokens = 148 * 128;
+// the GEMMs of the chain are launched with programmatic stream serialization (tc_gemm.cu); for the
+// small kernels between them it bought nothing (A/B, tools/ab) and they stay plain launches
+constexpr bool kEncPdlSmall = false;
 
 // tc_gemm.cu
 cudaError_t make_tmap_f16(CUtensorMap* out, const void* ptr, int64_t rows, int64_t cols, int64_t ld,
@@ -87,6 +90,8 @@ embed_ln_kernel(const int32_t* __restrict__ ids, int64_t n_tokens, int S, int vo
                 const float* __restrict__ b, __half* __restrict__ out) {
     const int lane = threadIdx.x & 31;
     const int64_t tok = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    pdl_trigger();
+    pdl_wait();                                // the previous chunk's pooling has read x
     if (tok >= n_tokens) return;
     int id = ids[tok];
     id = (id < 0 || id >= vocab) ? 0 : id;
@@ -174,6 +179,9 @@ __global__ void __launch_bounds__(kAttnThreads)
 attention_kernel(const __half* __restrict__ qkv, const int32_t* __restrict__ lens, int S,
                  __half* __restrict__ ctx) {
     extern __shared__ __align__(16) unsigned char attn_raw[];
+    // (no early trigger here: the next kernel is a GEMM of one 200 KB CTA per SM, and this grid
+    // has several waves of small CTAs still to place)
+    pdl_wait();                                // the QKV projection is complete
     const int head = blockIdx.x;
     const int seq = blockIdx.y;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -344,6 +352,8 @@ __global__ void __launch_bounds__(128)
 pool_normalize_kernel(const __half* __restrict__ x, const int32_t* __restrict__ lens, int S,
                       float* __restrict__ out_f32, __half* __restrict__ out_f16) {
     __shared__ float red[4];
+    pdl_trigger();
+    pdl_wait();                                // the last layer's output is complete
     const int seq = blockIdx.x;
     const int tid = threadIdx.x;
     int len = lens[seq];
@@ -1204,10 +1214,10 @@ cudaError_t encoder_forward(lrx_handle* h, const int32_t* ids, const int32_t* le
         const int64_t T = (int64_t)nb * S;
         const int32_t* cid = ids + (size_t)b0 * S;
         const int32_t* clen = lens + b0;
-        embed_ln_kernel<<<(unsigned)((T + 7) / 8), 256, 0, st>>>(cid, T, S, e->vocab, e->max_pos, e->word,
-                                                                 e->pos, e->type0, e->eln_g, e->eln_b, e->x);
+        ENC_CK(launch_pdl_if(kEncPdlSmall, embed_ln_kernel, dim3((unsigned)((T + 7) / 8)), dim3(256), 0, st, cid, T, S, e->vocab,
+                          e->max_pos, (const float*)e->word, (const float*)e->pos, (const float*)e->type0,
+                          (const float*)e->eln_g, (const float*)e->eln_b, e->x));
         h->launches++;
-        ENC_CK(cudaGetLastError());
         const int Sk = (S + 63) & ~63;
         const size_t attn_smem = (size_t)Sk * kKPad * 2 * 2;
         // which W tensor-map set matches the plan the GEMM launcher picks for this many rows
@@ -1216,9 +1226,9 @@ cudaError_t encoder_forward(lrx_handle* h, const int32_t* ids, const int32_t* le
             EncLayer& L = e->L[l];
             ENC_CK(launch_tc_gemm(h, e->t_x, L.t_wqkv[pl], e->io_qkv, e->io_qkv, (int)T, kQkv, kHidden, 0,
                                   L.bqkv, nullptr, nullptr, 0.f, e->qkv, kQkv));
-            attention_kernel<<<dim3(kHeads, nb), kAttnThreads, attn_smem, st>>>(e->qkv, clen, S, e->ctx);
+            ENC_CK(launch_pdl_if(kEncPdlSmall, attention_kernel, dim3(kHeads, nb), dim3(kAttnThreads), attn_smem, st,
+                              (const __half*)e->qkv, clen, S, e->ctx));
             h->launches++;
-            ENC_CK(cudaGetLastError());
             ENC_CK(launch_tc_gemm(h, e->t_ctx, L.t_wo[pl], e->io_x1, e->io_x, (int)T, kHidden, kHidden, 2,
                                   L.bo, L.ln1_g, L.ln1_b, kLnEps, e->x1, kHidden));
             ENC_CK(launch_tc_gemm(h, e->t_x1, L.t_w1[pl], e->io_ff, e->io_ff, (int)T, kFfn, kHidden, 1,
@@ -1226,11 +1236,10 @@ cudaError_t encoder_forward(lrx_handle* h, const int32_t* ids, const int32_t* le
             ENC_CK(launch_tc_gemm(h, e->t_ff, L.t_w2[pl], e->io_x, e->io_x1, (int)T, kHidden, kFfn, 2,
                                   L.b2, L.ln2_g, L.ln2_b, kLnEps, e->x, kHidden));
         }
-        pool_normalize_kernel<<<nb, 128, 0, st>>>(
-            e->x, clen, S, out_f32 ? out_f32 + (size_t)b0 * kHidden : nullptr,
-            out_f16 ? (__half*)out_f16 + (size_t)b0 * kHidden : nullptr);
+        ENC_CK(launch_pdl_if(kEncPdlSmall, pool_normalize_kernel, dim3(nb), dim3(128), 0, st, (const __half*)e->x, clen, S,
+                          out_f32 ? out_f32 + (size_t)b0 * kHidden : (float*)nullptr,
+                          out_f16 ? (__half*)out_f16 + (size_t)b0 * kHidden : (__half*)nullptr));
         h->launches++;
-        ENC_CK(cudaGetLastError());
     }
     return cudaSuccess;
 }

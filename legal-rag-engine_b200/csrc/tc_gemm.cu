@@ -48,6 +48,7 @@ struct GemmEpi {
     int M;                    // valid rows
     float eps;
     long long* trace;         // optional timeline of CTA 0 (lrx_debug_set_trace), else NULL
+    int pdl_early;            // let the next kernel be scheduled at this kernel's start (else at its end)
 };
 
 constexpr int kAResKB = 6;                        // k-blocks of a RESIDENT A tile (K = 384)
@@ -190,6 +191,12 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
     constexpr int kProducerWarp = kEpiWarps, kMmaWarp = kEpiWarps + 1;
 
     if (threadIdx.x == 0) LRX_TRACE(0);
+    // Programmatic dependent launch: from the trigger on, CTAs of the next kernel of the stream may
+    // take an SM as soon as one is free, run their prologue and wait.  A grid that leaves SMs idle
+    // (fewer row blocks than SMs) triggers at once -- 0.566 -> 0.521 ms for 64 sequences of 128
+    // tokens; a full grid triggers when its CTA is done, so that the successor's CTAs do not sit on
+    // the SMs it is still using -- 6.01 -> 5.73 ms for 1024 sequences (at once: 6.15).
+    if (ep.pdl_early) pdl_trigger();
     if (warp == kProducerWarp && lane == 0) {
         tma_prefetch_desc(&tma_a);
         tma_prefetch_desc(&tma_b);
@@ -216,6 +223,7 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
     if (CS > 1) cluster_sync_all();            // peers' barriers are initialised before any multicast
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
+    pdl_wait();                                // the previous kernel's outputs are complete and visible
     if (threadIdx.x == 0) LRX_TRACE(1);
 
     if (warp == kProducerWarp) {
@@ -525,6 +533,7 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap tma_a, const __grid_constant_
     }
     tc_fence_before();
     __syncthreads();
+    if (!ep.pdl_early) pdl_trigger();          // this CTA's work is done
     if (threadIdx.x == 0) LRX_TRACE(2);
     if (CS > 1) cluster_sync_all();            // nobody leaves while a peer may still multicast to it
     if (threadIdx.x == 0) LRX_TRACE(3);
@@ -610,14 +619,21 @@ static cudaError_t launch_cfg(lrx_handle* h, const CUtensorMap& ta, const CUtens
     cfg.blockDim = dim3(kGemmThreads);
     cfg.dynamicSmemBytes = smem;
     cfg.stream = h->stream;
-    cudaLaunchAttribute at[1];
+    // programmatic dependent launch: this kernel's CTAs may take an SM as soon as the previous
+    // kernel's CTA leaves it and run their prologue (barriers, TMEM, descriptor prefetch) while the
+    // rest of that grid drains; they wait (griddepcontrol.wait) before touching activations
+    cudaLaunchAttribute at[2];
     at[0].id = cudaLaunchAttributeClusterDimension;
     at[0].val.clusterDim.x = CS;
     at[0].val.clusterDim.y = 1;
     at[0].val.clusterDim.z = 1;
+    at[1].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    at[1].val.programmaticStreamSerializationAllowed = 1;
     cfg.attrs = at;
-    cfg.numAttrs = 1;
-    return cudaLaunchKernelEx(&cfg, kern, ta, tb, tout, tres, K / kBK, m_tiles, n_tiles, ep);
+    cfg.numAttrs = 2;
+    GemmEpi ep2 = ep;
+    ep2.pdl_early = (units < h->num_sms) ? 1 : 0;
+    return cudaLaunchKernelEx(&cfg, kern, ta, tb, tout, tres, K / kBK, m_tiles, n_tiles, ep2);
 }
 
 // Which variant runs (the W tensor map's box must match: gemm_box_rows_w).
