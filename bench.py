@@ -556,7 +556,8 @@ def measure_stages(dev, n_local, peaks, hbm_peak, th=None, ptr_h=None, fusion="r
         torch.cuda.synchronize()
         return ev0.elapsed_time(ev1) / n_it
 
-    enc = SentenceEncoder(dev, state_dict=synth.bert_state_dict(42, 0.02))
+    sd = synth.bert_state_dict(42, 0.02)
+    enc = SentenceEncoder(dev, state_dict=sd)
     sweep = []
     for S in (128, 256):
         for B in (1, 4, 16, 64, 256, 1024, 4096):
@@ -589,6 +590,39 @@ def measure_stages(dev, n_local, peaks, hbm_peak, th=None, ptr_h=None, fusion="r
         d_ids, d_lens = torch.from_numpy(ids).to(dev.device), torch.from_numpy(lens).to(dev.device)
         ms = timed(lambda: enc.encode_ids_device(d_ids, d_lens), 30)
         out["encoder_query_batch"] = {"batch": N_SUB, "seq_len": S, "ms": ms}
+        # the same call split in begin / end on three handles over the one index: three batches in
+        # flight, one batch's encoder and small kernels under another's scans
+        try:
+            views = [dev.clone_view() for _ in range(2)]
+            hs = [dev] + views
+            encs = [SentenceEncoder(v, state_dict=sd) for v in views]
+            sts = [torch.cuda.Stream(device=dev.device) for _ in hs]
+            for d_, s_ in zip(hs, sts):
+                with torch.cuda.stream(s_):
+                    d_.use_current_stream()
+
+            def run_pipe(n):
+                for i in range(n):
+                    d_ = hs[i % 3]
+                    if i >= 3:
+                        d_.search_host_end()
+                    d_.search_text_host_begin(ids, lens, lists[i % POOL], K_TOP, WEIGHTS, fusion)
+                for i in range(max(0, n - 3), n):
+                    hs[i % 3].search_host_end()
+            run_pipe(9)
+            torch.cuda.synchronize()
+            t0 = time.perf_counter()
+            run_pipe(90)
+            torch.cuda.synchronize()
+            dt = time.perf_counter() - t0
+            out["search_text_host_pipelined"] = {"queries_per_s": 90 / dt, "ms": dt / 90 * 1e3, "in_flight": 3,
+                                                 "call": "lrx_search_text_host_begin / lrx_search_host_end"}
+            del encs
+            for v in views:
+                v.close()
+            dev.use_current_stream()
+        except Exception as e:                                        # a reported extra, never fatal
+            out["search_text_host_pipelined"] = {"error": repr(e)}
     try:
         out["host_tokenisation"] = measure_tokenisation()
     except Exception as e:                                            # a reported extra, never fatal

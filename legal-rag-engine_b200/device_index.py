@@ -314,6 +314,20 @@ class DeviceIndex:
         self._ck(self.lib.lrx_search_host_end(self.h, vp(ids), vp(score), vp(sem), vp(kw)))
         return ids, score, sem, kw
 
+    def search_text_host_begin(self, tok_ids: np.ndarray, tok_lens: np.ndarray, term_lists, k: int,
+                               weights: Sequence[float], fusion: str = "linear"):
+        """`search_text_host` split in two: stage + enqueue (H2D, encoder, chain, D2H) and return at
+        once; `search_host_end` collects.  Several handles over one index keep several batches in
+        flight, the encoder of one under the scans of another."""
+        tok_ids = np.ascontiguousarray(tok_ids, dtype=np.int32)
+        tok_lens = np.ascontiguousarray(tok_lens, dtype=np.int32)
+        B, S = tok_ids.shape
+        _, _, terms, ptr, w = self._host_args(np.zeros((B, LRX_DIM), np.float16), term_lists, weights)
+        vp = lambda a: a.ctypes.data_as(C.c_void_p)
+        self._ck(self.lib.lrx_search_text_host_begin(self.h, vp(tok_ids), vp(tok_lens), S, vp(terms), vp(ptr),
+                                                     vp(w), B, k, FUSION[fusion]))
+        self._pending = (B, k)
+
     def search_text_host(self, tok_ids: np.ndarray, tok_lens: np.ndarray, term_lists, k: int,
                          weights: Sequence[float], fusion: str = "linear"):
         """The whole of RetrievalEngine.search for tokenised strings: WordPiece ids [B,S] + lens [B]
