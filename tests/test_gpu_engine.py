@@ -82,6 +82,58 @@ def test_search_batch_equals_sequential_search(built):
     assert len(heads) == len(set(heads)) and len(merged) <= 20
 
 
+def test_text_path_begin_end_equals_blocking_call(built):
+    """lrx_search_text_host_begin / lrx_search_host_end (encoder in the call) on two handles over the
+    one index, two batches in flight: the same results, bit for bit, as the blocking call."""
+    import torch
+    from legal_rag_engine_b200.bm25_index import tokenize
+    from legal_rag_engine_b200.encoder import SentenceEncoder
+    eng, sd, _ = built
+    tok = eng.model.tokenizer
+    batches = [["What is the procedure for Zero FIR?", "punishment for murder"],
+               ["Compensation for victims of acid attack", "bail for non-bailable offence", "theft"],
+               ["How to file FIR for robbery BNSS procedure"]]
+
+    def host_form(qs):
+        enc = [tok.encode(q, 256) for q in qs]
+        S = max(len(e) for e in enc)
+        ids = np.zeros((len(qs), S), dtype=np.int32)
+        for i, e in enumerate(enc):
+            ids[i, :len(e)] = e
+        lens = np.array([len(e) for e in enc], dtype=np.int32)
+        lists = [[t for t in eng.bm25.term_ids(tokenize(q)) if t >= 0] for q in qs]
+        return ids, lens, lists
+    forms = [host_form(qs) for qs in batches]
+    want = [eng.dev.search_text_host(i, l, t, 5, [0.5] * len(t), "rrf") for i, l, t in forms]
+    view = eng.dev.clone_view()
+    venc = SentenceEncoder(view, state_dict=sd, tokenizer=tok)      # the second handle's own encoder state
+    try:
+        hs = [eng.dev, view]
+        streams = [torch.cuda.Stream(), torch.cuda.Stream()]
+        for d, s in zip(hs, streams):
+            with torch.cuda.stream(s):
+                d.use_current_stream()
+        got = [None] * len(forms)
+        order = list(range(len(forms))) * 3                      # slots and captured chains are reused
+        pend = {}
+        for n, j in enumerate(order):
+            d = hs[n % 2]
+            if d in pend:
+                got[pend.pop(d)] = d.search_host_end()
+            i, l, t = forms[j]
+            d.search_text_host_begin(i, l, t, 5, [0.5] * len(t), "rrf")
+            pend[d] = j
+        for d, j in pend.items():
+            got[j] = d.search_host_end()
+        for g, w in zip(got, want):
+            for a, b in zip(g, w):
+                np.testing.assert_array_equal(a, b)
+    finally:
+        del venc
+        view.close()
+        eng.dev.use_current_stream()
+
+
 def test_small_k_and_bad_fusion(built):
     eng, _, _ = built
     assert len(eng.search("zero fir", k=3)) == 3
