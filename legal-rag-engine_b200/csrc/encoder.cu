@@ -400,16 +400,16 @@ pool_normalize_kernel(const __half* __restrict__ x, const int32_t* __restrict__ 
 // runs the WHOLE forward pass -- embeddings, 6 layers, pooling, both normalisations -- as one
 // launch, and spreads it: sequences are independent, so every GROUP of sequences with at most
 // M = 16 MT tokens (MT = 2: S <= 32, MT = 4: S <= 64) gets its own cluster of 8 CTAs, and inside a
-// cluster every GEMM is cut into UNITS of 8 output columns x 384 k for all M rows:
-//   * a unit's weights are 8 rows x 768 B of W, fetched as 12 independent 16-byte loads per lane
-//     straight into mma.sync B fragments (A and B agree on a permuted k order, as in dense.cu: no
-//     ldmatrix, no swizzle), all issued before the first MMA and one unit ahead -- the first
-//     version kept one 32-k chunk in flight per warp and spent its time waiting for L2;
+// cluster every GEMM is split over the 64 warps by output COLUMNS (sm_tile_mma below):
+//   * a warp owns half of the group's rows x up to 6 column tiles of 8; its weights are fetched as
+//     16-byte loads per lane straight into mma.sync B fragments (A and B agree on a permuted k
+//     order, as in dense.cu: no ldmatrix, no swizzle), four 32-k chunks ahead of the MMAs, the first
+//     four chunks of a phase before the cluster barrier in front of it;
 //   * the group's activations X [M x 384] live in every CTA's shared memory (replicated); A
 //     operands written by other CTAs (attention output, FFN activations) are staged by cp.async;
-//   * QKV: 144 units, FFN up: 192, attention output: 48 over the cluster's 64 warps; FFN down
-//     (K = 1536) is 48 column tiles x 4 k quarters = 192 units whose partial sums meet in the
-//     LayerNorm IN A FIXED ORDER, so the result does not depend on timing;
+//   * QKV: 144 column tiles = 16 warp pairs x 5 + 16 x 4, FFN up: 192 = 32 x 6, attention output:
+//     48 = 16 x 2 + 16 x 1; FFN down (K = 1536) is 48 column tiles x 4 k quarters whose partial
+//     sums meet in the LayerNorm IN A FIXED ORDER, so the result does not depend on timing;
 //   * slices meet in an L2-resident scratch, a cluster barrier (release / acquire) separates
 //     producer and consumer steps: 5 per layer; LayerNorm runs redundantly in every CTA (fp32);
 //   * attention: one (sequence, head) pair per warp, mma.sync QK^T / PV with one-shot softmax.
