@@ -675,7 +675,7 @@ def measure_stages(dev, n_local, peaks, hbm_peak, th=None, ptr_h=None, fusion="r
 def scan_traffic_from_profile(n_local):
     """dram bytes of dense_scan_kernel from the committed ncu --set full capture (profiles/),
     scaled per row: the kernel reads each row exactly once, so bytes/row is size independent."""
-    for name in ("r2_scan_kernels_full.json", "r1_scan_kernels_v3_full.json"):
+    for name in ("r2_scan_kernels_final_full.json", "r2_scan_kernels_full.json", "r1_scan_kernels_v3_full.json"):
         try:
             prof = json.loads((ROOT / "profiles" / name).read_text())
             for l in prof["launches"]:
