@@ -18,9 +18,12 @@ d_ids, d_lens = torch.from_numpy(ids).cuda(), torch.from_numpy(lens).cuda()
 x = synth.device_vectors(1_000_000, dev.device, seed=1234)
 dev.set_corpus(x, 0)
 q = torch.from_numpy(synth.host_queries(1024, seed=4321)).cuda()
+ids_q, lens_q = synth.token_batch(4, 32, seed=2, full=True)           # a fan-out query batch: the one-launch cluster kernel
+dq_ids, dq_lens = torch.from_numpy(ids_q).cuda(), torch.from_numpy(lens_q).cuda()
 for _ in range(a.warm + 1):
     enc.encode_ids_device(d_ids, d_lens)
     dev.dense_topk_batched(q, 20)
+    enc.encode_ids_device(dq_ids, dq_lens)
 torch.cuda.synchronize()
 print("ok")
 dev.close()
