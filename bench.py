@@ -893,6 +893,43 @@ def run_ours(args):
     e2e_ms = float(e2e_ms.item())
     assert last is not None and (last[0][:, 0] >= 0).all()
 
+    # ---- two user queries per launch chain (8 sub-queries): ONE pass of the matrix serves both --
+    #      the dense scan's MMA tile has 8 query columns either way ("matrix read once
+    #      regardless of B <= 16") -- which is what a serving front does with concurrent requests
+    #      (serving.MicroBatchingEngine).  Same host-buffer calls, same batches in flight; NOT the
+    #      headline (a step of `value` / `e2e` is one user query), reported beside it.
+    batched = None
+    try:
+        q2 = [np.ascontiguousarray(np.concatenate([qh[p], qh[(p + 1) % POOL]], 0)) for p in range(POOL)]
+        l2 = [lists[p] + lists[(p + 1) % POOL] for p in range(POOL)]
+
+        def two_run(n):
+            for i in range(n):
+                d = devs[i % n_fly]
+                if i >= n_fly:
+                    d.search_host_end()
+                d.search_host_begin(q2[i % POOL], l2[i % POOL], K_TOP, WEIGHTS * 2, args.fusion)
+            for i in range(max(0, n - n_fly), n):
+                devs[i % n_fly].search_host_end()
+        two_run(max(6, 3 * n_fly))
+        barrier()
+        two_steps = max(e2e_steps // 2, 10)
+        ev0.record()
+        two_run(two_steps)
+        ev1.record()
+        barrier()
+        two_ms = torch.tensor([ev0.elapsed_time(ev1)], dtype=torch.float64, device=device)
+        if world > 1:
+            dist.all_reduce(two_ms, op=dist.ReduceOp.MAX)
+        two_ms = float(two_ms.item())
+        batched = {"users_per_step": 2, "sub_queries_per_step": 2 * N_SUB,
+                   "value": 2 * two_steps / (two_ms * 1e-3), "unit": "queries/s",
+                   "ms_per_step": two_ms / two_steps, "steps": two_steps, "in_flight": n_fly,
+                   "call": "lrx_search_host_begin / lrx_search_host_end (host buffers in and out)",
+                   "note": "two user queries share one matrix pass; not the headline"}
+    except Exception as e:                                            # a reported extra, never fatal
+        batched = {"error": repr(e)}
+
     # ---- the dominant kernel ALONE (no BM25 scan beside it): the same launches through
     #      lrx_dense_topk, events inside the library -- what the kernel does with the HBM to itself
     dev.use_current_stream()           # handle 0 back on torch's default stream for what follows
@@ -943,6 +980,7 @@ def run_ours(args):
                     "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
                     "ms_per_step": e2e_ms / e2e_steps, "steps": e2e_steps, "in_flight": n_fly,
                     "call": "lrx_search_host_begin / lrx_search_host_end (host buffers in and out)"},
+            "two_users_per_step": batched,
             "gpu_launches": int(launches),
             "host_enqueue_ms_per_step": t_host * 1e3 / timed_steps,
             "clocks": clk,

@@ -377,14 +377,23 @@ int lrx_gemm_f16(lrx_handle* h, const void* dev_a, const void* dev_w, int32_t M,
     return LRX_OK;
 }
 
-// K2 by batch size ("K2a/K2b chosen by B"): up to 4 queries share one streaming pass
-// of the matrix (K2a, HBM-bound); from 5 queries on the tensor-core kernel scores the whole batch in
-// ONE pass (K2b) where K2a would need ceil(B/4) -- measured at 10 M rows: B = 8 1.30 ms against
-// 2.23 ms, B = 64 1.32 ms against 18.1 ms (tools/k2_crossover.py); both emit the same exact lists.
-// A widened retry (exactness guard / candidate overflow) makes K2b sample every tile.
+// K2 by batch size ("K2a/K2b chosen by B"): up to 8 queries share ONE streaming pass
+// of the matrix (K2a, HBM-bound: the 8 columns of its MMA tile are all queries then); from 9 queries
+// on the tensor-core kernel scores the whole batch in one pass (K2b) where K2a would need
+// ceil(B / 8) -- measured at 10 M rows: B = 64 1.32 ms against 18.1 ms (tools/k2_crossover.py); both
+// emit the same exact lists.  A widened retry (exactness guard / candidate overflow) makes K2b sample
+// every tile.  LRX_K2B_MIN_B overrides the crossover (A/B runs).
+static int k2b_min_b() {
+    static int v = -1;
+    if (v < 0) {
+        const char* e = getenv("LRX_K2B_MIN_B");
+        v = (e != nullptr && atoi(e) > 0) ? atoi(e) : 9;
+    }
+    return v;
+}
 static cudaError_t launch_dense_auto(lrx_handle* h, const void* q, int B, int K, int width, double* exact,
                                      float* D, int64_t* I, int32_t* flags) {
-    if (B > 4 && h->n_local > 0 && ((uintptr_t)q & 15) == 0) {
+    if (B >= k2b_min_b() && h->n_local > 0 && ((uintptr_t)q & 15) == 0) {
         const int stride = (width > dense_default_width(K)) ? 1 : 0;
         return launch_dense_topk_batched(h, q, B, K, stride, exact, D, I, flags);
     }

@@ -38,16 +38,19 @@ constexpr int kSoftCap = 256;                      // prune once a buffer holds 
                                                    // tile: sorting 256 keys costs ~3 us, 1024 keys ~40 us,
                                                    // and the threshold tightens 4x per prune either way
 constexpr int kMaxWidth = 512;                     // max per-CTA list length
+// candidate buffer entries per query: up to 4 queries per pass 1024 each, 5..8 queries 512 each (the
+// same 32 KB: a CTA of the BM25 scan must keep fitting beside this kernel's CTA; lists up to 256 wide)
+__host__ __device__ constexpr int scan_cap(int nq) { return nq > 4 ? 512 : kCap; }
 
 struct ScanSmem {
     // ring first (16-byte aligned bulk-copy destinations)
     unsigned char ring[kStages][kTileBytes];
-    float part[2][kTileRows][4];   // [k half][row][query] partial scores of one tile
+    float part[2][kTileRows][8];   // [k half][row][query] partial scores of one tile
     uint64_t full[kStages];
     int tile_of[kStages];          // tile held (or being loaded) by every stage
-    int count[4];
-    uint32_t tau[4];
-    uint64_t keys[1];   // [NQ][kCap], sized at launch
+    int count[8];
+    uint32_t tau[8];
+    uint64_t keys[1];   // [NQ][scan_cap(NQ)], sized at launch
 };
 
 // ---- register sorting networks of the fast prune (two keys per lane, 64 keys per warp)
@@ -97,6 +100,7 @@ __device__ __forceinline__ void warp64_sort_desc(uint64_t& v0, uint64_t& v1, int
 template <int NQ>
 __device__ __forceinline__ void scan_prune(uint64_t* keys, int* count, uint32_t* tau, int width,
                                            int tid, unsigned int* tau_g) {
+    constexpr int cap = scan_cap(NQ);
     int nmax = width;
 #pragma unroll
     for (int q = 0; q < NQ; ++q) nmax = max(nmax, count[q]);
@@ -104,10 +108,13 @@ __device__ __forceinline__ void scan_prune(uint64_t* keys, int* count, uint32_t*
         // fast path (the default list width, pruned at the soft cap): two warps per query, each
         // sorts two 64-key quarters in registers; the best 64 of two descending runs A, B are the
         // bitonic sequence max(A[i], B[63 - i]), sorted by one bitonic merge -- once inside the
-        // warp (B reversed by a shuffle), once across the two warps through shared memory.
+        // warp (B reversed by a shuffle), once across the two warps through shared memory.  Four
+        // queries at a time (8 warps): a pass of 5..8 queries takes two rounds.
         const int lane = tid & 31, warp = tid >> 5;
-        const int q = warp & 3, half = warp >> 2;            // 8 warps: (query, half)
-        uint64_t* kq = keys + q * kCap;
+#pragma unroll 1
+        for (int qb = 0; qb < NQ; qb += 4) {
+        const int q = qb + (warp & 3), half = warp >> 2;     // 8 warps: (query, half)
+        uint64_t* kq = keys + q * cap;
         const bool active = q < NQ;
         const int n = active ? count[q] : 0;
         uint64_t v0 = 0ull, v1 = 0ull;
@@ -141,22 +148,23 @@ __device__ __forceinline__ void scan_prune(uint64_t* keys, int* count, uint32_t*
             kq[2 * lane + 1] = v1;
         }
         __syncthreads();
+        }
     } else {
         // general path (wider lists): sort only as many slots as are in use (power of two >= the
         // fullest buffer, >= width; unused ones padded with the empty key), all NQ buffers at once.
         // Bitonic sort with the 64-key stages in registers: chunks of 64 are sorted by one warp
         // each (alternating direction), and of every later merge only the steps at distance >= 64
         // go through shared memory -- 10 block-wide steps for 1024 keys instead of 55.
-        const int n2 = min(kCap, next_pow2(nmax));
+        const int n2 = min(cap, next_pow2(nmax));
 #pragma unroll
         for (int q = 0; q < NQ; ++q) {
             const int n = count[q];
             for (int i = tid; i < n2; i += kScanThreads)
-                if (i >= n) keys[q * kCap + i] = 0ull;
+                if (i >= n) keys[q * cap + i] = 0ull;
         }
         __syncthreads();
         if (n2 < 128) {
-            block_bitonic_sort_desc<uint64_t>(keys, n2, NQ, kCap, tid, kScanThreads);
+            block_bitonic_sort_desc<uint64_t>(keys, n2, NQ, cap, tid, kScanThreads);
         } else {
             const int lane = tid & 31, warp = tid >> 5;
             const int chunks = n2 >> 6, total = chunks * NQ;
@@ -165,7 +173,7 @@ __device__ __forceinline__ void scan_prune(uint64_t* keys, int* count, uint32_t*
             auto chunk_pass = [&](int k, bool first) {
                 for (int c = warp; c < total; c += kScanThreads / 32) {
                     const int q = c / chunks, ch = c - q * chunks;
-                    uint64_t* kc = keys + q * kCap + ch * 64;
+                    uint64_t* kc = keys + q * cap + ch * 64;
                     uint64_t v0 = kc[2 * lane], v1 = kc[2 * lane + 1];
                     if (first) warp64_sort_desc(v0, v1, lane); else warp64_merge_desc(v0, v1, lane);
                     const bool desc = ((ch * 64) & k) == 0;
@@ -183,7 +191,7 @@ __device__ __forceinline__ void scan_prune(uint64_t* keys, int* count, uint32_t*
                         const int q = t >> lh, u = t & (half - 1);
                         const int i = ((u & ~(j - 1)) << 1) | (u & (j - 1));
                         const int p = i | j;
-                        uint64_t* kk = keys + q * kCap;
+                        uint64_t* kk = keys + q * cap;
                         const uint64_t a = kk[i], b = kk[p];
                         const bool desc = ((i & k) == 0);
                         if (desc ? (a < b) : (a > b)) { kk[i] = b; kk[p] = a; }
@@ -201,7 +209,7 @@ __device__ __forceinline__ void scan_prune(uint64_t* keys, int* count, uint32_t*
             // `width` rows of this CTA reach this score: no row below it, anywhere, can be among
             // the best `width` -- share it with every CTA of the grid (threshold warm-up once
             // per grid instead of once per CTA)
-            const uint32_t t = max(tau[tid], (uint32_t)(keys[tid * kCap + width - 1] >> 32));
+            const uint32_t t = max(tau[tid], (uint32_t)(keys[tid * cap + width - 1] >> 32));
             tau[tid] = t;
             atomicMax(tau_g + tid, t);
         }
@@ -227,7 +235,8 @@ dense_scan_kernel(const unsigned char* __restrict__ x, int64_t n_rows,
     const int warp = tid >> 5;
 
     // width <= 128: prune at 256 entries; wider lists keep the full buffer
-    const int soft_cap = (2 * width <= kSoftCap) ? kSoftCap : kCap;
+    constexpr int cap = scan_cap(NQ);
+    const int soft_cap = (2 * width <= kSoftCap) ? kSoftCap : cap;
     // Tiles are static, blockIdx + i * grid: at any moment the grid reads one contiguous ~7 MB
     // window of the matrix.  (Measured, tools/scan_sweep.sh: claiming tiles from a grid-wide counter
     // costs 25 % -- one contended atomic per 48 KB -- and re-filling a stage BEFORE the tile's
@@ -241,7 +250,7 @@ dense_scan_kernel(const unsigned char* __restrict__ x, int64_t n_rows,
         for (int s = 0; s < kStages; ++s) mbar_init(&sm.full[s], 1);
         fence_barrier_init();
     }
-    if (tid < 4) {
+    if (tid < 8) {
         sm.count[tid] = 0;
         sm.tau[tid] = 0u;   // ordinal 0: every finite score passes
     }
@@ -318,8 +327,8 @@ dense_scan_kernel(const unsigned char* __restrict__ x, int64_t n_rows,
                              : "r"(xa[j].z), "r"(xb[j].z), "r"(xa[j].w), "r"(xb[j].w),
                                "r"(qb[j][2]), "r"(qb[j][3]));
             }
-            // lanes t < 2 hold queries 2t, 2t + 1 of rows g and g + 8; the other columns are padding
-            if (t < 2) {
+            // lane t holds queries 2t, 2t + 1 of rows g and g + 8; columns >= NQ are padding
+            if (2 * t < NQ) {
                 *reinterpret_cast<float2*>(&sm.part[kh][mblk * 16 + g][2 * t]) =
                     make_float2(c0[0] + c1[0], c0[1] + c1[1]);
                 *reinterpret_cast<float2*>(&sm.part[kh][mblk * 16 + g + 8][2 * t]) =
@@ -330,14 +339,15 @@ dense_scan_kernel(const unsigned char* __restrict__ x, int64_t n_rows,
 
         // ---- one thread per (row, query): sum of the two halves, threshold test, rare append to
         //      the shared buffer
-        if (tid < kTileRows * 4) {
-            const int row_in_tile = tid >> 2, qi = tid & 3;
+#pragma unroll
+        for (int i = tid; i < kTileRows * NQ; i += kScanThreads) {
+            const int row_in_tile = i / NQ, qi = i % NQ;
             const float sc = sm.part[0][row_in_tile][qi] + sm.part[1][row_in_tile][qi];
             if (row_in_tile < rows && qi < n_q) {
                 const uint32_t o = f32_ord(sc);
                 if (o >= sm.tau[qi]) {
                     const int pos = atomicAdd(&sm.count[qi], 1);
-                    keys[qi * kCap + pos] =
+                    keys[qi * cap + pos] =
                         ((uint64_t)o << 32) | (uint32_t)(~(uint32_t)(row0 + row_in_tile));
                 }
             }
@@ -367,7 +377,7 @@ dense_scan_kernel(const unsigned char* __restrict__ x, int64_t n_rows,
     for (int i = tid; i < NQ * width; i += kScanThreads) {
         const int qi = i / width;
         const int j = i - qi * width;
-        const uint64_t k = (j < sm.count[qi]) ? keys[qi * kCap + j] : 0ull;
+        const uint64_t k = (j < sm.count[qi]) ? keys[qi * cap + j] : 0ull;
         part[((size_t)blockIdx.x * NQ + qi) * width + j] = k;
     }
     SCAN_TRACE(3);
@@ -548,8 +558,8 @@ static cudaError_t launch_scan(lrx_handle* h, const __half* q, int n_q, int widt
         attr = true;
     }
     // shared thresholds live behind the per-CTA lists in the same workspace
-    unsigned int* tau_g = reinterpret_cast<unsigned int*>(part + (size_t)grid * 4 * width);
-    cudaError_t e0 = cudaMemsetAsync(tau_g, 0, 4 * sizeof(unsigned int), h->stream);
+    unsigned int* tau_g = reinterpret_cast<unsigned int*>(part + (size_t)grid * 8 * width);
+    cudaError_t e0 = cudaMemsetAsync(tau_g, 0, 8 * sizeof(unsigned int), h->stream);
     if (e0 != cudaSuccess) return e0;
     prof_begin(h, 0);
     dense_scan_kernel<NQ><<<grid, kScanThreads, smem, h->stream>>>(
@@ -569,9 +579,9 @@ cudaError_t launch_dense_topk(lrx_handle* h, const void* qv, int B, int K, int w
                               double* exact, float* D, int64_t* I, int32_t* flags) {
     const int grid = dense_scan_grid(h);
     cudaError_t e;
-    // per-CTA lists for up to 4 queries per pass
+    // per-CTA lists for up to 8 queries per pass
     e = ensure_ws(h, &h->ws_dense_part, &h->ws_dense_part_bytes,
-                  (size_t)grid * 4 * width * sizeof(uint64_t) + 64);
+                  (size_t)grid * 8 * width * sizeof(uint64_t) + 64);
     if (e != cudaSuccess) return e;
     std::lock_guard<std::recursive_mutex> attr_guard(attr_mutex());   // the flags below are process-wide
     static bool attr_dev[64] = {false};   // function attributes are per device
@@ -584,13 +594,16 @@ cudaError_t launch_dense_topk(lrx_handle* h, const void* qv, int B, int K, int w
     }
     uint64_t* part = (uint64_t*)h->ws_dense_part;
     const __half* q = (const __half*)qv;
-    for (int b0 = 0; b0 < B; b0 += 4) {
-        const int nq = (B - b0 < 4) ? (B - b0) : 4;
-        // always the 4-query instantiation (absent queries are zero columns that never append): the
-        // 1- and 2-query instantiations measured SLOWER (batch 1 over 1 M rows: 0.179 ms against
-        // 0.124 ms for batch 4)
-        constexpr int NQ = 4;
-        e = launch_scan<4>(h, q + (size_t)b0 * kDim, nq, width, part, grid);
+    // One matrix pass serves up to 8 queries: the MMA tile has 8 columns either way (SURVEY 8(d)
+    // budgets ONE read of the matrix per batch).  5..8 queries take the 8-query instantiation (512
+    // candidate slots per query, lists up to 256 wide); up to 4 the 4-query one -- the 1- and 2-query
+    // instantiations measured SLOWER (batch 1 over 1 M rows: 0.179 ms against 0.124 ms for batch 4).
+    const int per_pass = (B > 4 && width <= 256) ? 8 : 4;
+    for (int b0 = 0; b0 < B; b0 += per_pass) {
+        const int nq = (B - b0 < per_pass) ? (B - b0) : per_pass;
+        const int NQ = nq > 4 ? 8 : 4;
+        e = (NQ == 8) ? launch_scan<8>(h, q + (size_t)b0 * kDim, nq, width, part, grid)
+                      : launch_scan<4>(h, q + (size_t)b0 * kDim, nq, width, part, grid);
         if (e != cudaSuccess) return e;
         // list l of query qi of this pass: part[(l * NQ + qi) * width]
         dense_merge_rescore_kernel<<<nq, kMergeThreads, kMergeCap * sizeof(uint64_t), h->stream>>>(

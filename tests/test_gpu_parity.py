@@ -38,7 +38,7 @@ def _cuda(a, dt=None):
 
 # ------------------------------------------------------------------ K2 dense
 @pytest.mark.parametrize("n", [1, 5, 63, 64, 65, 1000, 20011, 300000])
-@pytest.mark.parametrize("B", [1, 2, 3, 4, 7])
+@pytest.mark.parametrize("B", [1, 2, 3, 4, 5, 7, 8])     # 5..8: the 8-queries-per-pass instantiation
 def test_dense_topk_matches_oracle(dev, n, B):
     x = synth.host_vectors(n, seed=100 + n, dup_frac=0.01)
     q = synth.host_queries(B, seed=7 + B)
@@ -525,10 +525,11 @@ def test_host_begin_end_two_handles_pipelined(dev):
 
 
 @pytest.mark.parametrize("fusion", ["linear", "rrf"])
-@pytest.mark.parametrize("B", [5, 8, 33, 64])
+@pytest.mark.parametrize("B", [5, 8, 9, 33, 64])
 def test_search_batch_routes_larger_batches_to_tensor_core_scoring(dev, B, fusion):
-    """From 5 sub-queries on, the search chain scores the batch with the tensor-core kernel (K2b) in
-    one pass of the matrix instead of ceil(B/4) streaming passes: same exact results."""
+    """Up to 8 sub-queries share one streaming pass of the matrix (K2a, 8 query columns); from 9 on
+    the search chain scores the batch with the tensor-core kernel (K2b), still in one pass: same
+    exact results either way."""
     n = 90000
     x = synth.host_vectors(n, seed=61, dup_frac=0.01)
     idx = synth.host_bm25(n, seed=62, vocab=3000)
