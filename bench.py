@@ -60,6 +60,9 @@ def parse():
     ap.add_argument("--kernel-events", default="on", choices=["on", "off"],
                     help="CUDA event nodes around the two streaming kernels inside the captured chains of the "
                          "timed region (the roofline figure); off = A/B runs of the chain without them")
+    ap.add_argument("--prefilter", default="on", choices=["on", "off"],
+                    help="int8 shadow of the matrix for the dense scan (388 B/row instead of 768; results "
+                         "unchanged).  off: the plain fp16 scan")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-stages", action="store_true", help="skip the K1 / K2a / K2b stage measurements")
     ap.add_argument("--cpu-sample-rows", type=int, default=1_000_000)
@@ -666,8 +669,10 @@ def measure_stages(dev, n_local, peaks, hbm_peak, th=None, ptr_h=None, fusion="r
             ms = timed(lambda: d3.dense_topk(q, 2 * K_TOP), 20, warm=0)
             kms, kn = d3.profile_read(0)
             d3.profile(False)
-            gbs = rows * 768 / (kms / kn * 1e-3) / 1e9
+            kern, row_bytes, sbytes = scan_kernel_of(d3, rows, 2 * K_TOP)
+            gbs = sbytes / (kms / kn * 1e-3) / 1e9
             out[f"c3_dense_b{B}"] = {"rows": rows, "batch": B, "call_ms": ms, "queries_per_s": B / ms * 1e3,
+                                     "kernel": kern, "bytes_per_row": row_bytes,
                                      "scan_ms": kms / kn, "achieved_GBps": gbs, "frac": gbs / hbm_peak,
                                      "frac_of_8TBs_nominal": gbs / 8000.0, "bound": "hbm"}
         out["c3_dense_b1024"] = k2b(d3, rows, "C3: 1 M rows")
@@ -676,14 +681,27 @@ def measure_stages(dev, n_local, peaks, hbm_peak, th=None, ptr_h=None, fusion="r
     return out
 
 
-def scan_traffic_from_profile(n_local):
-    """dram bytes of dense_scan_kernel from the committed ncu --set full capture (profiles/),
+def scan_kernel_of(dev, n_local, K):
+    """(kernel name, algorithmic bytes per row, algorithmic bytes per launch) of the dense scan a
+    search of depth K runs on this index: with the int8 shadow resident (lrx_build_dense_prefilter)
+    the scan streams 384 B of int8 + a 4-byte scale per row of the shadow (padded to 128-row
+    tiles) instead of the 768-byte fp16 row."""
+    if dev.prefilter_bounds is not None and K <= 64:
+        n_pad = (n_local + 127) // 128 * 128
+        return "dense_scan_q8_kernel", 388, n_pad * 388
+    return "dense_scan_kernel<4>", 768, n_local * 768
+
+
+def scan_traffic_from_profile(n_local, kernel="dense_scan_kernel"):
+    """dram bytes of the dense scan kernel from the committed ncu --set full capture (profiles/),
     scaled per row: the kernel reads each row exactly once, so bytes/row is size independent."""
-    for name in ("r2_scan_kernels_final_full.json", "r2_scan_kernels_full.json", "r1_scan_kernels_v3_full.json"):
+    kernel = kernel.split("<")[0]
+    for name in ("r2_scan_q8_full.json", "r2_scan_kernels_final_full.json", "r2_scan_kernels_full.json",
+                 "r1_scan_kernels_v3_full.json"):
         try:
             prof = json.loads((ROOT / "profiles" / name).read_text())
             for l in prof["launches"]:
-                if "dense_scan_kernel" in l["kernel"] and "traffic_bytes_per_launch" in l:
+                if l["kernel"].split("<")[0].split("(")[0].endswith(kernel) and "traffic_bytes_per_launch" in l:
                     rows = prof.get("rows", 10_000_000)
                     return l["traffic_bytes_per_launch"] / rows * n_local, name
         except Exception:
@@ -728,7 +746,7 @@ def run_ours(args):
     idf, _ = okapi_idf(df.cpu().numpy(), args.rows)
     avgdl = int(tot_len.item()) / args.rows
     dev = DeviceIndex(local, rank, world)
-    dev.set_corpus(x, lo)
+    dev.set_corpus(x, lo, prefilter=(args.prefilter == "on"))
     dev.set_postings(bm["term_ptr"], bm["postings"], bm["doc_len"], idf, avgdl)
     nnz_local = bm["nnz"]
     df_local = bm["df"].cpu().numpy()
@@ -952,14 +970,15 @@ def run_ours(args):
         pass
     peak = float(peaks.get("hbm_gbs", 6650.0))
     peak_src = "measured (MEASURED_PEAKS.json hbm_gbs)" if "hbm_gbs" in peaks else "fallback 6650 GB/s"
-    scan_bytes = n_local * 768
+    scan_kernel, scan_row_bytes, scan_bytes = scan_kernel_of(dev, n_local, 2 * K_TOP)
     scan_gbs = scan_bytes / (scan_ms / max(scan_n, 1) * 1e-3) / 1e9 if scan_ms > 0 else 0.0
     # BM25 kernel: sum over query tokens of df_local * 8 B ({u32 doc, u16 tf, u16 len}),
     # averaged over the pool
     bm_bytes = float(np.mean([df_local[th[p]].sum() * 8 for p in range(POOL)]))
     bm_gbs = bm_bytes / (bm_ms / max(bm_n, 1) * 1e-3) / 1e9 if bm_ms > 0 else 0.0
     bm_alone_gbs = bm_bytes / (bm_alone_ms / max(bm_alone_n, 1) * 1e-3) / 1e9 if bm_alone_ms > 0 else 0.0
-    traffic, traffic_src = scan_traffic_from_profile(n_local)
+    traffic, traffic_src = scan_traffic_from_profile(n_local, scan_kernel)
+    q8 = scan_row_bytes != 768
 
     if rank == 0:
         qps = timed_steps / (ms * 1e-3)
@@ -970,11 +989,15 @@ def run_ours(args):
             "warmup": warm, "ms_per_step": step_ms,
             "timed_steps": timed_steps, "timed_blocks": blocks, "timed_region_ms": ms,
             "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
-            "dtype": "f16 matrix, f32 scan + exact f64 re-score; f64 BM25", "data": "synthetic",
+            "dtype": ("f16 matrix + its int8 shadow: s8 x s8 -> s32 scan of the shadow, exact f64 re-score "
+                      "of the fp16 rows; f64 BM25" if q8 else
+                      "f16 matrix, f32 scan + exact f64 re-score; f64 BM25"), "data": "synthetic",
             "config": dict(workload_config(args), parallelism=f"row-shard x{world}",
                            exchange=(searcher.exchange if world > 1 else "none"),
                            in_flight=n_fly, launch="one captured CUDA graph per batch",
-                           rows_per_gpu=n_local, nnz_per_gpu=nnz_local, build_s=round(t_build, 1)),
+                           rows_per_gpu=n_local, nnz_per_gpu=nnz_local, build_s=round(t_build, 1),
+                           dense_prefilter=("int8 shadow, bounds (max row error, max row norm) = "
+                                            f"{dev.prefilter_bounds}" if q8 else "off")),
             "parity": parity,
             "e2e": {"value": e2e_steps / (e2e_ms * 1e-3), "unit": "queries/s",
                     "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
@@ -984,14 +1007,21 @@ def run_ours(args):
             "gpu_launches": int(launches),
             "host_enqueue_ms_per_step": t_host * 1e3 / timed_steps,
             "clocks": clk,
-            "roofline": {"bound": "hbm", "kernel": "dense_scan_kernel<4>", "achieved": scan_gbs,
+            "roofline": {"bound": "hbm", "kernel": scan_kernel, "achieved": scan_gbs,
                          "peak": peak, "unit": "GB/s", "frac": scan_gbs / peak, "peak_source": peak_src,
                          "peak_note": "the measured peak is a COPY (reads + writes); a read-only stream can "
                                       "exceed it, so frac may pass 1 -- see frac_of_8TBs_nominal",
                          "frac_of_8TBs_nominal": scan_gbs / 8000.0, "traffic": traffic,
                          "traffic_source": f"ncu --set full dram__bytes_read+write per launch "
                                            f"(profiles/{traffic_src}), scaled by rows",
-                         "bytes_per_launch": scan_bytes, "ms_per_launch": scan_ms / max(scan_n, 1),
+                         "bytes_per_launch": scan_bytes, "bytes_per_row": scan_row_bytes,
+                         "bytes_note": ("algorithmic bytes of THIS kernel: 384 int8 + one fp32 scale per row of "
+                                        "the shadow; the fp16 matrix (768 B/row, SURVEY 8d) is only read at the "
+                                        "256 merged candidates per sub-query" if q8 else
+                                        "768 B per fp16 row (SURVEY 8d)"),
+                         "fp16_matrix_equivalent_GBps": (n_local * 768 / (scan_ms / max(scan_n, 1) * 1e-3) / 1e9
+                                                         if scan_ms > 0 else 0.0),
+                         "ms_per_launch": scan_ms / max(scan_n, 1),
                          "launches_timed": int(scan_n),
                          "timing": "CUDA event nodes around the kernel inside the captured chains; a pass of "
                                    f"{roof_steps} steps with ONE batch in flight right after the timed region "
@@ -999,12 +1029,12 @@ def run_ours(args):
                                    "batch's CTAs to leave the SMs); last replay of every chain",
                          "pass_ms_per_step": roof_step_ms if roof_steps else None,
                          "share_of_step": (scan_ms / max(scan_n, 1)) / roof_step_ms if roof_steps else None,
-                         "alone": {"note": "dense_scan_kernel with the GPU to itself (20 launches of "
+                         "alone": {"note": "the same kernel with the GPU to itself (20 launches of "
                                            "lrx_dense_topk after the timed region, same events)",
                                    "ms_per_launch": alone_ms / max(alone_n, 1),
-                                   "achieved": n_local * 768 / (alone_ms / max(alone_n, 1) * 1e-3) / 1e9
+                                   "achieved": scan_bytes / (alone_ms / max(alone_n, 1) * 1e-3) / 1e9
                                    if alone_ms > 0 else 0.0,
-                                   "frac": n_local * 768 / (alone_ms / max(alone_n, 1) * 1e-3) / 1e9 / peak
+                                   "frac": scan_bytes / (alone_ms / max(alone_n, 1) * 1e-3) / 1e9 / peak
                                    if alone_ms > 0 else 0.0},
                          "concurrent": {"note": "bm25_scan_kernel runs on the same SMs at the same time "
                                                 "(side stream) and, with two batches in flight, so do the "
@@ -1015,7 +1045,7 @@ def run_ours(args):
             "bm25_kernel": {"kernel": "bm25_scan_kernel", "bound": "hbm",
                             "in_step": {"achieved": bm_gbs, "frac": bm_gbs / peak,
                                         "ms_per_launch": bm_ms / max(bm_n, 1),
-                                        "note": "sharing the SMs and the HBM with dense_scan_kernel"},
+                                        "note": "sharing the SMs and the HBM with the dense scan"},
                             "alone": {"achieved": bm_alone_gbs, "frac": bm_alone_gbs / peak,
                                       "ms_per_launch": bm_alone_ms / max(bm_alone_n, 1)},
                             "unit": "GB/s", "bytes_per_launch": bm_bytes},

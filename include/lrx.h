@@ -85,6 +85,21 @@ const char* lrx_version(void);
 /* Row-major fp16 [n_local, 384] chunk matrix (768 B/row, 16-byte aligned). */
 int lrx_set_corpus(lrx_handle* h, const void* dev_x_fp16, int64_t n_local, int64_t id_base,
                    int32_t dim);
+/* Optional int8 pre-filter of K2 (up to 4 queries, K <= 64): the scan streams an int8 SHADOW of
+ * the matrix -- per-row scaled int8 rows, 388 B/row instead of 768 -- and the exact float64
+ * re-score of the merged candidate list reads the fp16 rows; the exactness guard uses the
+ * rigorous error bound of the shadow, so results stay bit-identical to the plain scan (a query
+ * whose candidates the bound cannot separate falls back to the fp16 scan through the widening
+ * retry).  The shadow lives in caller-owned device memory of lrx_dense_prefilter_bytes(n_local)
+ * bytes, 16-byte aligned.  lrx_build_dense_prefilter quantises the matrix set by lrx_set_corpus
+ * into it (synchronous), returns host_bounds_out[2] = {max row error norm, max row norm} and
+ * enables the pre-filter; lrx_set_dense_prefilter attaches a shadow built through another handle
+ * over the same matrix (dev_buf NULL: back to the plain fp16 scan).  lrx_set_corpus detaches it.
+ * (No counterpart in the reference: faiss.IndexFlatIP scans fp32 rows, retrieval_engine.py:64.) */
+int64_t lrx_dense_prefilter_bytes(int64_t n_local);
+int lrx_build_dense_prefilter(lrx_handle* h, void* dev_buf, int64_t bytes, double* host_bounds_out);
+int lrx_set_dense_prefilter(lrx_handle* h, const void* dev_buf, int64_t bytes,
+                            const double* host_bounds);
 /* Term-major CSR postings restricted to this shard's documents, doc ids LOCAL and
  * ascending within a term.  dev_postings: nnz 8-byte entries {u32 doc_local, u16 tf,
  * u16 doc_len} (lrx_bm25_build_postings fills them from (doc, tf) pairs and the document

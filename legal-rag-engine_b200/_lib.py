@@ -75,6 +75,9 @@ _SIGNATURES = {
     "lrx_set_stream": (C.c_int, [_vp, _vp]),
     "lrx_version": (C.c_char_p, []),
     "lrx_set_corpus": (C.c_int, [_vp, _vp, _i64, _i64, _i32]),
+    "lrx_dense_prefilter_bytes": (_i64, [_i64]),
+    "lrx_build_dense_prefilter": (C.c_int, [_vp, _vp, _i64, C.POINTER(C.c_double)]),
+    "lrx_set_dense_prefilter": (C.c_int, [_vp, _vp, _i64, C.POINTER(C.c_double)]),
     "lrx_set_postings": (C.c_int, [_vp, _vp, _vp, _vp, _i64, _i64, _f64, _f64, _f64, _i32]),
     "lrx_bm25_build_postings": (C.c_int, [_vp, _vp, _i64, _vp, _vp]),
     "lrx_set_encoder_weights": (C.c_int, [_vp, C.POINTER(lrx_bert_weights)]),

@@ -254,7 +254,51 @@ int lrx_set_corpus(lrx_handle* h, const void* dev_x_fp16, int64_t n_local, int64
     h->x = dev_x_fp16;
     h->n_local = n_local;
     h->id_base = id_base;
+    h->q8 = nullptr;                      // a shadow belongs to the matrix it was built from
+    h->q8_err = h->q8_norm = 0.0;
     h->ws_epoch++;                        // captured chains hold the old matrix
+    return LRX_OK;
+}
+
+int64_t lrx_dense_prefilter_bytes(int64_t n_local) {
+    if (n_local < 0 || n_local >= (1ll << 32)) return 0;
+    return dense_q8_bytes(n_local);
+}
+
+int lrx_build_dense_prefilter(lrx_handle* h, void* dev_buf, int64_t bytes, double* host_bounds_out) {
+    if (h == nullptr) return fail(nullptr, LRX_E_ARG, "lrx_build_dense_prefilter: null handle");
+    std::lock_guard<std::mutex> g(h->mu);
+    if (h->x == nullptr && h->n_local > 0) return fail(h, LRX_E_STATE, "lrx_build_dense_prefilter: corpus not set");
+    if (host_bounds_out == nullptr || (h->n_local > 0 && dev_buf == nullptr) || ((uintptr_t)dev_buf & 15) != 0)
+        return fail(h, LRX_E_ARG, "lrx_build_dense_prefilter: null or misaligned pointer");
+    if (bytes < dense_q8_bytes(h->n_local))
+        return fail(h, LRX_E_ARG, "lrx_build_dense_prefilter: buffer smaller than lrx_dense_prefilter_bytes(%lld)",
+                    (long long)h->n_local);
+    LRX_CUDA(h, cudaSetDevice(h->device));
+    LRX_CUDA(h, launch_dense_q8_build(h, dev_buf, host_bounds_out));
+    h->q8 = (h->n_local > 0) ? dev_buf : nullptr;
+    h->q8_err = host_bounds_out[0];
+    h->q8_norm = host_bounds_out[1];
+    h->ws_epoch++;                        // captured chains were built without the shadow
+    return LRX_OK;
+}
+
+int lrx_set_dense_prefilter(lrx_handle* h, const void* dev_buf, int64_t bytes, const double* host_bounds) {
+    if (h == nullptr) return fail(nullptr, LRX_E_ARG, "lrx_set_dense_prefilter: null handle");
+    std::lock_guard<std::mutex> g(h->mu);
+    if (dev_buf != nullptr) {
+        if (host_bounds == nullptr || ((uintptr_t)dev_buf & 15) != 0)
+            return fail(h, LRX_E_ARG, "lrx_set_dense_prefilter: null bounds or misaligned buffer");
+        if (bytes < dense_q8_bytes(h->n_local))
+            return fail(h, LRX_E_ARG, "lrx_set_dense_prefilter: buffer smaller than lrx_dense_prefilter_bytes(%lld)",
+                        (long long)h->n_local);
+        if (!(host_bounds[0] >= 0.0) || !(host_bounds[1] >= 0.0))
+            return fail(h, LRX_E_ARG, "lrx_set_dense_prefilter: bounds must be >= 0");
+    }
+    h->q8 = (h->n_local > 0) ? dev_buf : nullptr;
+    h->q8_err = dev_buf ? host_bounds[0] : 0.0;
+    h->q8_norm = dev_buf ? host_bounds[1] : 0.0;
+    h->ws_epoch++;
     return LRX_OK;
 }
 

@@ -23,6 +23,9 @@
 #include "handle.h"
 #include "merge.cuh"
 
+#include <cmath>
+#include <cstring>
+
 namespace lrx {
 
 constexpr int kScanThreads = 256;                  // 8 warps: the SM is shared with a BM25 scan CTA
@@ -385,6 +388,279 @@ dense_scan_kernel(const unsigned char* __restrict__ x, int64_t n_rows,
 }
 
 // ---------------------------------------------------------------------------
+// K2a with an int8 pre-filter (lrx_build_dense_prefilter): the scan streams a SHADOW of the matrix
+// -- int8 rows with one fp32 scale per row, 388 bytes per row instead of 768 -- and the exact
+// float64 re-score of the merged candidate list reads the fp16 rows as before.  Results stay
+// bit-exact: the guard band of the exactness test becomes the rigorous bound
+//     |x.q - A(x, q)|  <=  E * |q| + X * |q - qhat| + rounding,
+// E = max_r |x_r - xhat_r|, X = max_r |xhat_r| (measured when the shadow is built), qhat the
+// two-digit int8 image of the query (q ~= cq * (256 * hi + lo): its error is 1/256 of a row's).
+// The band is ~0.0085 for unit vectors instead of 1e-5, so the MERGED list is four times the
+// per-CTA list (256 candidates by default; per-CTA lists stay 64 wide and keep the register
+// prune), and the bound on every row outside the merged list is the larger of its last key and
+// the last key of every per-CTA list that is full (a full list may have dropped rows below it).
+//
+// dense_scan_q8_kernel: 128-row tiles (48 KB of int8 rows + 512 B of scales per stage, two bulk
+// copies on one mbarrier), one 16-row block per warp over the WHOLE k = 384 (no partial sums, one
+// block barrier per tile), mma.sync m16n8k32 s8 x s8 -> s32 (exact): the 8 "n" columns are the
+// hi and lo digits of the <= 4 queries, so lane (g, t) ends up with both digit sums of query t for
+// rows g and g + 8 and tests them against the threshold straight from registers.
+// Algorithmic HBM bytes per launch: n_pad * 388.
+constexpr int kQ8TileRows = 128;
+constexpr int kQ8RowBytes = kDim;                            // 384
+constexpr int kQ8TileBytes = kQ8TileRows * kQ8RowBytes;      // 49152
+
+__host__ __device__ inline int64_t q8_pad_rows(int64_t n) {
+    return (n + kQ8TileRows - 1) / kQ8TileRows * kQ8TileRows;
+}
+
+// The two int8 digits of one query element; `inv` = 127 / max|q| (0 for an all-zero query).  Explicit
+// round-to-nearest intrinsics: the scan and the re-score kernel must agree bit for bit on the
+// digits (no FMA contraction).
+__device__ __forceinline__ void q8_digits(float v, float inv, int& hi, int& lo) {
+    const float s = __fmul_rn(v, inv);
+    hi = max(-127, min(127, __float2int_rn(s)));
+    lo = max(-127, min(127, __float2int_rn(__fmul_rn(__fsub_rn(s, (float)hi), 256.f))));
+}
+__device__ __forceinline__ float q8_inv(float mx) { return mx > 0.f ? __fdiv_rn(127.f, mx) : 0.f; }
+__device__ __forceinline__ float q8_cq(float mx) { return __fmul_rn(mx, 1.0f / 32512.0f); }   // max / (127 * 256)
+// the 12 elements lane `lane` holds of a 384-wide fp16 vector: 4 consecutive ones per 128-column third
+__device__ __forceinline__ void q8_load12(const __half* __restrict__ v, int lane, float* out) {
+    const uint2* p = reinterpret_cast<const uint2*>(v);
+#pragma unroll
+    for (int j = 0; j < 3; ++j) {
+        const uint2 w = p[j * 32 + lane];
+        const float2 a = __half22float2(*reinterpret_cast<const __half2*>(&w.x));
+        const float2 b = __half22float2(*reinterpret_cast<const __half2*>(&w.y));
+        out[4 * j + 0] = a.x; out[4 * j + 1] = a.y; out[4 * j + 2] = b.x; out[4 * j + 3] = b.y;
+    }
+}
+__device__ __forceinline__ float warp_max_abs12(const float* v) {
+    float mx = 0.f;
+#pragma unroll
+    for (int i = 0; i < 12; ++i) mx = fmaxf(mx, fabsf(v[i]));
+#pragma unroll
+    for (int lb = 16; lb > 0; lb >>= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, lb));
+    return mx;
+}
+__device__ __forceinline__ double warp_sum_f64(double v) {
+#pragma unroll
+    for (int lb = 16; lb > 0; lb >>= 1) v += __shfl_xor_sync(0xffffffffu, v, lb);
+    return v;
+}
+__device__ __forceinline__ uint32_t pack_s8x4(int a, int b, int c, int d) {
+    return (uint32_t)(a & 0xff) | ((uint32_t)(b & 0xff) << 8) | ((uint32_t)(c & 0xff) << 16) |
+           ((uint32_t)(d & 0xff) << 24);
+}
+
+// Shadow build: one warp per row.  bounds[0], bounds[1]: ordered images of max_r |x_r - xhat_r|^2 and
+// max_r |xhat_r|^2 in float64 (every product below is exact in float64; the sums of 384 squares are
+// off by < 1e-13 relative, the host rounds the bounds up).
+__global__ void __launch_bounds__(256)
+dense_q8_build_kernel(const unsigned char* __restrict__ x, int64_t n_rows, int64_t n_pad,
+                      unsigned char* __restrict__ rows8, float* __restrict__ scales,
+                      unsigned long long* __restrict__ bounds) {
+    const int lane = threadIdx.x & 31;
+    const int64_t row = (int64_t)blockIdx.x * 8 + (threadIdx.x >> 5);
+    if (row >= n_pad) return;
+    uint32_t* dst = reinterpret_cast<uint32_t*>(rows8 + row * kQ8RowBytes);
+    if (row >= n_rows) {                                     // padding of the last tile
+#pragma unroll
+        for (int j = 0; j < 3; ++j) dst[j * 32 + lane] = 0u;
+        if (lane == 0) scales[row] = 0.f;
+        return;
+    }
+    float v[12];
+    q8_load12(reinterpret_cast<const __half*>(x + row * kRowBytes), lane, v);
+    const float mx = warp_max_abs12(v);
+    const float scale = __fdiv_rn(mx, 127.f), inv = q8_inv(mx);
+    double err2 = 0.0, n2 = 0.0;
+    int xi[12];
+#pragma unroll
+    for (int i = 0; i < 12; ++i) {
+        xi[i] = max(-127, min(127, __float2int_rn(__fmul_rn(v[i], inv))));
+        const double xh = (double)scale * (double)xi[i];
+        const double e = (double)v[i] - xh;
+        err2 = fma(e, e, err2);
+        n2 = fma(xh, xh, n2);
+    }
+    err2 = warp_sum_f64(err2);
+    n2 = warp_sum_f64(n2);
+#pragma unroll
+    for (int j = 0; j < 3; ++j)
+        dst[j * 32 + lane] = pack_s8x4(xi[4 * j], xi[4 * j + 1], xi[4 * j + 2], xi[4 * j + 3]);
+    if (lane == 0) {
+        scales[row] = scale;
+        atomicMax(bounds + 0, (unsigned long long)f64_ord(err2));
+        atomicMax(bounds + 1, (unsigned long long)f64_ord(n2));
+    }
+}
+
+struct ScanQ8Smem {
+    unsigned char ring[kStages][kQ8TileBytes];   // 16-byte aligned bulk-copy destinations
+    float scale[kStages][kQ8TileRows];
+    signed char qd[8][kDim];                     // query digits: row 2 * query (hi), 2 * query + 1 (lo)
+    float cq[4];
+    uint64_t full[kStages];
+    int tile_of[kStages];
+    int count[8];
+    uint32_t tau[8];
+    uint64_t keys[1];   // [4][kCap], sized at launch
+};
+
+__global__ void __launch_bounds__(kScanThreads, 2)
+dense_scan_q8_kernel(const unsigned char* __restrict__ rows8, const float* __restrict__ scales,
+                     int64_t n_rows, const __half* __restrict__ q, int n_q, int width,
+                     uint64_t* __restrict__ part /* [grid][4][width] */,
+                     unsigned int* __restrict__ tau_g /* [8] shared thresholds, zero at launch */) {
+    constexpr int NQ = 4;
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    ScanQ8Smem& sm = *reinterpret_cast<ScanQ8Smem*>(smem_raw);
+    uint64_t* keys = sm.keys;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    constexpr int cap = kCap;
+    const int soft_cap = (width <= 64) ? kSoftCap : cap;    // a tile appends up to 128 keys per query
+    const int n_tiles = (int)((n_rows + kQ8TileRows - 1) / kQ8TileRows);   // the shadow is padded to whole tiles
+
+    if (tid == 0) {
+        for (int s = 0; s < kStages; ++s) mbar_init(&sm.full[s], 1);
+        fence_barrier_init();
+    }
+    if (tid < 8) {
+        sm.count[tid] = 0;
+        sm.tau[tid] = 0u;
+    }
+    __syncthreads();
+    auto issue = [&](int tile, int s) {                      // thread 0 only
+        sm.tile_of[s] = tile;
+        if (tile >= n_tiles) return;
+        const int64_t row0 = (int64_t)tile * kQ8TileRows;
+        mbar_arrive_expect_tx(&sm.full[s], (uint32_t)(kQ8TileBytes + kQ8TileRows * sizeof(float)));
+        const uint64_t pol = l2_policy_evict_first();
+        bulk_g2s_hint(sm.ring[s], rows8 + row0 * kQ8RowBytes, kQ8TileBytes, &sm.full[s], pol);
+        bulk_g2s_hint(sm.scale[s], scales + row0, (uint32_t)(kQ8TileRows * sizeof(float)), &sm.full[s], pol);
+    };
+    int next_tile = (int)blockIdx.x + kStages * (int)gridDim.x;
+    if (tid == 0)
+        for (int s = 0; s < kStages; ++s) issue((int)blockIdx.x + s * (int)gridDim.x, s);
+
+    // ---- query digits (every CTA redoes the <= 4 queries: 1.5 K elements), warp w = query w
+    {
+        uint32_t* qrow = reinterpret_cast<uint32_t*>(&sm.qd[0][0]);
+        if (warp < NQ) {
+            uint32_t* hi_row = qrow + (2 * warp) * (kDim / 4);
+            uint32_t* lo_row = qrow + (2 * warp + 1) * (kDim / 4);
+            if (warp < n_q) {
+                float v[12];
+                q8_load12(q + (size_t)warp * kDim, lane, v);
+                const float mx = warp_max_abs12(v);
+                const float inv = q8_inv(mx);
+                int hi[12], lo[12];
+#pragma unroll
+                for (int i = 0; i < 12; ++i) q8_digits(v[i], inv, hi[i], lo[i]);
+#pragma unroll
+                for (int j = 0; j < 3; ++j) {
+                    hi_row[j * 32 + lane] = pack_s8x4(hi[4 * j], hi[4 * j + 1], hi[4 * j + 2], hi[4 * j + 3]);
+                    lo_row[j * 32 + lane] = pack_s8x4(lo[4 * j], lo[4 * j + 1], lo[4 * j + 2], lo[4 * j + 3]);
+                }
+                if (lane == 0) sm.cq[warp] = q8_cq(mx);
+            } else {
+#pragma unroll
+                for (int j = 0; j < 3; ++j) { hi_row[j * 32 + lane] = 0u; lo_row[j * 32 + lane] = 0u; }
+                if (lane == 0) sm.cq[warp] = 0.f;
+            }
+        }
+    }
+    __syncthreads();                                         // digits, tile_of[] visible
+
+    // B fragments: lane (g, t) holds 16 bytes per 64-column chunk of digit row g at the SAME columns
+    // as its A bytes, so A and B agree on a (permuted) k order -- no ldmatrix, no swizzle.
+    const int g = lane >> 2, t = lane & 3;
+    uint4 qb[6];
+#pragma unroll
+    for (int j = 0; j < 6; ++j) qb[j] = *reinterpret_cast<const uint4*>(&sm.qd[g][j * 64 + 16 * t]);
+    const float cq = sm.cq[t];
+    const uint32_t a_off = (uint32_t)((warp * 16 + g) * kQ8RowBytes + 16 * t);
+
+    for (int it = 0;; ++it) {
+        const int s = it % kStages;
+        const uint32_t parity = (uint32_t)((it / kStages) & 1);
+        const int tile = sm.tile_of[s];
+        if (tile >= n_tiles) break;
+        const int64_t row0 = (int64_t)tile * kQ8TileRows;
+        mbar_wait(&sm.full[s], parity);
+
+        int c0[4] = {0, 0, 0, 0}, c1[4] = {0, 0, 0, 0};     // two accumulation chains
+        {
+            const unsigned char* base = sm.ring[s] + a_off;
+            uint4 xa[6], xb[6];
+#pragma unroll
+            for (int j = 0; j < 6; ++j) {
+                xa[j] = *reinterpret_cast<const uint4*>(base + j * 64);                    // row g
+                xb[j] = *reinterpret_cast<const uint4*>(base + 8 * kQ8RowBytes + j * 64);  // row g + 8
+            }
+#pragma unroll
+            for (int j = 0; j < 6; ++j) {
+                asm volatile("mma.sync.aligned.m16n8k32.row.col.s32.s8.s8.s32 "
+                             "{%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+                             : "+r"(c0[0]), "+r"(c0[1]), "+r"(c0[2]), "+r"(c0[3])
+                             : "r"(xa[j].x), "r"(xb[j].x), "r"(xa[j].y), "r"(xb[j].y),
+                               "r"(qb[j].x), "r"(qb[j].y));
+                asm volatile("mma.sync.aligned.m16n8k32.row.col.s32.s8.s8.s32 "
+                             "{%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+                             : "+r"(c1[0]), "+r"(c1[1]), "+r"(c1[2]), "+r"(c1[3])
+                             : "r"(xa[j].z), "r"(xb[j].z), "r"(xa[j].w), "r"(xb[j].w),
+                               "r"(qb[j].z), "r"(qb[j].w));
+            }
+        }
+        // lane (g, t): digit sums (hi, lo) of query t for rows g and g + 8 of the warp's block.
+        // |256 * hi + lo| <= 257 * 384 * 127^2 < 2^31.
+        if (t < n_q) {
+            const int r0 = warp * 16 + g;
+            const uint32_t tau = sm.tau[t];
+#pragma unroll
+            for (int hrow = 0; hrow < 2; ++hrow) {
+                const int r = r0 + 8 * hrow;
+                const int D = (c0[2 * hrow] + c1[2 * hrow]) * 256 + (c0[2 * hrow + 1] + c1[2 * hrow + 1]);
+                const float sc = __fmul_rn(__fmul_rn(sm.scale[s][r], cq), (float)D);
+                const uint32_t o = f32_ord(sc);
+                if (o >= tau && row0 + r < n_rows) {
+                    const int pos = atomicAdd(&sm.count[t], 1);
+                    keys[t * cap + pos] = ((uint64_t)o << 32) | (uint32_t)(~(uint32_t)(row0 + r));
+                }
+            }
+        }
+        // ---- the one block barrier of a tile: the stage is consumed, the appends are visible, and
+        //      pruning is decided uniformly (a thread reads count[] after its own appends, so the
+        //      last appender of a query sees its final value; the OR makes every thread agree)
+        bool need = false;
+#pragma unroll
+        for (int qi = 0; qi < NQ; ++qi) need |= (sm.count[qi] > soft_cap - kQ8TileRows);
+        const int any = __syncthreads_or(need ? 1 : 0);
+        if (tid == 0) {                        // re-fill the stage with the CTA's next tile
+            issue(next_tile, s);
+            next_tile += (int)gridDim.x;
+        }
+        if (any) scan_prune<NQ>(keys, sm.count, sm.tau, width, tid, tau_g);
+        else if (tid < NQ) {
+            // thresholds published by other CTAs; the next tile's tests may still read the old
+            // value: a stale threshold is only conservative
+            const uint32_t tg = *(volatile unsigned int*)(tau_g + tid);
+            if (tg > sm.tau[tid]) sm.tau[tid] = tg;
+        }
+    }
+
+    __syncthreads();
+    scan_prune<NQ>(keys, sm.count, sm.tau, width, tid, tau_g);
+    for (int i = tid; i < NQ * width; i += kScanThreads) {
+        const int qi = i / width;
+        const int j = i - qi * width;
+        const uint64_t k = (j < sm.count[qi]) ? keys[qi * cap + j] : 0ull;
+        part[((size_t)blockIdx.x * NQ + qi) * width + j] = k;
+    }
+}
+
+// ---------------------------------------------------------------------------
 // Exact float64 inner product of one fp16 row with one fp16 query, by a warp.
 __device__ __forceinline__ double warp_exact_dot(const unsigned char* __restrict__ x, int64_t row,
                                                  const __half* __restrict__ qv, int lane) {
@@ -414,10 +690,13 @@ __device__ __forceinline__ double warp_exact_dot(const unsigned char* __restrict
 //   re-score           each warp takes 4 survivors per pass, all 12 row loads in flight before
 //                      the first reduction; exact float64 dot products (order independent)
 //   order              rank by counting on (exact score desc, id asc); emit the best K + guard flag
+//   lists are `list_width` long, the merged list `width` (>= list_width; longer only behind the int8
+//   pre-filter); q8_norm >= 0: the scan scored the int8 shadow, the guard band is computed per query
 __global__ void __launch_bounds__(kMergeThreads, 1)
-dense_merge_rescore_kernel(const uint64_t* __restrict__ part, int n_lists, int list_stride,
+dense_merge_rescore_kernel(const uint64_t* __restrict__ part, int n_lists, int list_stride, int list_width,
                            const unsigned char* __restrict__ x, int64_t n_rows, int64_t id_base,
                            const __half* __restrict__ q, int width, int K, double eps,
+                           double q8_err, double q8_norm,
                            double* __restrict__ out_exact, float* __restrict__ out_D,
                            int64_t* __restrict__ out_I, int32_t* __restrict__ out_flag) {
     extern __shared__ __align__(128) unsigned char merge_raw[];
@@ -427,10 +706,42 @@ dense_merge_rescore_kernel(const uint64_t* __restrict__ part, int n_lists, int l
     __shared__ u128 sorted[kMaxWidth];
     __shared__ int s_count, s_overflow;
     __shared__ uint64_t s_bound;
+    __shared__ unsigned long long s_full;       // largest last key of a per-CTA list that is full
+    __shared__ double s_eps;
     const int qi = blockIdx.x;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    merge_lists_block<uint64_t>(part, n_lists, list_stride, qi, width, buf, merged, &s_count,
+    if (tid == 0) s_full = 0ull;
+    if (warp == 1) {
+        // guard band of this query (see dense_scan_q8_kernel): the digits are recomputed with the
+        // scan's own operations, the norms in float64
+        double e = eps;
+        if (q8_norm >= 0.0) {
+            float v[12];
+            q8_load12(q + (size_t)qi * kDim, lane, v);
+            const float mx = warp_max_abs12(v);
+            const float inv = q8_inv(mx);
+            const double cq = (double)q8_cq(mx);
+            double nq = 0.0, ne = 0.0;
+#pragma unroll
+            for (int i = 0; i < 12; ++i) {
+                int hi, lo;
+                q8_digits(v[i], inv, hi, lo);
+                const double d = (double)v[i] - cq * (double)(256 * hi + lo);
+                nq = fma((double)v[i], (double)v[i], nq);
+                ne = fma(d, d, ne);
+            }
+            nq = sqrt(warp_sum_f64(nq));
+            ne = sqrt(warp_sum_f64(ne));
+            e = (q8_err * nq + q8_norm * ne + 2.0e-7 * q8_norm * (nq + ne)) * (1.0 + 1.0e-6) + 1.0e-12;
+        }
+        if (lane == 0) s_eps = e;
+    }
+    merge_lists_block<uint64_t>(part, n_lists, list_stride, qi, list_width, width, buf, merged, &s_count,
                                 &s_overflow, &s_bound);
+    for (int l = tid; l < n_lists; l += kMergeThreads) {
+        const uint64_t last = part[((size_t)qi + (size_t)l * list_stride) * list_width + list_width - 1];
+        if (last != 0ull) atomicMax(&s_full, (unsigned long long)last);
+    }
 
     constexpr int kWarps = kMergeThreads / 32;
     for (int j0 = warp * 4; j0 < width; j0 += kWarps * 4) {
@@ -493,17 +804,22 @@ dense_merge_rescore_kernel(const uint64_t* __restrict__ part, int n_lists, int l
     }
     if (tid == 0) {
         int flag = 0;
-        if (n_rows > width) {
-            // rows outside the candidate list have fp32 score <= s_last, hence exact
-            // score <= s_last + eps; they must lose strictly to the K-th exact score.
-            const uint64_t last = merged[width - 1];
+        // Rows outside the merged list: keys of the per-CTA lists that did not make it (below the
+        // merged list's last key, which is non-empty then) and rows a CTA dropped -- by its
+        // threshold or by a prune, both only once its list was full, and all below that list's
+        // final last key.  Their fast score is <= s_out, hence their exact score <= s_out + eps;
+        // they must lose strictly to the K-th exact score.  Neither bound present: every row is
+        // in the merged list and the result is exact as it stands.
+        const uint64_t last = merged[width - 1];
+        const uint64_t out_key = (last > (uint64_t)s_full) ? last : (uint64_t)s_full;
+        if (out_key != 0ull) {
             const int kk = (K < width) ? K : width;
             const u128 kth = sorted[kk - 1];
-            if (last == 0ull || kth == 0 || K > width) {
+            if (kth == 0 || K > width) {
                 flag = 1;
             } else {
-                const double s_last = (double)key64_score(last);
-                flag = (s_last + eps < key128_score(kth)) ? 0 : 1;
+                const double s_out = (double)key64_score(out_key);
+                flag = (s_out + s_eps < key128_score(kth)) ? 0 : 1;
             }
         }
         out_flag[qi] = flag;
@@ -531,6 +847,8 @@ static size_t scan_smem_bytes(int nq) {
 }
 
 int dense_scan_grid(const lrx_handle* h) {
+    // (tiles of the fp16 scan; the int8 scan's 128-row tiles run on the same grid -- a CTA without a
+    // tile of its own emits empty lists)
     const int64_t n_tiles = (h->n_local + kTileRows - 1) / kTileRows;
     return (int)((n_tiles < h->num_sms) ? (n_tiles > 0 ? n_tiles : 1) : h->num_sms);
 }
@@ -569,6 +887,83 @@ static cudaError_t launch_scan(lrx_handle* h, const __half* q, int n_q, int widt
     return cudaGetLastError();
 }
 
+// ---- int8 pre-filter
+bool dense_q8_applies(const lrx_handle* h, int B, int K, int width) {
+    // up to 4 queries per pass (their hi / lo digits fill the 8 MMA columns; 5..8 queries would need
+    // two passes of 388 B/row against one fp16 pass of 768), lists up to 128 wide per CTA -- a widened
+    // retry beyond that goes back to the fp16 scan and its 1e-5 band
+    return h->q8 != nullptr && h->n_local > 0 && B <= 4 && K <= 64 && width <= 128;
+}
+
+int64_t dense_q8_bytes(int64_t n_local) {
+    const int64_t n_pad = q8_pad_rows(n_local);
+    return n_pad * (kQ8RowBytes + (int64_t)sizeof(float));
+}
+
+// quantise h->x into buf (rows, then scales), bounds_out = {E, X} rounded up
+cudaError_t launch_dense_q8_build(lrx_handle* h, void* buf, double* bounds_out) {
+    const int64_t n_pad = q8_pad_rows(h->n_local);
+    bounds_out[0] = bounds_out[1] = 0.0;
+    if (n_pad == 0) return cudaSuccess;
+    unsigned long long* dev_bounds = nullptr;
+    cudaError_t e = cudaMalloc((void**)&dev_bounds, 2 * sizeof(unsigned long long));
+    if (e != cudaSuccess) return e;
+    e = cudaMemsetAsync(dev_bounds, 0, 2 * sizeof(unsigned long long), h->stream);
+    unsigned char* rows8 = (unsigned char*)buf;
+    float* scales = (float*)(rows8 + n_pad * kQ8RowBytes);
+    if (e == cudaSuccess) {
+        dense_q8_build_kernel<<<(unsigned)((n_pad + 7) / 8), 256, 0, h->stream>>>(
+            (const unsigned char*)h->x, h->n_local, n_pad, rows8, scales, dev_bounds);
+        h->launches++;
+        e = cudaGetLastError();
+    }
+    unsigned long long hb[2] = {0ull, 0ull};
+    if (e == cudaSuccess)
+        e = cudaMemcpyAsync(hb, dev_bounds, sizeof(hb), cudaMemcpyDeviceToHost, h->stream);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(h->stream);
+    cudaFree(dev_bounds);
+    if (e != cudaSuccess) return e;
+    for (int i = 0; i < 2; ++i) {
+        double sq = 0.0;
+        if (hb[i] != 0ull) {                                 // inverse of f64_ord for a non-negative value
+            const unsigned long long u = hb[i] & 0x7fffffffffffffffull;
+            memcpy(&sq, &u, sizeof(sq));
+        }
+        bounds_out[i] = sqrt(sq) * (1.0 + 1.0e-9);
+    }
+    return cudaSuccess;
+}
+
+static cudaError_t launch_scan_q8(lrx_handle* h, const __half* q, int n_q, int width, uint64_t* part,
+                                  int grid) {
+    std::lock_guard<std::recursive_mutex> attr_guard(attr_mutex());
+    static bool attr_dev[64] = {false};
+    bool& attr = attr_dev[h->device & 63];
+    // the same footprint as the fp16 scan (135 KB): one CTA per SM, a BM25 scan CTA fits beside it
+    const size_t smem = offsetof(ScanQ8Smem, keys) + (size_t)4 * kCap * sizeof(uint64_t);
+    if (!attr) {
+        cudaError_t e = cudaFuncSetAttribute(dense_scan_q8_kernel,
+                                             cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return e;
+        e = cudaFuncSetAttribute(dense_scan_q8_kernel, cudaFuncAttributePreferredSharedMemoryCarveout,
+                                 cudaSharedmemCarveoutMaxShared);
+        if (e != cudaSuccess) return e;
+        attr = true;
+    }
+    unsigned int* tau_g = reinterpret_cast<unsigned int*>(part + (size_t)grid * 8 * width);
+    cudaError_t e0 = cudaMemsetAsync(tau_g, 0, 8 * sizeof(unsigned int), h->stream);
+    if (e0 != cudaSuccess) return e0;
+    const int64_t n_pad = q8_pad_rows(h->n_local);
+    const unsigned char* rows8 = (const unsigned char*)h->q8;
+    const float* scales = (const float*)(rows8 + n_pad * kQ8RowBytes);
+    prof_begin(h, 0);
+    dense_scan_q8_kernel<<<grid, kScanThreads, smem, h->stream>>>(rows8, scales, h->n_local, q, n_q, width,
+                                                                   part, tau_g);
+    prof_end(h, 0);
+    h->launches++;
+    return cudaGetLastError();
+}
+
 int dense_default_width(int K) {
     int w = next_pow2(K + 32);
     if (w < 64) w = 64;
@@ -594,6 +989,17 @@ cudaError_t launch_dense_topk(lrx_handle* h, const void* qv, int B, int K, int w
     }
     uint64_t* part = (uint64_t*)h->ws_dense_part;
     const __half* q = (const __half*)qv;
+    if (dense_q8_applies(h, B, K, width)) {
+        // int8 pre-filter: per-CTA lists `width` long, merged list four times that
+        const int merged_width = (4 * width < kMaxWidth) ? 4 * width : kMaxWidth;
+        e = launch_scan_q8(h, q, B, width, part, grid);
+        if (e != cudaSuccess) return e;
+        dense_merge_rescore_kernel<<<B, kMergeThreads, kMergeCap * sizeof(uint64_t), h->stream>>>(
+            part, grid, 4, width, (const unsigned char*)h->x, h->n_local, h->id_base, q, merged_width, K,
+            kDenseEps, h->q8_err, h->q8_norm, exact, D, I, flags);
+        h->launches++;
+        return cudaGetLastError();
+    }
     // One matrix pass serves up to 8 queries: the MMA tile has 8 columns either way (SURVEY 8(d)
     // budgets ONE read of the matrix per batch).  5..8 queries take the 8-query instantiation (512
     // candidate slots per query, lists up to 256 wide); up to 4 the 4-query one -- the 1- and 2-query
@@ -607,8 +1013,8 @@ cudaError_t launch_dense_topk(lrx_handle* h, const void* qv, int B, int K, int w
         if (e != cudaSuccess) return e;
         // list l of query qi of this pass: part[(l * NQ + qi) * width]
         dense_merge_rescore_kernel<<<nq, kMergeThreads, kMergeCap * sizeof(uint64_t), h->stream>>>(
-            part, grid, NQ, (const unsigned char*)h->x, h->n_local, h->id_base,
-            q + (size_t)b0 * kDim, width, K, kDenseEps, exact + (size_t)b0 * K, D + (size_t)b0 * K,
+            part, grid, NQ, width, (const unsigned char*)h->x, h->n_local, h->id_base,
+            q + (size_t)b0 * kDim, width, K, kDenseEps, 0.0, -1.0, exact + (size_t)b0 * K, D + (size_t)b0 * K,
             I + (size_t)b0 * K, flags + b0);
         h->launches++;
         e = cudaGetLastError();

@@ -51,6 +51,11 @@ struct lrx_handle {
     const void* x = nullptr;      // fp16 [n_local, 384]
     int64_t n_local = 0, id_base = 0;
 
+    // int8 shadow of the corpus for the K2a pre-filter (caller-owned, lrx_build_dense_prefilter):
+    // [n_pad, 384] int8 rows, then [n_pad] fp32 row scales, n_pad = n_local rounded up to 128
+    const void* q8 = nullptr;
+    double q8_err = 0.0, q8_norm = 0.0;   // max_r |x_r - xhat_r|, max_r |xhat_r| (rounded up)
+
     // postings (caller-owned)
     const uint64_t* term_ptr = nullptr;
     const void* postings = nullptr;
@@ -113,6 +118,9 @@ int dense_scan_grid(const lrx_handle* h);
 int dense_default_width(int K);
 cudaError_t launch_dense_topk(lrx_handle* h, const void* q, int B, int K, int width,
                               double* exact, float* D, int64_t* I, int32_t* flags);
+bool dense_q8_applies(const lrx_handle* h, int B, int K, int width);
+int64_t dense_q8_bytes(int64_t n_local);
+cudaError_t launch_dense_q8_build(lrx_handle* h, void* buf, double* bounds_out);
 cudaError_t launch_dense_at(lrx_handle* h, const void* q, int B, const int64_t* ids, int n,
                             double* out);
 

@@ -42,25 +42,26 @@ __device__ __forceinline__ int merge_rank_of(const KeyT* buf, int n, KeyT key) {
     return rank;
 }
 
-// part: list l of this query is part[(list0 + l * list_stride) * width .. + width), sorted
-// descending, empty keys (0) at the end.  buf: kMergeCap keys of shared memory.  out_s: `width`
-// keys of shared memory (may not alias buf) -- the merged best keys, descending, 0-padded.
-// All kMergeThreads threads of the block must call; returns synced.
+// part: list l of this query is part[(list0 + l * list_stride) * list_width .. + list_width),
+// sorted descending, empty keys (0) at the end.  buf: kMergeCap keys of shared memory.  out_s:
+// `width` keys of shared memory (may not alias buf) -- the merged best keys, descending, 0-padded;
+// `width` may exceed `list_width` (the int8 pre-filter of K2a keeps short per-CTA lists and a long
+// merged one).  All kMergeThreads threads of the block must call; returns synced.
 template <typename KeyT>
 __device__ __forceinline__ void merge_lists_block(const KeyT* __restrict__ part, int n_lists,
-                                                  int list_stride, int list0, int width,
+                                                  int list_stride, int list0, int list_width, int width,
                                                   KeyT* buf, KeyT* out_s, int* s_count,
                                                   int* s_overflow, KeyT* s_bound) {
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     auto key_at = [&](int list, int pos) -> KeyT {
-        return part[((size_t)list0 + (size_t)list * list_stride) * width + pos];
+        return part[((size_t)list0 + (size_t)list * list_stride) * list_width + pos];
     };
     for (int i = tid; i < width; i += kMergeThreads) out_s[i] = 0;
 
     // ---- 1. lower bound from the heads of (up to 256 of) the lists
     const int nl = min(n_lists, 256);
     int depth = (nl > 0) ? (width + nl - 1) / nl : 0;
-    if (depth > width) depth = width;
+    if (depth > list_width) depth = list_width;
     const int ns = depth * nl;
     if (tid == 0) *s_bound = 0;
     for (int i = tid; i < ns; i += kMergeThreads) buf[i] = key_at(i / depth, i % depth);
@@ -91,13 +92,13 @@ __device__ __forceinline__ void merge_lists_block(const KeyT* __restrict__ part,
         __syncthreads();
         for (int list = tid; list < n_lists; list += kMergeThreads) {
             KeyT k = key_at(list, 0);
-            KeyT k_next = (width > 1) ? key_at(list, 1) : (KeyT)0;      // second load in flight
-            for (int pos = 0; pos < width; ++pos) {
+            KeyT k_next = (list_width > 1) ? key_at(list, 1) : (KeyT)0;      // second load in flight
+            for (int pos = 0; pos < list_width; ++pos) {
                 if (k == 0 || k < L) break;
                 const int p = atomicAdd(s_count, 1);
                 if (p < kMergeCap) buf[p] = k; else *s_overflow = 1;
                 k = k_next;
-                k_next = (pos + 2 < width) ? key_at(list, pos + 2) : (KeyT)0;
+                k_next = (pos + 2 < list_width) ? key_at(list, pos + 2) : (KeyT)0;
             }
         }
         __syncthreads();

@@ -3,6 +3,7 @@
 from __future__ import annotations
 
 import ctypes as C
+import os
 from typing import Optional, Sequence
 
 import numpy as np
@@ -30,6 +31,7 @@ class DeviceIndex:
         _lib.check(self.lib.lrx_open(C.byref(cfg), C.byref(h)))
         self.h = h
         self.x = None
+        self._q8 = None
         self.n_local = 0
         self.id_base = 0
         self._post = None
@@ -57,11 +59,42 @@ class DeviceIndex:
         self._ck(self.lib.lrx_set_stream(self.h, C.c_void_p(s)))
 
     # ------------------------------------------------------------- residency
-    def set_corpus(self, x: torch.Tensor, id_base: int = 0):
+    def set_corpus(self, x: torch.Tensor, id_base: int = 0, prefilter: Optional[bool] = None):
+        """Make the fp16 chunk matrix resident.  `prefilter` (default: on, LRX_DENSE_PREFILTER=0
+        turns it off): also build the int8 shadow K2a scans for up to 4 queries at a time
+        (388 B/row instead of 768; results unchanged, see include/lrx.h)."""
         assert x.dtype == torch.float16 and x.is_cuda and x.is_contiguous()
         assert x.dim() == 2 and x.shape[1] == LRX_DIM
         self.x, self.n_local, self.id_base = x, int(x.shape[0]), int(id_base)
         self._ck(self.lib.lrx_set_corpus(self.h, _ptr(x), self.n_local, self.id_base, LRX_DIM))
+        self._q8 = None
+        if prefilter is None:
+            prefilter = os.environ.get("LRX_DENSE_PREFILTER", "1") not in ("0", "", "off")
+        if prefilter and self.n_local > 0:
+            self.build_prefilter()
+
+    def build_prefilter(self):
+        nbytes = int(self.lib.lrx_dense_prefilter_bytes(self.n_local))
+        buf = torch.empty(nbytes, dtype=torch.uint8, device=self.device)
+        bounds = (C.c_double * 2)()
+        self._ck(self.lib.lrx_build_dense_prefilter(self.h, _ptr(buf), nbytes, bounds))
+        self._q8 = (buf, nbytes, (float(bounds[0]), float(bounds[1])))
+
+    def set_prefilter(self, on: bool):
+        """Switch the int8 pre-filter of an index that has a shadow (A/B runs, tests)."""
+        if on:
+            if self._q8 is None:
+                self.build_prefilter()
+                return
+            buf, nbytes, b = self._q8
+            self._ck(self.lib.lrx_set_dense_prefilter(self.h, _ptr(buf), nbytes, (C.c_double * 2)(*b)))
+        else:
+            self._ck(self.lib.lrx_set_dense_prefilter(self.h, C.c_void_p(0), 0, None))
+
+    @property
+    def prefilter_bounds(self):
+        """(max row error norm, max row norm) of the int8 shadow, or None."""
+        return self._q8[2] if self._q8 is not None else None
 
     def set_postings(self, term_ptr, postings, doc_len, idf, avgdl: float, k1: float = 1.5,
                      b: float = 0.75):
@@ -102,7 +135,10 @@ class DeviceIndex:
         batch's merges and fusion running under the other's scans."""
         other = DeviceIndex(self.device.index, self.rank, self.world)
         if self.x is not None:
-            other.set_corpus(self.x, self.id_base)
+            other.set_corpus(self.x, self.id_base, prefilter=False)
+            if self._q8 is not None:                        # the same shadow, no second copy
+                other._q8 = self._q8
+                other.set_prefilter(True)
         if self._post is not None:
             tp, p8, idf_t = self._post
             nnz, avgdl, k1, b, max_len = self._post_args

@@ -86,3 +86,63 @@ def flat_ip_search(Xh: np.ndarray, qh: np.ndarray, K: int, id_base: int = 0):
     """``IndexFlatIP.search`` on fp16 data: returns (D float32 [B,K], I int64 [B,K])."""
     _, D, I = topk_from_scores(exact_scores(Xh, qh), K, id_base)
     return D, I
+
+
+# ---------------------------------------------------------------------------
+# Checker for the int8 pre-filter of the CUDA scan (include/lrx.h,
+# lrx_build_dense_prefilter).  Not part of the reference path: a flat IP index
+# has no such stage; the stage must not change any result, which is what the
+# parity tests assert.  These functions restate the shadow's DEFINITION so that
+# the device-built bytes and the two error bounds can be checked on the CPU.
+def int8_shadow(Xh: np.ndarray):
+    """(xi int8 [n,384], scale float32 [n], E, X): per-row scaled int8 image of the
+    fp16 matrix -- scale = max|x| / 127 and xi = rint(x * (127 / max|x|)), both in
+    float32 -- with E = max_r ||x_r - scale_r xi_r||_2 and X = max_r ||scale_r xi_r||_2
+    in float64 (every term is exact in float64)."""
+    assert Xh.dtype == np.float16
+    x = Xh.astype(np.float32)
+    mx = np.abs(x).max(axis=1) if x.shape[0] else np.zeros(0, np.float32)
+    scale = (mx / np.float32(127.0)).astype(np.float32)
+    with np.errstate(divide="ignore"):
+        inv = np.where(mx > 0, np.float32(127.0) / mx, np.float32(0.0)).astype(np.float32)
+    xi = np.clip(np.rint(x * inv[:, None]), -127, 127).astype(np.int8)
+    xh = scale.astype(np.float64)[:, None] * xi.astype(np.float64)
+    err = np.sqrt(((x.astype(np.float64) - xh) ** 2).sum(axis=1))
+    nrm = np.sqrt((xh ** 2).sum(axis=1))
+    E = float(err.max()) if err.size else 0.0
+    X = float(nrm.max()) if nrm.size else 0.0
+    return xi, scale, E, X
+
+
+def int8_query_digits(qh: np.ndarray):
+    """(hi int [384], lo int [384], cq float32): q ~= cq * (256 * hi + lo), the two-digit
+    int8 image of one fp16 query the scan multiplies the shadow with."""
+    assert qh.dtype == np.float16 and qh.ndim == 1
+    q = qh.astype(np.float32)
+    mx = np.float32(np.abs(q).max())
+    inv = np.float32(127.0) / mx if mx > 0 else np.float32(0.0)
+    s = (q * inv).astype(np.float32)
+    hi = np.clip(np.rint(s), -127, 127)
+    lo = np.clip(np.rint(((s - hi.astype(np.float32)).astype(np.float32) * np.float32(256.0)).astype(np.float32)),
+                 -127, 127)
+    cq = np.float32(mx * np.float32(1.0 / 32512.0))
+    return hi.astype(np.int64), lo.astype(np.int64), cq
+
+
+def int8_guard_band(qh: np.ndarray, E: float, X: float) -> float:
+    """The rigorous bound |x.q - A(x, q)| <= E |q| + X |q - qhat| + rounding the exactness
+    guard of the pre-filtered scan uses (csrc/dense.cu:dense_merge_rescore_kernel)."""
+    hi, lo, cq = int8_query_digits(qh)
+    q = qh.astype(np.float64)
+    d = q - float(cq) * (256 * hi + lo).astype(np.float64)
+    nq, ne = float(np.sqrt((q * q).sum())), float(np.sqrt((d * d).sum()))
+    return (E * nq + X * ne + 2.0e-7 * X * (nq + ne)) * (1.0 + 1.0e-6) + 1.0e-12
+
+
+def int8_fast_scores(Xh: np.ndarray, qh: np.ndarray):
+    """float32 [n] scores as the pre-filtered scan computes them for one query:
+    fl(fl(scale_r * cq) * fl(256 * <xi_r, hi> + <xi_r, lo>))."""
+    xi, scale, _, _ = int8_shadow(Xh)
+    hi, lo, cq = int8_query_digits(qh)
+    D = xi.astype(np.int64) @ (256 * hi + lo)
+    return ((scale * cq).astype(np.float32) * D.astype(np.float32)).astype(np.float32)
