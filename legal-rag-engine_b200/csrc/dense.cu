@@ -496,29 +496,42 @@ dense_q8_build_kernel(const unsigned char* __restrict__ x, int64_t n_rows, int64
     }
 }
 
+template <int NT>
 struct ScanQ8Smem {
     unsigned char ring[kStages][kQ8TileBytes];   // 16-byte aligned bulk-copy destinations
     float scale[kStages][kQ8TileRows];
-    signed char qd[8][kDim];                     // query digits: row 2 * query (hi), 2 * query + 1 (lo)
-    float cq[4];
+    signed char qd[8 * NT][kDim];                // query digits: row 2 * query (hi), 2 * query + 1 (lo)
+    float cq[4 * NT];
     uint64_t full[kStages];
     int tile_of[kStages];
     int count[8];
     uint32_t tau[8];
-    uint64_t keys[1];   // [4][kCap], sized at launch
+    uint64_t keys[1];   // [4 * NT][scan_cap(4 * NT)], sized at launch
 };
 
+__device__ __forceinline__ void mma_s8(int* c, uint32_t a0, uint32_t a1, uint32_t a2, uint32_t a3,
+                                       uint32_t b0, uint32_t b1) {
+    asm volatile("mma.sync.aligned.m16n8k32.row.col.s32.s8.s8.s32 "
+                 "{%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+                 : "+r"(c[0]), "+r"(c[1]), "+r"(c[2]), "+r"(c[3])
+                 : "r"(a0), "r"(a1), "r"(a2), "r"(a3), "r"(b0), "r"(b1));
+}
+
+// NT = 1: up to 4 queries (one 8-column MMA tile of digits, B fragments in registers); NT = 2: 5..8
+// queries (two tiles; the second tile's -- and, to stay under 128 registers beside a BM25 CTA, the
+// first tile's -- B fragments are re-read from shared memory per chunk), 512 candidate slots each.
+template <int NT>
 __global__ void __launch_bounds__(kScanThreads, 2)
 dense_scan_q8_kernel(const unsigned char* __restrict__ rows8, const float* __restrict__ scales,
                      int64_t n_rows, const __half* __restrict__ q, int n_q, int width,
-                     uint64_t* __restrict__ part /* [grid][4][width] */,
+                     uint64_t* __restrict__ part /* [grid][NQ][width] */,
                      unsigned int* __restrict__ tau_g /* [8] shared thresholds, zero at launch */) {
-    constexpr int NQ = 4;
+    constexpr int NQ = 4 * NT;
     extern __shared__ __align__(128) unsigned char smem_raw[];
-    ScanQ8Smem& sm = *reinterpret_cast<ScanQ8Smem*>(smem_raw);
+    ScanQ8Smem<NT>& sm = *reinterpret_cast<ScanQ8Smem<NT>*>(smem_raw);
     uint64_t* keys = sm.keys;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    constexpr int cap = kCap;
+    constexpr int cap = scan_cap(NQ);
     const int soft_cap = (width <= 64) ? kSoftCap : cap;    // a tile appends up to 128 keys per query
     const int n_tiles = (int)((n_rows + kQ8TileRows - 1) / kQ8TileRows);   // the shadow is padded to whole tiles
 
@@ -544,7 +557,7 @@ dense_scan_q8_kernel(const unsigned char* __restrict__ rows8, const float* __res
     if (tid == 0)
         for (int s = 0; s < kStages; ++s) issue((int)blockIdx.x + s * (int)gridDim.x, s);
 
-    // ---- query digits (every CTA redoes the <= 4 queries: 1.5 K elements), warp w = query w
+    // ---- query digits (every CTA redoes the <= 8 queries: 3 K elements), warp w = query w
     {
         uint32_t* qrow = reinterpret_cast<uint32_t*>(&sm.qd[0][0]);
         if (warp < NQ) {
@@ -576,10 +589,14 @@ dense_scan_q8_kernel(const unsigned char* __restrict__ rows8, const float* __res
     // B fragments: lane (g, t) holds 16 bytes per 64-column chunk of digit row g at the SAME columns
     // as its A bytes, so A and B agree on a (permuted) k order -- no ldmatrix, no swizzle.
     const int g = lane >> 2, t = lane & 3;
-    uint4 qb[6];
+    uint4 qb[NT == 1 ? 6 : 1];
+    if (NT == 1) {
 #pragma unroll
-    for (int j = 0; j < 6; ++j) qb[j] = *reinterpret_cast<const uint4*>(&sm.qd[g][j * 64 + 16 * t]);
-    const float cq = sm.cq[t];
+        for (int j = 0; j < 6; ++j) qb[NT == 1 ? j : 0] = *reinterpret_cast<const uint4*>(&sm.qd[g][j * 64 + 16 * t]);
+    }
+    float cq[NT];
+#pragma unroll
+    for (int u = 0; u < NT; ++u) cq[u] = sm.cq[4 * u + t];
     const uint32_t a_off = (uint32_t)((warp * 16 + g) * kQ8RowBytes + 16 * t);
 
     for (int it = 0;; ++it) {
@@ -590,7 +607,11 @@ dense_scan_q8_kernel(const unsigned char* __restrict__ rows8, const float* __res
         const int64_t row0 = (int64_t)tile * kQ8TileRows;
         mbar_wait(&sm.full[s], parity);
 
-        int c0[4] = {0, 0, 0, 0}, c1[4] = {0, 0, 0, 0};     // two accumulation chains
+        int c0[NT][4], c1[NT][4];                            // two accumulation chains per digit tile
+#pragma unroll
+        for (int u = 0; u < NT; ++u)
+#pragma unroll
+            for (int i = 0; i < 4; ++i) c0[u][i] = c1[u][i] = 0;
         {
             const unsigned char* base = sm.ring[s] + a_off;
             uint4 xa[6], xb[6];
@@ -601,32 +622,34 @@ dense_scan_q8_kernel(const unsigned char* __restrict__ rows8, const float* __res
             }
 #pragma unroll
             for (int j = 0; j < 6; ++j) {
-                asm volatile("mma.sync.aligned.m16n8k32.row.col.s32.s8.s8.s32 "
-                             "{%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
-                             : "+r"(c0[0]), "+r"(c0[1]), "+r"(c0[2]), "+r"(c0[3])
-                             : "r"(xa[j].x), "r"(xb[j].x), "r"(xa[j].y), "r"(xb[j].y),
-                               "r"(qb[j].x), "r"(qb[j].y));
-                asm volatile("mma.sync.aligned.m16n8k32.row.col.s32.s8.s8.s32 "
-                             "{%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
-                             : "+r"(c1[0]), "+r"(c1[1]), "+r"(c1[2]), "+r"(c1[3])
-                             : "r"(xa[j].z), "r"(xb[j].z), "r"(xa[j].w), "r"(xb[j].w),
-                               "r"(qb[j].z), "r"(qb[j].w));
+#pragma unroll
+                for (int u = 0; u < NT; ++u) {
+                    const uint4 b = (NT == 1) ? qb[NT == 1 ? j : 0]
+                                              : *reinterpret_cast<const uint4*>(&sm.qd[8 * u + g][j * 64 + 16 * t]);
+                    mma_s8(c0[u], xa[j].x, xb[j].x, xa[j].y, xb[j].y, b.x, b.y);
+                    mma_s8(c1[u], xa[j].z, xb[j].z, xa[j].w, xb[j].w, b.z, b.w);
+                }
             }
         }
-        // lane (g, t): digit sums (hi, lo) of query t for rows g and g + 8 of the warp's block.
-        // |256 * hi + lo| <= 257 * 384 * 127^2 < 2^31.
-        if (t < n_q) {
-            const int r0 = warp * 16 + g;
-            const uint32_t tau = sm.tau[t];
+        // lane (g, t): digit sums (hi, lo) of queries t (and 4 + t) for rows g and g + 8 of the warp's
+        // block.  |256 * hi + lo| <= 257 * 384 * 127^2 < 2^31.
 #pragma unroll
-            for (int hrow = 0; hrow < 2; ++hrow) {
-                const int r = r0 + 8 * hrow;
-                const int D = (c0[2 * hrow] + c1[2 * hrow]) * 256 + (c0[2 * hrow + 1] + c1[2 * hrow + 1]);
-                const float sc = __fmul_rn(__fmul_rn(sm.scale[s][r], cq), (float)D);
-                const uint32_t o = f32_ord(sc);
-                if (o >= tau && row0 + r < n_rows) {
-                    const int pos = atomicAdd(&sm.count[t], 1);
-                    keys[t * cap + pos] = ((uint64_t)o << 32) | (uint32_t)(~(uint32_t)(row0 + r));
+        for (int u = 0; u < NT; ++u) {
+            const int qi = 4 * u + t;
+            if (qi < n_q) {
+                const int r0 = warp * 16 + g;
+                const uint32_t tau = sm.tau[qi];
+#pragma unroll
+                for (int hrow = 0; hrow < 2; ++hrow) {
+                    const int r = r0 + 8 * hrow;
+                    const int D = (c0[u][2 * hrow] + c1[u][2 * hrow]) * 256 +
+                                  (c0[u][2 * hrow + 1] + c1[u][2 * hrow + 1]);
+                    const float sc = __fmul_rn(__fmul_rn(sm.scale[s][r], cq[u]), (float)D);
+                    const uint32_t o = f32_ord(sc);
+                    if (o >= tau && row0 + r < n_rows) {
+                        const int pos = atomicAdd(&sm.count[qi], 1);
+                        keys[qi * cap + pos] = ((uint64_t)o << 32) | (uint32_t)(~(uint32_t)(row0 + r));
+                    }
                 }
             }
         }
@@ -889,10 +912,10 @@ static cudaError_t launch_scan(lrx_handle* h, const __half* q, int n_q, int widt
 
 // ---- int8 pre-filter
 bool dense_q8_applies(const lrx_handle* h, int B, int K, int width) {
-    // up to 4 queries per pass (their hi / lo digits fill the 8 MMA columns; 5..8 queries would need
-    // two passes of 388 B/row against one fp16 pass of 768), lists up to 128 wide per CTA -- a widened
-    // retry beyond that goes back to the fp16 scan and its 1e-5 band
-    return h->q8 != nullptr && h->n_local > 0 && B <= 4 && K <= 64 && width <= 128;
+    // up to 8 queries per pass (the hi / lo digits of 4 queries fill the 8 columns of one MMA tile;
+    // 5..8 queries take two tiles), lists up to 128 wide per CTA -- a widened retry beyond that goes
+    // back to the fp16 scan and its 1e-5 band
+    return h->q8 != nullptr && h->n_local > 0 && B <= 8 && K <= 64 && width <= 128;
 }
 
 int64_t dense_q8_bytes(int64_t n_local) {
@@ -934,18 +957,19 @@ cudaError_t launch_dense_q8_build(lrx_handle* h, void* buf, double* bounds_out) 
     return cudaSuccess;
 }
 
+template <int NT>
 static cudaError_t launch_scan_q8(lrx_handle* h, const __half* q, int n_q, int width, uint64_t* part,
                                   int grid) {
     std::lock_guard<std::recursive_mutex> attr_guard(attr_mutex());
     static bool attr_dev[64] = {false};
     bool& attr = attr_dev[h->device & 63];
-    // the same footprint as the fp16 scan (135 KB): one CTA per SM, a BM25 scan CTA fits beside it
-    const size_t smem = offsetof(ScanQ8Smem, keys) + (size_t)4 * kCap * sizeof(uint64_t);
+    // about the footprint of the fp16 scan (135 / 138 KB): one CTA per SM, a BM25 scan CTA fits beside it
+    const size_t smem = offsetof(ScanQ8Smem<NT>, keys) + (size_t)4 * kCap * sizeof(uint64_t);
     if (!attr) {
-        cudaError_t e = cudaFuncSetAttribute(dense_scan_q8_kernel,
+        cudaError_t e = cudaFuncSetAttribute(dense_scan_q8_kernel<NT>,
                                              cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) return e;
-        e = cudaFuncSetAttribute(dense_scan_q8_kernel, cudaFuncAttributePreferredSharedMemoryCarveout,
+        e = cudaFuncSetAttribute(dense_scan_q8_kernel<NT>, cudaFuncAttributePreferredSharedMemoryCarveout,
                                  cudaSharedmemCarveoutMaxShared);
         if (e != cudaSuccess) return e;
         attr = true;
@@ -957,8 +981,8 @@ static cudaError_t launch_scan_q8(lrx_handle* h, const __half* q, int n_q, int w
     const unsigned char* rows8 = (const unsigned char*)h->q8;
     const float* scales = (const float*)(rows8 + n_pad * kQ8RowBytes);
     prof_begin(h, 0);
-    dense_scan_q8_kernel<<<grid, kScanThreads, smem, h->stream>>>(rows8, scales, h->n_local, q, n_q, width,
-                                                                   part, tau_g);
+    dense_scan_q8_kernel<NT><<<grid, kScanThreads, smem, h->stream>>>(rows8, scales, h->n_local, q, n_q, width,
+                                                                       part, tau_g);
     prof_end(h, 0);
     h->launches++;
     return cudaGetLastError();
@@ -992,10 +1016,10 @@ cudaError_t launch_dense_topk(lrx_handle* h, const void* qv, int B, int K, int w
     if (dense_q8_applies(h, B, K, width)) {
         // int8 pre-filter: per-CTA lists `width` long, merged list four times that
         const int merged_width = (4 * width < kMaxWidth) ? 4 * width : kMaxWidth;
-        e = launch_scan_q8(h, q, B, width, part, grid);
+        e = (B > 4) ? launch_scan_q8<2>(h, q, B, width, part, grid) : launch_scan_q8<1>(h, q, B, width, part, grid);
         if (e != cudaSuccess) return e;
         dense_merge_rescore_kernel<<<B, kMergeThreads, kMergeCap * sizeof(uint64_t), h->stream>>>(
-            part, grid, 4, width, (const unsigned char*)h->x, h->n_local, h->id_base, q, merged_width, K,
+            part, grid, (B > 4) ? 8 : 4, width, (const unsigned char*)h->x, h->n_local, h->id_base, q, merged_width, K,
             kDenseEps, h->q8_err, h->q8_norm, exact, D, I, flags);
         h->launches++;
         return cudaGetLastError();

@@ -66,7 +66,7 @@ def test_guard_band_covers_every_row(dev):
 
 
 @pytest.mark.parametrize("n", [65, 129, 1000, 20011, 300000])
-@pytest.mark.parametrize("B", [1, 3, 4])
+@pytest.mark.parametrize("B", [1, 3, 4, 5, 8])            # 5..8: two digit tiles per pass
 def test_prefilter_on_and_off_give_the_oracle_result(dev, n, B):
     x = synth.host_vectors(n, seed=500 + n, dup_frac=0.01)
     q = synth.host_queries(B, seed=17 + B)
@@ -129,14 +129,15 @@ def test_unseparable_candidates_set_the_flag_and_the_search_falls_back(dev):
 
 
 @pytest.mark.parametrize("fusion", ["linear", "rrf"])
-def test_search_with_and_without_prefilter_bit_identical(dev, fusion):
-    n, B, k = 150000, 4, 10
+@pytest.mark.parametrize("B", [4, 8])
+def test_search_with_and_without_prefilter_bit_identical(dev, B, fusion):
+    n, k = 150000, 10
     x = synth.host_vectors(n, seed=31)
     idx = synth.host_bm25(n, seed=32, vocab=4000)
     q = synth.host_queries(B, seed=33)
     terms, ptr = synth.host_query_terms(B, 8, seed=34, vocab=4000)
     lists = [terms[ptr[b]:ptr[b + 1]].tolist() for b in range(B)]
-    w = [0.5, 0.6, 0.5, 0.6]
+    w = [0.5, 0.6, 0.5, 0.6] * (B // 4)
     xd = _cuda(x)
     out = {}
     for on in (True, False):
