@@ -686,7 +686,7 @@ def scan_kernel_of(dev, n_local, K):
     search of depth K runs on this index: with the int8 shadow resident (lrx_build_dense_prefilter)
     the scan streams 384 B of int8 + a 4-byte scale per row of the shadow (padded to 128-row
     tiles) instead of the 768-byte fp16 row."""
-    if dev.prefilter_bounds is not None and K <= 64:
+    if dev.prefilter_bounds is not None and (K <= 64 or (K <= 224 and n_local >= 32768)):
         n_pad = (n_local + 127) // 128 * 128
         return "dense_scan_q8_kernel", 388, n_pad * 388
     return "dense_scan_kernel<4>", 768, n_local * 768

@@ -41,6 +41,10 @@ constexpr int kSoftCap = 256;                      // prune once a buffer holds 
                                                    // tile: sorting 256 keys costs ~3 us, 1024 keys ~40 us,
                                                    // and the threshold tightens 4x per prune either way
 constexpr int kMaxWidth = 512;                     // max per-CTA list length
+constexpr int kMaxMerged = 2048;                   // max merged list (int8 pre-filter, deep lists)
+static size_t merge_smem_bytes(int merged_width) {
+    return (size_t)kMergeCap * sizeof(uint64_t) + (size_t)merged_width * (2 * sizeof(u128) + sizeof(uint64_t));
+}
 // candidate buffer entries per query: up to 4 queries per pass 1024 each, 5..8 queries 512 each (the
 // same 32 KB: a CTA of the BM25 scan must keep fitting beside this kernel's CTA; lists up to 256 wide)
 __host__ __device__ constexpr int scan_cap(int nq) { return nq > 4 ? 512 : kCap; }
@@ -722,11 +726,13 @@ dense_merge_rescore_kernel(const uint64_t* __restrict__ part, int n_lists, int l
                            double q8_err, double q8_norm,
                            double* __restrict__ out_exact, float* __restrict__ out_D,
                            int64_t* __restrict__ out_I, int32_t* __restrict__ out_flag) {
+    // dynamic shared memory (merge_smem_bytes): buf [kMergeCap] u64 | keys [width] u128 |
+    // sorted [width] u128 | merged [width] u64
     extern __shared__ __align__(128) unsigned char merge_raw[];
-    uint64_t* buf = reinterpret_cast<uint64_t*>(merge_raw);          // [kMergeCap]
-    __shared__ uint64_t merged[kMaxWidth];
-    __shared__ u128 keys[kMaxWidth];
-    __shared__ u128 sorted[kMaxWidth];
+    uint64_t* buf = reinterpret_cast<uint64_t*>(merge_raw);
+    u128* keys = reinterpret_cast<u128*>(merge_raw + kMergeCap * sizeof(uint64_t));
+    u128* sorted = keys + width;
+    uint64_t* merged = reinterpret_cast<uint64_t*>(sorted + width);
     __shared__ int s_count, s_overflow;
     __shared__ uint64_t s_bound;
     __shared__ unsigned long long s_full;       // largest last key of a per-CTA list that is full
@@ -915,7 +921,11 @@ bool dense_q8_applies(const lrx_handle* h, int B, int K, int width) {
     // up to 8 queries per pass (the hi / lo digits of 4 queries fill the 8 columns of one MMA tile;
     // 5..8 queries take two tiles), lists up to 128 wide per CTA -- a widened retry beyond that goes
     // back to the fp16 scan and its 1e-5 band
-    return h->q8 != nullptr && h->n_local > 0 && B <= 8 && K <= 64 && width <= 128;
+    if (h->q8 == nullptr || h->n_local <= 0 || B > 8) return false;
+    if (K <= 64) return width <= 128;
+    // deep lists: only at the default width (a retry goes to the fp16 scan) and on shards large
+    // enough that every CTA's share of the best K is far below its 64-entry list
+    return width == dense_default_width(K) && width <= 256 && h->n_local >= 32768;
 }
 
 int64_t dense_q8_bytes(int64_t n_local) {
@@ -1007,19 +1017,24 @@ cudaError_t launch_dense_topk(lrx_handle* h, const void* qv, int B, int K, int w
     bool& attr = attr_dev[h->device & 63];
     if (!attr) {
         e = cudaFuncSetAttribute(dense_merge_rescore_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                 (int)(kMergeCap * sizeof(uint64_t)));
+                                 (int)merge_smem_bytes(kMaxMerged));
         if (e != cudaSuccess) return e;
         attr = true;
     }
     uint64_t* part = (uint64_t*)h->ws_dense_part;
     const __half* q = (const __half*)qv;
     if (dense_q8_applies(h, B, K, width)) {
-        // int8 pre-filter: per-CTA lists `width` long, merged list four times that
-        const int merged_width = (4 * width < kMaxWidth) ? 4 * width : kMaxWidth;
-        e = (B > 4) ? launch_scan_q8<2>(h, q, B, width, part, grid) : launch_scan_q8<1>(h, q, B, width, part, grid);
+        // int8 pre-filter: short per-CTA lists, a long merged list.  K <= 64: lists `width` long (64,
+        // 128 on a retry), merged list four times that.  Deeper (config C5, K = 200): lists of 64 --
+        // a CTA holds 1 / 148 of the rows and ~K / 148 of the best K; a CTA that holds more fills its
+        // list, which the guard sees -- and a merged list of 2048 (the band needs ~10 K candidates).
+        const int list_width = (K <= 64) ? width : 64;
+        const int merged_width = (K <= 64) ? ((4 * width < kMaxWidth) ? 4 * width : kMaxWidth) : kMaxMerged;
+        e = (B > 4) ? launch_scan_q8<2>(h, q, B, list_width, part, grid)
+                    : launch_scan_q8<1>(h, q, B, list_width, part, grid);
         if (e != cudaSuccess) return e;
-        dense_merge_rescore_kernel<<<B, kMergeThreads, kMergeCap * sizeof(uint64_t), h->stream>>>(
-            part, grid, (B > 4) ? 8 : 4, width, (const unsigned char*)h->x, h->n_local, h->id_base, q, merged_width, K,
+        dense_merge_rescore_kernel<<<B, kMergeThreads, merge_smem_bytes(merged_width), h->stream>>>(
+            part, grid, (B > 4) ? 8 : 4, list_width, (const unsigned char*)h->x, h->n_local, h->id_base, q, merged_width, K,
             kDenseEps, h->q8_err, h->q8_norm, exact, D, I, flags);
         h->launches++;
         return cudaGetLastError();
@@ -1036,7 +1051,7 @@ cudaError_t launch_dense_topk(lrx_handle* h, const void* qv, int B, int K, int w
                       : launch_scan<4>(h, q + (size_t)b0 * kDim, nq, width, part, grid);
         if (e != cudaSuccess) return e;
         // list l of query qi of this pass: part[(l * NQ + qi) * width]
-        dense_merge_rescore_kernel<<<nq, kMergeThreads, kMergeCap * sizeof(uint64_t), h->stream>>>(
+        dense_merge_rescore_kernel<<<nq, kMergeThreads, merge_smem_bytes(width), h->stream>>>(
             part, grid, NQ, width, (const unsigned char*)h->x, h->n_local, h->id_base,
             q + (size_t)b0 * kDim, width, K, kDenseEps, 0.0, -1.0, exact + (size_t)b0 * K, D + (size_t)b0 * K,
             I + (size_t)b0 * K, flags + b0);

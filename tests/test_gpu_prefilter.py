@@ -76,7 +76,7 @@ def test_prefilter_on_and_off_give_the_oracle_result(dev, n, B):
     for on in (True, False):
         dev.set_corpus(xd, id_base=31, prefilter=on)
         assert (dev.prefilter_bounds is not None) == on
-        for K in (1, 10, 20, 64):
+        for K in (1, 10, 20, 64, 200):                      # 200 on >= 32768 rows: lists of 64, merged list of 2048
             Eo, Do, Io = flat_ip.topk_from_scores(s, K, id_base=31)
             E, D, I, flags = dev.dense_topk(qd, K)
             assert flags.cpu().numpy().sum() == 0, (on, K)
