@@ -490,9 +490,14 @@ dense_q8_build_kernel(const unsigned char* __restrict__ x, int64_t n_rows, int64
     }
     err2 = warp_sum_f64(err2);
     n2 = warp_sum_f64(n2);
+    // Odd rows are stored with their 64-byte chunks swapped pairwise (chunk c at 64 * (c ^ 1)): the
+    // scan's lanes of rows g and g + 1 then read the two different halves of a 128-byte line for the
+    // same logical columns, and a quarter warp's 16-byte loads cover all 32 banks (rows are 384 B =
+    // 0 mod 128 apart: unswizzled, every pair of rows collided -- 2 wavefronts per load instead of 1).
+    const int sw = (int)(row & 1) << 4;                      // word index ^ 16 = byte offset ^ 64
 #pragma unroll
     for (int j = 0; j < 3; ++j)
-        dst[j * 32 + lane] = pack_s8x4(xi[4 * j], xi[4 * j + 1], xi[4 * j + 2], xi[4 * j + 3]);
+        dst[(j * 32 + lane) ^ sw] = pack_s8x4(xi[4 * j], xi[4 * j + 1], xi[4 * j + 2], xi[4 * j + 3]);
     if (lane == 0) {
         scales[row] = scale;
         atomicMax(bounds + 0, (unsigned long long)f64_ord(err2));
@@ -620,9 +625,9 @@ dense_scan_q8_kernel(const unsigned char* __restrict__ rows8, const float* __res
             const unsigned char* base = sm.ring[s] + a_off;
             uint4 xa[6], xb[6];
 #pragma unroll
-            for (int j = 0; j < 6; ++j) {
-                xa[j] = *reinterpret_cast<const uint4*>(base + j * 64);                    // row g
-                xb[j] = *reinterpret_cast<const uint4*>(base + 8 * kQ8RowBytes + j * 64);  // row g + 8
+            for (int j = 0; j < 6; ++j) {                    // logical chunk j of an odd row sits at j ^ 1
+                xa[j] = *reinterpret_cast<const uint4*>(base + ((j ^ (g & 1)) * 64));                    // row g
+                xb[j] = *reinterpret_cast<const uint4*>(base + 8 * kQ8RowBytes + ((j ^ (g & 1)) * 64));  // row g + 8
             }
 #pragma unroll
             for (int j = 0; j < 6; ++j) {

@@ -38,7 +38,9 @@ def test_shadow_bytes_and_bounds_match_the_restatement(dev, n):
     n_pad = (n + 127) // 128 * 128
     assert nbytes == n_pad * 388
     raw = buf.cpu().numpy()
-    rows = raw[:n_pad * 384].view(np.int8).reshape(n_pad, 384)
+    rows = raw[:n_pad * 384].view(np.int8).reshape(n_pad, 384).copy()
+    # device layout: odd rows keep their 64-byte chunks swapped pairwise (bank-conflict-free scan)
+    rows[1::2] = rows[1::2].reshape(-1, 3, 2, 64)[:, :, ::-1, :].reshape(-1, 384)
     scales = raw[n_pad * 384:n_pad * 388].view(np.float32)
     xi, sc, Eo, Xo = flat_ip.int8_shadow(x)
     np.testing.assert_array_equal(rows[:n], xi)

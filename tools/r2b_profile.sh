@@ -10,7 +10,3 @@ ncu --metrics gpu__time_duration.sum --clock-control none \
 ncu --set full --clock-control none --import-source on -k regex:"dense_scan|bm25_scan" -s 200 -c 2 \
     -o gpurun_out/r2b/scan_q8_full -f $B > gpurun_out/r2b/ncu_full.log 2>&1; echo "full rc=$?"
 ls -la gpurun_out/r2b/*.ncu-rep
-for nf in 2 4; do for rows in 10000000 1250000; do
-  python bench.py --rows $rows --in-flight $nf --steps 100 --no-cpu-baseline --no-stages --parity-queries 2 > gpurun_out/r2b/fly${nf}_$rows.json 2>/dev/null
-  python tools/show2.py gpurun_out/r2b/fly${nf}_$rows.json | head -1
-done; done
