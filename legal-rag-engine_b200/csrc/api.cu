@@ -435,6 +435,15 @@ static int k2b_min_b() {
     }
     return v;
 }
+// LRX_BM_CHAIN_CTAS: BM25 scan CTAs per SM inside the search chain (1 = what fits beside the dense scan; 2 = as alone)
+static int bm_chain_ctas() {
+    static int v = -1;
+    if (v < 0) {
+        const char* e = getenv("LRX_BM_CHAIN_CTAS");
+        v = (e != nullptr && atoi(e) == 2) ? 2 : 1;
+    }
+    return v;
+}
 static cudaError_t launch_dense_auto(lrx_handle* h, const void* q, int B, int K, int width, double* exact,
                                      float* D, int64_t* I, int32_t* flags) {
     if (B >= k2b_min_b() && h->n_local > 0 && ((uintptr_t)q & 15) == 0) {
@@ -518,6 +527,7 @@ int lrx_bm25(lrx_handle* h, const int32_t* dev_q_terms, const int32_t* dev_q_ptr
     LRX_CUDA(h, cudaSetDevice(h->device));
     h->bm_rows = h->bm_rows_cfg;
     h->bm_list_k = K;
+    h->bm_ctas_per_sm = 0;
     LRX_CUDA(h, launch_bm25(h, dev_q_terms, dev_q_ptr, B, dev_cand_ids, n_cand, dev_cand_scores,
                             dev_max, K, dev_top_scores, dev_top_ids));
     return LRX_OK;
@@ -605,6 +615,10 @@ static int enqueue_local(lrx_handle* h, const void* q, const int32_t* q_terms, c
     packed_layout(B, k, &o_max, &o_flags, &total);
     const int Kb = (mode == LRX_FUSE_RRF) ? K : 0;
     h->bm_list_k = Kb;
+    // K2a's CTA shares the SM (profiles/r2_runs/ab_bm25_chain_ctas.txt; 5..8 queries on a small shard keep
+    // the second wave: there the BM25 scan outlasts the dense scan by far and the wave does real work)
+    h->bm_ctas_per_sm = (B < k2b_min_b() && h->n_local > 0 && (B <= 4 || h->n_local >= (4ll << 20)))
+                            ? bm_chain_ctas() : 0;
     LRX_CUDA(h, cudaEventRecord(h->ev_fork, h->stream));
     LRX_CUDA(h, cudaStreamWaitEvent(h->aux, h->ev_fork, 0));
     LRX_CUDA(h, launch_dense_auto(h, q, B, K, width, s.dense_exact, s.dense_D, s.dense_I, s.flags));

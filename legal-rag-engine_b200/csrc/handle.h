@@ -65,6 +65,7 @@ struct lrx_handle {
     // c[len] table needs no fallback)
     int bm_lut_ld = 0;
     int bm_list_k = 0;            // depth of the BM25 top list of the current call (sets the scan's geometry)
+    int bm_ctas_per_sm = 0;       // 1: the scan runs beside the dense scan (search chain), one CTA per SM; else 2
     int bm_rows = 0;              // token capacity of a query batch (rows of the bounds table); 0 = B * 64
     double* bm_ctab = nullptr;    // device float64 [2048]: c[len] = k1*(1 - b + b*len/avgdl), built at lrx_set_postings
     double bm_avgdl = 0.0, bm_k1 = 1.5, bm_b = 0.75;
