@@ -13,12 +13,17 @@
 //                       query), register sorting networks when a buffer fills, thresholds shared
 //                       grid-wide).  Scores never touch HBM.  256 threads, 133 KB: one BM25 scan
 //                       CTA fits beside it on the SM (api.cu runs the two scans side by side).
+//   dense_scan_q8_kernel  the same scan over an int8 SHADOW of the matrix (388 B/row for 768; the
+//                       default when lrx_build_dense_prefilter has run): mma.sync m16n8k32 s8 on
+//                       two int8 digits per query element, per-row fp32 scales, 128-row tiles, one
+//                       barrier per tile; see the block comment in front of it for the guard band
+//                       that keeps the results bit-identical.  dense_q8_build_kernel builds the shadow.
 //   dense_merge_rescore_kernel  one CTA per query merges the per-CTA lists (merge.cuh) and
 //                       re-scores the `width` survivors EXACTLY in float64 (exact
 //                       and order independent, see oracle/flat_ip.py), orders them by
 //                       (score desc, id asc), emits the best K and the guard flag.
 //
-// Algorithmic HBM bytes per launch of dense_scan_kernel: n_local * 768.
+// Algorithmic HBM bytes per launch: dense_scan_kernel n_local * 768, dense_scan_q8_kernel n_pad * 388.
 #include "common.cuh"
 #include "handle.h"
 #include "merge.cuh"
